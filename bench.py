@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/sec (fwd + BPTT), ALIF 784-128-10 recurrent, batch 256 per GPU, T = 100.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+One step = one pass of the hot path over one batch: input projection, fused recurrence + readout, fused
+max-over-time/log-softmax/NLL head, reverse-time BPTT, weight-gradient contraction, [gradient all-reduce],
+Adam step (reference snn.py:384-415).  Reported on the ONE JSON line:
+
+  value       whole-job samples/s with the spike rasters already resident in HBM (device-timed, max over ranks)
+  e2e         the same metric through the public API (SNN._exec_batch) from PINNED HOST images: H2D copy, GPU
+              spike encoder, train step, loss read-back -- every step, inside the timed region
+  roofline    the dominant kernel's algorithmic bytes / its CUDA-event duration against the measured HBM peak
+  cpu_baseline the CPU restatement of the reference (oracle/torch_port.py) timed on this box's host cores
+
+--impl reference times that CPU restatement alone (the reference itself is pure Python and cannot travel to the
+GPU box; oracle/torch_port.py is pinned against it by tests/test_oracle_golden.py).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, T, N, H, O = 256, 100, 784, 128, 10
+WORKLOAD = "ALIF 784-128-10 recurrent, learn_beta, periodic to_spikes (tau=0.02), batch 256/GPU, T=100, FastSigmoid"
+METRIC = "train samples/sec (fwd+BPTT) ALIF H=128"
+N_POOL = 4   # rotating input batches: 4 x 80 MB of rasters > 126 MB L2, so no step finds its input in L2
+
+
+def synthetic_images(n, seed):
+	"""MNIST-shaped images: k/255 levels with ink probability 0.19, uniform labels."""
+	g = torch.Generator().manual_seed(seed)
+	img = (torch.randint(1, 256, (n, N), generator=g).float() / 255.0) * (torch.rand(n, N, generator=g) < 0.19)
+	return img, torch.randint(0, O, (n,), generator=g)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+	"""Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+	REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+		0x80: "hw_power_brake_slowdown"}
+
+	def __init__(self, index):
+		super().__init__(daemon=True)
+		self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+		try:
+			import pynvml
+			pynvml.nvmlInit()
+			self.nv = pynvml
+			self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+			self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+		except Exception:
+			self.nv = None
+
+	def run(self):
+		while self.nv is not None and not self._stop_evt.is_set():
+			try:
+				self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+				mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+				for bit, name in self.REASONS.items():
+					if mask & bit:
+						self.reasons.add(name)
+			except Exception:
+				pass
+			time.sleep(0.02)
+
+	def stop(self):
+		self._stop_evt.set()
+		self.join(timeout=2)
+		return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+			"reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, budget_s=150.0):
+	"""Times oracle/torch_port.py (the reference's algorithm as PyTorch-CPU ops + autograd) on the host cores."""
+	from oracle.torch_port import TorchPortSNN
+	import oracle
+	cores = os.cpu_count() or 1
+	torch.set_num_threads(cores)
+	net = TorchPortSNN(N, H, O, T, layer_type=1, surrogate=0, recurrent=True, learn_beta=True, seed=0)
+	opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5)
+	img, labels = synthetic_images(B_PER_GPU, seed=0)
+	x = torch.from_numpy(oracle.encode(img.numpy(), T, None, tau=0.02, thr=0.2, periodic=True, eps=1e-7)).float()
+	t0 = time.perf_counter()
+	net.exec_batch(x, labels, opt)
+	first = time.perf_counter() - t0
+	b = B_PER_GPU
+	if first * (steps + warmup) > budget_s:      # keep the whole run within a few minutes: bound the sample
+		b = max(8, int(B_PER_GPU * budget_s / (first * (steps + warmup))))
+		x, labels = x[:b], labels[:b]
+	for _ in range(max(warmup - 1, 0)):
+		net.exec_batch(x, labels, opt)
+	t0 = time.perf_counter()
+	for _ in range(steps):
+		net.exec_batch(x, labels, opt)
+	dt = time.perf_counter() - t0
+	return {"value": b * steps / dt, "ms_per_step": 1e3 * dt / steps, "cores": cores, "batch": b, "steps": steps}
+
+
+def reference_arm(args, rank):
+	if rank != 0:
+		return
+	r = cpu_reference_run(args.steps, max(args.warmup, 1))
+	sample = f"{r['steps']} train steps of batch {r['batch']} (of {B_PER_GPU}), T={T}, rasters resident in host memory"
+	print(json.dumps({
+		"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+		"steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+		"scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+		"config": {"workload": WORKLOAD, "batch_per_step": r["batch"]},
+		"cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": sample},
+		"e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+	}))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument("--gpus", type=int, default=1)
+	ap.add_argument("--steps", type=int, default=50)
+	ap.add_argument("--warmup", type=int, default=10)
+	ap.add_argument("--impl", default="native", choices=["native", "reference"])
+	ap.add_argument("--no-cpu-baseline", action="store_true")
+	args = ap.parse_args()
+	args.warmup = max(args.warmup, 3)
+
+	rank = int(os.environ.get("RANK", "0"))
+	world = int(os.environ.get("WORLD_SIZE", "1"))
+	local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+	if args.impl == "reference":
+		reference_arm(args, rank)
+		return
+
+	import torch.distributed as dist
+	from snnimageclassification_b200 import SNN, LayerType, SpikeFuncType, ToSpikes, _cabi
+	dev = torch.device("cuda", local_rank)
+	torch.cuda.set_device(dev)
+	_cabi.require_b200(dev)          # fails loudly: no fallback
+	if world > 1:
+		dist.init_process_group("nccl", device_id=dev)
+
+	torch.manual_seed(0)             # same initial weights on every rank
+	enc = ToSpikes(T, use_periods=True)      # production encoder settings (tau = 0.02, datasets.py:21)
+	net = SNN(N, O, H, use_recurrent_connection=True, int_time_steps=T, spike_func=SpikeFuncType.FastSigmoid,
+		hidden_layer_type=LayerType.ALIF, device=dev, learn_beta=True, input_encoder=enc)
+	opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, fused=True)
+	crit = torch.nn.NLLLoss()
+	net.train()
+
+	pool_img, pool_lab = [], []
+	for i in range(N_POOL):
+		img, lab = synthetic_images(B_PER_GPU, seed=1000 * rank + i)
+		pool_img.append(img.pin_memory()); pool_lab.append(lab.pin_memory())
+	rasters = [enc.encode_batch(img.to(dev)) for img in pool_img]       # (B,T,N) fp32 resident in HBM
+	labels_dev = [lab.to(dev) for lab in pool_lab]
+
+	def step_resident(i):
+		loss = net.batch_loss(rasters[i % N_POOL], labels_dev[i % N_POOL], crit)
+		opt.zero_grad()
+		loss.backward()
+		net._allreduce_gradients()
+		opt.step()
+		return loss
+
+	def barrier():
+		if world > 1:
+			dist.barrier()
+		torch.cuda.synchronize()
+
+	def timed(fn, steps):
+		barrier()
+		e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		e0.record()
+		for i in range(steps):
+			fn(i)
+		e1.record()
+		barrier()
+		ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+		if world > 1:
+			dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+		return float(ms.item())
+
+	for i in range(args.warmup):
+		step_resident(i)
+	sampler = ClockSampler(local_rank)
+	sampler.start()
+	ms = timed(step_resident, args.steps)
+	clocks = sampler.stop()
+	value = world * B_PER_GPU * args.steps / (ms * 1e-3)
+
+	# end to end through the public API: pinned host images -> H2D -> GPU encoder -> train step -> loss read-back
+	def step_e2e(i):
+		return net._exec_batch(pool_img[i % N_POOL], pool_lab[i % N_POOL], crit, opt)
+	for i in range(3):
+		step_e2e(i)
+	ms_e2e = timed(step_e2e, args.steps)
+	e2e = world * B_PER_GPU * args.steps / (ms_e2e * 1e-3)
+	h2d = B_PER_GPU * N * 4 + B_PER_GPU * 8
+
+	# the same from pinned host RASTERS (what a reference DataLoader would hand over): H2D of 80 MB per step
+	host_rasters = [r.cpu().pin_memory() for r in rasters[:2]]
+	net.input_encoder = None
+	def step_e2e_raster(i):
+		return net._exec_batch(host_rasters[i % 2], pool_lab[i % 2], crit, opt)
+	for i in range(2):
+		step_e2e_raster(i)
+	ms_r = timed(step_e2e_raster, max(args.steps // 5, 3))
+	e2e_raster = world * B_PER_GPU * max(args.steps // 5, 3) / (ms_r * 1e-3)
+	net.input_encoder = enc
+
+	# per-kernel CUDA-event timing (separate short loop, same process) -> roofline of the dominant kernel
+	kern = profile_kernels(net, rasters, labels_dev, crit, dev)
+
+	if rank != 0:
+		if world > 1:
+			dist.destroy_process_group()
+		return
+	peaks = {}
+	try:
+		peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+	except Exception:
+		pass
+	peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+	top = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+	roofline = None
+	if top:
+		ach = kern[top]["bytes"] / (kern[top]["ms"] * 1e-3) / 1e9
+		roofline = {"bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
+			"traffic": None, "kernel": top, "peak_source": "measured" if peaks else "fallback",
+			"kernel_ms": kern[top]["ms"], "algorithmic_bytes": kern[top]["bytes"],
+			"all_kernels_ms": {k: round(v["ms"], 4) for k, v in kern.items()}}
+	cpu = None
+	if world == 1 and not args.no_cpu_baseline:
+		r = cpu_reference_run(steps=40, warmup=2, budget_s=25.0)
+		cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+			"sample": f"{r['steps']} train steps of batch {r['batch']} (of {B_PER_GPU}), T={T}, oracle/torch_port.py"}
+	launches_per_step = 9
+	print(json.dumps({
+		"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+		"warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+		"vs_baseline": None, "dtype": "f32", "data": "synthetic",
+		"config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
+			"l2": f"{N_POOL} rotating input batches ({N_POOL * B_PER_GPU * T * N * 4 >> 20} MiB) > 126 MB L2",
+			"optimizer": "Adam(lr=1e-3, weight_decay=1e-5), fused"},
+		"clocks": clocks,
+		"e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+			"ms_per_step": ms_e2e / args.steps, "input": "pinned host images (B,784) fp32 + labels; GPU to_spikes",
+			"from_host_rasters": {"value": e2e_raster, "h2d_bytes_per_step": B_PER_GPU * T * N * 4 + B_PER_GPU * 8}},
+		"gpu_launches": launches_per_step * args.steps,
+		"roofline": roofline, "cpu_baseline": cpu,
+	}))
+	if world > 1:
+		dist.destroy_process_group()
+
+
+def profile_kernels(net, rasters, labels_dev, crit, dev, iters=10):
+	"""CUDA-event duration of each kernel group of one train step, by calling the C-ABI stages back to back."""
+	from snnimageclassification_b200.modules import functional as F_
+	consts = net._consts()
+	W = [F_._c(w) for w in net._weights()]
+	Wi, Wr, M, be, Wo, bo = W
+	B = rasters[0].shape[0]
+	res = {}
+
+	def ev():
+		return torch.cuda.Event(enable_timing=True)
+	acc = {"forward(K1 proj + K2 recurrence)": 0.0, "head(K6)": 0.0, "backward(K3 bptt + K4 wgrad)": 0.0}
+	for i in range(iters + 2):
+		x = rasters[i % len(rasters)]
+		e = [ev() for _ in range(4)]
+		e[0].record()
+		out = F_.run_forward(consts, x, Wi, Wr, M, be, Wo, bo, traces=True)
+		e[1].record()
+		loss, logp, g = F_.run_head_nll(out["logits"], labels_dev[i % len(rasters)])
+		e[2].record()
+		F_.run_backward(consts, x, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits=g, tstar=out["tstar"])
+		e[3].record()
+		torch.cuda.synchronize()
+		if i >= 2:
+			acc["forward(K1 proj + K2 recurrence)"] += e[0].elapsed_time(e[1])
+			acc["head(K6)"] += e[1].elapsed_time(e[2])
+			acc["backward(K3 bptt + K4 wgrad)"] += e[2].elapsed_time(e[3])
+	fwd_bytes = B * T * N * 4 + 3 * B * T * H * 4 + B * T * O * 4
+	bwd_bytes = B * T * N * 4 + 2 * B * T * H * 4 + B * T * H // 8
+	res["forward(K1 proj + K2 recurrence)"] = {"ms": acc["forward(K1 proj + K2 recurrence)"] / iters, "bytes": fwd_bytes}
+	res["head(K6)"] = {"ms": acc["head(K6)"] / iters, "bytes": B * O * 4 * 3}
+	res["backward(K3 bptt + K4 wgrad)"] = {"ms": acc["backward(K3 bptt + K4 wgrad)"] / iters, "bytes": bwd_bytes}
+	return res
+
+
+if __name__ == "__main__":
+	main()

@@ -1,0 +1,173 @@
+/*
+ * snnk.h -- C ABI of the B200-native spiking hot path (libsnnk.so).
+ *
+ * The reference (JeremieGince/SNNImageClassification) is pure Python and has no
+ * FFI layer of its own; its boundary for this path is the Python surface
+ *   SNN.forward                    src/modules/snn.py:201-219
+ *   LIFLayer/ALIFLayer/ReadoutLayer.forward
+ *                                  src/modules/spiking_layers.py:156-171, :229-243, :402-408
+ *   SpikeFunction / surrogate backward
+ *                                  src/modules/spike_funcs.py:12-29, :46-62, :65-79
+ *   loss.backward() over the unrolled graph
+ *                                  src/modules/snn.py:413
+ *   ToSpikes.__call__              src/datasets/datasets.py:42-54, :72-86, :93-97
+ *   max-over-time/log_softmax/NLL  src/modules/snn.py:228, :258, :297
+ * Each entry point below replaces the loop named beside it; the Python mirror
+ * in snnimageclassification_b200/ binds them with ctypes (INTEGRATION.md shows
+ * the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     stated otherwise; all tensors are dense, C-contiguous, fp32 unless stated
+ *   - the caller owns every buffer and the workspace; the library never
+ *     allocates device memory and never synchronises; all work is enqueued on
+ *     the stream passed in (a cudaStream_t cast to void*)
+ *   - return value: SNNK_OK (0) or a negative SNNK_ERR_* code; no exceptions
+ *     cross the ABI; snnk_strerror() gives the text, snnk_last_cuda_error() the
+ *     CUDA runtime message behind SNNK_ERR_CUDA
+ *   - stateless and re-entrant (one host thread per rank; data-parallel ranks
+ *     are separate processes)
+ *   - sm_100 only: there is no fallback path; on any other device every compute
+ *     entry point returns SNNK_ERR_DEVICE
+ */
+#ifndef SNNK_H
+#define SNNK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNNK_ABI_VERSION 1
+
+typedef void* snnk_stream_t; /* cudaStream_t */
+
+/* LayerType, src/modules/spiking_layers.py:11-14 (Izhikevich is not on this path) */
+enum { SNNK_LIF = 0, SNNK_ALIF = 1 };
+/* SpikeFuncType, src/modules/spike_funcs.py:7-9 */
+enum { SNNK_FAST_SIGMOID = 0, SNNK_PHI = 1 };
+/* element types accepted by snnk_encode */
+enum { SNNK_F32 = 0, SNNK_F64 = 1, SNNK_U8 = 2, SNNK_I64 = 3 };
+
+enum {
+    SNNK_OK = 0,
+    SNNK_ERR_ARG = -1,         /* null pointer / bad enum / bad flag */
+    SNNK_ERR_SHAPE = -2,       /* geometry outside what the kernels support */
+    SNNK_ERR_DEVICE = -3,      /* current device is not sm_100 */
+    SNNK_ERR_WORKSPACE = -4,   /* workspace too small */
+    SNNK_ERR_CUDA = -5,        /* a CUDA runtime call failed: see snnk_last_cuda_error() */
+    SNNK_ERR_UNSUPPORTED = -6  /* valid request the library does not implement */
+};
+
+/* SnnkDesc.flags */
+#define SNNK_F_TRACES 0x1u     /* write the hidden traces V,(a),Z (snn.py:216-219) */
+#define SNNK_F_TENSOR_CORE 0x2u /* allow the tcgen05 projection / weight-gradient GEMMs (exact for {0,1}
+                                  inputs; the library falls back to the fp32 SIMT GEMM when x is not
+                                  exactly representable) */
+
+/* Geometry and constants of one hidden spiking layer + leaky readout. */
+typedef struct SnnkDesc {
+    int32_t B;          /* batch rows (independent)                           */
+    int32_t T;          /* time steps, snn.py:58 int_time_steps               */
+    int32_t N;          /* input features (784)                               */
+    int32_t H;          /* hidden neurons                                     */
+    int32_t O;          /* readout units (10); O <= 16                        */
+    int32_t layer_type; /* SNNK_LIF | SNNK_ALIF                               */
+    int32_t surrogate;  /* SNNK_FAST_SIGMOID | SNNK_PHI                       */
+    int32_t recurrent;  /* use_recurrent_connection                           */
+    float alpha;        /* exp(-dt/tau_m),  spiking_layers.py:119             */
+    float rho;          /* exp(-dt/tau_a),  spiking_layers.py:199 (ALIF)      */
+    float theta;        /* threshold,       spiking_layers.py:120             */
+    float gamma;        /* surrogate scale, spiking_layers.py:121             */
+    float kappa;        /* exp(-dt/tau_out),spiking_layers.py:377             */
+    uint32_t flags;     /* SNNK_F_*                                           */
+} SnnkDesc;
+
+int snnk_abi_version(void);
+const char* snnk_strerror(int code);
+/* Host string describing the last CUDA runtime error seen by this thread ("" if none). */
+const char* snnk_last_cuda_error(void);
+/* 1 if the CURRENT CUDA device is sm_100 (B200), 0 if not, <0 on error. */
+int snnk_device_supported(void);
+
+/*
+ * Image -> spike-train encoder.  Replaces ToSpikes.__call__ (datasets.py:93-97) for a whole batch.
+ *   x    (n_items, n_pix)            x_dtype  SNNK_F32 | SNNK_F64 (arithmetic is done in that type, as numpy does)
+ *                                    or SNNK_I64: x already holds firing times / periods, i.e. the call is
+ *                                    firing_times_to_spikes (datasets.py:81-86) / firing_periods_to_spikes (:72-79)
+ *   out  (n_items, n_steps, n_pix)   out_dtype SNNK_F32 | SNNK_F64 | SNNK_U8, values in {0,1}
+ *   periods (n_items, n_pix) int64, optional (may be NULL): pixels_to_firing_periods (datasets.py:42-54)
+ *   periodic = use_periods (datasets.py:40)
+ */
+int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps,
+                double t_max, double tau, double thr, double eps, int32_t periodic, void* out,
+                int32_t out_dtype, int64_t* periods, snnk_stream_t stream);
+
+/*
+ * SpikeFunction.apply used stand-alone (spike_funcs.py:12-29): out = (v >= thr) ? 1 : 0, and its surrogate
+ * backward (spike_funcs.py:46-62 FastSigmoid, :65-79 Phi): g_in = g_out * sigma'(v, thr, gamma).  thr has n
+ * elements or 1 (broadcast); gamma is a device scalar.  The threshold and gamma get no gradient.
+ */
+int snnk_spike_forward(const float* v, const float* thr, int64_t n, int64_t thr_n, float* out,
+                       snnk_stream_t stream);
+int snnk_spike_backward(int32_t surrogate, const float* v, const float* thr, const float* gamma,
+                        const float* g_out, int64_t n, int64_t thr_n, float* g_in, snnk_stream_t stream);
+
+size_t snnk_forward_workspace_bytes(const SnnkDesc* d);
+size_t snnk_backward_workspace_bytes(const SnnkDesc* d);
+
+/*
+ * Forward over all T steps.  Replaces the time loop of SNN.forward (snn.py:209-214) around
+ * LIFLayer/ALIFLayer.forward and ReadoutLayer.forward, plus torch.stack (snn.py:216-218) and the
+ * max over time of get_prediction_logits (snn.py:228).
+ *   x        (B,T,N)  input spikes / currents
+ *   W_in     (N,H)    forward_weights;  W_rec (H,H) recurrent_weights (raw), NULL iff !recurrent
+ *   rec_mask (H,H)    or NULL for all-ones (spiking_layers.py:50-57)
+ *   beta     device scalar (ALIF; may be an nn.Parameter), NULL for LIF
+ *   W_out    (H,O), b_out (O)
+ *   V0,a0,Z0 (B,H)    optional initial state, NULL = zeros (spiking_layers.py:69-83)
+ * outputs
+ *   V,a,Z    (B,T,H)  traces; required iff SNNK_F_TRACES (a only for ALIF)
+ *   zbits    (B,T,H/32) uint32, bit l of word w = spike of neuron 32*w+l; always written
+ *   y        (B,T,O)  readout trace; logits (B,O) = max_t y, tstar (B,O) int32 = first argmax_t
+ *   workspace: >= snnk_forward_workspace_bytes(); on return its first B*T*H floats hold the input
+ *   current I_in = x @ W_in (exposed for tests)
+ */
+int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec,
+                 const float* rec_mask, const float* beta, const float* W_out, const float* b_out,
+                 const float* V0, const float* a0, const float* Z0, float* V, float* a, float* Z,
+                 uint32_t* zbits, float* y, float* logits, int32_t* tstar, void* workspace,
+                 size_t workspace_bytes, snnk_stream_t stream);
+
+/*
+ * Fused head: log_softmax over the max-over-time logits (snn.py:258) + NLLLoss mean (snn.py:297)
+ * and the gradient of that loss w.r.t. the logits.
+ *   logits (B,O), labels (B) int64 -> logp (B,O), loss (1), g_logits (B,O) = (softmax - onehot)/B
+ */
+int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labels, float* logp,
+                  float* loss, float* g_logits, snnk_stream_t stream);
+
+/*
+ * Reverse-time BPTT.  Replaces autograd's sweep for batch_loss.backward() (snn.py:413) over the graph
+ * built by the forward loop, with the surrogate derivatives of spike_funcs.py:59-62 / :75-79.
+ * Gradient seeds: either g_y (B,T,O) dense w.r.t. the output trace, or -- the fused-head form --
+ * g_logits (B,O) with tstar (B,O) (the gradient lands on y[b,tstar[b,o],o]).  Exactly one of the
+ * two forms must be given.  g_V, g_Z (B,T,H) are optional extra seeds on the hidden traces.
+ * Outputs: dW_in (N,H), dW_rec (H,H, masked; NULL iff !recurrent), dW_out (H,O), db (O); they are
+ * OVERWRITTEN.  beta receives no gradient (the threshold input of the spike function has none,
+ * spike_funcs.py:62).  workspace: on return its first B*T*H floats hold gI, the gradient w.r.t. the
+ * input current (exposed for tests).
+ */
+int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const float* rec_mask,
+                  const float* beta, const float* W_out, const float* Z0, const float* V,
+                  const float* a, const uint32_t* zbits, const float* g_y, const float* g_logits,
+                  const int32_t* tstar, const float* g_V, const float* g_Z, float* dW_in,
+                  float* dW_rec, float* dW_out, float* db, void* workspace, size_t workspace_bytes,
+                  snnk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNNK_H */

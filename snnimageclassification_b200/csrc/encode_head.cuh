@@ -1,0 +1,118 @@
+// encode_head.cuh -- K5 (image -> spike train encoder) and K6 (fused classification head).
+#pragma once
+#include "common.cuh"
+
+namespace snnk {
+
+// ---- K5: ToSpikes.__call__ (src/datasets/datasets.py:93-97) for a whole batch ---------------------------------
+// pixels_to_firing_periods (datasets.py:42-54).  The arithmetic type follows the input dtype, as numpy does.
+__device__ __forceinline__ long long period_of(double x, double t_max, double tau, double thr, double eps)
+{
+    const bool below = x < thr;                                   // :49
+    const double lo = thr + eps;
+    const double xc = x < lo ? lo : (x > 1.0e9 ? 1.0e9 : x);      // :50
+    double Tv = tau * log(xc / (xc - thr));                       // :51
+    if (below) Tv = t_max;                                        // :52
+    return (long long)Tv;                                         // :54 (truncation)
+}
+
+// float32 inputs: numpy keeps float32 (python-float parameters are weak scalars), so every constant is
+// rounded to float32 first.  The logarithm is the correctly rounded fp32 log (fp64 log rounded once),
+// exactly as oracle/snn_oracle.c defines it.
+__device__ __forceinline__ long long period_of(float x, double t_max, double tau, double thr, double eps)
+{
+    const float thr_f = (float)thr, lo = (float)(thr + eps), hi = (float)1.0e9;
+    const bool below = x < thr_f;
+    const float xc = x < lo ? lo : (x > hi ? hi : x);
+    const float d = __fsub_rn(xc, thr_f);
+    const float q = __fdiv_rn(xc, d);
+    const float l = (float)log((double)q);
+    float Tv = __fmul_rn((float)tau, l);
+    if (below) Tv = (float)t_max;
+    return (long long)Tv;
+}
+
+// One thread per (item, pixel): the latency/period is computed once, then the thread writes its T raster
+// entries; consecutive threads own consecutive pixels, so every store instruction is fully coalesced.
+//   non-periodic (datasets.py:81-86): one spike at t = period if period < n_steps
+//   periodic     (datasets.py:72-79): p = clamp(period, 1, n_steps-1); spike iff t >= p and (t - p) % p == 0
+// int64 inputs already hold latencies/periods (firing_times_to_spikes / firing_periods_to_spikes called directly)
+__device__ __forceinline__ long long period_of(long long x, double, double, double, double) { return x; }
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) k_encode(const TIn* __restrict__ x, long long n_items, long long n_pix,
+                                               int n_steps, double t_max, double tau, double thr, double eps,
+                                               int periodic, TOut* __restrict__ out,
+                                               long long* __restrict__ periods)
+{
+    const long long pix = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+    const long long item = blockIdx.x;
+    if (pix >= n_pix || item >= n_items) return;
+    const long long per = period_of(x[item * n_pix + pix], t_max, tau, thr, eps);
+    if (periods) periods[item * n_pix + pix] = per;
+    TOut* col = out + item * (long long)n_steps * n_pix + pix;
+    if (!periodic) {
+        for (int t = 0; t < n_steps; ++t) col[(long long)t * n_pix] = (TOut)((long long)t == per ? 1 : 0);
+    } else {
+        long long p = per > n_steps - 1 ? n_steps - 1 : per;
+        p = p < 1 ? 1 : p;
+        long long next = p;
+        for (int t = 0; t < n_steps; ++t) {
+            const bool s = (long long)t == next;
+            if (s) next += p;
+            col[(long long)t * n_pix] = (TOut)(s ? 1 : 0);
+        }
+    }
+}
+
+// ---- SpikeFunction.apply stand-alone (src/modules/spike_funcs.py:12-29, :46-62, :65-79) --------------------------
+// thr is a tensor of the same shape as v, or a single element (thr_n == 1) broadcast over it.
+__global__ void __launch_bounds__(256) k_spike_fwd(const float* __restrict__ v, const float* __restrict__ thr,
+                                                  long long n, long long thr_n, float* __restrict__ out)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = v[e] >= thr[thr_n == 1 ? 0 : e] ? 1.0f : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) k_spike_bwd(int kind, const float* __restrict__ v,
+                                                  const float* __restrict__ thr, const float* __restrict__ gamma,
+                                                  const float* __restrict__ g, long long n, long long thr_n,
+                                                  float* __restrict__ out)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = __fmul_rn(g[e], surrogate_grad(kind, gamma[0], v[e], thr[thr_n == 1 ? 0 : e]));
+}
+
+// ---- K6: log_softmax (snn.py:258) + NLLLoss mean (snn.py:297) + d loss / d logits -----------------------------
+// One CTA; B is a few thousand at most.  The loss is reduced in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) k_head_nll(int B, int O, const float* __restrict__ logits,
+                                                 const long long* __restrict__ labels, float* __restrict__ logp,
+                                                 float* __restrict__ loss, float* __restrict__ g_logits)
+{
+    __shared__ double s_part[256];
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float lg[kOMax];
+        float mx = -INFINITY;
+        for (int c = 0; c < O; ++c) { lg[c] = logits[(size_t)b * O + c]; mx = fmaxf(mx, lg[c]); }
+        float se = 0.f;
+        for (int c = 0; c < O; ++c) se += expf(lg[c] - mx);
+        const float lse = logf(se);
+        const int lab = (int)labels[b];
+        for (int c = 0; c < O; ++c) {
+            const float lp = (lg[c] - mx) - lse;
+            if (logp) logp[(size_t)b * O + c] = lp;
+            if (c == lab) acc += -(double)lp;
+            if (g_logits) g_logits[(size_t)b * O + c] = __fdiv_rn(expf(lp) - (c == lab ? 1.0f : 0.0f), (float)B);
+        }
+    }
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int q = 0; q < (int)blockDim.x; ++q) s += s_part[q];
+        *loss = (float)(s / (double)B);
+    }
+}
+
+}  // namespace snnk

@@ -1,0 +1,197 @@
+// recur_bwd.cuh -- K3: persistent fused reverse-time BPTT.
+//
+// Replaces what autograd does for batch_loss.backward() (src/modules/snn.py:413) over the graph the
+// forward loop builds: per step, MmBackward for the readout and recurrent matmuls, the surrogate
+// backward (src/modules/spike_funcs.py:59-62 FastSigmoid, :75-79 Phi), and the Mul/Add backwards of
+// spiking_layers.py:169/239.  The reset factor is detached (:169) and the spike threshold receives no
+// gradient (spike_funcs.py:62/79), so the adaptation variable and beta are outside the sweep.
+//
+//   gy_t = seed_t + kappa gy_{t+1}
+//   gZ_t = gy_t W_out^T + gI_{t+1} (W_rec . M)^T               [+ seed on Z]
+//   gV_t = gZ_t sigma'(V_t, A_t) + alpha gV_{t+1} (1 - Z_t)    [+ seed on V]
+//   gI_t = gV_t (1 - Z_{t-1})
+//
+// Same ownership as the forward kernel: one CTA = R batch rows, thread i = neuron i, ROW i of the
+// masked recurrent matrix in registers, gI_{t+1} broadcast from shared memory, one __syncthreads per
+// step.  dW_out and db are accumulated in registers / a pre-scan and leave as per-CTA partials (summed
+// in a fixed order by k_reduce_parts, so results are run-to-run deterministic); dW_in and dW_rec are
+// contractions over (batch x time) and belong to the weight-gradient GEMM (K4).
+#pragma once
+#include "common.cuh"
+
+namespace snnk {
+
+template <int H, int R>
+constexpr size_t bwd_smem_bytes(int T, bool rec)
+{
+    size_t loop = sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)(R * T * (H / 32)) +
+                  sizeof(float) * (size_t)(R * T * kOMax);
+    size_t stage = rec ? sizeof(float) * (size_t)H * (H + 1) : 0;   // transpose staging, prologue only
+    return loop > stage ? loop : stage;
+}
+
+template <int H, int R, bool REC>
+__global__ void __launch_bounds__(H) k_recur_bwd(const BwdParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int W32 = H / 32;
+    constexpr int PF = 4;
+    const int T = p.T, O = p.O, B = p.B;
+    const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+    const int b0 = blockIdx.x * R;
+
+    // row i of W_rec (.) rec_mask, staged through padded shared memory so the global read is coalesced
+    float w[REC ? H : 1];
+    if constexpr (REC) {
+        float* s_t = reinterpret_cast<float*>(smem_raw);   // [H][H+1]
+        for (int idx = i; idx < H * H; idx += H) {
+            const int row = idx / H, col = idx - row * H;
+            const float m = p.rec_mask ? __ldg(p.rec_mask + idx) : 1.0f;
+            s_t[row * (H + 1) + col] = __fmul_rn(__ldg(p.W_rec + idx), m);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < H; ++k) w[k] = s_t[i * (H + 1) + k];
+        __syncthreads();
+    }
+
+    float* s_g = reinterpret_cast<float*>(smem_raw);                       // [2][R][H]
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_g + 2 * R * H);       // [R][T][W32]
+    float* s_gy = reinterpret_cast<float*>(s_mask + R * T * W32);          // [R][T][kOMax]
+
+    float wo[kOMax], dwo[kOMax];
+#pragma unroll
+    for (int c = 0; c < kOMax; ++c) {
+        wo[c] = c < O ? __ldg(p.W_out + (size_t)i * O + c) : 0.f;
+        dwo[c] = 0.f;
+    }
+    const float beta = (p.alif && p.beta) ? __ldg(p.beta) : 0.f;
+
+    for (int idx = i; idx < 2 * R * H; idx += H) s_g[idx] = 0.f;
+    for (int idx = i; idx < R * T * kOMax; idx += H) s_gy[idx] = 0.f;
+    for (int idx = i; idx < R * T * W32; idx += H) {
+        const int r = idx / (T * W32), rem = idx - r * (T * W32);
+        s_mask[idx] = (b0 + r < B) ? __ldg(p.zbits + (size_t)(b0 + r) * T * W32 + rem) : 0u;
+    }
+    __syncthreads();
+    if (p.g_y) {
+        for (int idx = i; idx < R * T * O; idx += H) {
+            const int r = idx / (T * O), rem = idx - r * (T * O);
+            const int t = rem / O, c = rem - t * O;
+            if (b0 + r < B) s_gy[(r * T + t) * kOMax + c] = __ldg(p.g_y + (size_t)(b0 + r) * T * O + rem);
+        }
+    } else {
+        for (int idx = i; idx < R * O; idx += H) {
+            const int r = idx / O, c = idx - r * O;
+            if (b0 + r < B) {
+                const int ts = __ldg(p.tstar + (size_t)(b0 + r) * O + c);
+                s_gy[(r * T + ts) * kOMax + c] = __ldg(p.g_logits + (size_t)(b0 + r) * O + c);
+            }
+        }
+    }
+    __syncthreads();
+    // readout adjoint scan gy_t = seed_t + kappa gy_{t+1}  (spiking_layers.py:407 backwards) and db
+    for (int idx = i; idx < R * O; idx += H) {
+        const int r = idx / O, c = idx - r * O;
+        float g = 0.f, sum = 0.f;
+        for (int t = T - 1; t >= 0; --t) {
+            float* gp = s_gy + (r * T + t) * kOMax + c;
+            g = __fadd_rn(*gp, __fmul_rn(p.kappa, g));
+            *gp = g;
+            sum += g;
+        }
+        p.part_db[((size_t)blockIdx.x * R + r) * O + c] = sum;
+    }
+    __syncthreads();
+
+    float gv[R];
+    bool valid[R];
+    float vpf[PF][R], apf[PF][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        gv[r] = 0.f;
+        valid[r] = b0 + r < B;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int t = T - 1 - u;
+            const bool ok = valid[r] && t >= 0;
+            const size_t o = ok ? ((size_t)(b0 + r) * T + t) * H + i : 0;
+            vpf[u][r] = ok ? __ldg(p.V + o) : 0.f;
+            apf[u][r] = (ok && p.alif) ? __ldg(p.a + o) : 0.f;
+        }
+    }
+
+    for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int t = t0 - u;
+            if (t >= 0) {
+                float vt[R], at[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    vt[r] = vpf[u][r];
+                    at[r] = apf[u][r];
+                    const int tn = t - PF;
+                    const bool ok = valid[r] && tn >= 0;
+                    const size_t o = ok ? ((size_t)(b0 + r) * T + tn) * H + i : 0;
+                    vpf[u][r] = ok ? __ldg(p.V + o) : 0.f;
+                    apf[u][r] = (ok && p.alif) ? __ldg(p.a + o) : 0.f;
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4* gyv = reinterpret_cast<const float4*>(s_gy + (r * T + t) * kOMax);
+                    float gy[kOMax];
+#pragma unroll
+                    for (int q = 0; q < kOMax / 4; ++q) {
+                        const float4 g4 = gyv[q];
+                        gy[4 * q + 0] = g4.x; gy[4 * q + 1] = g4.y; gy[4 * q + 2] = g4.z; gy[4 * q + 3] = g4.w;
+                    }
+                    const float zt = (float)((s_mask[(r * T + t) * W32 + warp] >> lane) & 1u);
+                    float zprev;
+                    if (t > 0) zprev = (float)((s_mask[(r * T + t - 1) * W32 + warp] >> lane) & 1u);
+                    else zprev = (valid[r] && p.Z0) ? __ldg(p.Z0 + (size_t)(b0 + r) * H + i) : 0.f;
+                    float s = 0.f;
+#pragma unroll
+                    for (int c = 0; c < kOMax; ++c) {
+                        s = fmaf(gy[c], wo[c], s);               // gy_t W_out^T
+                        dwo[c] = fmaf(zt, gy[c], dwo[c]);        // dW_out += Z_t^T gy_t
+                    }
+                    if constexpr (REC) {
+                        const float4* gv4 =
+                            reinterpret_cast<const float4*>(s_g + ((t + 1) & 1) * R * H + r * H);
+                        s = __fadd_rn(s, dot_rec4<REC ? H : 1>(w, gv4));   // gI_{t+1} (W_rec . M)^T
+                    }
+                    const size_t o = ((size_t)(valid[r] ? b0 + r : 0) * T + t) * H + i;
+                    if (p.g_Z && valid[r]) s = __fadd_rn(s, __ldg(p.g_Z + o));
+                    float thr = p.theta;
+                    if (p.alif) thr = __fadd_rn(p.theta, __fmul_rn(beta, at[r]));
+                    const float sg = surrogate_grad(p.surrogate, p.gamma, vt[r], thr);
+                    const float carry = __fmul_rn(__fmul_rn(p.alpha, gv[r]), __fsub_rn(1.0f, zt));
+                    float g = __fadd_rn(__fmul_rn(s, sg), carry);
+                    if (p.g_V && valid[r]) g = __fadd_rn(g, __ldg(p.g_V + o));
+                    gv[r] = g;
+                    const float gi = __fmul_rn(g, __fsub_rn(1.0f, zprev));
+                    if (valid[r]) p.gI[o] = gi;
+                    if (REC) s_g[(t & 1) * R * H + r * H + i] = gi;
+                }
+                if (REC) __syncthreads();
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kOMax; ++c)
+        if (c < O) p.part_wout[((size_t)blockIdx.x * H + i) * O + c] = dwo[c];
+}
+
+// out[e] = mask[e] * sum_p parts[p*stride + e]  (ascending p: deterministic)
+__global__ void k_reduce_parts(const float* __restrict__ parts, int nparts, size_t stride, int n,
+                               const float* __restrict__ mask, float* __restrict__ out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float s = 0.f;
+    for (int q = 0; q < nparts; ++q) s += parts[(size_t)q * stride + e];
+    out[e] = mask ? s * mask[e] : s;
+}
+
+}  // namespace snnk

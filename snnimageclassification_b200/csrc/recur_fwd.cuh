@@ -1,0 +1,169 @@
+// recur_fwd.cuh -- K2: persistent fused forward recurrence.
+//
+// Replaces the time loop of SNN.forward (src/modules/snn.py:209-214) around LIFLayer/ALIFLayer.forward
+// (src/modules/spiking_layers.py:156-171, :229-243) and ReadoutLayer.forward (:402-408).
+//
+// One CTA owns R batch rows for all T steps (rows are independent, so there is no grid-wide sync).
+// Thread i owns hidden neuron i: its membrane/adaptation state lives in registers for the whole
+// sequence and column i of the masked recurrent matrix (H floats) is register-resident too, so one
+// step is H FFMAs against the previous spike vector broadcast from shared memory + the elementwise
+// update + one __syncthreads.  Spikes are bit-packed with warp ballots; all T spike words stay in
+// shared memory, so the leaky readout (linear in the spikes) is evaluated after the loop instead of
+// inside the latency-critical chain.
+#pragma once
+#include "common.cuh"
+
+namespace snnk {
+
+template <int H, int R>
+constexpr size_t fwd_smem_bytes(int T, int O)
+{
+    return sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)(R * T * (H / 32)) +
+           sizeof(float) * (size_t)(H * O) + sizeof(float) * (size_t)(R * T * O);
+}
+
+template <int H, int R, bool REC>
+__global__ void __launch_bounds__(H) k_recur_fwd(const FwdParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int W32 = H / 32;
+    constexpr int PF = 4;   // input-current prefetch distance (steps)
+    const int T = p.T, O = p.O, B = p.B;
+    const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+    const int b0 = blockIdx.x * R;
+
+    float* s_z = reinterpret_cast<float*>(smem_raw);                       // [2][R][H]
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_z + 2 * R * H);       // [R][T][W32]
+    float* s_wout = reinterpret_cast<float*>(s_mask + R * T * W32);        // [H][O]
+    float* s_s = s_wout + H * O;                                           // [R][T][O]
+
+    // column i of W_rec (.) rec_mask  (spiking_layers.py:165/235 multiplies the mask in at every step)
+    float w[REC ? H : 1];
+    if constexpr (REC) {
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const float m = p.rec_mask ? __ldg(p.rec_mask + k * H + i) : 1.0f;
+            w[k] = __fmul_rn(__ldg(p.W_rec + k * H + i), m);
+        }
+    }
+    const float beta = (p.alif && p.beta) ? __ldg(p.beta) : 0.f;
+
+    float v[R], a[R], zp[R];
+    bool valid[R];
+    float ipf[PF][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int b = b0 + r;
+        valid[r] = b < B;
+        const size_t s = (size_t)(valid[r] ? b : 0) * H + i;
+        v[r] = (valid[r] && p.V0) ? p.V0[s] : 0.f;
+        a[r] = (valid[r] && p.a0) ? p.a0[s] : 0.f;
+        zp[r] = (valid[r] && p.Z0) ? p.Z0[s] : 0.f;
+        if (REC) s_z[1 * R * H + r * H + i] = zp[r];   // step 0 reads buffer (0+1)&1
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            ipf[u][r] = (valid[r] && u < T) ? __ldg(p.I_in + ((size_t)b * T + u) * H + i) : 0.f;
+    }
+    for (int idx = i; idx < H * O; idx += H) s_wout[idx] = __ldg(p.W_out + idx);
+    __syncthreads();
+
+    for (int t0 = 0; t0 < T; t0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int t = t0 + u;
+            if (t < T) {
+                float cur[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    cur[r] = ipf[u][r];
+                    const int tn = t + PF;
+                    ipf[u][r] = (valid[r] && tn < T)
+                                    ? __ldg(p.I_in + ((size_t)(b0 + r) * T + tn) * H + i) : 0.f;
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float rec = 0.0f;
+                    if constexpr (REC) {
+                        const float4* zv =
+                            reinterpret_cast<const float4*>(s_z + ((t + 1) & 1) * R * H + r * H);
+                        rec = dot_rec4<REC ? H : 1>(w, zv);
+                    }
+                    // V' = (alpha V + I_in + I_rec) (1 - Z.detach())     spiking_layers.py:169/239
+                    const float t1 = __fmul_rn(p.alpha, v[r]);
+                    const float t2 = __fadd_rn(t1, cur[r]);
+                    const float t3 = __fadd_rn(t2, rec);
+                    const float vn = __fmul_rn(t3, __fsub_rn(1.0f, zp[r]));
+                    float thr = p.theta;
+                    if (p.alif) {
+                        a[r] = __fadd_rn(__fmul_rn(p.rho, a[r]), zp[r]);          // :240
+                        thr = __fadd_rn(p.theta, __fmul_rn(beta, a[r]));          // :241
+                    }
+                    const float zn = vn >= thr ? 1.0f : 0.0f;                     // spike_funcs.py:27-28
+                    if (p.traces && valid[r]) {
+                        const size_t o = ((size_t)(b0 + r) * T + t) * H + i;
+                        p.V[o] = vn;
+                        p.Z[o] = zn;
+                        if (p.alif) p.a[o] = a[r];
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, zn != 0.f);
+                    if (lane == 0) s_mask[(r * T + t) * W32 + warp] = m;
+                    if (REC) s_z[(t & 1) * R * H + r * H + i] = zn;
+                    v[r] = vn;
+                    zp[r] = zn;
+                }
+                if (REC) __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+
+    // bit-packed raster for the backward pass
+    for (int idx = i; idx < R * T * W32; idx += H) {
+        const int r = idx / (T * W32), rem = idx - r * (T * W32);
+        if (b0 + r < B) p.zbits[(size_t)(b0 + r) * T * W32 + rem] = s_mask[idx];
+    }
+
+    // Leaky readout, spiking_layers.py:407:  y_t = kappa y_{t-1} + Z_t @ W_out + b.
+    // (A) s[t][c] = sum_j Z_t[j] W_out[j][c], ascending j, for all (t,c) in parallel
+    for (int idx = i; idx < R * T * O; idx += H) {
+        const int r = idx / (T * O), rem = idx - r * (T * O);
+        const int t = rem / O, c = rem - t * O;
+        const uint32_t* mw = s_mask + (r * T + t) * W32;
+        float s = 0.f;
+        for (int wd = 0; wd < W32; ++wd) {
+            const uint32_t m = mw[wd];
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) {
+                const float wv = s_wout[(wd * 32 + l) * O + c];
+                s = __fadd_rn(s, ((m >> l) & 1u) ? wv : 0.f);
+            }
+        }
+        s_s[idx] = s;
+    }
+    __syncthreads();
+    // (B) the scan over t (sequential per (row, class)) + max over time, snn.py:228 (first max wins)
+    for (int idx = i; idx < R * O; idx += H) {
+        const int r = idx / O, c = idx - r * O;
+        const float bc = __ldg(p.b_out + c);
+        float yv = 0.f, mx = 0.f;
+        int mt = 0;
+        for (int t = 0; t < T; ++t) {
+            float* sp = s_s + (r * T + t) * O + c;
+            yv = __fadd_rn(__fadd_rn(__fmul_rn(p.kappa, yv), *sp), bc);
+            *sp = yv;
+            if (t == 0 || yv > mx) { mx = yv; mt = t; }
+        }
+        if (b0 + r < B) {
+            p.logits[(size_t)(b0 + r) * O + c] = mx;
+            p.tstar[(size_t)(b0 + r) * O + c] = mt;
+        }
+    }
+    __syncthreads();
+    // (C) coalesced write of the output trace
+    for (int idx = i; idx < R * T * O; idx += H) {
+        const int r = idx / (T * O), rem = idx - r * (T * O);
+        if (b0 + r < B) p.y[(size_t)(b0 + r) * T * O + rem] = s_s[idx];
+    }
+}
+
+}  // namespace snnk

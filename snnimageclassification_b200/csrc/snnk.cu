@@ -1,0 +1,381 @@
+// snnk.cu -- C-ABI entry points of libsnnk.so (see include/snnk.h for the contract).
+//
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared
+#include "../../include/snnk.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "encode_head.cuh"
+#include "gemm_simt.cuh"
+#include "recur_bwd.cuh"
+#include "recur_fwd.cuh"
+
+using namespace snnk;
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* where)
+{
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+    return SNNK_ERR_CUDA;
+}
+
+#define SNNK_CUDA(call)                                        \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);  \
+    } while (0)
+
+int device_ok()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// How the batch is cut into CTAs and how the weight-gradient GEMM is split; shared by the workspace
+// query and the launches so they can never disagree.
+struct Plan {
+    int R;            // batch rows per recurrence CTA
+    int grid_rows;    // recurrence CTAs
+    int m_total;      // rows of the stacked weight gradient [dW_in ; dW_rec]
+    int mtiles_x, mtiles_z, ntiles, BN;
+    int S;            // split-K factor of the weight-gradient GEMM
+    int rows_per_split;
+    size_t off_gI, off_pwout, off_pdb, off_pw, bwd_bytes, fwd_bytes;
+};
+
+int check_desc(const SnnkDesc* d)
+{
+    if (!d) return SNNK_ERR_ARG;
+    if (d->B <= 0 || d->T <= 0 || d->N <= 0 || d->H <= 0 || d->O <= 0) return SNNK_ERR_SHAPE;
+    if (d->layer_type != SNNK_LIF && d->layer_type != SNNK_ALIF) return SNNK_ERR_ARG;
+    if (d->surrogate != SNNK_FAST_SIGMOID && d->surrogate != SNNK_PHI) return SNNK_ERR_ARG;
+    if (d->O > kOMax) return SNNK_ERR_SHAPE;
+    if (d->H != 32 && d->H != 64 && d->H != 128) return SNNK_ERR_UNSUPPORTED;
+    if ((long long)d->B * d->T >= (1ll << 31) / 4) return SNNK_ERR_SHAPE;
+    return SNNK_OK;
+}
+
+Plan make_plan(const SnnkDesc* d)
+{
+    Plan p{};
+    p.R = d->B > 1024 ? 2 : 1;
+    p.grid_rows = (d->B + p.R - 1) / p.R;
+    const int BT = d->B * d->T;
+    p.BN = d->H >= 64 ? 64 : 32;
+    p.ntiles = d->H / p.BN;
+    p.mtiles_x = (d->N + kGemmBM - 1) / kGemmBM;
+    p.mtiles_z = d->recurrent ? (d->H + kGemmBM - 1) / kGemmBM : 0;
+    p.m_total = d->N + (d->recurrent ? d->H : 0);
+    const int tiles = (p.mtiles_x + p.mtiles_z) * p.ntiles;
+    int S = (4 * 148 + tiles - 1) / tiles;
+    const int maxS = (BT + 63) / 64;
+    if (S > maxS) S = maxS;
+    if (S < 1) S = 1;
+    p.rows_per_split = (BT + S - 1) / S;
+    p.rows_per_split = (p.rows_per_split + kGemmBK - 1) / kGemmBK * kGemmBK;
+    p.S = (BT + p.rows_per_split - 1) / p.rows_per_split;
+    size_t off = 0;
+    p.off_gI = off;     off = align_up(off + sizeof(float) * (size_t)BT * d->H, 256);
+    p.off_pwout = off;  off = align_up(off + sizeof(float) * (size_t)p.grid_rows * d->H * d->O, 256);
+    p.off_pdb = off;    off = align_up(off + sizeof(float) * (size_t)p.grid_rows * p.R * d->O, 256);
+    p.off_pw = off;     off = align_up(off + sizeof(float) * (size_t)p.S * p.m_total * d->H, 256);
+    p.bwd_bytes = off;
+    p.fwd_bytes = align_up(sizeof(float) * (size_t)BT * d->H, 256);
+    return p;
+}
+
+template <int H, int R, bool REC>
+int launch_fwd(const FwdParams& fp, int grid, cudaStream_t st)
+{
+    const size_t smem = fwd_smem_bytes<H, R>(fp.T, fp.O);
+    if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
+    auto kern = k_recur_fwd<H, R, REC>;
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, H, smem, st>>>(fp);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+template <int H, int R>
+int launch_fwd_rec(const FwdParams& fp, bool rec, int grid, cudaStream_t st)
+{
+    return rec ? launch_fwd<H, R, true>(fp, grid, st) : launch_fwd<H, R, false>(fp, grid, st);
+}
+
+template <int H>
+int launch_fwd_r(const FwdParams& fp, bool rec, int R, int grid, cudaStream_t st)
+{
+    return R == 1 ? launch_fwd_rec<H, 1>(fp, rec, grid, st) : launch_fwd_rec<H, 2>(fp, rec, grid, st);
+}
+
+template <int H, int R, bool REC>
+int launch_bwd(const BwdParams& bp, int grid, cudaStream_t st)
+{
+    const size_t smem = bwd_smem_bytes<H, R>(bp.T, REC);
+    if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
+    auto kern = k_recur_bwd<H, R, REC>;
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, H, smem, st>>>(bp);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+template <int H, int R>
+int launch_bwd_rec(const BwdParams& bp, bool rec, int grid, cudaStream_t st)
+{
+    return rec ? launch_bwd<H, R, true>(bp, grid, st) : launch_bwd<H, R, false>(bp, grid, st);
+}
+
+template <int H>
+int launch_bwd_r(const BwdParams& bp, bool rec, int R, int grid, cudaStream_t st)
+{
+    return R == 1 ? launch_bwd_rec<H, 1>(bp, rec, grid, st) : launch_bwd_rec<H, 2>(bp, rec, grid, st);
+}
+
+template <typename TIn>
+int launch_encode(const TIn* x, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max, double tau,
+                  double thr, double eps, int32_t periodic, void* out, int32_t out_dtype, int64_t* periods,
+                  cudaStream_t st)
+{
+    dim3 grid((unsigned)n_items, (unsigned)((n_pix + 255) / 256));
+    long long* per = reinterpret_cast<long long*>(periods);
+    switch (out_dtype) {
+    case SNNK_F32:
+        k_encode<TIn, float><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                  static_cast<float*>(out), per);
+        break;
+    case SNNK_F64:
+        k_encode<TIn, double><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                   static_cast<double*>(out), per);
+        break;
+    case SNNK_U8:
+        k_encode<TIn, uint8_t><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                    static_cast<uint8_t*>(out), per);
+        break;
+    default:
+        return SNNK_ERR_ARG;
+    }
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int snnk_abi_version(void) { return SNNK_ABI_VERSION; }
+
+const char* snnk_strerror(int code)
+{
+    switch (code) {
+    case SNNK_OK: return "ok";
+    case SNNK_ERR_ARG: return "invalid argument (null pointer, bad enum or flag)";
+    case SNNK_ERR_SHAPE: return "geometry outside what the kernels support";
+    case SNNK_ERR_DEVICE: return "current CUDA device is not sm_100 (B200); there is no fallback path";
+    case SNNK_ERR_WORKSPACE: return "workspace too small";
+    case SNNK_ERR_CUDA: return "CUDA runtime error (see snnk_last_cuda_error)";
+    case SNNK_ERR_UNSUPPORTED: return "request not implemented by the B200 path";
+    default: return "unknown snnk error code";
+    }
+}
+
+const char* snnk_last_cuda_error(void) { return g_cuda_err; }
+
+int snnk_device_supported(void) { return device_ok(); }
+
+int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max,
+                double tau, double thr, double eps, int32_t periodic, void* out, int32_t out_dtype,
+                int64_t* periods, snnk_stream_t stream)
+{
+    if (!x || !out) return SNNK_ERR_ARG;
+    if (n_items < 0 || n_pix < 0 || n_steps <= 0 || n_items > 0x7fffffffll || n_pix > 65535ll * 256) return SNNK_ERR_SHAPE;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    if (n_items == 0 || n_pix == 0) return SNNK_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (x_dtype == SNNK_F32)
+        return launch_encode(static_cast<const float*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
+                             periodic, out, out_dtype, periods, st);
+    if (x_dtype == SNNK_F64)
+        return launch_encode(static_cast<const double*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
+                             periodic, out, out_dtype, periods, st);
+    if (x_dtype == SNNK_I64)
+        return launch_encode(static_cast<const long long*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
+                             periodic, out, out_dtype, periods, st);
+    return SNNK_ERR_ARG;
+}
+
+int snnk_spike_forward(const float* v, const float* thr, int64_t n, int64_t thr_n, float* out,
+                       snnk_stream_t stream)
+{
+    if (!v || !thr || !out) return SNNK_ERR_ARG;
+    if (n < 0 || (thr_n != 1 && thr_n != n)) return SNNK_ERR_SHAPE;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    if (n == 0) return SNNK_OK;
+    k_spike_fwd<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(v, thr, n, thr_n, out);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int snnk_spike_backward(int32_t surrogate, const float* v, const float* thr, const float* gamma,
+                        const float* g_out, int64_t n, int64_t thr_n, float* g_in, snnk_stream_t stream)
+{
+    if (!v || !thr || !gamma || !g_out || !g_in) return SNNK_ERR_ARG;
+    if (surrogate != SNNK_FAST_SIGMOID && surrogate != SNNK_PHI) return SNNK_ERR_ARG;
+    if (n < 0 || (thr_n != 1 && thr_n != n)) return SNNK_ERR_SHAPE;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    if (n == 0) return SNNK_OK;
+    k_spike_bwd<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        surrogate, v, thr, gamma, g_out, n, thr_n, g_in);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+size_t snnk_forward_workspace_bytes(const SnnkDesc* d)
+{
+    if (check_desc(d) != SNNK_OK) return 0;
+    return make_plan(d).fwd_bytes;
+}
+
+size_t snnk_backward_workspace_bytes(const SnnkDesc* d)
+{
+    if (check_desc(d) != SNNK_OK) return 0;
+    return make_plan(d).bwd_bytes;
+}
+
+int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec, const float* rec_mask,
+                 const float* beta, const float* W_out, const float* b_out, const float* V0, const float* a0,
+                 const float* Z0, float* V, float* a, float* Z, uint32_t* zbits, float* y, float* logits,
+                 int32_t* tstar, void* workspace, size_t workspace_bytes, snnk_stream_t stream)
+{
+    int rc = check_desc(d);
+    if (rc != SNNK_OK) return rc;
+    if (!x || !W_in || !W_out || !b_out || !zbits || !y || !logits || !tstar || !workspace) return SNNK_ERR_ARG;
+    if (d->recurrent && !W_rec) return SNNK_ERR_ARG;
+    if (d->layer_type == SNNK_ALIF && !beta) return SNNK_ERR_ARG;
+    const bool traces = (d->flags & SNNK_F_TRACES) != 0;
+    if (traces && (!V || !Z || (d->layer_type == SNNK_ALIF && !a))) return SNNK_ERR_ARG;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    const Plan pl = make_plan(d);
+    if (workspace_bytes < pl.fwd_bytes) return SNNK_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* I_in = static_cast<float*>(workspace);
+
+    // K1: input projection for all T steps at once
+    {
+        const int M = d->B * d->T;
+        dim3 grid((M + kGemmBM - 1) / kGemmBM, pl.ntiles);
+        if (pl.BN == 64) k_proj_simt<64><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H);
+        else k_proj_simt<32><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H);
+        SNNK_CUDA(cudaGetLastError());
+    }
+    // K2: fused recurrence + readout
+    FwdParams fp{};
+    fp.B = d->B; fp.T = d->T; fp.H = d->H; fp.O = d->O;
+    fp.alif = d->layer_type == SNNK_ALIF; fp.traces = traces;
+    fp.alpha = d->alpha; fp.rho = d->rho; fp.theta = d->theta; fp.kappa = d->kappa;
+    fp.I_in = I_in; fp.W_rec = W_rec; fp.rec_mask = rec_mask; fp.beta = beta; fp.W_out = W_out; fp.b_out = b_out;
+    fp.V0 = V0; fp.a0 = a0; fp.Z0 = Z0; fp.V = V; fp.a = a; fp.Z = Z; fp.zbits = zbits; fp.y = y;
+    fp.logits = logits; fp.tstar = tstar;
+    const bool rec = d->recurrent != 0;
+    switch (d->H) {
+    case 32: return launch_fwd_r<32>(fp, rec, pl.R, pl.grid_rows, st);
+    case 64: return launch_fwd_r<64>(fp, rec, pl.R, pl.grid_rows, st);
+    case 128: return launch_fwd_r<128>(fp, rec, pl.R, pl.grid_rows, st);
+    default: return SNNK_ERR_UNSUPPORTED;
+    }
+}
+
+int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labels, float* logp, float* loss,
+                  float* g_logits, snnk_stream_t stream)
+{
+    if (!logits || !labels || !loss) return SNNK_ERR_ARG;
+    if (B <= 0 || O <= 0 || O > kOMax) return SNNK_ERR_SHAPE;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    k_head_nll<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        B, O, logits, reinterpret_cast<const long long*>(labels), logp, loss, g_logits);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const float* rec_mask, const float* beta,
+                  const float* W_out, const float* Z0, const float* V, const float* a, const uint32_t* zbits,
+                  const float* g_y, const float* g_logits, const int32_t* tstar, const float* g_V,
+                  const float* g_Z, float* dW_in, float* dW_rec, float* dW_out, float* db, void* workspace,
+                  size_t workspace_bytes, snnk_stream_t stream)
+{
+    int rc = check_desc(d);
+    if (rc != SNNK_OK) return rc;
+    if (!x || !W_out || !V || !zbits || !dW_in || !dW_out || !db || !workspace) return SNNK_ERR_ARG;
+    if (d->recurrent && (!W_rec || !dW_rec)) return SNNK_ERR_ARG;
+    if (d->layer_type == SNNK_ALIF && (!beta || !a)) return SNNK_ERR_ARG;
+    const bool dense = g_y != nullptr, sparse = g_logits != nullptr && tstar != nullptr;
+    if (dense == sparse) return SNNK_ERR_ARG;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    const Plan pl = make_plan(d);
+    if (workspace_bytes < pl.bwd_bytes) return SNNK_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    float* gI = reinterpret_cast<float*>(ws + pl.off_gI);
+    float* pwout = reinterpret_cast<float*>(ws + pl.off_pwout);
+    float* pdb = reinterpret_cast<float*>(ws + pl.off_pdb);
+    float* pw = reinterpret_cast<float*>(ws + pl.off_pw);
+    const bool rec = d->recurrent != 0;
+
+    // K3: reverse-time sweep
+    BwdParams bp{};
+    bp.B = d->B; bp.T = d->T; bp.H = d->H; bp.O = d->O;
+    bp.alif = d->layer_type == SNNK_ALIF; bp.surrogate = d->surrogate;
+    bp.alpha = d->alpha; bp.theta = d->theta; bp.gamma = d->gamma; bp.kappa = d->kappa;
+    bp.W_rec = W_rec; bp.rec_mask = rec_mask; bp.beta = beta; bp.W_out = W_out; bp.Z0 = Z0;
+    bp.V = V; bp.a = a; bp.zbits = zbits; bp.g_y = g_y; bp.g_logits = dense ? nullptr : g_logits;
+    bp.tstar = dense ? nullptr : tstar; bp.g_V = g_V; bp.g_Z = g_Z;
+    bp.gI = gI; bp.part_wout = pwout; bp.part_db = pdb;
+    switch (d->H) {
+    case 32: rc = launch_bwd_r<32>(bp, rec, pl.R, pl.grid_rows, st); break;
+    case 64: rc = launch_bwd_r<64>(bp, rec, pl.R, pl.grid_rows, st); break;
+    case 128: rc = launch_bwd_r<128>(bp, rec, pl.R, pl.grid_rows, st); break;
+    default: rc = SNNK_ERR_UNSUPPORTED;
+    }
+    if (rc != SNNK_OK) return rc;
+    {
+        const int n1 = d->H * d->O;
+        k_reduce_parts<<<(n1 + 255) / 256, 256, 0, st>>>(pwout, pl.grid_rows, (size_t)n1, n1, nullptr, dW_out);
+        k_reduce_parts<<<1, 256, 0, st>>>(pdb, pl.grid_rows * pl.R, (size_t)d->O, d->O, nullptr, db);
+        SNNK_CUDA(cudaGetLastError());
+    }
+    // K4: weight-gradient GEMM (split-K partials, then a fixed-order reduction)
+    {
+        WgradParams wp{};
+        wp.BT = d->B * d->T; wp.T = d->T; wp.N = d->N; wp.H = d->H;
+        wp.mtiles_x = pl.mtiles_x; wp.rows_per_split = pl.rows_per_split;
+        wp.x = x; wp.zbits = zbits; wp.Z0 = Z0; wp.gI = gI; wp.part = pw; wp.m_total = pl.m_total;
+        dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.ntiles, pl.S);
+        if (pl.BN == 64) k_wgrad_simt<64><<<grid, kGemmThreads, 0, st>>>(wp);
+        else k_wgrad_simt<32><<<grid, kGemmThreads, 0, st>>>(wp);
+        SNNK_CUDA(cudaGetLastError());
+        const size_t stride = (size_t)pl.m_total * d->H;
+        const int n_in = d->N * d->H;
+        k_reduce_parts<<<(n_in + 255) / 256, 256, 0, st>>>(pw, pl.S, stride, n_in, nullptr, dW_in);
+        if (rec) {
+            const int n_rec = d->H * d->H;
+            k_reduce_parts<<<(n_rec + 255) / 256, 256, 0, st>>>(pw + (size_t)d->N * d->H, pl.S, stride, n_rec,
+                                                                 rec_mask, dW_rec);
+        }
+        SNNK_CUDA(cudaGetLastError());
+    }
+    return SNNK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+"""Autograd glue between the PyTorch-facing modules and the C ABI (include/snnk.h).
+
+Two ``torch.autograd.Function``s wrap one hidden spiking layer + leaky readout over all T steps:
+
+* ``SpikingSequence``      -- returns the output trace and the hidden traces, differentiable w.r.t. the weights;
+  any PyTorch head / criterion can follow (the generic path of ``SNN.forward``, reference snn.py:201-219).
+* ``SpikingSequenceNLL``   -- the fused training path of ``SNN._exec_batch`` (reference snn.py:384-415 with the
+  default ``nn.NLLLoss``): max-over-time, log_softmax and the loss are evaluated by the library and the backward
+  receives its seeds in sparse form.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every FLOP of the path is issued by
+libsnnk.so.  Nothing in this file has a CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from .. import _cabi
+
+
+@dataclass(frozen=True)
+class LayerConsts:
+	"""Scalar constants of the hidden layer + readout (python floats, rounded to fp32 by the ABI struct)."""
+	layer_type: int      # _cabi.SNNK_LIF | SNNK_ALIF
+	surrogate: int       # _cabi.SNNK_FAST_SIGMOID | SNNK_PHI
+	recurrent: bool
+	alpha: float
+	rho: float
+	theta: float
+	gamma: float
+	kappa: float
+	tensor_core: bool = False
+
+
+def make_desc(c: LayerConsts, B: int, T: int, N: int, H: int, O: int, traces: bool) -> _cabi.SnnkDesc:
+	flags = (_cabi.SNNK_F_TRACES if traces else 0) | (_cabi.SNNK_F_TENSOR_CORE if c.tensor_core else 0)
+	return _cabi.SnnkDesc(
+		B, T, N, H, O, c.layer_type, c.surrogate, int(c.recurrent), c.alpha, c.rho, c.theta, c.gamma, c.kappa, flags)
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+	return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+	if t is None:
+		return None
+	t = t.detach()
+	if t.dtype != torch.float32:
+		t = t.float()
+	return t if t.is_contiguous() else t.contiguous()
+
+
+def run_forward(
+		c: LayerConsts, x, W_in, W_rec, rec_mask, beta, W_out, b_out, traces: bool = True,
+		state: Optional[Tuple[Optional[torch.Tensor], ...]] = None,
+):
+	"""Calls ``snnk_forward``.  Returns dict(y, V, a, Z, zbits, logits, tstar, I_in, desc)."""
+	lib = _cabi.lib()
+	_cabi.require_b200(x.device)
+	B, T, N = x.shape
+	H, O = W_out.shape
+	if W_in.shape != (N, H):
+		raise RuntimeError(f"forward_weights has shape {tuple(W_in.shape)}, expected {(N, H)}")
+	desc = make_desc(c, B, T, N, H, O, traces)
+	dev = x.device
+	f32 = dict(dtype=torch.float32, device=dev)
+	alif = c.layer_type == _cabi.SNNK_ALIF
+	V = torch.empty((B, T, H), **f32) if traces else None
+	Z = torch.empty((B, T, H), **f32) if traces else None
+	a = torch.empty((B, T, H), **f32) if (traces and alif) else None
+	zbits = torch.empty((B, T, H // 32), dtype=torch.int32, device=dev)
+	y = torch.empty((B, T, O), **f32)
+	logits = torch.empty((B, O), **f32)
+	tstar = torch.empty((B, O), dtype=torch.int32, device=dev)
+	ws = _workspace(lib.snnk_forward_workspace_bytes(ctypes.byref(desc)), dev)
+	V0 = a0 = Z0 = None
+	if state is not None:
+		if alif:
+			V0, a0, Z0 = (_c(s) for s in state)
+		else:
+			V0, Z0 = (_c(s) for s in state)
+	with torch.cuda.device(dev):
+		rc = lib.snnk_forward(
+			ctypes.byref(desc), _cabi.ptr(x), _cabi.ptr(W_in), _cabi.ptr(W_rec), _cabi.ptr(rec_mask),
+			_cabi.ptr(beta), _cabi.ptr(W_out), _cabi.ptr(b_out), _cabi.ptr(V0), _cabi.ptr(a0), _cabi.ptr(Z0),
+			_cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(y), _cabi.ptr(logits),
+			_cabi.ptr(tstar), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr())
+	_cabi.check(rc, "snnk_forward")
+	I_in = ws[: B * T * H * 4].view(torch.float32).view(B, T, H)
+	return dict(y=y, V=V, a=a, Z=Z, zbits=zbits, logits=logits, tstar=tstar, I_in=I_in, desc=desc, Z0=Z0)
+
+
+def run_backward(
+		c: LayerConsts, x, W_rec, rec_mask, beta, W_out, V, a, zbits, g_y=None, g_logits=None, tstar=None,
+		g_V=None, g_Z=None, Z0=None,
+):
+	"""Calls ``snnk_backward``.  Returns dict(dW_in, dW_rec, dW_out, db, gI)."""
+	lib = _cabi.lib()
+	B, T, N = x.shape
+	H, O = W_out.shape
+	desc = make_desc(c, B, T, N, H, O, True)
+	dev = x.device
+	f32 = dict(dtype=torch.float32, device=dev)
+	dW_in = torch.empty((N, H), **f32)
+	dW_rec = torch.empty((H, H), **f32) if c.recurrent else None
+	dW_out = torch.empty((H, O), **f32)
+	db = torch.empty((O,), **f32)
+	ws = _workspace(lib.snnk_backward_workspace_bytes(ctypes.byref(desc)), dev)
+	with torch.cuda.device(dev):
+		rc = lib.snnk_backward(
+			ctypes.byref(desc), _cabi.ptr(x), _cabi.ptr(W_rec), _cabi.ptr(rec_mask), _cabi.ptr(beta),
+			_cabi.ptr(W_out), _cabi.ptr(Z0), _cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(zbits), _cabi.ptr(g_y),
+			_cabi.ptr(g_logits), _cabi.ptr(tstar), _cabi.ptr(g_V), _cabi.ptr(g_Z), _cabi.ptr(dW_in),
+			_cabi.ptr(dW_rec), _cabi.ptr(dW_out), _cabi.ptr(db), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr())
+	_cabi.check(rc, "snnk_backward")
+	gI = ws[: B * T * H * 4].view(torch.float32).view(B, T, H)
+	return dict(dW_in=dW_in, dW_rec=dW_rec, dW_out=dW_out, db=db, gI=gI)
+
+
+def run_head_nll(logits: torch.Tensor, labels: torch.Tensor, want_grad: bool = True):
+	"""Calls ``snnk_head_nll``.  Returns (loss (), logp (B,O), g_logits (B,O) | None)."""
+	lib = _cabi.lib()
+	B, O = logits.shape
+	dev = logits.device
+	labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+	logp = torch.empty_like(logits)
+	loss = torch.empty((), dtype=torch.float32, device=dev)
+	g = torch.empty_like(logits) if want_grad else None
+	with torch.cuda.device(dev):
+		rc = lib.snnk_head_nll(
+			B, O, _cabi.ptr(logits), _cabi.ptr(labels), _cabi.ptr(logp), _cabi.ptr(loss), _cabi.ptr(g),
+			_cabi.stream_ptr())
+	_cabi.check(rc, "snnk_head_nll")
+	return loss, logp, g
+
+
+class SpikingSequence(torch.autograd.Function):
+	"""(x, weights) -> (y, V, a, Z): generic differentiable forward over all T steps."""
+
+	@staticmethod
+	def forward(ctx, consts: LayerConsts, x, W_in, W_rec, rec_mask, beta, W_out, b_out):
+		xc, Wi, Wr, M, be, Wo, bo = (_c(t) for t in (x, W_in, W_rec, rec_mask, beta, W_out, b_out))
+		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=True)
+		ctx.consts = consts
+		ctx.has_rec = Wr is not None
+		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"])
+		alif = consts.layer_type == _cabi.SNNK_ALIF
+		a = out["a"] if alif else out["V"].new_zeros(())
+		ctx.mark_non_differentiable(a)
+		return out["y"], out["V"], a, out["Z"]
+
+	@staticmethod
+	def backward(ctx, g_y, g_V, g_a, g_Z):
+		xc, Wr, M, be, Wo, V, a, zbits = ctx.saved_tensors
+		if g_y is None:
+			g_y = torch.zeros((V.shape[0], V.shape[1], Wo.shape[1]), dtype=torch.float32, device=V.device)
+		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=_c(g_V), g_Z=_c(g_Z))
+		# (consts, x, W_in, W_rec, rec_mask, beta, W_out, b_out); beta gets no gradient -- the threshold input of
+		# the reference's spike function returns None (spike_funcs.py:62/79)
+		return None, None, g["dW_in"], g["dW_rec"], None, None, g["dW_out"], g["db"]
+
+
+class SpikingSequenceNLL(torch.autograd.Function):
+	"""(x, labels, weights) -> (loss, logp, y, V, a, Z) with the head fused (snn.py:228, :258, :297)."""
+
+	@staticmethod
+	def forward(ctx, consts: LayerConsts, x, labels, W_in, W_rec, rec_mask, beta, W_out, b_out, traces: bool):
+		xc, Wi, Wr, M, be, Wo, bo = (_c(t) for t in (x, W_in, W_rec, rec_mask, beta, W_out, b_out))
+		need_grad = any(ctx.needs_input_grad)
+		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=traces or need_grad)
+		loss, logp, g_logits = run_head_nll(out["logits"], labels, want_grad=need_grad)
+		ctx.consts = consts
+		if need_grad:
+			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"])
+		empty = logp.new_zeros(())
+		extras = tuple(out[k] if out[k] is not None else empty for k in ("y", "V", "a", "Z"))
+		ctx.mark_non_differentiable(logp, *extras)
+		return (loss, logp) + extras
+
+	@staticmethod
+	def backward(ctx, g_loss, *_):
+		xc, Wr, M, be, Wo, V, a, zbits, g_logits, tstar = ctx.saved_tensors
+		g = run_backward(
+			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=(g_logits * g_loss).contiguous(), tstar=tstar)
+		return None, None, None, g["dW_in"], g["dW_rec"], None, None, g["dW_out"], g["db"], None

@@ -1,0 +1,514 @@
+"""``SNN`` -- mirror of the reference's src/modules/snn.py with the hot path on B200 kernels.
+
+Same constructor, parameter names, ``state_dict`` layout, return values of ``forward`` /
+``get_prediction_*`` / ``fit`` and checkpoint files as the reference.  What changes underneath:
+
+* ``forward`` (reference snn.py:201-219, a Python loop of T x layers small matmuls and elementwise ops) makes ONE
+  call into libsnnk.so: projection GEMM for all T steps, persistent fused recurrence + readout kernel.
+* ``_exec_batch`` (reference snn.py:384-415) with the default ``nn.NLLLoss`` uses the fused head and the fused
+  reverse-time BPTT kernels; any other criterion goes through ordinary autograd on top of the same kernels.
+* data-parallel training: when ``torch.distributed`` is initialised, ``_exec_batch`` all-reduces (averages) the
+  gradients over the ranks before the optimizer step -- one flat NCCL call.
+
+Extra constructor keywords (all optional, the reference ignores unknown kwargs the same way):
+``input_encoder`` (a ``ToSpikes`` applied on the GPU to (B, F) image batches) and ``tensor_core``.
+"""
+from __future__ import annotations
+
+import enum
+import json
+import logging
+import os
+import shutil
+from typing import Any, Dict, Iterable, List, Optional, Tuple, Type, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+from torch.utils.data import DataLoader
+
+from .. import _cabi
+from . import functional as F_
+from .spike_funcs import HeavisideSigmoidApprox, SpikeFuncType, SpikeFuncType2Func, SpikeFunction
+from .spiking_layers import ALIFLayer, IzhikevichLayer, LayerType, LayerType2Layer, LIFLayer, ReadoutLayer
+from .utils import LossHistory, mapping_update_recursively
+
+try:  # progress bars are cosmetic
+	from tqdm.auto import tqdm
+except ImportError:  # pragma: no cover
+	def tqdm(it=None, **kw):
+		return it
+
+
+class ReadoutMth(enum.Enum):
+	RNN = 0
+
+
+class ForwardMth(enum.Enum):
+	LAYER_THEN_TIME = 0
+	TIME_THEN_LAYER = 1
+
+
+class LoadCheckpointMode(enum.Enum):
+	BEST_EPOCH = enum.auto()
+	LAST_EPOCH = enum.auto()
+
+
+class SNN(torch.nn.Module):
+	SAVE_EXT = ".pth"
+	SUFFIX_SEP = "-"
+	CHECKPOINTS_META_SUFFIX = "checkpoints"
+	CHECKPOINT_SAVE_PATH_KEY = "save_path"
+	CHECKPOINT_BEST_KEY = "best"
+	CHECKPOINT_EPOCHS_KEY = "epochs"
+	CHECKPOINT_EPOCH_KEY = "epoch"
+	CHECKPOINT_LOSS_KEY = "loss"
+	CHECKPOINT_OPTIMIZER_STATE_DICT_KEY = "optimizer_state_dict"
+	CHECKPOINT_STATE_DICT_KEY = "model_state_dict"
+	CHECKPOINT_FILE_STRUCT: Dict[str, Union[str, Dict[int, str]]] = {
+		CHECKPOINT_BEST_KEY: CHECKPOINT_SAVE_PATH_KEY,
+		CHECKPOINT_EPOCHS_KEY: {0: CHECKPOINT_SAVE_PATH_KEY},
+	}
+	load_mode_to_suffix = {mode: mode.name for mode in list(LoadCheckpointMode)}
+
+	def __init__(
+			self,
+			inputs_size: int,
+			output_size: int,
+			n_hidden_neurons: Iterable[int] = None,
+			use_recurrent_connection: Union[bool, Iterable[bool]] = True,
+			dt=1e-3,
+			int_time_steps=100,
+			spike_func: Union[Type[SpikeFunction], SpikeFuncType] = HeavisideSigmoidApprox,
+			hidden_layer_type: Union[Type[LIFLayer], LayerType] = LIFLayer,
+			device=None,
+			checkpoint_folder: str = "checkpoints",
+			model_name: str = "snn",
+			**kwargs
+	):
+		super().__init__()
+		self.input_size = inputs_size
+		self.output_size = output_size
+		# keywords of the B200 build; everything else is threaded to the layers exactly as in the reference
+		self.input_encoder = kwargs.pop("input_encoder", None)
+		self.tensor_core = bool(kwargs.pop("tensor_core", False))
+		self.kwargs = kwargs
+
+		self.device = device
+		if self.device is None:
+			self._set_default_device_()
+		self.device = torch.device(self.device)
+
+		self.dt = dt
+		self.int_time_steps = int_time_steps
+		if isinstance(spike_func, SpikeFuncType):
+			spike_func = SpikeFuncType2Func[spike_func]
+		self.spike_func = spike_func
+		if isinstance(hidden_layer_type, LayerType):
+			hidden_layer_type = LayerType2Layer[hidden_layer_type]
+		self.hidden_layer_type = hidden_layer_type
+
+		self.checkpoint_folder = checkpoint_folder
+		self.model_name = model_name
+
+		if isinstance(n_hidden_neurons, int):
+			n_hidden_neurons = [n_hidden_neurons]
+		self.n_hidden_neurons = n_hidden_neurons if n_hidden_neurons is not None else []
+		self.use_recurrent_connection = use_recurrent_connection
+		self.layers = nn.ModuleDict()
+		self._add_layers_()
+		self.initialize_weights_()
+		self.loss_history = LossHistory()
+		self._consts_cache: Optional[F_.LayerConsts] = None
+
+	# ---- construction (reference snn.py:96-157) -----------------------------------------------------------------
+	@property
+	def checkpoints_meta_path(self) -> str:
+		return f"{self.checkpoint_folder}/{self.model_name}{SNN.SUFFIX_SEP}{SNN.CHECKPOINTS_META_SUFFIX}.json"
+
+	def _set_default_device_(self):
+		self.device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+
+	def _add_input_layer_(self):
+		if not self.n_hidden_neurons:
+			return
+		self.layers["input"] = self.hidden_layer_type(
+			input_size=self.input_size, output_size=self.n_hidden_neurons[0],
+			use_recurrent_connection=self.use_recurrent_connection, dt=self.dt, spike_func=self.spike_func,
+			device=self.device, **self.kwargs)
+
+	def _add_hidden_layers_(self):
+		if not self.n_hidden_neurons:
+			return
+		for i, hn in enumerate(self.n_hidden_neurons[:-1]):
+			self.layers[f"hidden_{i}"] = self.hidden_layer_type(
+				input_size=hn, output_size=self.n_hidden_neurons[i + 1],
+				use_recurrent_connection=self.use_recurrent_connection, dt=self.dt, spike_func=self.spike_func,
+				device=self.device, **self.kwargs)
+
+	def _add_readout_layer(self):
+		in_size = self.n_hidden_neurons[-1] if self.n_hidden_neurons else self.input_size
+		self.layers["readout"] = ReadoutLayer(
+			input_size=in_size, output_size=self.output_size, dt=self.dt, spike_func=self.spike_func,
+			device=self.device, **self.kwargs)
+
+	def _add_layers_(self):
+		self._add_input_layer_()
+		self._add_hidden_layers_()
+		self._add_readout_layer()
+
+	def initialize_weights_(self):
+		# Same order as the reference (snn.py:149-157): every parameter is re-drawn ~N(0,1) -- including a learnable
+		# beta -- and then each layer applies its own initialiser, so a given torch seed yields the same weights.
+		for param in self.parameters():
+			if param.ndim > 2:
+				torch.nn.init.xavier_normal_(param)
+			else:
+				torch.nn.init.normal_(param)
+		for layer_name, layer in self.layers.items():
+			if getattr(layer, "initialize_weights_") and callable(layer.initialize_weights_):
+				layer.initialize_weights_()
+
+	# ---- input formatting (reference snn.py:159-184) ------------------------------------------------------------
+	def _format_inputs(self, inputs: torch.Tensor) -> torch.Tensor:
+		"""(B, F) -> repeated over int_time_steps; (B, T' <= T, F) -> zero-padded to T; cast to float32."""
+		with torch.no_grad():
+			if inputs.ndim == 2:
+				inputs = torch.unsqueeze(inputs, 1).repeat(1, self.int_time_steps, 1)
+			assert inputs.ndim == 3, \
+				"shape of inputs must be (batch_size, time_steps, nb_features) or (batch_size, nb_features)"
+			t_diff = self.int_time_steps - inputs.shape[1]
+			assert t_diff >= 0, "inputs time steps must me less or equal to int_time_steps"
+			if t_diff > 0:
+				pad = torch.zeros((inputs.shape[0], t_diff, inputs.shape[-1]), dtype=torch.float32, device=inputs.device)
+				inputs = torch.cat([inputs.float(), pad], dim=1)
+		return inputs.float().contiguous()
+
+	def _encode_if_needed(self, inputs: torch.Tensor) -> torch.Tensor:
+		"""Image batches (B, F) are turned into spike trains on the GPU when an ``input_encoder`` was given."""
+		if self.input_encoder is not None and inputs.ndim == 2:
+			return self.input_encoder.encode_batch(inputs)
+		return inputs
+
+	# ---- the fused path -------------------------------------------------------------------------------------------
+	def _hot_layers(self) -> Tuple[LIFLayer, ReadoutLayer]:
+		if len(self.n_hidden_neurons) != 1:
+			raise NotImplementedError(
+				"the B200 path fuses exactly one hidden spiking layer with the readout (every published configuration "
+				f"of the reference); n_hidden_neurons={list(self.n_hidden_neurons)} is not supported yet and there is "
+				"no eager fallback")
+		layer = self.layers["input"]
+		if isinstance(layer, IzhikevichLayer) or not isinstance(layer, LIFLayer):
+			raise NotImplementedError(
+				f"{type(layer).__name__} is not supported by the B200 path (only LIF and ALIF are fused)")
+		return layer, self.layers["readout"]
+
+	def refresh_constants(self):
+		"""Re-reads alpha/rho/theta/gamma/kappa from the layers (call after editing them by hand)."""
+		self._consts_cache = None
+
+	def _consts(self) -> F_.LayerConsts:
+		if self._consts_cache is None:
+			layer, readout = self._hot_layers()
+			self._consts_cache = layer.snnk_consts(kappa=float(readout.kappa), tensor_core=self.tensor_core)
+		return self._consts_cache
+
+	def _weights(self):
+		layer, readout = self._hot_layers()
+		beta = layer.beta.reshape(1) if isinstance(layer, ALIFLayer) else None
+		return (
+			layer.forward_weights, layer.recurrent_weights, layer.rec_mask, beta, readout.forward_weights,
+			readout.bias_weights)
+
+	def forward(self, inputs):
+		"""-> (outputs_trace (B,T,O), {"input": (V,[a],Z), "readout": (y,)}), as reference snn.py:201-219."""
+		layer, _ = self._hot_layers()
+		inputs = self._format_inputs(self._encode_if_needed(inputs))
+		y, V, a, Z = F_.SpikingSequence.apply(self._consts(), inputs, *self._weights())
+		hidden = (V, a, Z) if isinstance(layer, ALIFLayer) else (V, Z)
+		return y, {"input": hidden, "readout": (y,)}
+
+	def _infer_logits(self, inputs: torch.Tensor) -> torch.Tensor:
+		"""Forward without materialising the hidden traces; the max over time comes out of the kernel."""
+		inputs = self._format_inputs(self._encode_if_needed(inputs))
+		W = tuple(F_._c(w) for w in self._weights())
+		return F_.run_forward(self._consts(), inputs, *W, traces=False)["logits"]
+
+	# ---- prediction heads (reference snn.py:221-259) --------------------------------------------------------------
+	def get_prediction_logits(self, inputs: torch.Tensor, re_outputs_trace: bool = True, re_hidden_states: bool = True):
+		inputs = inputs.to(self.device)
+		if not re_outputs_trace and not re_hidden_states and not torch.is_grad_enabled():
+			return self._infer_logits(inputs)
+		outputs_trace, hidden_states = self(inputs)
+		logits, _ = torch.max(outputs_trace, dim=1)
+		if re_outputs_trace and re_hidden_states:
+			return logits, outputs_trace, hidden_states
+		elif re_outputs_trace:
+			return logits, outputs_trace
+		elif re_hidden_states:
+			return logits, hidden_states
+		return logits
+
+	def get_prediction_proba(self, inputs: torch.Tensor, re_outputs_trace: bool = True, re_hidden_states: bool = True):
+		if re_outputs_trace or re_hidden_states:
+			m, *outs = self.get_prediction_logits(inputs, re_outputs_trace, re_hidden_states)
+			return (F.softmax(m, dim=-1), *outs)
+		# the reference returns the raw logits in this branch (snn.py:246-248); kept
+		return self.get_prediction_logits(inputs, re_outputs_trace, re_hidden_states)
+
+	def get_prediction_log_proba(self, inputs: torch.Tensor, re_outputs_trace: bool = True, re_hidden_states: bool = True):
+		if re_outputs_trace or re_hidden_states:
+			m, *outs = self.get_prediction_logits(inputs, re_outputs_trace, re_hidden_states)
+			return (F.log_softmax(m, dim=-1), *outs)
+		return self.get_prediction_logits(inputs, re_outputs_trace, re_hidden_states)
+
+	def get_spikes_count_per_neuron(self, hidden_states: Dict[str, List[torch.Tensor]]) -> torch.Tensor:
+		counts = []
+		for l_name, traces in hidden_states.items():
+			if isinstance(self.layers[l_name], LIFLayer):
+				counts.extend(traces[-1].sum(dim=(0, 1)).tolist())
+		return torch.tensor(counts, dtype=torch.float32, device=self.device)
+
+	def _check_early_stopping(self, patience: int, tol: float = 1e-2) -> bool:
+		losses = self.loss_history["val"][-patience:]
+		return bool(np.all(np.abs(np.diff(losses)) < tol))
+
+	# ---- training loop (reference snn.py:280-415) -----------------------------------------------------------------
+	def fit(
+			self,
+			train_dataloader: DataLoader,
+			val_dataloader: DataLoader,
+			lr=1e-3,
+			nb_epochs=15,
+			criterion=None,
+			optimizer=None,
+			load_checkpoint_mode: LoadCheckpointMode = None,
+			force_overwrite: bool = False,
+			early_stopping: bool = False,
+			early_stopping_patience: int = 5,
+			verbose: bool = True,
+			p_bar_position: Optional[int] = None,
+			p_bar_leave: Optional[bool] = None,
+	):
+		if criterion is None:
+			criterion = nn.NLLLoss()
+		if optimizer is None:
+			optimizer = torch.optim.Adam(self.parameters(), lr=lr, weight_decay=1e-5)
+
+		start_epoch = 0
+		if load_checkpoint_mode is None:
+			assert os.path.exists(self.checkpoints_meta_path) or force_overwrite, \
+				f"{self.checkpoints_meta_path} already exists. " \
+				f"Set force_overwrite flag to True to overwrite existing saves."
+			if os.path.exists(self.checkpoints_meta_path) and force_overwrite:
+				shutil.rmtree(self.checkpoint_folder)
+		else:
+			try:
+				checkpoint = self.load_checkpoint(load_checkpoint_mode)
+				self.load_state_dict(checkpoint[SNN.CHECKPOINT_STATE_DICT_KEY], strict=True)
+				optimizer.load_state_dict(checkpoint[SNN.CHECKPOINT_OPTIMIZER_STATE_DICT_KEY])
+				start_epoch = int(checkpoint[SNN.CHECKPOINT_EPOCH_KEY]) + 1
+				self.loss_history = self.get_checkpoints_loss_history()
+			except FileNotFoundError:
+				if verbose:
+					logging.warning("No such checkpoint. Fit from beginning.")
+
+		if start_epoch >= nb_epochs:
+			return self.loss_history
+
+		best_loss = self.loss_history.min("val")
+		p_bar = tqdm(
+			range(start_epoch, nb_epochs), desc="Training", disable=not verbose, position=p_bar_position,
+			unit="epoch", leave=p_bar_leave)
+		for epoch in p_bar:
+			epoch_loss = self._exec_phase(train_dataloader, val_dataloader, criterion, optimizer)
+			epoch_val_acc = self.compute_classification_accuracy(val_dataloader, verbose=False)
+			self.loss_history.concat(epoch_loss)
+			is_best = epoch_loss["val"] < best_loss
+			self.save_checkpoint(optimizer, epoch, epoch_loss, is_best)
+			if is_best:
+				best_loss = epoch_loss["val"]
+			if hasattr(p_bar, "set_postfix"):
+				p_bar.set_postfix(
+					train_loss=f"{epoch_loss['train']:.5e}", val_loss=f"{epoch_loss['val']:.5e}",
+					val_acc=f"{epoch_val_acc:.5f}")
+			if early_stopping and self._check_early_stopping(early_stopping_patience):
+				if verbose:
+					logging.info(f"Early stopping stopped the training at epoch {epoch}.")
+				break
+		if hasattr(p_bar, "close"):
+			p_bar.close()
+		self.plot_loss_history(show=False)
+		return self.loss_history
+
+	def _exec_phase(self, train_dataloader, val_dataloader, criterion, optimizer):
+		self.train()
+		train_loss = self._exec_epoch(train_dataloader, criterion, optimizer)
+		self.eval()
+		val_loss = self._exec_epoch(val_dataloader, criterion, optimizer)
+		return dict(train=train_loss, val=val_loss)
+
+	def _exec_epoch(self, dataloader, criterion, optimizer):
+		batch_losses = []
+		for x_batch, y_batch in dataloader:
+			batch_losses.append(self._exec_batch(x_batch, y_batch, criterion, optimizer))
+		return np.mean(batch_losses)
+
+	@staticmethod
+	def _is_plain_nll(criterion) -> bool:
+		return (
+			type(criterion) is nn.NLLLoss and criterion.weight is None and criterion.reduction == "mean"
+			and criterion.ignore_index == -100)
+
+	def batch_loss(self, x_batch, y_batch, criterion=None, traces: bool = False) -> torch.Tensor:
+		"""Loss tensor of one batch (on the device, attached to the graph in train mode).
+
+		With the default criterion (``nn.NLLLoss`` mean) the fused head + fused BPTT kernels are used; any other
+		criterion receives log-probabilities exactly as in the reference and is differentiated by autograd.
+		"""
+		x = self._encode_if_needed(x_batch.to(self.device, non_blocking=True))
+		y = y_batch.to(self.device, non_blocking=True)
+		if criterion is None or self._is_plain_nll(criterion):
+			x = self._format_inputs(x)
+			loss, *_ = F_.SpikingSequenceNLL.apply(self._consts(), x, y.long(), *self._weights(), traces)
+			return loss
+		log_p_y, out, h_states = self.get_prediction_log_proba(x, re_outputs_trace=True, re_hidden_states=True)
+		return criterion(log_p_y, y.long())
+
+	def _exec_batch(self, x_batch, y_batch, criterion, optimizer):
+		"""forward (+ backward + optimizer step in train mode) -> python float (reference snn.py:384-415)."""
+		if self.training:
+			batch_loss = self.batch_loss(x_batch, y_batch, criterion)
+			optimizer.zero_grad()
+			batch_loss.backward()
+			self._allreduce_gradients()
+			optimizer.step()
+		else:
+			with torch.no_grad():
+				batch_loss = self.batch_loss(x_batch, y_batch, criterion)
+		return batch_loss.item()
+
+	def _allreduce_gradients(self):
+		"""Data-parallel training: average the (small) gradients over the ranks with one flat NCCL all-reduce."""
+		import torch.distributed as dist
+		if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+			return
+		grads = [p.grad for p in self.parameters() if p.grad is not None]
+		if not grads:
+			return
+		flat = torch.cat([g.reshape(-1) for g in grads])
+		dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+		flat.div_(dist.get_world_size())
+		off = 0
+		for g in grads:
+			n = g.numel()
+			g.copy_(flat[off:off + n].view_as(g))
+			off += n
+
+	# ---- checkpoints (reference snn.py:417-505; same files, so checkpoints interchange) -----------------------------
+	def plot_loss_history(self, loss_history: LossHistory = None, show=False):
+		if loss_history is None:
+			loss_history = self.loss_history
+		os.makedirs(self._folder(), exist_ok=True)
+		loss_history.plot(f"{self._folder()}/loss_history.png", show)
+
+	def _folder(self) -> str:
+		# the reference writes "./{checkpoint_folder}/..." (snn.py:421, :425); absolute folders are kept usable here
+		f = str(self.checkpoint_folder)
+		return f if os.path.isabs(f) else f"./{f}"
+
+	def _create_checkpoint_path(self, epoch: int = -1):
+		return f"{self._folder()}/{self.model_name}{SNN.SUFFIX_SEP}{SNN.CHECKPOINT_EPOCH_KEY}{epoch}{SNN.SAVE_EXT}"
+
+	def _create_new_checkpoint_meta(self, epoch: int, best: bool = False) -> dict:
+		save_path = self._create_checkpoint_path(epoch)
+		new_info = {SNN.CHECKPOINT_EPOCHS_KEY: {epoch: save_path}}
+		if best:
+			new_info[SNN.CHECKPOINT_BEST_KEY] = save_path
+		return new_info
+
+	def save_checkpoint(self, optimizer, epoch: int, epoch_losses: Dict[str, Any], best: bool = False):
+		os.makedirs(self.checkpoint_folder, exist_ok=True)
+		save_path = self._create_checkpoint_path(epoch)
+		torch.save({
+			SNN.CHECKPOINT_EPOCH_KEY: epoch,
+			SNN.CHECKPOINT_STATE_DICT_KEY: self.state_dict(),
+			SNN.CHECKPOINT_OPTIMIZER_STATE_DICT_KEY: optimizer.state_dict(),
+			SNN.CHECKPOINT_LOSS_KEY: {k: float(v) for k, v in epoch_losses.items()},
+		}, save_path)
+		self.save_checkpoints_meta(self._create_new_checkpoint_meta(epoch, best))
+
+	@staticmethod
+	def get_save_path_from_checkpoints(
+			checkpoints_meta: Dict[str, Union[str, Dict[Any, str]]],
+			load_checkpoint_mode: LoadCheckpointMode = LoadCheckpointMode.BEST_EPOCH
+	) -> str:
+		if load_checkpoint_mode == LoadCheckpointMode.BEST_EPOCH:
+			return checkpoints_meta[SNN.CHECKPOINT_BEST_KEY]
+		elif load_checkpoint_mode == LoadCheckpointMode.LAST_EPOCH:
+			epochs_dict = checkpoints_meta[SNN.CHECKPOINT_EPOCHS_KEY]
+			last_epoch: int = max([int(e) for e in epochs_dict])
+			return checkpoints_meta[SNN.CHECKPOINT_EPOCHS_KEY][str(last_epoch)]
+		raise ValueError()
+
+	def get_checkpoints_loss_history(self) -> LossHistory:
+		history = LossHistory()
+		with open(self.checkpoints_meta_path, "r+") as jsonFile:
+			meta: dict = json.load(jsonFile)
+		for path in meta[SNN.CHECKPOINT_EPOCHS_KEY].values():
+			history.concat(torch.load(path, map_location=self.device, weights_only=False)[SNN.CHECKPOINT_LOSS_KEY])
+		return history
+
+	def load_checkpoint(self, load_checkpoint_mode: LoadCheckpointMode = LoadCheckpointMode.BEST_EPOCH) -> dict:
+		with open(self.checkpoints_meta_path, "r+") as jsonFile:
+			info: dict = json.load(jsonFile)
+		path = self.get_save_path_from_checkpoints(info, load_checkpoint_mode)
+		checkpoint = torch.load(path, map_location=self.device, weights_only=False)
+		self.load_state_dict(checkpoint[SNN.CHECKPOINT_STATE_DICT_KEY], strict=True)
+		return checkpoint
+
+	def save_checkpoints_meta(self, new_info: dict):
+		info = dict()
+		if os.path.exists(self.checkpoints_meta_path):
+			with open(self.checkpoints_meta_path, "r+") as jsonFile:
+				info = json.load(jsonFile)
+		mapping_update_recursively(info, new_info)
+		with open(self.checkpoints_meta_path, "w+") as jsonFile:
+			json.dump(info, jsonFile, indent=4)
+
+	# ---- evaluation (reference snn.py:507-555) ---------------------------------------------------------------------
+	def compute_classification_accuracy(self, dataloader: DataLoader, verbose: bool = False, desc: Optional[str] = None) -> float:
+		"""Accuracy over a dataloader; the per-batch comparison stays on the device, one host read at the end."""
+		self.eval()
+		correct = torch.zeros((), dtype=torch.float64, device=self.device)
+		total = 0
+		with torch.no_grad():
+			for inputs, classes in tqdm(dataloader, total=len(dataloader), desc=desc, disable=not verbose):
+				classes = classes.to(self.device)
+				outputs = self.get_prediction_logits(inputs, re_outputs_trace=False, re_hidden_states=False)
+				_, preds = torch.max(outputs, -1)
+				correct += torch.eq(preds, classes).sum()
+				total += classes.numel()
+		return (correct / max(total, 1)).item()
+
+	def compute_confusion_matrix(self, nb_classes: int, dataloaders: Dict[str, DataLoader], fit=False, fit_kwargs=None,
+			load_checkpoint_mode: LoadCheckpointMode = None):
+		if fit_kwargs is None:
+			fit_kwargs = {}
+		if fit:
+			self.fit(dataloaders["train"], dataloaders["val"], **fit_kwargs)
+		if load_checkpoint_mode is not None:
+			self.load_checkpoint(load_checkpoint_mode)
+		return {key: self._compute_single_confusion_matrix(nb_classes, d) for key, d in dataloaders.items()}
+
+	def _compute_single_confusion_matrix(self, nb_classes: int, dataloader: DataLoader) -> np.ndarray:
+		self.eval()
+		cm = torch.zeros((nb_classes, nb_classes), dtype=torch.int64, device=self.device)
+		with torch.no_grad():
+			for inputs, classes in dataloader:
+				classes = classes.to(self.device).view(-1).long()
+				outputs = self.get_prediction_logits(inputs, re_outputs_trace=False, re_hidden_states=False)
+				preds = torch.max(outputs, -1)[1].view(-1)
+				cm.view(-1).index_add_(0, classes * nb_classes + preds, torch.ones_like(preds))
+		return cm.cpu().numpy().astype(np.float64)

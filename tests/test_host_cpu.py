@@ -1,0 +1,134 @@
+"""CPU-side checks: the Python mirror of the reference interface, and that the C-ABI library loads and exports
+every symbol include/snnk.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from snnimageclassification_b200 import _cabi
+from snnimageclassification_b200 import (
+	ALIFLayer, LayerType, LayerType2Layer, LIFLayer, LoadCheckpointMode, ReadoutLayer, SNN, SpikeFuncType,
+	SpikeFuncType2Func, HeavisidePhiApprox, HeavisideSigmoidApprox, ToSpikes)
+from snnimageclassification_b200.modules.utils import LossHistory, batchwise_temporal_filter
+from _util import load
+
+CPU = torch.device("cpu")
+
+
+def test_library_exports_every_declared_symbol():
+	_cabi.build_extension()
+	header = open(_cabi.INCLUDE).read()
+	declared = sorted(set(re.findall(r"\b(snnk_[a-z_0-9]+)\s*\(", header)))
+	assert declared, "no entry points parsed from include/snnk.h"
+	lib = ctypes.CDLL(_cabi.LIB_PATH)
+	for name in declared:
+		assert hasattr(lib, name), f"{name} declared in snnk.h but not exported by libsnnk.so"
+	assert sorted(_cabi.EXPORTS) == declared, "python binding and header disagree on the entry points"
+	assert _cabi.lib().snnk_abi_version() == 1
+	assert b"sm_100" in _cabi.lib().snnk_strerror(-3)
+
+
+def test_desc_struct_matches_header_layout():
+	assert ctypes.sizeof(_cabi.SnnkDesc) == 14 * 4
+	assert _cabi.SnnkDesc.alpha.offset == 32 and _cabi.SnnkDesc.flags.offset == 52
+
+
+SPECS = {
+	"alif_rec_lb": dict(hidden_layer_type=LayerType.ALIF, use_recurrent_connection=True, learn_beta=True),
+	"alif_nonrec": dict(hidden_layer_type=LayerType.ALIF, use_recurrent_connection=False, learn_beta=False),
+	"lif_rec": dict(hidden_layer_type=LayerType.LIF, use_recurrent_connection=True),
+	"lif_two_hidden": dict(hidden_layer_type=LayerType.LIF, use_recurrent_connection=True),
+}
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_same_seed_same_weights_as_reference(name):
+	"""Parameter names, order, shapes and the RNG consumption order match the reference's SNN (snn.py:93, :149-157)."""
+	z = load("init_golden.npz")
+	torch.manual_seed(42)
+	hidden = [24, 16] if name == "lif_two_hidden" else 24
+	net = SNN(20, 10, hidden, int_time_steps=5, spike_func=SpikeFuncType.FastSigmoid, device=CPU, **SPECS[name])
+	assert list(net.state_dict().keys()) == list(z[f"{name}/__keys__"])
+	assert [n for n, _ in net.named_parameters()] == list(z[f"{name}/__params__"])
+	for k, v in net.state_dict().items():
+		assert np.array_equal(v.numpy(), z[f"{name}/{k}"]), k
+
+
+def test_reference_quirks_are_kept():
+	torch.manual_seed(0)
+	net = SNN(16, 10, 32, hidden_layer_type=LayerType.ALIF, spike_func=SpikeFuncType.FastSigmoid, device=CPU,
+		learn_beta=True)
+	L = net.layers["input"]
+	assert isinstance(L, ALIFLayer) and isinstance(L.beta, torch.nn.Parameter)
+	assert abs(float(L.beta)) < 0.5          # re-drawn ~N(0, 0.03^2), not 1.6
+	assert float(L.gamma) == pytest.approx(0.3) and float(L.threshold) == pytest.approx(0.03)
+	assert float(L.alpha) == pytest.approx(np.exp(-1 / 20), rel=1e-6)
+	assert float(L.rho) == pytest.approx(np.exp(-1 / 200), rel=1e-6)
+	assert float(net.layers["readout"].kappa) == pytest.approx(np.exp(-1 / 10), rel=1e-6)
+	assert torch.equal(L.rec_mask, 1 - torch.eye(32))
+	assert "rec_mask" not in dict(L.named_buffers())
+	lif = LIFLayer(8, 32, device=CPU)
+	assert float(lif.gamma) == 1.0 and float(lif.threshold) == 1.0
+	assert float(lif.alpha) == pytest.approx(np.exp(-1 / 10), rel=1e-6)
+	assert LayerType2Layer[LayerType.ALIF] is ALIFLayer
+	assert SpikeFuncType2Func[SpikeFuncType.Phi] is HeavisidePhiApprox
+	assert SpikeFuncType2Func[SpikeFuncType.FastSigmoid] is HeavisideSigmoidApprox
+	assert HeavisidePhiApprox.epsilon == 1e-5
+	assert [m.name for m in LoadCheckpointMode] == ["BEST_EPOCH", "LAST_EPOCH"]
+
+
+def test_no_cpu_fallback():
+	net = SNN(16, 10, 32, hidden_layer_type=LayerType.LIF, device=CPU, int_time_steps=4)
+	with pytest.raises(RuntimeError, match="no CPU fallback"):
+		net(torch.zeros(2, 4, 16))
+	with pytest.raises(RuntimeError, match="no CPU fallback"):
+		HeavisideSigmoidApprox.apply(torch.zeros(4), torch.tensor(1.0), torch.tensor(1.0))
+	if not torch.cuda.is_available():
+		with pytest.raises(RuntimeError, match="no CPU fallback"):
+			ToSpikes(10)(np.zeros(4))
+	izh = SNN(16, 10, 32, hidden_layer_type=LayerType.Izhikevich, device=CPU, int_time_steps=4)
+	with pytest.raises(NotImplementedError, match="not supported by the B200 path"):
+		izh(torch.zeros(2, 4, 16))
+
+
+def test_format_inputs():
+	net = SNN(6, 10, 32, device=CPU, int_time_steps=5)
+	x = torch.arange(12, dtype=torch.float64).reshape(2, 6)
+	f = net._format_inputs(x)
+	assert f.shape == (2, 5, 6) and f.dtype == torch.float32
+	assert torch.equal(f[:, 3], x.float())
+	f = net._format_inputs(torch.ones(2, 3, 6))
+	assert f.shape == (2, 5, 6) and f[:, 3:].abs().sum() == 0 and f[:, :3].sum() == 36
+	with pytest.raises(AssertionError):
+		net._format_inputs(torch.ones(2, 6, 6))
+
+
+def test_checkpoint_files_interchange(tmp_path):
+	net = SNN(6, 10, 32, hidden_layer_type=LayerType.ALIF, device=CPU, int_time_steps=5, learn_beta=True,
+		checkpoint_folder=str(tmp_path / "ck"), model_name="m")
+	opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5)
+	net.save_checkpoint(opt, 0, dict(train=1.0, val=2.0), best=True)
+	net.save_checkpoint(opt, 1, dict(train=0.5, val=2.5), best=False)
+	assert net.checkpoints_meta_path.endswith("ck/m-checkpoints.json")
+	assert os.path.exists(tmp_path / "ck" / "m-epoch1.pth")
+	w = net.layers["input"].forward_weights.detach().clone()
+	with torch.no_grad():
+		net.layers["input"].forward_weights.zero_()
+	ck = net.load_checkpoint(LoadCheckpointMode.LAST_EPOCH)
+	assert ck["epoch"] == 1 and torch.equal(net.layers["input"].forward_weights, w)
+	assert net.load_checkpoint(LoadCheckpointMode.BEST_EPOCH)["epoch"] == 0
+	hist = net.get_checkpoints_loss_history()
+	assert hist["val"] == [2.0, 2.5] and hist.min("val") == 2.0
+
+
+def test_loss_history_and_temporal_filter():
+	h = LossHistory()
+	assert h.min("val") == np.inf
+	h.concat(dict(train=1.0, val=3.0)); h.concat(dict(train=[0.5], val=[2.0]))
+	assert h["train"] == [1.0, 0.5] and h.min_item("val") == dict(train=0.5, val=2.0)
+	# known answers of the reference's test/test_temporal_filter.py
+	x = torch.ones(1, 3, 1)
+	assert torch.allclose(batchwise_temporal_filter(x, 0.5), torch.tensor([[1.75]]))
