@@ -217,7 +217,7 @@ def main():
 	net.input_encoder = enc
 
 	# per-kernel CUDA-event timing (separate short loop, same process) -> roofline of the dominant kernel
-	kern = profile_kernels(net, rasters, labels_dev, crit, dev)
+	kern = profile_kernels(step_resident)
 
 	if rank != 0:
 		if world > 1:
@@ -229,20 +229,21 @@ def main():
 	except Exception:
 		pass
 	peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
-	top = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+	top = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
 	roofline = None
 	if top:
 		ach = kern[top]["bytes"] / (kern[top]["ms"] * 1e-3) / 1e9
 		roofline = {"bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
 			"traffic": None, "kernel": top, "peak_source": "measured" if peaks else "fallback",
 			"kernel_ms": kern[top]["ms"], "algorithmic_bytes": kern[top]["bytes"],
-			"all_kernels_ms": {k: round(v["ms"], 4) for k, v in kern.items()}}
+			"all_kernels": {k: {"ms": round(v["ms"], 4), "per_step": v["launches_per_step"],
+				"GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} for k, v in kern.items()}}
+	launches_per_step = sum(v["launches_per_step"] for v in kern.values()) if kern else 0
 	cpu = None
 	if world == 1 and not args.no_cpu_baseline:
 		r = cpu_reference_run(steps=40, warmup=2, budget_s=25.0)
 		cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
 			"sample": f"{r['steps']} train steps of batch {r['batch']} (of {B_PER_GPU}), T={T}, oracle/torch_port.py"}
-	launches_per_step = 9
 	print(json.dumps({
 		"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
 		"warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -254,45 +255,37 @@ def main():
 		"e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
 			"ms_per_step": ms_e2e / args.steps, "input": "pinned host images (B,784) fp32 + labels; GPU to_spikes",
 			"from_host_rasters": {"value": e2e_raster, "h2d_bytes_per_step": B_PER_GPU * T * N * 4 + B_PER_GPU * 8}},
-		"gpu_launches": launches_per_step * args.steps,
+		"gpu_launches": int(round(launches_per_step * args.steps)),
 		"roofline": roofline, "cpu_baseline": cpu,
 	}))
 	if world > 1:
 		dist.destroy_process_group()
 
 
-def profile_kernels(net, rasters, labels_dev, crit, dev, iters=10):
-	"""CUDA-event duration of each kernel group of one train step, by calling the C-ABI stages back to back."""
-	from snnimageclassification_b200.modules import functional as F_
-	consts = net._consts()
-	W = [F_._c(w) for w in net._weights()]
-	Wi, Wr, M, be, Wo, bo = W
-	B = rasters[0].shape[0]
+def profile_kernels(step_fn, iters=10):
+	"""Average CUDA-event duration and launch count of every kernel of the library over ``iters`` train steps
+	(snnk_profile_begin/end: events recorded on the launching stream around each launch)."""
+	from snnimageclassification_b200 import _cabi
+	for i in range(2):
+		step_fn(i)
+	torch.cuda.synchronize()
+	with _cabi.kernel_profile() as prof:
+		for i in range(iters):
+			step_fn(i)
+	# algorithmic bytes per launch (DESIGN.md "Kernels"): what the kernel must read and write at least once
+	BT = B_PER_GPU * T
+	algo = {
+		"K1": BT * N * 4 + BT * H * 4,                                   # read X, write I_in
+		"K2": BT * H * 4 + 3 * BT * H * 4 + BT * O * 4 + BT * H // 8,      # read I_in; write V,a,Z,y,zbits
+		"K3": 2 * BT * H * 4 + BT * H // 8 + BT * H * 4,                   # read V,a,zbits; write gI
+		"K4": BT * N * 4 + BT * H * 4 + BT * H // 8,                       # read X, gI, zbits
+		"K5": B_PER_GPU * N * 4 + BT * N * 4,                              # read images, write rasters
+		"K6": B_PER_GPU * O * 4 * 3,
+	}
 	res = {}
-
-	def ev():
-		return torch.cuda.Event(enable_timing=True)
-	acc = {"forward(K1 proj + K2 recurrence)": 0.0, "head(K6)": 0.0, "backward(K3 bptt + K4 wgrad)": 0.0}
-	for i in range(iters + 2):
-		x = rasters[i % len(rasters)]
-		e = [ev() for _ in range(4)]
-		e[0].record()
-		out = F_.run_forward(consts, x, Wi, Wr, M, be, Wo, bo, traces=True)
-		e[1].record()
-		loss, logp, g = F_.run_head_nll(out["logits"], labels_dev[i % len(rasters)])
-		e[2].record()
-		F_.run_backward(consts, x, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits=g, tstar=out["tstar"])
-		e[3].record()
-		torch.cuda.synchronize()
-		if i >= 2:
-			acc["forward(K1 proj + K2 recurrence)"] += e[0].elapsed_time(e[1])
-			acc["head(K6)"] += e[1].elapsed_time(e[2])
-			acc["backward(K3 bptt + K4 wgrad)"] += e[2].elapsed_time(e[3])
-	fwd_bytes = B * T * N * 4 + 3 * B * T * H * 4 + B * T * O * 4
-	bwd_bytes = B * T * N * 4 + 2 * B * T * H * 4 + B * T * H // 8
-	res["forward(K1 proj + K2 recurrence)"] = {"ms": acc["forward(K1 proj + K2 recurrence)"] / iters, "bytes": fwd_bytes}
-	res["head(K6)"] = {"ms": acc["head(K6)"] / iters, "bytes": B * O * 4 * 3}
-	res["backward(K3 bptt + K4 wgrad)"] = {"ms": acc["backward(K3 bptt + K4 wgrad)"] / iters, "bytes": bwd_bytes}
+	for name, (ms, n) in prof.result.items():
+		res[name] = {"ms": ms / n, "launches_per_step": n / iters, "ms_per_step": ms / iters,
+			"bytes": algo.get(name.split()[0], 0)}
 	return res
 
 

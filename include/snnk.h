@@ -85,12 +85,29 @@ typedef struct SnnkDesc {
     uint32_t flags;     /* SNNK_F_*                                           */
 } SnnkDesc;
 
+/* kernel groups reported by the optional profiler below */
+enum {
+    SNNK_K_ENCODE = 0, SNNK_K_PROJ = 1, SNNK_K_RECUR_FWD = 2, SNNK_K_HEAD = 3, SNNK_K_RECUR_BWD = 4,
+    SNNK_K_REDUCE_OUT = 5, SNNK_K_WGRAD = 6, SNNK_K_REDUCE_W = 7, SNNK_K_COUNT = 8
+};
+
 int snnk_abi_version(void);
 const char* snnk_strerror(int code);
 /* Host string describing the last CUDA runtime error seen by this thread ("" if none). */
 const char* snnk_last_cuda_error(void);
 /* 1 if the CURRENT CUDA device is sm_100 (B200), 0 if not, <0 on error. */
 int snnk_device_supported(void);
+
+/*
+ * Optional per-kernel timing (bench.py's roofline): between snnk_profile_begin() and snnk_profile_end()
+ * every kernel launch of this library is bracketed by CUDA events on its stream.  snnk_profile_end()
+ * synchronises the device (the one exception to "never synchronises") and fills ms_total[SNNK_K_COUNT]
+ * (summed kernel time per group, milliseconds) and launches[SNNK_K_COUNT].  Process-global debug
+ * facility; not for concurrent use.
+ */
+const char* snnk_kernel_name(int id);
+int snnk_profile_begin(void);
+int snnk_profile_end(double* ms_total, int64_t* launches);
 
 /*
  * Image -> spike-train encoder.  Replaces ToSpikes.__call__ (datasets.py:93-97) for a whole batch.

@@ -64,6 +64,9 @@ _SIGNATURES = {
 	"snnk_strerror": (ctypes.c_char_p, [ctypes.c_int]),
 	"snnk_last_cuda_error": (ctypes.c_char_p, []),
 	"snnk_device_supported": (ctypes.c_int, []),
+	"snnk_kernel_name": (ctypes.c_char_p, [ctypes.c_int]),
+	"snnk_profile_begin": (ctypes.c_int, []),
+	"snnk_profile_end": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
 	"snnk_encode": (ctypes.c_int, [
 		_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_double,
 		ctypes.c_double, ctypes.c_double, ctypes.c_int32, _p, ctypes.c_int32, _p, _p]),
@@ -96,6 +99,27 @@ def lib() -> ctypes.CDLL:
 			raise RuntimeError("libsnnk.so ABI version mismatch; rebuild the extension")
 		_lib = l
 	return _lib
+
+
+SNNK_K_COUNT = 8
+
+
+class kernel_profile:
+	"""Context manager around snnk_profile_begin/end -> {kernel name: (total ms, launches)} in ``.result``."""
+
+	def __enter__(self):
+		check(lib().snnk_profile_begin(), "snnk_profile_begin")
+		self.result = {}
+		return self
+
+	def __exit__(self, *exc):
+		ms = (ctypes.c_double * SNNK_K_COUNT)()
+		n = (ctypes.c_int64 * SNNK_K_COUNT)()
+		check(lib().snnk_profile_end(ms, n), "snnk_profile_end")
+		for k in range(SNNK_K_COUNT):
+			if n[k]:
+				self.result[lib().snnk_kernel_name(k).decode()] = (float(ms[k]), int(n[k]))
+		return False
 
 
 def check(rc: int, what: str) -> None:

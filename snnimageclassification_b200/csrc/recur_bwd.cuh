@@ -24,7 +24,8 @@ namespace snnk {
 template <int H, int R>
 constexpr size_t bwd_smem_bytes(int T, bool rec)
 {
-    size_t loop = sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)(R * T * (H / 32)) +
+    // the spike-word region is padded to 16 bytes: s_gy behind it is read with float4 loads
+    size_t loop = sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)((R * T * (H / 32) + 3) & ~3) +
                   sizeof(float) * (size_t)(R * T * kOMax);
     size_t stage = rec ? sizeof(float) * (size_t)H * (H + 1) : 0;   // transpose staging, prologue only
     return loop > stage ? loop : stage;
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(H) k_recur_bwd(const BwdParams p)
 
     float* s_g = reinterpret_cast<float*>(smem_raw);                       // [2][R][H]
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_g + 2 * R * H);       // [R][T][W32]
-    float* s_gy = reinterpret_cast<float*>(s_mask + R * T * W32);          // [R][T][kOMax]
+    float* s_gy = reinterpret_cast<float*>(s_mask + ((R * T * W32 + 3) & ~3));   // [R][T][kOMax], 16-B aligned
 
     float wo[kOMax], dwo[kOMax];
 #pragma unroll

@@ -18,7 +18,7 @@ namespace snnk {
 template <int H, int R>
 constexpr size_t fwd_smem_bytes(int T, int O)
 {
-    return sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)(R * T * (H / 32)) +
+    return sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)((R * T * (H / 32) + 3) & ~3) +
            sizeof(float) * (size_t)(H * O) + sizeof(float) * (size_t)(R * T * O);
 }
 
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(H) k_recur_fwd(const FwdParams p)
 
     float* s_z = reinterpret_cast<float*>(smem_raw);                       // [2][R][H]
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_z + 2 * R * H);       // [R][T][W32]
-    float* s_wout = reinterpret_cast<float*>(s_mask + R * T * W32);        // [H][O]
+    float* s_wout = reinterpret_cast<float*>(s_mask + ((R * T * W32 + 3) & ~3));   // [H][O]
     float* s_s = s_wout + H * O;                                           // [R][T][O]
 
     // column i of W_rec (.) rec_mask  (spiking_layers.py:165/235 multiplies the mask in at every step)

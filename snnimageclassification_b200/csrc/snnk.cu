@@ -32,6 +32,29 @@ int cuda_fail(cudaError_t e, const char* where)
         if (e__ != cudaSuccess) return cuda_fail(e__, #call);  \
     } while (0)
 
+// ---- optional per-kernel CUDA-event profiler (bench.py's roofline numbers; off by default) ----------------
+// When enabled, every launch is bracketed by two cudaEventRecord calls on the launching stream.  Debug
+// facility: process-global, not thread-safe, never touched on the normal path.
+constexpr int kMaxProfiledLaunches = 1 << 14;
+struct ProfiledLaunch { int id; cudaEvent_t a, b; };
+bool g_prof_on = false;
+int g_prof_n = 0;
+ProfiledLaunch g_prof[kMaxProfiledLaunches];
+
+struct ProfScope {
+    cudaStream_t st; int slot;
+    ProfScope(int id, cudaStream_t s) : st(s), slot(-1)
+    {
+        if (!g_prof_on || g_prof_n >= kMaxProfiledLaunches) return;
+        ProfiledLaunch& L = g_prof[g_prof_n];
+        if (cudaEventCreate(&L.a) != cudaSuccess || cudaEventCreate(&L.b) != cudaSuccess) return;
+        L.id = id;
+        slot = g_prof_n++;
+        cudaEventRecord(L.a, st);
+    }
+    ~ProfScope() { if (slot >= 0) cudaEventRecord(g_prof[slot].b, st); }
+};
+
 int device_ok()
 {
     int dev = 0;
@@ -103,7 +126,7 @@ int launch_fwd(const FwdParams& fp, int grid, cudaStream_t st)
     if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
     auto kern = k_recur_fwd<H, R, REC>;
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, H, smem, st>>>(fp);
+    { ProfScope ps(SNNK_K_RECUR_FWD, st); kern<<<grid, H, smem, st>>>(fp); }
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -127,7 +150,7 @@ int launch_bwd(const BwdParams& bp, int grid, cudaStream_t st)
     if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
     auto kern = k_recur_bwd<H, R, REC>;
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, H, smem, st>>>(bp);
+    { ProfScope ps(SNNK_K_RECUR_BWD, st); kern<<<grid, H, smem, st>>>(bp); }
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -151,6 +174,7 @@ int launch_encode(const TIn* x, int64_t n_items, int64_t n_pix, int32_t n_steps,
 {
     dim3 grid((unsigned)n_items, (unsigned)((n_pix + 255) / 256));
     long long* per = reinterpret_cast<long long*>(periods);
+    ProfScope ps(SNNK_K_ENCODE, st);
     switch (out_dtype) {
     case SNNK_F32:
         k_encode<TIn, float><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
@@ -195,14 +219,56 @@ const char* snnk_last_cuda_error(void) { return g_cuda_err; }
 
 int snnk_device_supported(void) { return device_ok(); }
 
+const char* snnk_kernel_name(int id)
+{
+    switch (id) {
+    case SNNK_K_ENCODE: return "K5 k_encode (to_spikes)";
+    case SNNK_K_PROJ: return "K1 k_proj (input projection GEMM)";
+    case SNNK_K_RECUR_FWD: return "K2 k_recur_fwd (fused recurrence + readout)";
+    case SNNK_K_HEAD: return "K6 k_head_nll";
+    case SNNK_K_RECUR_BWD: return "K3 k_recur_bwd (fused reverse-time BPTT)";
+    case SNNK_K_REDUCE_OUT: return "k_reduce_parts (dW_out, db)";
+    case SNNK_K_WGRAD: return "K4 k_wgrad (weight-gradient GEMM)";
+    case SNNK_K_REDUCE_W: return "k_reduce_parts (dW_in, dW_rec)";
+    default: return "?";
+    }
+}
+
+int snnk_profile_begin(void)
+{
+    if (g_prof_on) return SNNK_ERR_ARG;
+    g_prof_n = 0;
+    g_prof_on = true;
+    return SNNK_OK;
+}
+
+int snnk_profile_end(double* ms_total, int64_t* launches)
+{
+    if (!g_prof_on || !ms_total || !launches) return SNNK_ERR_ARG;
+    g_prof_on = false;
+    for (int k = 0; k < SNNK_K_COUNT; ++k) { ms_total[k] = 0.0; launches[k] = 0; }
+    SNNK_CUDA(cudaDeviceSynchronize());
+    for (int q = 0; q < g_prof_n; ++q) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof[q].a, g_prof[q].b) == cudaSuccess) {
+            ms_total[g_prof[q].id] += ms;
+            launches[g_prof[q].id] += 1;
+        }
+        cudaEventDestroy(g_prof[q].a);
+        cudaEventDestroy(g_prof[q].b);
+    }
+    g_prof_n = 0;
+    return SNNK_OK;
+}
+
 int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max,
                 double tau, double thr, double eps, int32_t periodic, void* out, int32_t out_dtype,
                 int64_t* periods, snnk_stream_t stream)
 {
-    if (!x || !out) return SNNK_ERR_ARG;
     if (n_items < 0 || n_pix < 0 || n_steps <= 0 || n_items > 0x7fffffffll || n_pix > 65535ll * 256) return SNNK_ERR_SHAPE;
+    if (n_items == 0 || n_pix == 0) return SNNK_OK;   /* empty batch: nothing to do (pointers may be NULL) */
+    if (!x || !out) return SNNK_ERR_ARG;
     if (!device_ok()) return SNNK_ERR_DEVICE;
-    if (n_items == 0 || n_pix == 0) return SNNK_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (x_dtype == SNNK_F32)
         return launch_encode(static_cast<const float*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
@@ -276,6 +342,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     {
         const int M = d->B * d->T;
         dim3 grid((M + kGemmBM - 1) / kGemmBM, pl.ntiles);
+        ProfScope ps(SNNK_K_PROJ, st);
         if (pl.BN == 64) k_proj_simt<64><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H);
         else k_proj_simt<32><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H);
         SNNK_CUDA(cudaGetLastError());
@@ -303,8 +370,11 @@ int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labe
     if (!logits || !labels || !loss) return SNNK_ERR_ARG;
     if (B <= 0 || O <= 0 || O > kOMax) return SNNK_ERR_SHAPE;
     if (!device_ok()) return SNNK_ERR_DEVICE;
-    k_head_nll<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        B, O, logits, reinterpret_cast<const long long*>(labels), logp, loss, g_logits);
+    {
+        ProfScope ps(SNNK_K_HEAD, static_cast<cudaStream_t>(stream));
+        k_head_nll<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            B, O, logits, reinterpret_cast<const long long*>(labels), logp, loss, g_logits);
+    }
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -351,6 +421,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     if (rc != SNNK_OK) return rc;
     {
         const int n1 = d->H * d->O;
+        ProfScope ps(SNNK_K_REDUCE_OUT, st);
         k_reduce_parts<<<(n1 + 255) / 256, 256, 0, st>>>(pwout, pl.grid_rows, (size_t)n1, n1, nullptr, dW_out);
         k_reduce_parts<<<1, 256, 0, st>>>(pdb, pl.grid_rows * pl.R, (size_t)d->O, d->O, nullptr, db);
         SNNK_CUDA(cudaGetLastError());
@@ -362,9 +433,13 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         wp.mtiles_x = pl.mtiles_x; wp.rows_per_split = pl.rows_per_split;
         wp.x = x; wp.zbits = zbits; wp.Z0 = Z0; wp.gI = gI; wp.part = pw; wp.m_total = pl.m_total;
         dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.ntiles, pl.S);
-        if (pl.BN == 64) k_wgrad_simt<64><<<grid, kGemmThreads, 0, st>>>(wp);
-        else k_wgrad_simt<32><<<grid, kGemmThreads, 0, st>>>(wp);
+        {
+            ProfScope ps(SNNK_K_WGRAD, st);
+            if (pl.BN == 64) k_wgrad_simt<64><<<grid, kGemmThreads, 0, st>>>(wp);
+            else k_wgrad_simt<32><<<grid, kGemmThreads, 0, st>>>(wp);
+        }
         SNNK_CUDA(cudaGetLastError());
+        ProfScope ps2(SNNK_K_REDUCE_W, st);
         const size_t stride = (size_t)pl.m_total * d->H;
         const int n_in = d->N * d->H;
         k_reduce_parts<<<(n_in + 255) / 256, 256, 0, st>>>(pw, pl.S, stride, n_in, nullptr, dW_in);
