@@ -66,7 +66,7 @@ class ToSpikes:
 		if on_cpu:
 			t = t.to(self._device())
 		shape = tuple(t.shape)
-		t2 = t.reshape(1, -1) if t.ndim <= 1 else t.reshape(shape[0], -1)
+		t2 = t.reshape(1, t.numel()) if t.ndim <= 1 else t.reshape(shape[0], int(np.prod(shape[1:])))
 		return t2.contiguous(), shape, on_cpu, was_numpy
 
 	def _run(self, x2: torch.Tensor, periodic: bool, out_dtype: torch.dtype, want_periods: bool, want_raster: bool = True):
@@ -124,7 +124,7 @@ class ToSpikes:
 	def encode_batch(self, images: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
 		"""images (B, n_pix) float32|float64 (any device) -> spike trains (B, n_steps, n_pix) on the GPU."""
 		if images.ndim != 2:
-			images = images.reshape(images.shape[0], -1)
+			images = images.reshape(images.shape[0], int(np.prod(images.shape[1:])))
 		x2, _, _, _ = self._stage(images)
 		out, _ = self._run(x2, self.use_periods, out_dtype, want_periods=False)
 		return out

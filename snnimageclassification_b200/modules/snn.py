@@ -224,7 +224,7 @@ class SNN(torch.nn.Module):
 	def forward(self, inputs):
 		"""-> (outputs_trace (B,T,O), {"input": (V,[a],Z), "readout": (y,)}), as reference snn.py:201-219."""
 		layer, _ = self._hot_layers()
-		inputs = self._format_inputs(self._encode_if_needed(inputs))
+		inputs = self._format_inputs(self._encode_if_needed(inputs.to(self.device, non_blocking=True)))
 		y, V, a, Z = F_.SpikingSequence.apply(self._consts(), inputs, *self._weights())
 		hidden = (V, a, Z) if isinstance(layer, ALIFLayer) else (V, Z)
 		return y, {"input": hidden, "readout": (y,)}
