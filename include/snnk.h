@@ -88,7 +88,8 @@ typedef struct SnnkDesc {
 /* kernel groups reported by the optional profiler below */
 enum {
     SNNK_K_ENCODE = 0, SNNK_K_PROJ = 1, SNNK_K_RECUR_FWD = 2, SNNK_K_HEAD = 3, SNNK_K_RECUR_BWD = 4,
-    SNNK_K_REDUCE_OUT = 5, SNNK_K_WGRAD = 6, SNNK_K_REDUCE_W = 7, SNNK_K_COUNT = 8
+    SNNK_K_REDUCE_OUT = 5, SNNK_K_WGRAD = 6, SNNK_K_REDUCE_W = 7, SNNK_K_PROJ_FALLBACK = 8,
+    SNNK_K_WGRAD_FALLBACK = 9, SNNK_K_COUNT = 10
 };
 
 int snnk_abi_version(void);
@@ -172,14 +173,17 @@ int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labe
  * Gradient seeds: either g_y (B,T,O) dense w.r.t. the output trace, or -- the fused-head form --
  * g_logits (B,O) with tstar (B,O) (the gradient lands on y[b,tstar[b,o],o]).  Exactly one of the
  * two forms must be given.  g_V, g_Z (B,T,H) are optional extra seeds on the hidden traces.
+ * V, a (ALIF), Z (B,T,H) and zbits are the traces the forward wrote (Z, the fp32 spike trace, is read by the
+ * tensor-core weight-gradient GEMM only and may be NULL without SNNK_F_TENSOR_CORE).
  * Outputs: dW_in (N,H), dW_rec (H,H, masked; NULL iff !recurrent), dW_out (H,O), db (O); they are
  * OVERWRITTEN.  beta receives no gradient (the threshold input of the spike function has none,
  * spike_funcs.py:62).  workspace: on return its first B*T*H floats hold gI, the gradient w.r.t. the
- * input current (exposed for tests).
+ * input current (exposed for tests); with SNNK_F_TENSOR_CORE gI is stored as two tf32 planes, high plane
+ * first and the exact remainder in the next B*T*H floats (256-byte aligned), whose sum is gI.
  */
 int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const float* rec_mask,
                   const float* beta, const float* W_out, const float* Z0, const float* V,
-                  const float* a, const uint32_t* zbits, const float* g_y, const float* g_logits,
+                  const float* a, const float* Z, const uint32_t* zbits, const float* g_y, const float* g_logits,
                   const int32_t* tstar, const float* g_V, const float* g_Z, float* dW_in,
                   float* dW_rec, float* dW_out, float* db, void* workspace, size_t workspace_bytes,
                   snnk_stream_t stream);

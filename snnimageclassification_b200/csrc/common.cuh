@@ -36,6 +36,7 @@ struct BwdParams {
     const float* g_logits; const int32_t* tstar;    // (B,O) sparse seeds, or null
     const float* g_V; const float* g_Z;             // optional (B,T,H) seeds
     float* gI;          // (B,T,H)
+    float* gI_lo;       // (B,T,H) or null: when set, gI receives trunc_tf32(gI) and gI_lo the exact remainder
     float* part_wout;   // [grid][H][O]
     float* part_db;     // [grid*R][O]
 };

@@ -21,8 +21,11 @@ constexpr int kGemmThreads = 256;
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads) k_proj_simt(const float* __restrict__ A,
                                                            const float* __restrict__ W,
-                                                           float* __restrict__ C, int M, int K, int Hn)
+                                                           float* __restrict__ C, int M, int K, int Hn,
+                                                           const unsigned int* __restrict__ run_if_flag)
 {
+    // behind the tcgen05 kernel this launch is a fallback: it only runs when that kernel raised the flag
+    if (run_if_flag && *run_if_flag == 0) return;
     constexpr int TN = BN / 4;                  // thread columns
     constexpr int TMG = kGemmThreads / TN;      // thread row groups
     constexpr int TM = kGemmBM / TMG;           // rows per thread
@@ -94,6 +97,8 @@ struct WgradParams {
     const uint32_t* zbits;      // (BT, H/32)
     const float* Z0;            // (B, H) or null
     const float* gI;            // (BT, H)
+    const float* gI_lo;         // (BT, H) low tf32 plane of gI (tensor-core mode: gI holds the high plane) or null
+    const unsigned int* run_if_flag;   // fallback gating, see k_proj_simt
     float* part;                // [S][N + H][H]   (rows N.. only when recurrent)
     int m_total;
 };
@@ -107,6 +112,7 @@ __global__ void __launch_bounds__(kGemmThreads) k_wgrad_simt(const WgradParams p
     __shared__ __align__(16) float As[kGemmBK][kGemmBM];
     __shared__ __align__(16) float Bs[kGemmBK][BN];
 
+    if (p.run_if_flag && *p.run_if_flag == 0) return;
     const int tid = threadIdx.x;
     const bool from_x = (int)blockIdx.x < p.mtiles_x;
     const int m0 = from_x ? blockIdx.x * kGemmBM : (blockIdx.x - p.mtiles_x) * kGemmBM;
@@ -142,7 +148,12 @@ __global__ void __launch_bounds__(kGemmThreads) k_wgrad_simt(const WgradParams p
         for (int idx = tid; idx < kGemmBK * BN; idx += kGemmThreads) {
             const int kk = idx / BN, nn = idx - kk * BN;
             const int r = r0 + kk;
-            Bs[kk][nn] = (r < rend) ? __ldg(p.gI + (size_t)r * p.H + n0 + nn) : 0.f;
+            float g = 0.f;
+            if (r < rend) {
+                g = __ldg(p.gI + (size_t)r * p.H + n0 + nn);
+                if (p.gI_lo) g += __ldg(p.gI_lo + (size_t)r * p.H + n0 + nn);   // hi + lo is exact
+            }
+            Bs[kk][nn] = g;
         }
         __syncthreads();
 #pragma unroll

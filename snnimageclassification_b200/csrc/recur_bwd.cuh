@@ -172,7 +172,15 @@ __global__ void __launch_bounds__(H) k_recur_bwd(const BwdParams p)
                     if (p.g_V && valid[r]) g = __fadd_rn(g, __ldg(p.g_V + o));
                     gv[r] = g;
                     const float gi = __fmul_rn(g, __fsub_rn(1.0f, zprev));
-                    if (valid[r]) p.gI[o] = gi;
+                    if (valid[r]) {
+                        if (p.gI_lo) {   // tensor-core mode: exact two-plane tf32 split for the weight-gradient GEMM
+                            const float hi = __uint_as_float(__float_as_uint(gi) & 0xFFFFE000u);
+                            p.gI[o] = hi;
+                            p.gI_lo[o] = __fsub_rn(gi, hi);
+                        } else {
+                            p.gI[o] = gi;
+                        }
+                    }
                     if (REC) s_g[(t & 1) * R * H + r * H + i] = gi;
                 }
                 if (REC) __syncthreads();

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "encode_head.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "recur_bwd.cuh"
 #include "recur_fwd.cuh"
 
@@ -73,9 +74,12 @@ struct Plan {
     int grid_rows;    // recurrence CTAs
     int m_total;      // rows of the stacked weight gradient [dW_in ; dW_rec]
     int mtiles_x, mtiles_z, ntiles, BN;
-    int S;            // split-K factor of the weight-gradient GEMM
-    int rows_per_split;
-    size_t off_gI, off_pwout, off_pdb, off_pw, bwd_bytes, fwd_bytes;
+    int S;            // split-K factor of the weight-gradient GEMM (splits are whole samples)
+    int samples_per_split;
+    bool tc;          // tcgen05 GEMMs eligible for this geometry (the flag asks for them and TMA can address x)
+    int kpad;         // K of the projection padded to the k-block
+    size_t off_gI, off_gIlo, off_pwout, off_pdb, off_pw, off_flag, bwd_bytes;
+    size_t off_wplanes, off_fflag, fwd_bytes;
 };
 
 int check_desc(const SnnkDesc* d)
@@ -101,22 +105,145 @@ Plan make_plan(const SnnkDesc* d)
     p.mtiles_x = (d->N + kGemmBM - 1) / kGemmBM;
     p.mtiles_z = d->recurrent ? (d->H + kGemmBM - 1) / kGemmBM : 0;
     p.m_total = d->N + (d->recurrent ? d->H : 0);
-    const int tiles = (p.mtiles_x + p.mtiles_z) * p.ntiles;
-    int S = (4 * 148 + tiles - 1) / tiles;
-    const int maxS = (BT + 63) / 64;
-    if (S > maxS) S = maxS;
+    // TMA needs 16-byte global strides: N % 4 == 0 (H is a multiple of 32 already)
+    p.tc = (d->flags & SNNK_F_TENSOR_CORE) != 0 && d->N % 4 == 0;
+    p.kpad = (d->N + tc::kBlockK - 1) / tc::kBlockK * tc::kBlockK;
+    int S;
+    if (p.tc) {
+        S = 148 / (p.mtiles_x + p.mtiles_z);          // one CTA per SM: the tcgen05 kernel owns the whole smem
+    } else {
+        const int tiles = (p.mtiles_x + p.mtiles_z) * p.ntiles;
+        S = (4 * 148 + tiles - 1) / tiles;
+    }
+    if (S > d->B) S = d->B;
     if (S < 1) S = 1;
-    p.rows_per_split = (BT + S - 1) / S;
-    p.rows_per_split = (p.rows_per_split + kGemmBK - 1) / kGemmBK * kGemmBK;
-    p.S = (BT + p.rows_per_split - 1) / p.rows_per_split;
+    p.samples_per_split = (d->B + S - 1) / S;
+    p.S = (d->B + p.samples_per_split - 1) / p.samples_per_split;
     size_t off = 0;
     p.off_gI = off;     off = align_up(off + sizeof(float) * (size_t)BT * d->H, 256);
+    p.off_gIlo = off;   off = align_up(off + (p.tc ? sizeof(float) * (size_t)BT * d->H : 0), 256);
     p.off_pwout = off;  off = align_up(off + sizeof(float) * (size_t)p.grid_rows * d->H * d->O, 256);
     p.off_pdb = off;    off = align_up(off + sizeof(float) * (size_t)p.grid_rows * p.R * d->O, 256);
     p.off_pw = off;     off = align_up(off + sizeof(float) * (size_t)p.S * p.m_total * d->H, 256);
+    p.off_flag = off;   off = align_up(off + 256, 256);
     p.bwd_bytes = off;
-    p.fwd_bytes = align_up(sizeof(float) * (size_t)BT * d->H, 256);
+    off = align_up(sizeof(float) * (size_t)BT * d->H, 256);
+    p.off_wplanes = off; off = align_up(off + (p.tc ? sizeof(float) * 3 * (size_t)d->H * p.kpad : 0), 256);
+    p.off_fflag = off;   off = align_up(off + 256, 256);
+    p.fwd_bytes = off;
     return p;
+}
+
+// ---- TMA tensor maps (driver entry point resolved at run time: the library does not link libcuda) ------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp32 tensor, innermost dimension first; strides in bytes for dims 1..rank-1; 128-byte swizzle; OOB -> 0
+int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+             const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled unavailable"); return SNNK_ERR_CUDA; }
+    const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                    ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return SNNK_ERR_CUDA;
+    }
+    return SNNK_OK;
+}
+
+template <int H>
+int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const float* W_in, float* I_in, float* planes,
+                   unsigned int* flag, cudaStream_t st)
+{
+    constexpr int P = 3;
+    using Cfg = tc::ProjCfg<H, P>;
+    const int M = d->B * d->T;
+    {
+        const int n = H * pl.kpad;
+        tc::k_split_w<<<(n + 255) / 256, 256, 0, st>>>(W_in, d->N, H, pl.kpad, planes);
+        SNNK_CUDA(cudaGetLastError());
+    }
+    CUtensorMap mx, mw;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)d->N, (cuuint64_t)M};
+        const cuuint64_t str[1] = {(cuuint64_t)d->N * 4};
+        const cuuint32_t box[2] = {tc::kBlockK, tc::kBlockM};
+        int rc = make_map(&mx, x, 2, dims, str, box);
+        if (rc != SNNK_OK) return rc;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)pl.kpad, (cuuint64_t)H, 3};
+        const cuuint64_t str[2] = {(cuuint64_t)pl.kpad * 4, (cuuint64_t)pl.kpad * 4 * H};
+        const cuuint32_t box[3] = {tc::kBlockK, (cuuint32_t)H, 1};
+        int rc = make_map(&mw, planes, 3, dims, str, box);
+        if (rc != SNNK_OK) return rc;
+    }
+    auto kern = tc::k_proj_tc<H, P>;
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    ProfScope ps(SNNK_K_PROJ, st);
+    kern<<<(M + tc::kBlockM - 1) / tc::kBlockM, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mw, I_in, M,
+                                                                                    pl.kpad / tc::kBlockK, flag);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+template <int H>
+int launch_wgrad_tc(const SnnkDesc* d, const Plan& pl, const float* x, const float* Ztrace, const float* gI_planes,
+                    float* part, unsigned int* flag, cudaStream_t st)
+{
+    constexpr int P = 2;
+    using Cfg = tc::WgradCfg<H, P>;
+    const cuuint64_t T = d->T, B = d->B, N = d->N;
+    CUtensorMap mx, mz, mg;
+    {
+        const cuuint64_t dims[3] = {N, T, B};
+        const cuuint64_t str[2] = {N * 4, T * N * 4};
+        const cuuint32_t box[3] = {32, tc::kBlockK, 1};
+        int rc = make_map(&mx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc != SNNK_OK) return rc;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)H, T, B};
+        const cuuint64_t str[2] = {(cuuint64_t)H * 4, T * H * 4};
+        const cuuint32_t box[3] = {32, tc::kBlockK, 1};
+        int rc = make_map(&mz, Ztrace ? Ztrace : gI_planes, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc != SNNK_OK) return rc;
+    }
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)H, T, B, (cuuint64_t)P};
+        const cuuint64_t str[3] = {(cuuint64_t)H * 4, T * H * 4, B * T * H * 4};
+        const cuuint32_t box[4] = {32, tc::kBlockK, 1, 1};
+        int rc = make_map(&mg, gI_planes, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc != SNNK_OK) return rc;
+    }
+    tc::WgradTcParams wp{};
+    wp.N = d->N; wp.T = d->T; wp.B = d->B; wp.mtiles_x = pl.mtiles_x; wp.m_total = pl.m_total;
+    wp.samples_per_split = pl.samples_per_split; wp.part = part; wp.inexact_flag = flag;
+    auto kern = tc::k_wgrad_tc<H, P>;
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.S);
+    ProfScope ps(SNNK_K_WGRAD, st);
+    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mz, mg, wp);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
 }
 
 template <int H, int R, bool REC>
@@ -229,6 +356,8 @@ const char* snnk_kernel_name(int id)
     case SNNK_K_RECUR_BWD: return "K3 k_recur_bwd (fused reverse-time BPTT)";
     case SNNK_K_REDUCE_OUT: return "k_reduce_parts (dW_out, db)";
     case SNNK_K_WGRAD: return "K4 k_wgrad (weight-gradient GEMM)";
+    case SNNK_K_PROJ_FALLBACK: return "K1f k_proj_simt (gated fallback)";
+    case SNNK_K_WGRAD_FALLBACK: return "K4f k_wgrad_simt (gated fallback)";
     case SNNK_K_REDUCE_W: return "k_reduce_parts (dW_in, dW_rec)";
     default: return "?";
     }
@@ -338,13 +467,27 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* I_in = static_cast<float*>(workspace);
 
-    // K1: input projection for all T steps at once
+    // K1: input projection for all T steps at once.  Tensor-core path first (when asked for and addressable by
+    // TMA); the fp32 SIMT kernel behind it only runs if x turned out not to be tf32-exact (device-side flag).
     {
         const int M = d->B * d->T;
+        unsigned int* flag = nullptr;
+        if (pl.tc) {
+            char* ws = static_cast<char*>(workspace);
+            flag = reinterpret_cast<unsigned int*>(ws + pl.off_fflag);
+            float* planes = reinterpret_cast<float*>(ws + pl.off_wplanes);
+            SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
+            switch (d->H) {
+            case 32: rc = launch_proj_tc<32>(d, pl, x, W_in, I_in, planes, flag, st); break;
+            case 64: rc = launch_proj_tc<64>(d, pl, x, W_in, I_in, planes, flag, st); break;
+            default: rc = launch_proj_tc<128>(d, pl, x, W_in, I_in, planes, flag, st); break;
+            }
+            if (rc != SNNK_OK) return rc;
+        }
         dim3 grid((M + kGemmBM - 1) / kGemmBM, pl.ntiles);
-        ProfScope ps(SNNK_K_PROJ, st);
-        if (pl.BN == 64) k_proj_simt<64><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H);
-        else k_proj_simt<32><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H);
+        ProfScope ps(pl.tc ? SNNK_K_PROJ_FALLBACK : SNNK_K_PROJ, st);
+        if (pl.BN == 64) k_proj_simt<64><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H, flag);
+        else k_proj_simt<32><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H, flag);
         SNNK_CUDA(cudaGetLastError());
     }
     // K2: fused recurrence + readout
@@ -380,8 +523,8 @@ int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labe
 }
 
 int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const float* rec_mask, const float* beta,
-                  const float* W_out, const float* Z0, const float* V, const float* a, const uint32_t* zbits,
-                  const float* g_y, const float* g_logits, const int32_t* tstar, const float* g_V,
+                  const float* W_out, const float* Z0, const float* V, const float* a, const float* Z,
+                  const uint32_t* zbits, const float* g_y, const float* g_logits, const int32_t* tstar, const float* g_V,
                   const float* g_Z, float* dW_in, float* dW_rec, float* dW_out, float* db, void* workspace,
                   size_t workspace_bytes, snnk_stream_t stream)
 {
@@ -389,6 +532,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     if (rc != SNNK_OK) return rc;
     if (!x || !W_out || !V || !zbits || !dW_in || !dW_out || !db || !workspace) return SNNK_ERR_ARG;
     if (d->recurrent && (!W_rec || !dW_rec)) return SNNK_ERR_ARG;
+    if (d->recurrent && (d->flags & SNNK_F_TENSOR_CORE) && !Z) return SNNK_ERR_ARG;
     if (d->layer_type == SNNK_ALIF && (!beta || !a)) return SNNK_ERR_ARG;
     const bool dense = g_y != nullptr, sparse = g_logits != nullptr && tstar != nullptr;
     if (dense == sparse) return SNNK_ERR_ARG;
@@ -411,7 +555,8 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     bp.W_rec = W_rec; bp.rec_mask = rec_mask; bp.beta = beta; bp.W_out = W_out; bp.Z0 = Z0;
     bp.V = V; bp.a = a; bp.zbits = zbits; bp.g_y = g_y; bp.g_logits = dense ? nullptr : g_logits;
     bp.tstar = dense ? nullptr : tstar; bp.g_V = g_V; bp.g_Z = g_Z;
-    bp.gI = gI; bp.part_wout = pwout; bp.part_db = pdb;
+    float* gI_lo = pl.tc ? reinterpret_cast<float*>(ws + pl.off_gIlo) : nullptr;
+    bp.gI = gI; bp.gI_lo = gI_lo; bp.part_wout = pwout; bp.part_db = pdb;
     switch (d->H) {
     case 32: rc = launch_bwd_r<32>(bp, rec, pl.R, pl.grid_rows, st); break;
     case 64: rc = launch_bwd_r<64>(bp, rec, pl.R, pl.grid_rows, st); break;
@@ -426,15 +571,27 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         k_reduce_parts<<<1, 256, 0, st>>>(pdb, pl.grid_rows * pl.R, (size_t)d->O, d->O, nullptr, db);
         SNNK_CUDA(cudaGetLastError());
     }
-    // K4: weight-gradient GEMM (split-K partials, then a fixed-order reduction)
+    // K4: weight-gradient GEMM (split-K partials over whole samples, then a fixed-order reduction)
     {
+        unsigned int* flag = nullptr;
+        if (pl.tc) {
+            flag = reinterpret_cast<unsigned int*>(ws + pl.off_flag);
+            SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
+            switch (d->H) {
+            case 32: rc = launch_wgrad_tc<32>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
+            case 64: rc = launch_wgrad_tc<64>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
+            default: rc = launch_wgrad_tc<128>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
+            }
+            if (rc != SNNK_OK) return rc;
+        }
         WgradParams wp{};
         wp.BT = d->B * d->T; wp.T = d->T; wp.N = d->N; wp.H = d->H;
-        wp.mtiles_x = pl.mtiles_x; wp.rows_per_split = pl.rows_per_split;
-        wp.x = x; wp.zbits = zbits; wp.Z0 = Z0; wp.gI = gI; wp.part = pw; wp.m_total = pl.m_total;
+        wp.mtiles_x = pl.mtiles_x; wp.rows_per_split = pl.samples_per_split * d->T;
+        wp.x = x; wp.zbits = zbits; wp.Z0 = Z0; wp.gI = gI; wp.gI_lo = gI_lo; wp.run_if_flag = flag;
+        wp.part = pw; wp.m_total = pl.m_total;
         dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.ntiles, pl.S);
         {
-            ProfScope ps(SNNK_K_WGRAD, st);
+            ProfScope ps(pl.tc ? SNNK_K_WGRAD_FALLBACK : SNNK_K_WGRAD, st);
             if (pl.BN == 64) k_wgrad_simt<64><<<grid, kGemmThreads, 0, st>>>(wp);
             else k_wgrad_simt<32><<<grid, kGemmThreads, 0, st>>>(wp);
         }

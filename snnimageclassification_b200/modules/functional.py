@@ -97,7 +97,7 @@ def run_forward(
 
 def run_backward(
 		c: LayerConsts, x, W_rec, rec_mask, beta, W_out, V, a, zbits, g_y=None, g_logits=None, tstar=None,
-		g_V=None, g_Z=None, Z0=None,
+		g_V=None, g_Z=None, Z0=None, Z=None,
 ):
 	"""Calls ``snnk_backward``.  Returns dict(dW_in, dW_rec, dW_out, db, gI)."""
 	lib = _cabi.lib()
@@ -114,11 +114,15 @@ def run_backward(
 	with torch.cuda.device(dev):
 		rc = lib.snnk_backward(
 			ctypes.byref(desc), _cabi.ptr(x), _cabi.ptr(W_rec), _cabi.ptr(rec_mask), _cabi.ptr(beta),
-			_cabi.ptr(W_out), _cabi.ptr(Z0), _cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(zbits), _cabi.ptr(g_y),
+			_cabi.ptr(W_out), _cabi.ptr(Z0), _cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(g_y),
 			_cabi.ptr(g_logits), _cabi.ptr(tstar), _cabi.ptr(g_V), _cabi.ptr(g_Z), _cabi.ptr(dW_in),
 			_cabi.ptr(dW_rec), _cabi.ptr(dW_out), _cabi.ptr(db), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr())
 	_cabi.check(rc, "snnk_backward")
-	gI = ws[: B * T * H * 4].view(torch.float32).view(B, T, H)
+	n = B * T * H * 4
+	gI = ws[:n].view(torch.float32).view(B, T, H)
+	if c.tensor_core and N % 4 == 0:   # stored as two tf32 planes (high, exact remainder); see include/snnk.h
+		off = (n + 255) // 256 * 256
+		gI = gI + ws[off: off + n].view(torch.float32).view(B, T, H)
 	return dict(dW_in=dW_in, dW_rec=dW_rec, dW_out=dW_out, db=db, gI=gI)
 
 
@@ -148,7 +152,7 @@ class SpikingSequence(torch.autograd.Function):
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=True)
 		ctx.consts = consts
 		ctx.has_rec = Wr is not None
-		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"])
+		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], out["Z"])
 		alif = consts.layer_type == _cabi.SNNK_ALIF
 		a = out["a"] if alif else out["V"].new_zeros(())
 		ctx.mark_non_differentiable(a)
@@ -156,10 +160,10 @@ class SpikingSequence(torch.autograd.Function):
 
 	@staticmethod
 	def backward(ctx, g_y, g_V, g_a, g_Z):
-		xc, Wr, M, be, Wo, V, a, zbits = ctx.saved_tensors
+		xc, Wr, M, be, Wo, V, a, zbits, Z = ctx.saved_tensors
 		if g_y is None:
 			g_y = torch.zeros((V.shape[0], V.shape[1], Wo.shape[1]), dtype=torch.float32, device=V.device)
-		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=_c(g_V), g_Z=_c(g_Z))
+		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=_c(g_V), g_Z=_c(g_Z), Z=Z)
 		# (consts, x, W_in, W_rec, rec_mask, beta, W_out, b_out); beta gets no gradient -- the threshold input of
 		# the reference's spike function returns None (spike_funcs.py:62/79)
 		return None, None, g["dW_in"], g["dW_rec"], None, None, g["dW_out"], g["db"]
@@ -176,7 +180,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		loss, logp, g_logits = run_head_nll(out["logits"], labels, want_grad=need_grad)
 		ctx.consts = consts
 		if need_grad:
-			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"])
+			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"], out["Z"])
 		empty = logp.new_zeros(())
 		extras = tuple(out[k] if out[k] is not None else empty for k in ("y", "V", "a", "Z"))
 		ctx.mark_non_differentiable(logp, *extras)
@@ -184,7 +188,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 
 	@staticmethod
 	def backward(ctx, g_loss, *_):
-		xc, Wr, M, be, Wo, V, a, zbits, g_logits, tstar = ctx.saved_tensors
+		xc, Wr, M, be, Wo, V, a, zbits, g_logits, tstar, Z = ctx.saved_tensors
 		g = run_backward(
-			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=(g_logits * g_loss).contiguous(), tstar=tstar)
+			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=(g_logits * g_loss).contiguous(), tstar=tstar, Z=Z)
 		return None, None, None, g["dW_in"], g["dW_rec"], None, None, g["dW_out"], g["db"], None
