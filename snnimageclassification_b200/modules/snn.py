@@ -92,7 +92,9 @@ class SNN(torch.nn.Module):
 		self.output_size = output_size
 		# keywords of the B200 build; everything else is threaded to the layers exactly as in the reference
 		self.input_encoder = kwargs.pop("input_encoder", None)
-		self.tensor_core = bool(kwargs.pop("tensor_core", False))
+		# tcgen05 GEMMs by default (exact for spike inputs, automatic fp32 fallback otherwise); SNNK_TENSOR_CORE=0 or
+		# tensor_core=False selects the fp32 CUDA-core GEMMs, which are bit-identical to the CPU oracle
+		self.tensor_core = bool(kwargs.pop("tensor_core", os.environ.get("SNNK_TENSOR_CORE", "1") != "0"))
 		self.kwargs = kwargs
 
 		self.device = device
