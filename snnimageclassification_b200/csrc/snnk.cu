@@ -229,7 +229,7 @@ int launch_wgrad_tc(const SnnkDesc* d, const Plan& pl, const float* x, const flo
     }
     {
         const cuuint64_t dims[4] = {(cuuint64_t)H, T, B, (cuuint64_t)P};
-        const cuuint64_t str[3] = {(cuuint64_t)H * 4, T * H * 4, B * T * H * 4};
+        const cuuint64_t str[3] = {(cuuint64_t)H * 4, T * H * 4, (cuuint64_t)(pl.off_gIlo - pl.off_gI)};   // planes are 256-B aligned
         const cuuint32_t box[4] = {32, tc::kBlockK, 1, 1};
         int rc = make_map(&mg, gI_planes, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != SNNK_OK) return rc;

@@ -1,0 +1,105 @@
+"""CUDA-graph capture of one training step (reference snn.py:384-415: forward, loss, backward, [all-reduce],
+optimizer step).
+
+At the reference's batch size the B200 kernels of a step run for a few hundred microseconds in total, less than
+the Python/launch overhead of issuing them one by one, so ``SNN._exec_batch`` captures the whole step once per
+input geometry and replays it: the host then does two small copies into static buffers and one graph launch.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+def _optimizer_is_capturable(optimizer) -> bool:
+	groups = getattr(optimizer, "param_groups", None)
+	return bool(groups) and all(g.get("capturable", False) for g in groups)
+
+
+class GraphedTrainStep:
+	"""``step(x, y) -> loss`` (0-d device tensor, overwritten by the next call) replaying a captured CUDA graph.
+
+	``x``/``y`` may live on the host (pinned memory makes the copy asynchronous) or on the device; they are
+	copied into static buffers.  The optimizer step is part of the graph when the optimizer is capturable
+	(``torch.optim.Adam(..., capturable=True)``), otherwise it runs eagerly after the replay.
+	"""
+
+	def __init__(self, net, x_example: torch.Tensor, y_example: torch.Tensor, criterion, optimizer, warmup: int = 3,
+			static_inputs: bool = False):
+		self.net, self.optimizer, self.criterion = net, optimizer, criterion
+		dev = net.device
+		self.static_inputs = static_inputs
+		if static_inputs:
+			# the caller's device tensors ARE the graph inputs (data resident in HBM: nothing to copy per step)
+			assert x_example.is_cuda and y_example.is_cuda
+			self.x, self.y = x_example, y_example
+		else:
+			self.x = torch.empty(x_example.shape, dtype=x_example.dtype, device=dev)
+			self.y = torch.empty(y_example.shape, dtype=y_example.dtype, device=dev)
+			self.x.copy_(x_example, non_blocking=True)
+			self.y.copy_(y_example, non_blocking=True)
+		self.step_in_graph = _optimizer_is_capturable(optimizer)
+		self.loss: Optional[torch.Tensor] = None
+
+		# Snapshot what the warm-up iterations would change: capture must not advance the training state.
+		params = [p for p in net.parameters()]
+		saved_params = [p.detach().clone() for p in params]
+		saved_opt = _clone_state(optimizer.state_dict()) if self.step_in_graph else None
+
+		side = torch.cuda.Stream(device=dev)
+		side.wait_stream(torch.cuda.current_stream(dev))
+		with torch.cuda.stream(side):
+			for _ in range(warmup):
+				self._body()
+		torch.cuda.current_stream(dev).wait_stream(side)
+		torch.cuda.synchronize(dev)
+
+		optimizer.zero_grad(set_to_none=True)
+		self.graph = torch.cuda.CUDAGraph()
+		with torch.cuda.graph(self.graph):
+			self.loss = self._body()
+		with torch.no_grad():
+			for p, s in zip(params, saved_params):
+				p.copy_(s)
+		if saved_opt is not None:
+			_restore_state(optimizer, saved_opt)
+
+	def _body(self) -> torch.Tensor:
+		net = self.net
+		loss = net.batch_loss(self.x, self.y, self.criterion)
+		self.optimizer.zero_grad(set_to_none=True)
+		loss.backward()
+		net._allreduce_gradients()
+		if self.step_in_graph:
+			self.optimizer.step()
+		return loss
+
+	def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+		if not self.static_inputs:
+			self.x.copy_(x, non_blocking=True)
+			self.y.copy_(y, non_blocking=True)
+		self.graph.replay()
+		if not self.step_in_graph:
+			self.optimizer.step()
+		return self.loss
+
+
+def _clone_state(sd):
+	out = {"param_groups": [dict(g) for g in sd["param_groups"]], "state": {}}
+	for k, st in sd["state"].items():
+		out["state"][k] = {n: (v.detach().clone() if torch.is_tensor(v) else v) for n, v in st.items()}
+	return out
+
+
+def _restore_state(optimizer, saved):
+	"""In-place restore: the graph holds pointers to the optimizer's state tensors, so they must not be replaced."""
+	cur = optimizer.state_dict()["state"]
+	with torch.no_grad():
+		for k, st in cur.items():
+			for n, v in st.items():
+				if torch.is_tensor(v):
+					if k in saved["state"] and n in saved["state"][k]:
+						v.copy_(saved["state"][k][n])
+					else:
+						v.zero_()

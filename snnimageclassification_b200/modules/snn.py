@@ -95,6 +95,10 @@ class SNN(torch.nn.Module):
 		# tcgen05 GEMMs by default (exact for spike inputs, automatic fp32 fallback otherwise); SNNK_TENSOR_CORE=0 or
 		# tensor_core=False selects the fp32 CUDA-core GEMMs, which are bit-identical to the CPU oracle
 		self.tensor_core = bool(kwargs.pop("tensor_core", os.environ.get("SNNK_TENSOR_CORE", "1") != "0"))
+		# replay a captured CUDA graph for training steps whose input geometry repeats (see modules/graphed.py)
+		self.cuda_graphs = bool(kwargs.pop("cuda_graphs", os.environ.get("SNNK_CUDA_GRAPHS", "1") != "0"))
+		self._graphed_steps: Dict[Any, Any] = {}
+		self._graph_seen: Dict[Any, int] = {}
 		self.kwargs = kwargs
 
 		self.device = device
@@ -296,7 +300,10 @@ class SNN(torch.nn.Module):
 		if criterion is None:
 			criterion = nn.NLLLoss()
 		if optimizer is None:
-			optimizer = torch.optim.Adam(self.parameters(), lr=lr, weight_decay=1e-5)
+			# same hyper-parameters as the reference (snn.py:299); on the GPU the multi-tensor capturable variant is
+			# used so that the step can live inside the captured training graph
+			extra = dict(fused=True, capturable=True) if self.device.type == "cuda" else {}
+			optimizer = torch.optim.Adam(self.parameters(), lr=lr, weight_decay=1e-5, **extra)
 
 		start_epoch = 0
 		if load_checkpoint_mode is None:
@@ -378,8 +385,29 @@ class SNN(torch.nn.Module):
 		log_p_y, out, h_states = self.get_prediction_log_proba(x, re_outputs_trace=True, re_hidden_states=True)
 		return criterion(log_p_y, y.long())
 
+	def graphed_train_step(self, x_example, y_example, criterion, optimizer, static_inputs: bool = False):
+		"""Captures (once per input geometry) and returns the CUDA-graph version of one training step.
+
+		With ``static_inputs`` the given device tensors themselves are the graph's inputs (call the step without
+		arguments); otherwise every call copies its batch into the graph's static buffers first."""
+		from .graphed import GraphedTrainStep
+		key = (tuple(x_example.shape), x_example.dtype, tuple(y_example.shape), y_example.dtype, id(optimizer), id(criterion),
+			(x_example.data_ptr(), y_example.data_ptr()) if static_inputs else None)
+		step = self._graphed_steps.get(key)
+		if step is None:
+			step = GraphedTrainStep(self, x_example, y_example, criterion, optimizer, static_inputs=static_inputs)
+			self._graphed_steps[key] = step
+		return step
+
 	def _exec_batch(self, x_batch, y_batch, criterion, optimizer):
 		"""forward (+ backward + optimizer step in train mode) -> python float (reference snn.py:384-415)."""
+		if self.training and self.cuda_graphs and self.device.type == "cuda":
+			key = (tuple(x_batch.shape), x_batch.dtype, tuple(y_batch.shape), y_batch.dtype, id(optimizer), id(criterion))
+			seen = self._graph_seen.get(key, 0)
+			self._graph_seen[key] = seen + 1
+			if seen >= 1:   # a geometry that repeats (every full batch of an epoch): capture once, replay afterwards
+				step = self.graphed_train_step(x_batch, y_batch, criterion, optimizer)
+				return step(x_batch, y_batch).item()
 		if self.training:
 			batch_loss = self.batch_loss(x_batch, y_batch, criterion)
 			optimizer.zero_grad()

@@ -3,7 +3,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, ctypes
 from snnimageclassification_b200.modules import functional as F_
 from snnimageclassification_b200 import _cabi
-H = 128; B, T, N, O = 4, 32, 256, 10
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+B, T, N = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (4, 32, 256)
+O = 10
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 x = (torch.rand(B, T, N, generator=g) < 0.3).float().to(dev)
@@ -33,3 +35,14 @@ for name, got, exp in (("dW_in", g1["dW_in"], exp_in), ("dW_rec", g1["dW_rec"], 
 		print("   exp[:4,:6]", exp[:4,:6].cpu().numpy().round(4).tolist())
 		nzr = (got.abs().sum(1) > 0).nonzero().flatten()[:20].tolist(); nzc = (got.abs().sum(0) > 0).nonzero().flatten()[:20].tolist()
 		print("   nonzero rows", nzr, "cols", nzc)
+
+gI32 = g0["gI"].reshape(B*T, H)
+hi = (gI32.view(torch.int32) & -8192).view(torch.float32).double()
+lo = gI.double() - hi
+X = x.double().reshape(B*T, N)
+got = g1["dW_in"].double()
+for name, e in (("hi only", X.t() @ hi), ("hi+lo", X.t() @ (hi+lo)), ("hi+2lo", X.t() @ (hi+2*lo)), ("2hi", X.t() @ (2*hi))):
+	print(name, float((got - e).abs().max() / e.abs().max()))
+err = (got - exp_in).abs()
+print("rows with err>1e-3*max:", (err.max(1)[0] > 1e-3*exp_in.abs().max()).nonzero().flatten()[:40].tolist())
+print("cols with err>1e-3*max:", (err.max(0)[0] > 1e-3*exp_in.abs().max()).nonzero().flatten()[:40].tolist())
