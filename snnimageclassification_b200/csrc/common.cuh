@@ -55,17 +55,27 @@ __device__ __forceinline__ float surrogate_grad(int kind, float gamma, float v, 
 }
 
 // sum_k w[k] * z[k] with four accumulators over k mod 4 (the order oracle/snn_oracle.c fixes).
-template <int H>
+// The broadcast vector is fetched NB float4 at a time before the FFMAs that use them, so NB shared-memory
+// loads are in flight together instead of one 29-cycle LDS round trip per 4 FFMAs.
+template <int H, int NB = 4>
 __device__ __forceinline__ float dot_rec4(const float (&w)[H], const float4* __restrict__ zv)
 {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    constexpr int NV = H / 4;
+    constexpr int BATCH = NB < NV ? NB : NV;
 #pragma unroll
-    for (int k = 0; k < H; k += 4) {
-        const float4 z = zv[k >> 2];
-        s0 = fmaf(w[k + 0], z.x, s0);
-        s1 = fmaf(w[k + 1], z.y, s1);
-        s2 = fmaf(w[k + 2], z.z, s2);
-        s3 = fmaf(w[k + 3], z.w, s3);
+    for (int k0 = 0; k0 < NV; k0 += BATCH) {
+        float4 z[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) z[j] = zv[k0 + j];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int k = 4 * (k0 + j);
+            s0 = fmaf(w[k + 0], z[j].x, s0);
+            s1 = fmaf(w[k + 1], z[j].y, s1);
+            s2 = fmaf(w[k + 2], z[j].z, s2);
+            s3 = fmaf(w[k + 3], z[j].w, s3);
+        }
     }
     return __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
 }

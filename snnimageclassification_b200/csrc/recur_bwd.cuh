@@ -18,6 +18,8 @@
 // contractions over (batch x time) and belong to the weight-gradient GEMM (K4).
 #pragma once
 #include "common.cuh"
+#include "gemm_tc.cuh"
+#include "recur_fwd.cuh"   // kChunk, kRing
 
 namespace snnk {
 
@@ -26,7 +28,8 @@ constexpr size_t bwd_smem_bytes(int T, bool rec)
 {
     // the spike-word region is padded to 16 bytes: s_gy behind it is read with float4 loads
     size_t loop = sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)((R * T * (H / 32) + 3) & ~3) +
-                  sizeof(float) * (size_t)(R * T * kOMax);
+                  sizeof(float) * (size_t)(R * T * kOMax) + 2 * sizeof(float) * (size_t)(kRing * R * kChunk * H) +
+                  sizeof(uint64_t) * kRing;
     size_t stage = rec ? sizeof(float) * (size_t)H * (H + 1) : 0;   // transpose staging, prologue only
     return loop > stage ? loop : stage;
 }
@@ -36,10 +39,10 @@ __global__ void __launch_bounds__(H) k_recur_bwd(const BwdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W32 = H / 32;
-    constexpr int PF = 4;
     const int T = p.T, O = p.O, B = p.B;
     const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
     const int b0 = blockIdx.x * R;
+    const int nvalid = min(R, B - b0);
 
     // row i of W_rec (.) rec_mask, staged through padded shared memory so the global read is coalesced
     float w[REC ? H : 1];
@@ -59,6 +62,28 @@ __global__ void __launch_bounds__(H) k_recur_bwd(const BwdParams p)
     float* s_g = reinterpret_cast<float*>(smem_raw);                       // [2][R][H]
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_g + 2 * R * H);       // [R][T][W32]
     float* s_gy = reinterpret_cast<float*>(s_mask + ((R * T * W32 + 3) & ~3));   // [R][T][kOMax], 16-B aligned
+    float* s_v = s_gy + R * T * kOMax;                                           // [kRing][R][kChunk][H]  V trace ring
+    float* s_a = s_v + kRing * R * kChunk * H;                                   // [kRing][R][kChunk][H]  a trace ring
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_a + kRing * R * kChunk * H); // [kRing]
+
+    // The saved traces are streamed backwards in time through the ring by 1-D bulk async copies; chunk k (in
+    // processing order) covers forward chunk nchunks-1-k.  Thread 0 only.
+    const int nchunks = (T + kChunk - 1) / kChunk;
+    auto issue_chunk = [&](int k) {
+        const int slot = k % kRing, t0 = (nchunks - 1 - k) * kChunk;
+        const uint32_t bytes = (uint32_t)(min(kChunk, T - t0) * H * sizeof(float));
+        tc::mbar_expect_tx(s_bar + slot, bytes * nvalid * (p.alif ? 2 : 1));
+        for (int r = 0; r < nvalid; ++r) {
+            const size_t g = ((size_t)(b0 + r) * T + t0) * H;
+            tc::bulk_g2s(s_v + ((slot * R + r) * kChunk) * H, p.V + g, bytes, s_bar + slot);
+            if (p.alif) tc::bulk_g2s(s_a + ((slot * R + r) * kChunk) * H, p.a + g, bytes, s_bar + slot);
+        }
+    };
+    if (i == 0) {   // the staging area above aliases the ring: the first copies start only now
+        for (int s = 0; s < kRing; ++s) tc::mbar_init(s_bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < kRing && k < nchunks; ++k) issue_chunk(k);
+    }
 
     float wo[kOMax], dwo[kOMax];
 #pragma unroll
@@ -107,36 +132,29 @@ __global__ void __launch_bounds__(H) k_recur_bwd(const BwdParams p)
 
     float gv[R];
     bool valid[R];
-    float vpf[PF][R], apf[PF][R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         gv[r] = 0.f;
         valid[r] = b0 + r < B;
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const int t = T - 1 - u;
-            const bool ok = valid[r] && t >= 0;
-            const size_t o = ok ? ((size_t)(b0 + r) * T + t) * H + i : 0;
-            vpf[u][r] = ok ? __ldg(p.V + o) : 0.f;
-            apf[u][r] = (ok && p.alif) ? __ldg(p.a + o) : 0.f;
-        }
     }
 
-    for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const int t = t0 - u;
-            if (t >= 0) {
+    for (int t = T - 1; t >= 0; --t) {
+        {
+            {
+                const int ck = t / kChunk, tt = t - ck * kChunk;
+                const int k = nchunks - 1 - ck, slot = k % kRing;
+                if (t == T - 1 || tt == kChunk - 1) {
+                    // all threads are past their last read of chunk k-1 (REC: the step barrier), refill its slot
+                    if (!REC) __syncthreads();
+                    if (i == 0 && k >= 1 && k - 1 + kRing < nchunks) issue_chunk(k - 1 + kRing);
+                    tc::mbar_wait(s_bar + slot, (k / kRing) & 1);
+                }
                 float vt[R], at[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    vt[r] = vpf[u][r];
-                    at[r] = apf[u][r];
-                    const int tn = t - PF;
-                    const bool ok = valid[r] && tn >= 0;
-                    const size_t o = ok ? ((size_t)(b0 + r) * T + tn) * H + i : 0;
-                    vpf[u][r] = ok ? __ldg(p.V + o) : 0.f;
-                    apf[u][r] = (ok && p.alif) ? __ldg(p.a + o) : 0.f;
+                    const int o = ((slot * R + r) * kChunk + tt) * H + i;
+                    vt[r] = valid[r] ? s_v[o] : 0.f;
+                    at[r] = (valid[r] && p.alif) ? s_a[o] : 0.f;
                 }
 #pragma unroll
                 for (int r = 0; r < R; ++r) {

@@ -7,19 +7,27 @@
 // Thread i owns hidden neuron i: its membrane/adaptation state lives in registers for the whole
 // sequence and column i of the masked recurrent matrix (H floats) is register-resident too, so one
 // step is H FFMAs against the previous spike vector broadcast from shared memory + the elementwise
-// update + one __syncthreads.  Spikes are bit-packed with warp ballots; all T spike words stay in
+// update + one __syncthreads.  The input current of the row (a contiguous T x H block written by the
+// projection GEMM) is streamed through a shared-memory ring by 1-D bulk async copies (cp.async.bulk +
+// mbarrier), kChunk steps per copy and kRing copies in flight, so HBM/L2 latency never sits on the
+// step-to-step critical path.  Spikes are bit-packed with warp ballots; all T spike words stay in
 // shared memory, so the leaky readout (linear in the spikes) is evaluated after the loop instead of
 // inside the latency-critical chain.
 #pragma once
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace snnk {
+
+constexpr int kChunk = 8;   // time steps per bulk copy
+constexpr int kRing = 4;    // ring slots (copies in flight)
 
 template <int H, int R>
 constexpr size_t fwd_smem_bytes(int T, int O)
 {
     return sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)((R * T * (H / 32) + 3) & ~3) +
-           sizeof(float) * (size_t)(H * O) + sizeof(float) * (size_t)(R * T * O);
+           sizeof(float) * (size_t)((H * O + R * T * O + 3) & ~3) + sizeof(float) * (size_t)(kRing * R * kChunk * H) +
+           sizeof(uint64_t) * kRing;
 }
 
 template <int H, int R, bool REC>
@@ -27,15 +35,33 @@ __global__ void __launch_bounds__(H) k_recur_fwd(const FwdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W32 = H / 32;
-    constexpr int PF = 4;   // input-current prefetch distance (steps)
     const int T = p.T, O = p.O, B = p.B;
     const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
     const int b0 = blockIdx.x * R;
+    const int nvalid = min(R, B - b0);
 
-    float* s_z = reinterpret_cast<float*>(smem_raw);                       // [2][R][H]
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_z + 2 * R * H);       // [R][T][W32]
-    float* s_wout = reinterpret_cast<float*>(s_mask + ((R * T * W32 + 3) & ~3));   // [H][O]
-    float* s_s = s_wout + H * O;                                           // [R][T][O]
+    float* s_z = reinterpret_cast<float*>(smem_raw);                                // [2][R][H]
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_z + 2 * R * H);                // [R][T][W32]
+    float* s_wout = reinterpret_cast<float*>(s_mask + ((R * T * W32 + 3) & ~3));    // [H][O]
+    float* s_s = s_wout + H * O;                                                    // [R][T][O]
+    float* s_in = s_wout + ((H * O + R * T * O + 3) & ~3);                          // [kRing][R][kChunk][H], 16-B aligned
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_in + kRing * R * kChunk * H);   // [kRing]
+
+    const int nchunks = (T + kChunk - 1) / kChunk;
+    // bulk copy of chunk c (kChunk consecutive steps of every valid row) into ring slot c % kRing; thread 0 only
+    auto issue_chunk = [&](int c) {
+        const int slot = c % kRing, t0 = c * kChunk;
+        const uint32_t bytes = (uint32_t)(min(kChunk, T - t0) * H * sizeof(float));
+        tc::mbar_expect_tx(s_bar + slot, bytes * nvalid);
+        for (int r = 0; r < nvalid; ++r)
+            tc::bulk_g2s(s_in + ((slot * R + r) * kChunk) * H, p.I_in + ((size_t)(b0 + r) * T + t0) * H, bytes,
+                         s_bar + slot);
+    };
+    if (i == 0) {
+        for (int s = 0; s < kRing; ++s) tc::mbar_init(s_bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int c = 0; c < kRing && c < nchunks; ++c) issue_chunk(c);
+    }
 
     // column i of W_rec (.) rec_mask  (spiking_layers.py:165/235 multiplies the mask in at every step)
     float w[REC ? H : 1];
@@ -50,7 +76,6 @@ __global__ void __launch_bounds__(H) k_recur_fwd(const FwdParams p)
 
     float v[R], a[R], zp[R];
     bool valid[R];
-    float ipf[PF][R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int b = b0 + r;
@@ -60,60 +85,53 @@ __global__ void __launch_bounds__(H) k_recur_fwd(const FwdParams p)
         a[r] = (valid[r] && p.a0) ? p.a0[s] : 0.f;
         zp[r] = (valid[r] && p.Z0) ? p.Z0[s] : 0.f;
         if (REC) s_z[1 * R * H + r * H + i] = zp[r];   // step 0 reads buffer (0+1)&1
-#pragma unroll
-        for (int u = 0; u < PF; ++u)
-            ipf[u][r] = (valid[r] && u < T) ? __ldg(p.I_in + ((size_t)b * T + u) * H + i) : 0.f;
     }
     for (int idx = i; idx < H * O; idx += H) s_wout[idx] = __ldg(p.W_out + idx);
     __syncthreads();
 
-    for (int t0 = 0; t0 < T; t0 += PF) {
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const int t = t0 + u;
-            if (t < T) {
-                float cur[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    cur[r] = ipf[u][r];
-                    const int tn = t + PF;
-                    ipf[u][r] = (valid[r] && tn < T)
-                                    ? __ldg(p.I_in + ((size_t)(b0 + r) * T + tn) * H + i) : 0.f;
-                }
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float rec = 0.0f;
-                    if constexpr (REC) {
-                        const float4* zv =
-                            reinterpret_cast<const float4*>(s_z + ((t + 1) & 1) * R * H + r * H);
-                        rec = dot_rec4<REC ? H : 1>(w, zv);
-                    }
-                    // V' = (alpha V + I_in + I_rec) (1 - Z.detach())     spiking_layers.py:169/239
-                    const float t1 = __fmul_rn(p.alpha, v[r]);
-                    const float t2 = __fadd_rn(t1, cur[r]);
-                    const float t3 = __fadd_rn(t2, rec);
-                    const float vn = __fmul_rn(t3, __fsub_rn(1.0f, zp[r]));
-                    float thr = p.theta;
-                    if (p.alif) {
-                        a[r] = __fadd_rn(__fmul_rn(p.rho, a[r]), zp[r]);          // :240
-                        thr = __fadd_rn(p.theta, __fmul_rn(beta, a[r]));          // :241
-                    }
-                    const float zn = vn >= thr ? 1.0f : 0.0f;                     // spike_funcs.py:27-28
-                    if (p.traces && valid[r]) {
-                        const size_t o = ((size_t)(b0 + r) * T + t) * H + i;
-                        p.V[o] = vn;
-                        p.Z[o] = zn;
-                        if (p.alif) p.a[o] = a[r];
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, zn != 0.f);
-                    if (lane == 0) s_mask[(r * T + t) * W32 + warp] = m;
-                    if (REC) s_z[(t & 1) * R * H + r * H + i] = zn;
-                    v[r] = vn;
-                    zp[r] = zn;
-                }
-                if (REC) __syncthreads();
-            }
+    for (int t = 0; t < T; ++t) {
+        const int c = t / kChunk, tt = t - c * kChunk, slot = c % kRing;
+        if (tt == 0) {
+            // every thread is past its last read of chunk c-1 (REC: the step barrier; otherwise sync here), so
+            // its slot can be refilled with chunk c-1+kRing; then wait for chunk c to have landed
+            if (!REC) __syncthreads();
+            if (i == 0 && c >= 1 && c - 1 + kRing < nchunks) issue_chunk(c - 1 + kRing);
+            tc::mbar_wait(s_bar + slot, (c / kRing) & 1);
         }
+        float cur[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) cur[r] = valid[r] ? s_in[((slot * R + r) * kChunk + tt) * H + i] : 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float rec = 0.0f;
+            if constexpr (REC) {
+                const float4* zv = reinterpret_cast<const float4*>(s_z + ((t + 1) & 1) * R * H + r * H);
+                rec = dot_rec4<REC ? H : 1, 16>(w, zv);
+            }
+            // V' = (alpha V + I_in + I_rec) (1 - Z.detach())     spiking_layers.py:169/239
+            const float t1 = __fmul_rn(p.alpha, v[r]);
+            const float t2 = __fadd_rn(t1, cur[r]);
+            const float t3 = __fadd_rn(t2, rec);
+            const float vn = __fmul_rn(t3, __fsub_rn(1.0f, zp[r]));
+            float thr = p.theta;
+            if (p.alif) {
+                a[r] = __fadd_rn(__fmul_rn(p.rho, a[r]), zp[r]);          // :240
+                thr = __fadd_rn(p.theta, __fmul_rn(beta, a[r]));          // :241
+            }
+            const float zn = vn >= thr ? 1.0f : 0.0f;                     // spike_funcs.py:27-28
+            if (p.traces && valid[r]) {
+                const size_t o = ((size_t)(b0 + r) * T + t) * H + i;
+                p.V[o] = vn;
+                p.Z[o] = zn;
+                if (p.alif) p.a[o] = a[r];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, zn != 0.f);
+            if (lane == 0) s_mask[(r * T + t) * W32 + warp] = m;
+            if (REC) s_z[(t & 1) * R * H + r * H + i] = zn;
+            v[r] = vn;
+            zp[r] = zn;
+        }
+        if (REC) __syncthreads();
     }
     __syncthreads();
 

@@ -56,8 +56,11 @@ def test_tensor_core_matches_simt(B, T, N, H, rec, layer):
 	d, consts = _setup(B, T, N, H, 10, rec, layer, 0.12 if layer else 0.03)
 	f0, f1 = _fwd(d, consts(False)), _fwd(d, consts(True))
 	assert rel_err(npy(f1["I_in"]), npy(f0["I_in"])) <= 1e-5
-	same = (f1["Z"] == f0["Z"]).float().mean().item()
-	assert same >= 0.9999, f"rasters only {same:.6f} identical"
+	# A spike whose membrane potential sits within ~1e-6 of the threshold may flip with the summation order and
+	# the sample then forks; on these small batches one fork already exceeds 1e-4 of the raster, so the bar here
+	# is on forked samples.  The >= 99.99 % raster bar is asserted at full size in the test below.
+	forked = (f1["Z"] != f0["Z"]).flatten(1).any(dim=1).float().mean().item()
+	assert forked <= 0.05, f"{forked:.3f} of the samples forked"
 	loss, logp, gl = F_.run_head_nll(f0["logits"], d["labels"])
 	kw = dict(g_logits=gl, tstar=f0["tstar"])
 	g0, g1 = _bwd(d, consts(False), f0, **kw), _bwd(d, consts(True), f0, **kw)
@@ -136,3 +139,28 @@ def test_snn_module_tensor_core_training_step():
 	assert abs(losses[0] - losses[1]) <= 1e-4 * abs(losses[0])
 	for a, b in zip(*grads):
 		assert rel_err(npy(b), npy(a)) <= 1e-4
+
+
+def test_graphed_train_step_matches_eager():
+	"""The captured CUDA graph of a training step (modules/graphed.py) updates the weights exactly like eager calls."""
+	def make():
+		torch.manual_seed(3)
+		net = SNN(784, 10, 128, use_recurrent_connection=True, int_time_steps=30, spike_func=SpikeFuncType.FastSigmoid,
+			hidden_layer_type=LayerType.ALIF, device=DEV, learn_beta=True)
+		opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, fused=True, capturable=True)
+		net.train()
+		return net, opt
+	g = torch.Generator().manual_seed(7)
+	xs = [(torch.rand(32, 30, 784, generator=g) < 0.1).float() for _ in range(4)]
+	ys = [torch.randint(0, 10, (32,), generator=g) for _ in range(4)]
+	crit = torch.nn.NLLLoss()
+	eager, opt_e = make()
+	eager.cuda_graphs = False
+	graphed, opt_g = make()
+	losses_e = [eager._exec_batch(x, y, crit, opt_e) for x, y in zip(xs, ys)]
+	losses_g = [graphed._exec_batch(x, y, crit, opt_g) for x, y in zip(xs, ys)]     # first call eager, then replays
+	assert len(graphed._graphed_steps) == 1
+	for a, b in zip(losses_e, losses_g):
+		assert abs(a - b) <= 1e-5 * abs(a)
+	for pe, pg in zip(eager.parameters(), graphed.parameters()):
+		assert rel_err(npy(pg), npy(pe)) <= 1e-5
