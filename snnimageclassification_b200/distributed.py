@@ -1,0 +1,41 @@
+"""Data-parallel plumbing: one process per GPU, batch rows sharded, weights replicated.
+
+The spiking path has exactly one exchange step per training iteration: the mean of the (small) weight gradients
+over the ranks.  It is issued as ONE flat all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests); with equal
+shards and a mean-reduced local loss this reproduces the single-process full-batch gradient up to summation order.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+def world_size() -> int:
+	return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def allreduce_mean_(tensors: Iterable[torch.Tensor]) -> None:
+	"""In-place mean over the ranks of every tensor in ``tensors`` with a single flat all-reduce."""
+	ws = world_size()
+	if ws == 1:
+		return
+	ts: List[torch.Tensor] = [t for t in tensors if t is not None]
+	if not ts:
+		return
+	flat = torch.cat([t.reshape(-1) for t in ts])
+	dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+	flat.div_(ws)
+	off = 0
+	for t in ts:
+		n = t.numel()
+		t.copy_(flat[off:off + n].view_as(t))
+		off += n
+
+
+def shard_batch(x: torch.Tensor, rank: int, ws: int) -> torch.Tensor:
+	"""Equal contiguous shard of the batch dimension (equal shards are required for exact equivalence)."""
+	assert x.shape[0] % ws == 0, "global batch must be divisible by the number of ranks"
+	n = x.shape[0] // ws
+	return x[rank * n:(rank + 1) * n]

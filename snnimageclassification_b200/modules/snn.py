@@ -421,20 +421,8 @@ class SNN(torch.nn.Module):
 
 	def _allreduce_gradients(self):
 		"""Data-parallel training: average the (small) gradients over the ranks with one flat NCCL all-reduce."""
-		import torch.distributed as dist
-		if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-			return
-		grads = [p.grad for p in self.parameters() if p.grad is not None]
-		if not grads:
-			return
-		flat = torch.cat([g.reshape(-1) for g in grads])
-		dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-		flat.div_(dist.get_world_size())
-		off = 0
-		for g in grads:
-			n = g.numel()
-			g.copy_(flat[off:off + n].view_as(g))
-			off += n
+		from ..distributed import allreduce_mean_
+		allreduce_mean_(p.grad for p in self.parameters())
 
 	# ---- checkpoints (reference snn.py:417-505; same files, so checkpoints interchange) -----------------------------
 	def plot_loss_history(self, loss_history: LossHistory = None, show=False):
