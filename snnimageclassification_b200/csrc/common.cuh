@@ -12,8 +12,7 @@ struct FwdParams {
     int alif, traces;
     float alpha, rho, theta, kappa;
     const float* I_in;      // (B,T,H) input current from the projection GEMM
-    const float* W_rec;     // (H,H) raw
-    const float* rec_mask;  // (H,H) or null
+    const float* W_eff;     // (H,H) W_rec (.) rec_mask, prepared by k_prep_rec: column i belongs to thread i
     const float* beta;      // device scalar or null
     const float* W_out;     // (H,O)
     const float* b_out;     // (O)
@@ -29,7 +28,8 @@ struct BwdParams {
     int B, T, H, O;
     int alif, surrogate;
     float alpha, theta, gamma, kappa;
-    const float* W_rec; const float* rec_mask; const float* beta; const float* W_out;
+    const float* W_effT;    // (H,H) transpose of W_rec (.) rec_mask: column i = row i of the masked matrix
+    const float* beta; const float* W_out;
     const float* Z0;
     const float* V; const float* a; const uint32_t* zbits;
     const float* g_y;                               // (B,T,O) dense seeds, or null
@@ -40,6 +40,18 @@ struct BwdParams {
     float* part_wout;   // [grid][H][O]
     float* part_db;     // [grid*R][O]
 };
+
+// W_rec (.) rec_mask (spiking_layers.py:165/235 re-multiplies the mask at every step) and its transpose, once per call.
+__global__ void __launch_bounds__(256) k_prep_rec(const float* __restrict__ W_rec, const float* __restrict__ mask,
+                                                 int H, float* __restrict__ W_eff, float* __restrict__ W_effT)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * H) return;
+    const int r = idx / H, c = idx - r * H;
+    const float v = mask ? __fmul_rn(W_rec[idx], mask[idx]) : W_rec[idx];
+    if (W_eff) W_eff[idx] = v;
+    if (W_effT) W_effT[c * H + r] = v;
+}
 
 // Surrogate derivatives, spike_funcs.py:59-62 (FastSigmoid) and :75-79 (Phi, epsilon = 1e-5).
 __device__ __forceinline__ float surrogate_grad(int kind, float gamma, float v, float thr)
@@ -54,30 +66,24 @@ __device__ __forceinline__ float surrogate_grad(int kind, float gamma, float v, 
     return __fmul_rn(__fdiv_rn(gamma, te), r);
 }
 
-// sum_k w[k] * z[k] with four accumulators over k mod 4 (the order oracle/snn_oracle.c fixes).
-// The broadcast vector is fetched NB float4 at a time before the FFMAs that use them, so NB shared-memory
-// loads are in flight together instead of one 29-cycle LDS round trip per 4 FFMAs.
-template <int H, int NB = 4>
-__device__ __forceinline__ float dot_rec4(const float (&w)[H], const float4* __restrict__ zv)
+// sum_k w[k] * z[k] with eight accumulators over k mod 8 (the order oracle/snn_oracle.c fixes), held as four
+// float2 and advanced with the packed FFMA2 of sm_100: H/2 FMA instructions instead of H.  Each lane of an
+// FFMA2 is an independent IEEE fma, so the result is bit-identical to eight scalar fmaf chains.
+template <int H>
+__device__ __forceinline__ float dot_rec8(const float (&w)[H], const float4* __restrict__ zv)
 {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    constexpr int NV = H / 4;
-    constexpr int BATCH = NB < NV ? NB : NV;
+    float2 acc[4];
 #pragma unroll
-    for (int k0 = 0; k0 < NV; k0 += BATCH) {
-        float4 z[BATCH];
+    for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j) z[j] = zv[k0 + j];
-#pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-            const int k = 4 * (k0 + j);
-            s0 = fmaf(w[k + 0], z[j].x, s0);
-            s1 = fmaf(w[k + 1], z[j].y, s1);
-            s2 = fmaf(w[k + 2], z[j].z, s2);
-            s3 = fmaf(w[k + 3], z[j].w, s3);
-        }
+    for (int j = 0; j < H / 4; ++j) {
+        const float4 z = zv[j];
+        const int k = 4 * j, q = 2 * (j & 1);
+        acc[q] = __ffma2_rn(make_float2(w[k], w[k + 1]), make_float2(z.x, z.y), acc[q]);
+        acc[q + 1] = __ffma2_rn(make_float2(w[k + 2], w[k + 3]), make_float2(z.z, z.w), acc[q + 1]);
     }
-    return __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+    return __fadd_rn(__fadd_rn(__fadd_rn(acc[0].x, acc[0].y), __fadd_rn(acc[1].x, acc[1].y)),
+                     __fadd_rn(__fadd_rn(acc[2].x, acc[2].y), __fadd_rn(acc[3].x, acc[3].y)));
 }
 
 }  // namespace snnk

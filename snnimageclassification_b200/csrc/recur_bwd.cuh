@@ -30,12 +30,12 @@ constexpr size_t bwd_smem_bytes(int T, bool rec)
     size_t loop = sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)((R * T * (H / 32) + 3) & ~3) +
                   sizeof(float) * (size_t)(R * T * kOMax) + 2 * sizeof(float) * (size_t)(kRing * R * kChunk * H) +
                   sizeof(uint64_t) * kRing;
-    size_t stage = rec ? sizeof(float) * (size_t)H * (H + 1) : 0;   // transpose staging, prologue only
+    size_t stage = rec ? sizeof(float) * (size_t)H * H + 16 : 0;   // weight staging + its mbarrier, prologue only
     return loop > stage ? loop : stage;
 }
 
 template <int H, int R, bool REC>
-__global__ void __launch_bounds__(H) k_recur_bwd(const BwdParams p)
+__global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W32 = H / 32;
@@ -44,19 +44,24 @@ __global__ void __launch_bounds__(H) k_recur_bwd(const BwdParams p)
     const int b0 = blockIdx.x * R;
     const int nvalid = min(R, B - b0);
 
-    // row i of W_rec (.) rec_mask, staged through padded shared memory so the global read is coalesced
-    float w[REC ? H : 1];
+    // row i of W_rec (.) rec_mask = column i of its transpose (k_prep_rec), staged by ONE bulk copy through shared
+    // memory (the staging area aliases the loop buffers, which are initialised afterwards)
+    float w[REC ? H : 8];
     if constexpr (REC) {
-        float* s_t = reinterpret_cast<float*>(smem_raw);   // [H][H+1]
-        for (int idx = i; idx < H * H; idx += H) {
-            const int row = idx / H, col = idx - row * H;
-            const float m = p.rec_mask ? __ldg(p.rec_mask + idx) : 1.0f;
-            s_t[row * (H + 1) + col] = __fmul_rn(__ldg(p.W_rec + idx), m);
+        float* s_t = reinterpret_cast<float*>(smem_raw);                        // [H][H]
+        uint64_t* wbar = reinterpret_cast<uint64_t*>(s_t + H * H);
+        if (i == 0) {
+            tc::mbar_init(wbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            tc::mbar_expect_tx(wbar, (uint32_t)(H * H * sizeof(float)));
+            tc::bulk_g2s(s_t, p.W_effT, (uint32_t)(H * H * sizeof(float)), wbar);
         }
         __syncthreads();
+        tc::mbar_wait(wbar, 0);
 #pragma unroll
-        for (int k = 0; k < H; ++k) w[k] = s_t[i * (H + 1) + k];
+        for (int k = 0; k < H; ++k) w[k] = s_t[k * H + i];
         __syncthreads();
+        if (i == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(wbar)) : "memory");
     }
 
     float* s_g = reinterpret_cast<float*>(smem_raw);                       // [2][R][H]
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(H) k_recur_bwd(const BwdParams p)
                     if constexpr (REC) {
                         const float4* gv4 =
                             reinterpret_cast<const float4*>(s_g + ((t + 1) & 1) * R * H + r * H);
-                        s = __fadd_rn(s, dot_rec4<REC ? H : 1>(w, gv4));   // gI_{t+1} (W_rec . M)^T
+                        s = __fadd_rn(s, dot_rec8<REC ? H : 8>(w, gv4));   // gI_{t+1} (W_rec . M)^T
                     }
                     const size_t o = ((size_t)(valid[r] ? b0 + r : 0) * T + t) * H + i;
                     if (p.g_Z && valid[r]) s = __fadd_rn(s, __ldg(p.g_Z + o));

@@ -27,11 +27,11 @@ constexpr size_t fwd_smem_bytes(int T, int O)
 {
     return sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)((R * T * (H / 32) + 3) & ~3) +
            sizeof(float) * (size_t)((H * O + R * T * O + 3) & ~3) + sizeof(float) * (size_t)(kRing * R * kChunk * H) +
-           sizeof(uint64_t) * kRing;
+           sizeof(uint64_t) * (kRing + 1) + sizeof(float) * (size_t)H * H;   // + staging of the recurrent matrix
 }
 
 template <int H, int R, bool REC>
-__global__ void __launch_bounds__(H) k_recur_fwd(const FwdParams p)
+__global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W32 = H / 32;
@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(H) k_recur_fwd(const FwdParams p)
     float* s_wout = reinterpret_cast<float*>(s_mask + ((R * T * W32 + 3) & ~3));    // [H][O]
     float* s_s = s_wout + H * O;                                                    // [R][T][O]
     float* s_in = s_wout + ((H * O + R * T * O + 3) & ~3);                          // [kRing][R][kChunk][H], 16-B aligned
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_in + kRing * R * kChunk * H);   // [kRing]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_in + kRing * R * kChunk * H);   // [kRing] + 1 for the weights
+    float* s_w = reinterpret_cast<float*>(s_bar + kRing + 1);                       // [H][H] staging, prologue only
 
     const int nchunks = (T + kChunk - 1) / kChunk;
     // bulk copy of chunk c (kChunk consecutive steps of every valid row) into ring slot c % kRing; thread 0 only
@@ -58,19 +59,22 @@ __global__ void __launch_bounds__(H) k_recur_fwd(const FwdParams p)
                          s_bar + slot);
     };
     if (i == 0) {
-        for (int s = 0; s < kRing; ++s) tc::mbar_init(s_bar + s, 1);
+        for (int s = 0; s <= kRing; ++s) tc::mbar_init(s_bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (REC) {   // the whole masked recurrent matrix in one bulk copy (64 KB at H = 128)
+            tc::mbar_expect_tx(s_bar + kRing, (uint32_t)(H * H * sizeof(float)));
+            tc::bulk_g2s(s_w, p.W_eff, (uint32_t)(H * H * sizeof(float)), s_bar + kRing);
+        }
         for (int c = 0; c < kRing && c < nchunks; ++c) issue_chunk(c);
     }
+    __syncthreads();   // barrier inits visible before anyone waits
 
-    // column i of W_rec (.) rec_mask  (spiking_layers.py:165/235 multiplies the mask in at every step)
-    float w[REC ? H : 1];
+    // column i of W_rec (.) rec_mask -> registers for the whole sequence
+    float w[REC ? H : 8];
     if constexpr (REC) {
+        tc::mbar_wait(s_bar + kRing, 0);
 #pragma unroll
-        for (int k = 0; k < H; ++k) {
-            const float m = p.rec_mask ? __ldg(p.rec_mask + k * H + i) : 1.0f;
-            w[k] = __fmul_rn(__ldg(p.W_rec + k * H + i), m);
-        }
+        for (int k = 0; k < H; ++k) w[k] = s_w[k * H + i];
     }
     const float beta = (p.alif && p.beta) ? __ldg(p.beta) : 0.f;
 
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(H) k_recur_fwd(const FwdParams p)
             float rec = 0.0f;
             if constexpr (REC) {
                 const float4* zv = reinterpret_cast<const float4*>(s_z + ((t + 1) & 1) * R * H + r * H);
-                rec = dot_rec4<REC ? H : 1, 16>(w, zv);
+                rec = dot_rec8<REC ? H : 8>(w, zv);
             }
             // V' = (alpha V + I_in + I_rec) (1 - Z.detach())     spiking_layers.py:169/239
             const float t1 = __fmul_rn(p.alpha, v[r]);

@@ -79,7 +79,8 @@ struct Plan {
     bool tc;          // tcgen05 GEMMs eligible for this geometry (the flag asks for them and TMA can address x)
     int kpad;         // K of the projection padded to the k-block
     size_t off_gI, off_gIlo, off_pwout, off_pdb, off_pw, off_flag, bwd_bytes;
-    size_t off_wplanes, off_fflag, fwd_bytes;
+    size_t off_wplanes, off_fflag, off_weff, fwd_bytes;
+    size_t off_weffT;
 };
 
 int check_desc(const SnnkDesc* d)
@@ -126,10 +127,12 @@ Plan make_plan(const SnnkDesc* d)
     p.off_pdb = off;    off = align_up(off + sizeof(float) * (size_t)p.grid_rows * p.R * d->O, 256);
     p.off_pw = off;     off = align_up(off + sizeof(float) * (size_t)p.S * p.m_total * d->H, 256);
     p.off_flag = off;   off = align_up(off + 256, 256);
+    p.off_weffT = off;  off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
     p.bwd_bytes = off;
     off = align_up(sizeof(float) * (size_t)BT * d->H, 256);
     p.off_wplanes = off; off = align_up(off + (p.tc ? sizeof(float) * 3 * (size_t)d->H * p.kpad : 0), 256);
     p.off_fflag = off;   off = align_up(off + 256, 256);
+    p.off_weff = off;    off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
     p.fwd_bytes = off;
     return p;
 }
@@ -491,11 +494,18 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
         SNNK_CUDA(cudaGetLastError());
     }
     // K2: fused recurrence + readout
+    float* W_eff = nullptr;
+    if (d->recurrent) {
+        W_eff = reinterpret_cast<float*>(static_cast<char*>(workspace) + pl.off_weff);
+        const int n = d->H * d->H;
+        k_prep_rec<<<(n + 255) / 256, 256, 0, st>>>(W_rec, rec_mask, d->H, W_eff, nullptr);
+        SNNK_CUDA(cudaGetLastError());
+    }
     FwdParams fp{};
     fp.B = d->B; fp.T = d->T; fp.H = d->H; fp.O = d->O;
     fp.alif = d->layer_type == SNNK_ALIF; fp.traces = traces;
     fp.alpha = d->alpha; fp.rho = d->rho; fp.theta = d->theta; fp.kappa = d->kappa;
-    fp.I_in = I_in; fp.W_rec = W_rec; fp.rec_mask = rec_mask; fp.beta = beta; fp.W_out = W_out; fp.b_out = b_out;
+    fp.I_in = I_in; fp.W_eff = W_eff; fp.beta = beta; fp.W_out = W_out; fp.b_out = b_out;
     fp.V0 = V0; fp.a0 = a0; fp.Z0 = Z0; fp.V = V; fp.a = a; fp.Z = Z; fp.zbits = zbits; fp.y = y;
     fp.logits = logits; fp.tstar = tstar;
     const bool rec = d->recurrent != 0;
@@ -548,11 +558,18 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     const bool rec = d->recurrent != 0;
 
     // K3: reverse-time sweep
+    float* W_effT = nullptr;
+    if (rec) {
+        W_effT = reinterpret_cast<float*>(ws + pl.off_weffT);
+        const int n = d->H * d->H;
+        k_prep_rec<<<(n + 255) / 256, 256, 0, st>>>(W_rec, rec_mask, d->H, nullptr, W_effT);
+        SNNK_CUDA(cudaGetLastError());
+    }
     BwdParams bp{};
     bp.B = d->B; bp.T = d->T; bp.H = d->H; bp.O = d->O;
     bp.alif = d->layer_type == SNNK_ALIF; bp.surrogate = d->surrogate;
     bp.alpha = d->alpha; bp.theta = d->theta; bp.gamma = d->gamma; bp.kappa = d->kappa;
-    bp.W_rec = W_rec; bp.rec_mask = rec_mask; bp.beta = beta; bp.W_out = W_out; bp.Z0 = Z0;
+    bp.W_effT = W_effT; bp.beta = beta; bp.W_out = W_out; bp.Z0 = Z0;
     bp.V = V; bp.a = a; bp.zbits = zbits; bp.g_y = g_y; bp.g_logits = dense ? nullptr : g_logits;
     bp.tstar = dense ? nullptr : tstar; bp.g_V = g_V; bp.g_Z = g_Z;
     float* gI_lo = pl.tc ? reinterpret_cast<float*>(ws + pl.off_gIlo) : nullptr;
