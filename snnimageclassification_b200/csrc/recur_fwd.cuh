@@ -27,7 +27,7 @@ constexpr size_t fwd_smem_bytes(int T, int O)
 {
     return sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)((R * T * (H / 32) + 3) & ~3) +
            sizeof(float) * (size_t)((H * O + R * T * O + 3) & ~3) + sizeof(float) * (size_t)(kRing * R * kChunk * H) +
-           sizeof(uint64_t) * (kRing + 1) + sizeof(float) * (size_t)H * H;   // + staging of the recurrent matrix
+           sizeof(uint64_t) * (kRing + 2) + sizeof(float) * (size_t)H * H;   // + staging of the recurrent matrix
 }
 
 template <int H, int R, bool REC>
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
     float* s_s = s_wout + H * O;                                                    // [R][T][O]
     float* s_in = s_wout + ((H * O + R * T * O + 3) & ~3);                          // [kRing][R][kChunk][H], 16-B aligned
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_in + kRing * R * kChunk * H);   // [kRing] + 1 for the weights
-    float* s_w = reinterpret_cast<float*>(s_bar + kRing + 1);                       // [H][H] staging, prologue only
+    float* s_w = reinterpret_cast<float*>(s_bar + kRing + 2);                       // [H][H] staging (16-B aligned), prologue only
 
     const int nchunks = (T + kChunk - 1) / kChunk;
     // bulk copy of chunk c (kChunk consecutive steps of every valid row) into ring slot c % kRing; thread 0 only
