@@ -215,15 +215,58 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
         if (c < O) p.part_wout[((size_t)blockIdx.x * H + i) * O + c] = dwo[c];
 }
 
-// out[e] = mask[e] * sum_p parts[p*stride + e]  (ascending p: deterministic)
-__global__ void k_reduce_parts(const float* __restrict__ parts, int nparts, size_t stride, int n,
-                               const float* __restrict__ mask, float* __restrict__ out)
+// ---- gradient finalisation: every split-K / per-CTA partial buffer reduced in ONE launch ------------------------
+// All sums run in a fixed order (ascending partial index per lane, then a fixed shuffle tree), so the gradients
+// are run-to-run deterministic.  Loads are issued in independent batches so the kernel is bandwidth- rather than
+// latency-bound.
+struct FinalizeParams {
+    // (a) thread per element, few partials:  dW_in (n_in elements) then dW_rec (n_rec elements, masked)
+    const float* pw; int S; size_t w_stride; int n_in; int n_rec; const float* rec_mask;
+    float* dW_in; float* dW_rec;
+    // (b) warp per element, many partials:   dW_out (n_out elements, P_out partials) then db (n_b, P_b partials)
+    const float* pwout; int P_out; int n_out; float* dW_out;
+    const float* pdb; int P_b; int n_b; float* db;
+    int blocks_a;   // blocks [0, blocks_a) do (a), the rest do (b)
+};
+
+__device__ __forceinline__ float sum_partials_seq(const float* __restrict__ base, int nparts, size_t stride)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
     float s = 0.f;
-    for (int q = 0; q < nparts; ++q) s += parts[(size_t)q * stride + e];
-    out[e] = mask ? s * mask[e] : s;
+    int q = 0;
+    for (; q + 8 <= nparts; q += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(base + (size_t)(q + j) * stride);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    for (; q < nparts; ++q) s += __ldg(base + (size_t)q * stride);
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k_finalize_grads(const FinalizeParams p)
+{
+    if ((int)blockIdx.x < p.blocks_a) {
+        const int e = blockIdx.x * blockDim.x + threadIdx.x;
+        if (e < p.n_in) {
+            p.dW_in[e] = sum_partials_seq(p.pw + e, p.S, p.w_stride);
+        } else if (e - p.n_in < p.n_rec) {
+            const int r = e - p.n_in;
+            const float s = sum_partials_seq(p.pw + p.n_in + r, p.S, p.w_stride);
+            p.dW_rec[r] = p.rec_mask ? s * __ldg(p.rec_mask + r) : s;
+        }
+        return;
+    }
+    const int warp = (blockIdx.x - p.blocks_a) * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const float* base; int nparts, n; float* out; int e;
+    if (warp < p.n_out) { base = p.pwout; nparts = p.P_out; n = p.n_out; out = p.dW_out; e = warp; }
+    else if (warp - p.n_out < p.n_b) { base = p.pdb; nparts = p.P_b; n = p.n_b; out = p.db; e = warp - p.n_out; }
+    else return;
+    float s = 0.f;
+    for (int q = lane; q < nparts; q += 32) s += __ldg(base + (size_t)q * n + e);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[e] = s;
 }
 
 }  // namespace snnk

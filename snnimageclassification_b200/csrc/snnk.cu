@@ -361,7 +361,7 @@ const char* snnk_kernel_name(int id)
     case SNNK_K_WGRAD: return "K4 k_wgrad (weight-gradient GEMM)";
     case SNNK_K_PROJ_FALLBACK: return "K1f k_proj_simt (gated fallback)";
     case SNNK_K_WGRAD_FALLBACK: return "K4f k_wgrad_simt (gated fallback)";
-    case SNNK_K_REDUCE_W: return "k_reduce_parts (dW_in, dW_rec)";
+    case SNNK_K_REDUCE_W: return "k_finalize_grads (all partial reductions)";
     default: return "?";
     }
 }
@@ -581,13 +581,6 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     default: rc = SNNK_ERR_UNSUPPORTED;
     }
     if (rc != SNNK_OK) return rc;
-    {
-        const int n1 = d->H * d->O;
-        ProfScope ps(SNNK_K_REDUCE_OUT, st);
-        k_reduce_parts<<<(n1 + 255) / 256, 256, 0, st>>>(pwout, pl.grid_rows, (size_t)n1, n1, nullptr, dW_out);
-        k_reduce_parts<<<1, 256, 0, st>>>(pdb, pl.grid_rows * pl.R, (size_t)d->O, d->O, nullptr, db);
-        SNNK_CUDA(cudaGetLastError());
-    }
     // K4: weight-gradient GEMM (split-K partials over whole samples, then a fixed-order reduction)
     {
         unsigned int* flag = nullptr;
@@ -613,15 +606,16 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
             else k_wgrad_simt<32><<<grid, kGemmThreads, 0, st>>>(wp);
         }
         SNNK_CUDA(cudaGetLastError());
+        // every partial buffer (dW_in, dW_rec, dW_out, db) reduced by one launch
+        FinalizeParams fz{};
+        fz.pw = pw; fz.S = pl.S; fz.w_stride = (size_t)pl.m_total * d->H; fz.n_in = d->N * d->H;
+        fz.n_rec = rec ? d->H * d->H : 0; fz.rec_mask = rec_mask; fz.dW_in = dW_in; fz.dW_rec = dW_rec;
+        fz.pwout = pwout; fz.P_out = pl.grid_rows; fz.n_out = d->H * d->O; fz.dW_out = dW_out;
+        fz.pdb = pdb; fz.P_b = pl.grid_rows * pl.R; fz.n_b = d->O; fz.db = db;
+        fz.blocks_a = (fz.n_in + fz.n_rec + 255) / 256;
+        const int blocks_b = (fz.n_out + fz.n_b + 7) / 8;
         ProfScope ps2(SNNK_K_REDUCE_W, st);
-        const size_t stride = (size_t)pl.m_total * d->H;
-        const int n_in = d->N * d->H;
-        k_reduce_parts<<<(n_in + 255) / 256, 256, 0, st>>>(pw, pl.S, stride, n_in, nullptr, dW_in);
-        if (rec) {
-            const int n_rec = d->H * d->H;
-            k_reduce_parts<<<(n_rec + 255) / 256, 256, 0, st>>>(pw + (size_t)d->N * d->H, pl.S, stride, n_rec,
-                                                                 rec_mask, dW_rec);
-        }
+        k_finalize_grads<<<fz.blocks_a + blocks_b, 256, 0, st>>>(fz);
         SNNK_CUDA(cudaGetLastError());
     }
     return SNNK_OK;
