@@ -226,8 +226,7 @@ def main():
 	kern = profile_kernels(step_eager)     # event brackets need real launches, not a graph replay
 
 	if rank != 0:
-		if world > 1:
-			dist.destroy_process_group()
+		finish(world)
 		return
 	peaks = {}
 	try:
@@ -264,8 +263,16 @@ def main():
 		"gpu_launches": int(round(launches_per_step * args.steps)),
 		"roofline": roofline, "cpu_baseline": cpu,
 	}))
+	finish(world)
+
+
+def finish(world):
+	"""Leave without tearing NCCL down: destroy_process_group() can block behind the captured graphs' communicator
+	references, and there is nothing left to flush but stdout."""
+	sys.stdout.flush()
+	sys.stderr.flush()
 	if world > 1:
-		dist.destroy_process_group()
+		os._exit(0)
 
 
 def profile_kernels(step_fn, iters=10):
