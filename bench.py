@@ -129,6 +129,7 @@ def main():
 	ap.add_argument("--warmup", type=int, default=10)
 	ap.add_argument("--impl", default="native", choices=["native", "reference"])
 	ap.add_argument("--no-cpu-baseline", action="store_true")
+	ap.add_argument("--no-large-batch", action="store_true")
 	args = ap.parse_args()
 	args.warmup = max(args.warmup, 3)
 
@@ -225,6 +226,9 @@ def main():
 	# per-kernel CUDA-event timing (separate short loop, same process) -> roofline of the dominant kernel
 	kern = profile_kernels(step_eager)     # event brackets need real launches, not a graph replay
 
+	big = None
+	if world == 1 and not args.no_large_batch:
+		big = large_batch_rooflines(net, enc, dev)
 	if rank != 0:
 		finish(world)
 		return
@@ -261,9 +265,46 @@ def main():
 			"ms_per_step": ms_e2e / args.steps, "input": "pinned host images (B,784) fp32 + labels; GPU to_spikes",
 			"from_host_rasters": {"value": e2e_raster, "h2d_bytes_per_step": B_PER_GPU * T * N * 4 + B_PER_GPU * 8}},
 		"gpu_launches": int(round(launches_per_step * args.steps)),
-		"roofline": roofline, "cpu_baseline": cpu,
+		"roofline": roofline, "cpu_baseline": cpu, "large_batch_kernels": big,
 	}))
 	finish(world)
+
+
+def large_batch_rooflines(net, enc, dev, B=4096, iters=5):
+	"""Per-kernel achieved bandwidth of the same kernels at batch 4096 (BASELINE configs[4] regime), where the
+	recurrence is no longer bound by the latency of its 2T sequential steps.  Extra information, not the headline."""
+	from snnimageclassification_b200 import _cabi
+	img, lab = synthetic_images(B, seed=77)
+	x = enc.encode_batch(img.to(dev))
+	lab = lab.to(dev)
+	crit = torch.nn.NLLLoss()
+
+	def step():
+		loss = net.batch_loss(x, lab, crit)
+		net.zero_grad()
+		loss.backward()
+	for _ in range(2):
+		step()
+	torch.cuda.synchronize()
+	with _cabi.kernel_profile() as prof:
+		for _ in range(iters):
+			step()
+	BT = B * T
+	algo = {"K1": BT * N * 4 + BT * H * 4, "K2": BT * H * 4 + 3 * BT * H * 4 + BT * O * 4 + BT * H // 8,
+		"K3": 2 * BT * H * 4 + BT * H // 8 + 2 * BT * H * 4, "K4": BT * N * 4 + 2 * BT * H * 4 + BT * H * 4}
+	peak = 6560.0
+	try:
+		peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+	except Exception:
+		pass
+	out = {"batch": B}
+	for name, (ms, n) in prof.result.items():
+		key = name.split()[0]
+		if key in algo:
+			gbs = algo[key] / (ms / n * 1e-3) / 1e9
+			out[name] = {"ms": round(ms / n, 4), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 3)}
+	del x
+	return out
 
 
 def finish(world):

@@ -221,8 +221,9 @@ struct ProjCfg {
 template <int H, int P>
 __global__ void __launch_bounds__(kThreads, 1)
 k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, float* __restrict__ C,
-          int M, int kblocks, unsigned int* __restrict__ inexact_flag)
+          int M, int kblocks, int ldc, unsigned int* __restrict__ inexact_flag)
 {
+    // H is the N extent of this CTA's tile; blockIdx.y selects the tile, ldc is the full hidden width
     using Cfg = ProjCfg<H, P>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ unsigned char smem_dyn[];
@@ -235,6 +236,7 @@ k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM;
+    const int n0 = blockIdx.y * H;
     constexpr uint32_t kTmemCols = tmem_cols_for(H);
 
     if (warp == 0 && lane == 0) {
@@ -261,7 +263,7 @@ k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
                 tma_load_2d(st, &map_x, full + s, kb * kBlockK, m0);
 #pragma unroll
                 for (int p = 0; p < P; ++p)
-                    tma_load_3d(st + kATileBytes + p * Cfg::kBPlaneBytes, &map_w, full + s, kb * kBlockK, 0, p);
+                    tma_load_3d(st + kATileBytes + p * Cfg::kBPlaneBytes, &map_w, full + s, kb * kBlockK, n0, p);
             }
         }
     } else if (warp == 1) {
@@ -310,7 +312,7 @@ k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
             float v[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c0, v);
             if (row < M) {
-                float4* dst = reinterpret_cast<float4*>(C + (size_t)row * H + c0);
+                float4* dst = reinterpret_cast<float4*>(C + (size_t)row * ldc + n0 + c0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
@@ -360,7 +362,8 @@ struct WgradCfg {
 struct WgradTcParams {
     int N, T, B;
     int mtiles_x;              // tiles taking A from x; the remaining blockIdx.x take it from the spike trace
-    int m_total;               // N + H
+    int m_total;               // N + H_full
+    int H_full;                // full hidden width (the template H is the N extent of one CTA tile)
     int samples_per_split;
     float* part;               // [S][m_total][H]
     unsigned int* inexact_flag;   // raised when an x tile holds values that are not tf32-exact
@@ -384,6 +387,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool from_x = (int)blockIdx.x < p.mtiles_x;
     const int m0 = from_x ? blockIdx.x * kBlockM : (blockIdx.x - p.mtiles_x) * kBlockM;
+    const int n0 = blockIdx.z * H;
     const int b_lo = blockIdx.y * p.samples_per_split;
     const int b_hi = min(b_lo + p.samples_per_split, p.B);
     const int tblocks = (p.T + kBlockK - 1) / kBlockK;
@@ -421,7 +425,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
                 }
 #pragma unroll
                 for (int q = 0; q < P * (H / 32); ++q)
-                    tma_load_4d(st + kATileBytes + q * Cfg::kBoxBytes, &map_g, full + s, 32 * (q % (H / 32)), t0, b,
+                    tma_load_4d(st + kATileBytes + q * Cfg::kBoxBytes, &map_g, full + s, n0 + 32 * (q % (H / 32)), t0, b,
                                 q / (H / 32));
             }
         }
@@ -468,7 +472,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
         }
         const int q = warp & 3;
         const int m = m0 + 32 * q + lane;
-        const int mlim = from_x ? p.N : H;
+        const int mlim = from_x ? p.N : p.H_full;
         const int mbase = from_x ? 0 : p.N;
 #pragma unroll
         for (int c0 = 0; c0 < H; c0 += 32) {
@@ -480,7 +484,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
             if (m < mlim) {
-                float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)blockIdx.y * p.m_total + mbase + m) * H + c0);
+                float4* dst = reinterpret_cast<float4*>(p.part + ((size_t)blockIdx.y * p.m_total + mbase + m) * p.H_full + n0 + c0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }

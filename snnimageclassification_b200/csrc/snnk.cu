@@ -14,6 +14,7 @@
 #include "gemm_tc.cuh"
 #include "recur_bwd.cuh"
 #include "recur_fwd.cuh"
+#include "recur_gen.cuh"
 
 using namespace snnk;
 
@@ -78,9 +79,13 @@ struct Plan {
     int samples_per_split;
     bool tc;          // tcgen05 GEMMs eligible for this geometry (the flag asks for them and TMA can address x)
     int kpad;         // K of the projection padded to the k-block
+    bool wide;        // H > 128: generic recurrence kernels (recur_gen.cuh), N-tiled tensor-core GEMMs
+    int tileN;        // N extent of one tensor-core tile
+    int ntiles_tc;
+    int n_pwout, n_pdb;   // number of dW_out / db partial buffers
     size_t off_gI, off_gIlo, off_pwout, off_pdb, off_pw, off_flag, bwd_bytes;
     size_t off_wplanes, off_fflag, off_weff, fwd_bytes;
-    size_t off_weffT;
+    size_t off_weffT, off_gyscan;
 };
 
 int check_desc(const SnnkDesc* d)
@@ -90,7 +95,7 @@ int check_desc(const SnnkDesc* d)
     if (d->layer_type != SNNK_LIF && d->layer_type != SNNK_ALIF) return SNNK_ERR_ARG;
     if (d->surrogate != SNNK_FAST_SIGMOID && d->surrogate != SNNK_PHI) return SNNK_ERR_ARG;
     if (d->O > kOMax) return SNNK_ERR_SHAPE;
-    if (d->H != 32 && d->H != 64 && d->H != 128) return SNNK_ERR_UNSUPPORTED;
+    if (d->H != 32 && d->H != 64 && d->H != 128 && !(d->H % 128 == 0 && d->H <= 2048)) return SNNK_ERR_UNSUPPORTED;
     if ((long long)d->B * d->T >= (1ll << 31) / 4) return SNNK_ERR_SHAPE;
     return SNNK_OK;
 }
@@ -98,9 +103,14 @@ int check_desc(const SnnkDesc* d)
 Plan make_plan(const SnnkDesc* d)
 {
     Plan p{};
-    p.R = d->B > 1024 ? 2 : 1;
+    p.wide = d->H > 128;
+    p.R = p.wide ? gen_rows(d->H) : (d->B > 1024 ? 2 : 1);
     p.grid_rows = (d->B + p.R - 1) / p.R;
     const int BT = d->B * d->T;
+    p.tileN = p.wide ? 128 : d->H;
+    p.ntiles_tc = d->H / p.tileN;
+    p.n_pwout = p.wide ? (BT < 256 ? BT : 256) : p.grid_rows;
+    p.n_pdb = p.wide ? p.n_pwout : p.grid_rows * p.R;
     p.BN = d->H >= 64 ? 64 : 32;
     p.ntiles = d->H / p.BN;
     p.mtiles_x = (d->N + kGemmBM - 1) / kGemmBM;
@@ -111,7 +121,7 @@ Plan make_plan(const SnnkDesc* d)
     p.kpad = (d->N + tc::kBlockK - 1) / tc::kBlockK * tc::kBlockK;
     int S;
     if (p.tc) {
-        S = 148 / (p.mtiles_x + p.mtiles_z);          // one CTA per SM: the tcgen05 kernel owns the whole smem
+        S = 148 / ((p.mtiles_x + p.mtiles_z) * p.ntiles_tc);   // one CTA per SM: the tcgen05 kernel owns the whole smem
     } else {
         const int tiles = (p.mtiles_x + p.mtiles_z) * p.ntiles;
         S = (4 * 148 + tiles - 1) / tiles;
@@ -123,11 +133,12 @@ Plan make_plan(const SnnkDesc* d)
     size_t off = 0;
     p.off_gI = off;     off = align_up(off + sizeof(float) * (size_t)BT * d->H, 256);
     p.off_gIlo = off;   off = align_up(off + (p.tc ? sizeof(float) * (size_t)BT * d->H : 0), 256);
-    p.off_pwout = off;  off = align_up(off + sizeof(float) * (size_t)p.grid_rows * d->H * d->O, 256);
-    p.off_pdb = off;    off = align_up(off + sizeof(float) * (size_t)p.grid_rows * p.R * d->O, 256);
+    p.off_pwout = off;  off = align_up(off + sizeof(float) * (size_t)p.n_pwout * d->H * d->O, 256);
+    p.off_pdb = off;    off = align_up(off + sizeof(float) * (size_t)p.n_pdb * d->O, 256);
     p.off_pw = off;     off = align_up(off + sizeof(float) * (size_t)p.S * p.m_total * d->H, 256);
     p.off_flag = off;   off = align_up(off + 256, 256);
     p.off_weffT = off;  off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
+    p.off_gyscan = off; off = align_up(off + (p.wide ? sizeof(float) * (size_t)BT * kOMax : 0), 256);
     p.bwd_bytes = off;
     off = align_up(sizeof(float) * (size_t)BT * d->H, 256);
     p.off_wplanes = off; off = align_up(off + (p.tc ? sizeof(float) * 3 * (size_t)d->H * p.kpad : 0), 256);
@@ -172,16 +183,17 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
     return SNNK_OK;
 }
 
-template <int H>
+template <int H>   // H = N extent of one CTA tile (the whole hidden width when it is <= 128)
 int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const float* W_in, float* I_in, float* planes,
                    unsigned int* flag, cudaStream_t st)
 {
     constexpr int P = 3;
     using Cfg = tc::ProjCfg<H, P>;
     const int M = d->B * d->T;
+    const int Hf = d->H;
     {
-        const int n = H * pl.kpad;
-        tc::k_split_w<<<(n + 255) / 256, 256, 0, st>>>(W_in, d->N, H, pl.kpad, planes);
+        const int n = Hf * pl.kpad;
+        tc::k_split_w<<<(n + 255) / 256, 256, 0, st>>>(W_in, d->N, Hf, pl.kpad, planes);
         SNNK_CUDA(cudaGetLastError());
     }
     CUtensorMap mx, mw;
@@ -193,8 +205,8 @@ int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const floa
         if (rc != SNNK_OK) return rc;
     }
     {
-        const cuuint64_t dims[3] = {(cuuint64_t)pl.kpad, (cuuint64_t)H, 3};
-        const cuuint64_t str[2] = {(cuuint64_t)pl.kpad * 4, (cuuint64_t)pl.kpad * 4 * H};
+        const cuuint64_t dims[3] = {(cuuint64_t)pl.kpad, (cuuint64_t)Hf, 3};
+        const cuuint64_t str[2] = {(cuuint64_t)pl.kpad * 4, (cuuint64_t)pl.kpad * 4 * Hf};
         const cuuint32_t box[3] = {tc::kBlockK, (cuuint32_t)H, 1};
         int rc = make_map(&mw, planes, 3, dims, str, box);
         if (rc != SNNK_OK) return rc;
@@ -202,8 +214,8 @@ int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const floa
     auto kern = tc::k_proj_tc<H, P>;
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     ProfScope ps(SNNK_K_PROJ, st);
-    kern<<<(M + tc::kBlockM - 1) / tc::kBlockM, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mw, I_in, M,
-                                                                                    pl.kpad / tc::kBlockK, flag);
+    dim3 grid((M + tc::kBlockM - 1) / tc::kBlockM, Hf / H);
+    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mw, I_in, M, pl.kpad / tc::kBlockK, Hf, flag);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -214,7 +226,7 @@ int launch_wgrad_tc(const SnnkDesc* d, const Plan& pl, const float* x, const flo
 {
     constexpr int P = 2;
     using Cfg = tc::WgradCfg<H, P>;
-    const cuuint64_t T = d->T, B = d->B, N = d->N;
+    const cuuint64_t T = d->T, B = d->B, N = d->N, Hf = d->H;
     CUtensorMap mx, mz, mg;
     {
         const cuuint64_t dims[3] = {N, T, B};
@@ -224,25 +236,25 @@ int launch_wgrad_tc(const SnnkDesc* d, const Plan& pl, const float* x, const flo
         if (rc != SNNK_OK) return rc;
     }
     {
-        const cuuint64_t dims[3] = {(cuuint64_t)H, T, B};
-        const cuuint64_t str[2] = {(cuuint64_t)H * 4, T * H * 4};
+        const cuuint64_t dims[3] = {Hf, T, B};
+        const cuuint64_t str[2] = {Hf * 4, T * Hf * 4};
         const cuuint32_t box[3] = {32, tc::kBlockK, 1};
         int rc = make_map(&mz, Ztrace ? Ztrace : gI_planes, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != SNNK_OK) return rc;
     }
     {
-        const cuuint64_t dims[4] = {(cuuint64_t)H, T, B, (cuuint64_t)P};
-        const cuuint64_t str[3] = {(cuuint64_t)H * 4, T * H * 4, (cuuint64_t)(pl.off_gIlo - pl.off_gI)};   // planes are 256-B aligned
+        const cuuint64_t dims[4] = {Hf, T, B, (cuuint64_t)P};
+        const cuuint64_t str[3] = {Hf * 4, T * Hf * 4, (cuuint64_t)(pl.off_gIlo - pl.off_gI)};   // planes are 256-B aligned
         const cuuint32_t box[4] = {32, tc::kBlockK, 1, 1};
         int rc = make_map(&mg, gI_planes, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != SNNK_OK) return rc;
     }
     tc::WgradTcParams wp{};
-    wp.N = d->N; wp.T = d->T; wp.B = d->B; wp.mtiles_x = pl.mtiles_x; wp.m_total = pl.m_total;
+    wp.N = d->N; wp.T = d->T; wp.B = d->B; wp.mtiles_x = pl.mtiles_x; wp.m_total = pl.m_total; wp.H_full = d->H;
     wp.samples_per_split = pl.samples_per_split; wp.part = part; wp.inexact_flag = flag;
     auto kern = tc::k_wgrad_tc<H, P>;
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-    dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.S);
+    dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.S, d->H / H);
     ProfScope ps(SNNK_K_WGRAD, st);
     kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mz, mg, wp);
     SNNK_CUDA(cudaGetLastError());
@@ -295,6 +307,74 @@ template <int H>
 int launch_bwd_r(const BwdParams& bp, bool rec, int R, int grid, cudaStream_t st)
 {
     return R == 1 ? launch_bwd_rec<H, 1>(bp, rec, grid, st) : launch_bwd_rec<H, 2>(bp, rec, grid, st);
+}
+
+// ---- wide hidden layers (H > 128): generic recurrence + separate readout / dW_out kernels -------------------------
+template <int NPT, int R>
+int launch_fwd_wide_t(const SnnkDesc* d, const FwdParams& fp, bool rec, const Plan& pl, cudaStream_t st)
+{
+    const size_t smem = sizeof(float) * 2 * (size_t)d->H * R;
+    const int threads = d->H / NPT;
+    {
+        ProfScope ps(SNNK_K_RECUR_FWD, st);
+        if (rec) {
+            auto kern = k_recur_fwd_gen<NPT, R, true>;
+            SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<pl.grid_rows, threads, smem, st>>>(fp);
+        } else {
+            auto kern = k_recur_fwd_gen<NPT, R, false>;
+            SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<pl.grid_rows, threads, smem, st>>>(fp);
+        }
+    }
+    SNNK_CUDA(cudaGetLastError());
+    const size_t smem2 = sizeof(uint32_t) * (size_t)d->T * (d->H / 32) + sizeof(float) * ((size_t)d->H * d->O + (size_t)d->T * d->O);
+    if (smem2 > 200 * 1024) return SNNK_ERR_SHAPE;
+    SNNK_CUDA(cudaFuncSetAttribute(k_readout_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    ProfScope ps2(SNNK_K_HEAD, st);
+    k_readout_scan<<<d->B, 128, smem2, st>>>(d->T, d->H, d->O, d->kappa, fp.zbits, fp.W_out, fp.b_out, fp.y, fp.logits,
+                                             fp.tstar);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int launch_fwd_wide(const SnnkDesc* d, const FwdParams& fp, bool rec, const Plan& pl, cudaStream_t st)
+{
+    return gen_npt(d->H) == 1 ? launch_fwd_wide_t<1, 4>(d, fp, rec, pl, st) : launch_fwd_wide_t<2, 2>(d, fp, rec, pl, st);
+}
+
+template <int NPT, int R>
+int launch_bwd_wide_t(const SnnkDesc* d, const BwdParams& bp, bool rec, const Plan& pl, float* gy_scan,
+                      const uint32_t* zbits, cudaStream_t st)
+{
+    const size_t smem = sizeof(float) * (2 * (size_t)d->H * R + (size_t)R * d->T * kOMax);
+    if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
+    const int threads = d->H / NPT;
+    {
+        ProfScope ps(SNNK_K_RECUR_BWD, st);
+        if (rec) {
+            auto kern = k_recur_bwd_gen<NPT, R, true>;
+            SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<pl.grid_rows, threads, smem, st>>>(bp, gy_scan);
+        } else {
+            auto kern = k_recur_bwd_gen<NPT, R, false>;
+            SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<pl.grid_rows, threads, smem, st>>>(bp, gy_scan);
+        }
+    }
+    SNNK_CUDA(cudaGetLastError());
+    ProfScope ps2(SNNK_K_REDUCE_OUT, st);
+    k_wout_grad<<<dim3(pl.n_pwout, d->H / 128), 128, 0, st>>>(d->B * d->T, d->H, d->O, zbits, gy_scan, bp.part_wout,
+                                                             bp.part_db);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int launch_bwd_wide(const SnnkDesc* d, const BwdParams& bp, bool rec, const Plan& pl, float* gy_scan,
+                    const uint32_t* zbits, cudaStream_t st)
+{
+    return gen_npt(d->H) == 1 ? launch_bwd_wide_t<1, 4>(d, bp, rec, pl, gy_scan, zbits, st)
+                              : launch_bwd_wide_t<2, 2>(d, bp, rec, pl, gy_scan, zbits, st);
 }
 
 template <typename TIn>
@@ -357,7 +437,7 @@ const char* snnk_kernel_name(int id)
     case SNNK_K_RECUR_FWD: return "K2 k_recur_fwd (fused recurrence + readout)";
     case SNNK_K_HEAD: return "K6 k_head_nll";
     case SNNK_K_RECUR_BWD: return "K3 k_recur_bwd (fused reverse-time BPTT)";
-    case SNNK_K_REDUCE_OUT: return "k_reduce_parts (dW_out, db)";
+    case SNNK_K_REDUCE_OUT: return "k_wout_grad (wide layers: dW_out, db partials)";
     case SNNK_K_WGRAD: return "K4 k_wgrad (weight-gradient GEMM)";
     case SNNK_K_PROJ_FALLBACK: return "K1f k_proj_simt (gated fallback)";
     case SNNK_K_WGRAD_FALLBACK: return "K4f k_wgrad_simt (gated fallback)";
@@ -480,7 +560,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
             flag = reinterpret_cast<unsigned int*>(ws + pl.off_fflag);
             float* planes = reinterpret_cast<float*>(ws + pl.off_wplanes);
             SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
-            switch (d->H) {
+            switch (pl.tileN) {
             case 32: rc = launch_proj_tc<32>(d, pl, x, W_in, I_in, planes, flag, st); break;
             case 64: rc = launch_proj_tc<64>(d, pl, x, W_in, I_in, planes, flag, st); break;
             default: rc = launch_proj_tc<128>(d, pl, x, W_in, I_in, planes, flag, st); break;
@@ -509,6 +589,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     fp.V0 = V0; fp.a0 = a0; fp.Z0 = Z0; fp.V = V; fp.a = a; fp.Z = Z; fp.zbits = zbits; fp.y = y;
     fp.logits = logits; fp.tstar = tstar;
     const bool rec = d->recurrent != 0;
+    if (pl.wide) return launch_fwd_wide(d, fp, rec, pl, st);
     switch (d->H) {
     case 32: return launch_fwd_r<32>(fp, rec, pl.R, pl.grid_rows, st);
     case 64: return launch_fwd_r<64>(fp, rec, pl.R, pl.grid_rows, st);
@@ -574,11 +655,15 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     bp.tstar = dense ? nullptr : tstar; bp.g_V = g_V; bp.g_Z = g_Z;
     float* gI_lo = pl.tc ? reinterpret_cast<float*>(ws + pl.off_gIlo) : nullptr;
     bp.gI = gI; bp.gI_lo = gI_lo; bp.part_wout = pwout; bp.part_db = pdb;
-    switch (d->H) {
-    case 32: rc = launch_bwd_r<32>(bp, rec, pl.R, pl.grid_rows, st); break;
-    case 64: rc = launch_bwd_r<64>(bp, rec, pl.R, pl.grid_rows, st); break;
-    case 128: rc = launch_bwd_r<128>(bp, rec, pl.R, pl.grid_rows, st); break;
-    default: rc = SNNK_ERR_UNSUPPORTED;
+    if (pl.wide) {
+        rc = launch_bwd_wide(d, bp, rec, pl, reinterpret_cast<float*>(ws + pl.off_gyscan), zbits, st);
+    } else {
+        switch (d->H) {
+        case 32: rc = launch_bwd_r<32>(bp, rec, pl.R, pl.grid_rows, st); break;
+        case 64: rc = launch_bwd_r<64>(bp, rec, pl.R, pl.grid_rows, st); break;
+        case 128: rc = launch_bwd_r<128>(bp, rec, pl.R, pl.grid_rows, st); break;
+        default: rc = SNNK_ERR_UNSUPPORTED;
+        }
     }
     if (rc != SNNK_OK) return rc;
     // K4: weight-gradient GEMM (split-K partials over whole samples, then a fixed-order reduction)
@@ -587,7 +672,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         if (pl.tc) {
             flag = reinterpret_cast<unsigned int*>(ws + pl.off_flag);
             SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
-            switch (d->H) {
+            switch (pl.tileN) {
             case 32: rc = launch_wgrad_tc<32>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
             case 64: rc = launch_wgrad_tc<64>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
             default: rc = launch_wgrad_tc<128>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
@@ -610,8 +695,8 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         FinalizeParams fz{};
         fz.pw = pw; fz.S = pl.S; fz.w_stride = (size_t)pl.m_total * d->H; fz.n_in = d->N * d->H;
         fz.n_rec = rec ? d->H * d->H : 0; fz.rec_mask = rec_mask; fz.dW_in = dW_in; fz.dW_rec = dW_rec;
-        fz.pwout = pwout; fz.P_out = pl.grid_rows; fz.n_out = d->H * d->O; fz.dW_out = dW_out;
-        fz.pdb = pdb; fz.P_b = pl.grid_rows * pl.R; fz.n_b = d->O; fz.db = db;
+        fz.pwout = pwout; fz.P_out = pl.n_pwout; fz.n_out = d->H * d->O; fz.dW_out = dW_out;
+        fz.pdb = pdb; fz.P_b = pl.n_pdb; fz.n_b = d->O; fz.db = db;
         fz.blocks_a = (fz.n_in + fz.n_rec + 255) / 256;
         const int blocks_b = (fz.n_out + fz.n_b + 7) / 8;
         ProfScope ps2(SNNK_K_REDUCE_W, st);

@@ -42,6 +42,29 @@ def make_desc(c: LayerConsts, B: int, T: int, N: int, H: int, O: int, traces: bo
 		B, T, N, H, O, c.layer_type, c.surrogate, int(c.recurrent), c.alpha, c.rho, c.theta, c.gamma, c.kappa, flags)
 
 
+def padded_width(H: int) -> int:
+	"""Hidden widths the kernels are instantiated for: 32, 64, 128 (register-resident recurrent weights) and the
+	multiples of 128 up to 2048 (wide path).  Any other width (the reference's sweeps use 100 and 200,
+	training.py:37) is zero-padded to the next one: padded neurons have no incoming, recurrent or outgoing weights,
+	so they change nothing for the real ones and their traces / gradients are sliced away."""
+	for h in (32, 64, 128):
+		if H <= h:
+			return h
+	hp = (H + 127) // 128 * 128
+	if hp > 2048:
+		raise NotImplementedError(f"hidden width {H} > 2048 is not supported by the B200 path")
+	return hp
+
+
+def _pad_hidden(H: int, Hp: int, W_in, W_rec, rec_mask, W_out):
+	if Hp == H:
+		return W_in, W_rec, rec_mask, W_out
+	pad = Hp - H
+	P = torch.nn.functional.pad
+	return (P(W_in, (0, pad)), None if W_rec is None else P(W_rec, (0, pad, 0, pad)),
+		None if rec_mask is None else P(rec_mask, (0, pad, 0, pad)), P(W_out, (0, 0, 0, pad)))
+
+
 def _workspace(nbytes: int, device) -> torch.Tensor:
 	return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -149,24 +172,32 @@ class SpikingSequence(torch.autograd.Function):
 	@staticmethod
 	def forward(ctx, consts: LayerConsts, x, W_in, W_rec, rec_mask, beta, W_out, b_out):
 		xc, Wi, Wr, M, be, Wo, bo = (_c(t) for t in (x, W_in, W_rec, rec_mask, beta, W_out, b_out))
+		H = Wo.shape[0]
+		Hp = padded_width(H)
+		Wi, Wr, M, Wo = _pad_hidden(H, Hp, Wi, Wr, M, Wo)
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=True)
-		ctx.consts = consts
-		ctx.has_rec = Wr is not None
+		ctx.consts, ctx.H, ctx.Hp = consts, H, Hp
 		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], out["Z"])
 		alif = consts.layer_type == _cabi.SNNK_ALIF
-		a = out["a"] if alif else out["V"].new_zeros(())
+		a = out["a"][..., :H] if alif else out["V"].new_zeros(())
 		ctx.mark_non_differentiable(a)
-		return out["y"], out["V"], a, out["Z"]
+		return out["y"], out["V"][..., :H], a, out["Z"][..., :H]
 
 	@staticmethod
 	def backward(ctx, g_y, g_V, g_a, g_Z):
 		xc, Wr, M, be, Wo, V, a, zbits, Z = ctx.saved_tensors
 		if g_y is None:
 			g_y = torch.zeros((V.shape[0], V.shape[1], Wo.shape[1]), dtype=torch.float32, device=V.device)
-		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=_c(g_V), g_Z=_c(g_Z), Z=Z)
+		H, Hp = ctx.H, ctx.Hp
+		g_V, g_Z = _c(g_V), _c(g_Z)
+		if Hp != H:
+			g_V = None if g_V is None else torch.nn.functional.pad(g_V, (0, Hp - H))
+			g_Z = None if g_Z is None else torch.nn.functional.pad(g_Z, (0, Hp - H))
+		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=g_V, g_Z=g_Z, Z=Z)
 		# (consts, x, W_in, W_rec, rec_mask, beta, W_out, b_out); beta gets no gradient -- the threshold input of
 		# the reference's spike function returns None (spike_funcs.py:62/79)
-		return None, None, g["dW_in"], g["dW_rec"], None, None, g["dW_out"], g["db"]
+		return (None, None, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
+			g["dW_out"][:H], g["db"])
 
 
 class SpikingSequenceNLL(torch.autograd.Function):
@@ -175,14 +206,18 @@ class SpikingSequenceNLL(torch.autograd.Function):
 	@staticmethod
 	def forward(ctx, consts: LayerConsts, x, labels, W_in, W_rec, rec_mask, beta, W_out, b_out, traces: bool):
 		xc, Wi, Wr, M, be, Wo, bo = (_c(t) for t in (x, W_in, W_rec, rec_mask, beta, W_out, b_out))
+		H = Wo.shape[0]
+		Hp = padded_width(H)
+		Wi, Wr, M, Wo = _pad_hidden(H, Hp, Wi, Wr, M, Wo)
 		need_grad = any(ctx.needs_input_grad)
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=traces or need_grad)
 		loss, logp, g_logits = run_head_nll(out["logits"], labels, want_grad=need_grad)
-		ctx.consts = consts
+		ctx.consts, ctx.H = consts, H
 		if need_grad:
 			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"], out["Z"])
 		empty = logp.new_zeros(())
-		extras = tuple(out[k] if out[k] is not None else empty for k in ("y", "V", "a", "Z"))
+		extras = tuple(
+			(out[k] if k == "y" else out[k][..., :H]) if out[k] is not None else empty for k in ("y", "V", "a", "Z"))
 		ctx.mark_non_differentiable(logp, *extras)
 		return (loss, logp) + extras
 
@@ -191,4 +226,6 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		xc, Wr, M, be, Wo, V, a, zbits, g_logits, tstar, Z = ctx.saved_tensors
 		g = run_backward(
 			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=(g_logits * g_loss).contiguous(), tstar=tstar, Z=Z)
-		return None, None, None, g["dW_in"], g["dW_rec"], None, None, g["dW_out"], g["db"], None
+		H = ctx.H
+		return (None, None, None, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
+			g["dW_out"][:H], g["db"], None)

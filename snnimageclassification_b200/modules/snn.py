@@ -238,8 +238,10 @@ class SNN(torch.nn.Module):
 	def _infer_logits(self, inputs: torch.Tensor) -> torch.Tensor:
 		"""Forward without materialising the hidden traces; the max over time comes out of the kernel."""
 		inputs = self._format_inputs(self._encode_if_needed(inputs))
-		W = tuple(F_._c(w) for w in self._weights())
-		return F_.run_forward(self._consts(), inputs, *W, traces=False)["logits"]
+		Wi, Wr, M, be, Wo, bo = (F_._c(w) for w in self._weights())
+		H = Wo.shape[0]
+		Wi, Wr, M, Wo = F_._pad_hidden(H, F_.padded_width(H), Wi, Wr, M, Wo)
+		return F_.run_forward(self._consts(), inputs, Wi, Wr, M, be, Wo, bo, traces=False)["logits"]
 
 	# ---- prediction heads (reference snn.py:221-259) --------------------------------------------------------------
 	def get_prediction_logits(self, inputs: torch.Tensor, re_outputs_trace: bool = True, re_hidden_states: bool = True):

@@ -167,9 +167,16 @@ class LIFLayer(RNNLayer):
 		zero_out = torch.zeros((H, 1), dtype=torch.float32, device=inputs.device)
 		zero_b = torch.zeros((1,), dtype=torch.float32, device=inputs.device)
 		x = inputs.detach().float().reshape(B, 1, -1).contiguous()
-		out = F_.run_forward(
-			self._snnk_const_cache, x, F_._c(self.forward_weights), F_._c(self.recurrent_weights),
-			F_._c(self.rec_mask), F_._c(self._beta_tensor()), zero_out, zero_b, traces=True, state=state)
+		Hp = F_.padded_width(H)
+		Wi, Wr, M, Wo = F_._pad_hidden(H, Hp, F_._c(self.forward_weights), F_._c(self.recurrent_weights),
+			F_._c(self.rec_mask), zero_out)
+		if Hp != H:
+			state = tuple(torch.nn.functional.pad(F_._c(s_), (0, Hp - H)) for s_ in state)
+		out = F_.run_forward(self._snnk_const_cache, x, Wi, Wr, M, F_._c(self._beta_tensor()), Wo, zero_b, traces=True,
+			state=state)
+		for k in ("V", "a", "Z"):
+			if out[k] is not None:
+				out[k] = out[k][..., :H]
 		return out
 
 	def forward(self, inputs: torch.Tensor, state: Tuple[torch.Tensor, ...] = None):

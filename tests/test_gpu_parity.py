@@ -395,3 +395,75 @@ def test_exec_batch_and_fit_on_synthetic_data(tmp_path):
 	from snnimageclassification_b200 import LoadCheckpointMode
 	hist2 = net.fit(train, train, nb_epochs=3, load_checkpoint_mode=LoadCheckpointMode.LAST_EPOCH, verbose=False)
 	assert len(hist2["train"]) == 3
+
+
+# ---- wide hidden layers (BASELINE configs[3], [4]) and non-power-of-two widths -------------------------------------
+@pytest.mark.parametrize("H,B,T,N,layer,rec", [
+	(256, 6, 10, 64, 1, 1), (512, 5, 9, 40, 0, 1), (1024, 5, 6, 784, 1, 1), (2048, 3, 5, 32, 1, 1), (384, 4, 7, 20, 1, 0)])
+def test_wide_hidden_vs_oracle(H, B, T, N, layer, rec):
+	"""H > 128 goes through recur_gen.cuh: same summation orders, so the fp32 forward is still bit-identical."""
+	O = 10
+	rng = np.random.default_rng(H + B)
+	theta = 0.03 if layer else 1.0
+	W_in = (rng.standard_normal((N, H)) * theta).astype(np.float32)
+	W_rec = (rng.standard_normal((H, H)) * theta / 4).astype(np.float32) if rec else None
+	mask = (1 - np.eye(H)).astype(np.float32) if rec else None
+	W_out = (rng.standard_normal((H, O)) / 8).astype(np.float32)
+	b_out = (rng.standard_normal(O) * 0.1).astype(np.float32)
+	x = (rng.random((B, T, N)) < (0.1 if layer else 0.03)).astype(np.float32)
+	labels = rng.integers(0, O, B)
+	cfg = OracleCfg(B, T, N, H, O, layer_type=layer, surrogate=0, recurrent=rec, alpha=float(np.float32(np.exp(-1 / 20))),
+		rho=float(np.float32(np.exp(-1 / 200))), theta=theta, gamma=0.3 if layer else 1.0,
+		kappa=float(np.float32(np.exp(-1 / 10))), beta=1.6)
+	out, beta = _gpu_forward(cfg, x, W_in, W_rec, mask, W_out, b_out)
+	f = oracle.forward(cfg, x, W_in, W_rec, mask, W_out, b_out)
+	for k in ("I_in", "V", "Z", "y") + (("a",) if layer else ()):
+		assert np.array_equal(npy(out[k]), f[k]), k
+	assert 0.0005 < f["Z"].mean() < 0.999
+	h = oracle.head(f["y"], labels)
+	assert np.array_equal(npy(out["logits"]), h["logits"]) and np.array_equal(npy(out["tstar"]), h["tstar"])
+	loss, logp, g_logits = F_.run_head_nll(out["logits"], cu(labels, torch.int64))
+	gref = oracle.backward(cfg, x, W_rec, mask, W_out, f["V"], f["a"], f["Z"], h["g_y"])
+	for tc in (False, True):
+		c = F_.LayerConsts(cfg.layer_type, cfg.surrogate, bool(cfg.recurrent), cfg.alpha, cfg.rho, cfg.theta, cfg.gamma,
+			cfg.kappa, tensor_core=tc)
+		g = F_.run_backward(c, cu(x), cu(W_rec), cu(mask), beta, cu(W_out), out["V"], out["a"], out["zbits"],
+			g_logits=g_logits, tstar=out["tstar"], Z=out["Z"])
+		assert rel_err(npy(g["gI"]), gref["gI"]) <= 1e-5, tc
+		for k in ("dW_in", "dW_out", "db") + (("dW_rec",) if rec else ()):
+			assert rel_err(npy(g[k]), gref[k]) <= 1e-4, (tc, k)
+	# tensor-core projection on the wide path
+	c = F_.LayerConsts(cfg.layer_type, cfg.surrogate, bool(cfg.recurrent), cfg.alpha, cfg.rho, cfg.theta, cfg.gamma,
+		cfg.kappa, tensor_core=True)
+	o2 = F_.run_forward(c, cu(x), cu(W_in), cu(W_rec), cu(mask), beta, cu(W_out), cu(b_out))
+	assert rel_err(npy(o2["I_in"]), f["I_in"]) <= 1e-5
+
+
+@pytest.mark.parametrize("H", [100, 200, 20])
+def test_hidden_widths_of_the_reference_sweeps(H):
+	"""n_hidden_neurons in {100, 200} (training.py:37) are zero-padded to a supported width inside the glue."""
+	torch.manual_seed(1)
+	net = SNN(40, 10, H, use_recurrent_connection=True, int_time_steps=12, spike_func=SpikeFuncType.FastSigmoid,
+		hidden_layer_type=LayerType.ALIF, device=DEV, learn_beta=False, tensor_core=False)
+	L, R = net.layers["input"], net.layers["readout"]
+	assert tuple(L.forward_weights.shape) == (40, H) and tuple(L.recurrent_weights.shape) == (H, H)
+	port = TorchPortSNN(40, H, 10, 12, layer_type=1, surrogate=0, recurrent=True, seed=0)
+	port.load(npy(L.forward_weights), npy(L.recurrent_weights), npy(R.forward_weights), npy(R.bias_weights), beta=float(L.beta))
+	g = torch.Generator().manual_seed(4)
+	x = (torch.rand(5, 12, 40, generator=g) < 0.2).float()
+	labels = torch.randint(0, 10, (5,), generator=g)
+	net.train()
+	y, hs = net(x)
+	assert tuple(hs["input"][0].shape) == (5, 12, H) and tuple(hs["input"][2].shape) == (5, 12, H)
+	p_out, p_hs = port.forward(x)
+	assert np.array_equal(npy(hs["input"][2]), npy(p_hs["input"][2]))
+	assert rel_err(npy(y), npy(p_out)) <= 1e-5
+	loss = net.batch_loss(x, labels)
+	net.zero_grad()
+	loss.backward()
+	p_loss = port.exec_batch(x, labels)
+	assert abs(loss.item() - p_loss) <= 1e-5 * abs(p_loss)
+	assert tuple(L.forward_weights.grad.shape) == (40, H)
+	for mine, theirs in ((L.forward_weights, port.W_in), (L.recurrent_weights, port.W_rec), (R.forward_weights, port.W_out),
+			(R.bias_weights, port.b_out)):
+		assert rel_err(npy(mine.grad), npy(theirs.grad)) <= 1e-4
