@@ -89,7 +89,7 @@ typedef struct SnnkDesc {
 enum {
     SNNK_K_ENCODE = 0, SNNK_K_PROJ = 1, SNNK_K_RECUR_FWD = 2, SNNK_K_HEAD = 3, SNNK_K_RECUR_BWD = 4,
     SNNK_K_REDUCE_OUT = 5, SNNK_K_WGRAD = 6, SNNK_K_REDUCE_W = 7, SNNK_K_PROJ_FALLBACK = 8,
-    SNNK_K_WGRAD_FALLBACK = 9, SNNK_K_COUNT = 10
+    SNNK_K_WGRAD_FALLBACK = 9, SNNK_K_INPUT_GRAD = 10, SNNK_K_COUNT = 11
 };
 
 int snnk_abi_version(void);
@@ -187,6 +187,14 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
                   const int32_t* tstar, const float* g_V, const float* g_Z, float* dW_in,
                   float* dW_rec, float* dW_out, float* db, void* workspace, size_t workspace_bytes,
                   snnk_stream_t stream);
+
+/*
+ * Gradient w.r.t. the layer input, for stacked hidden layers (snn.py:116-128): gX (B,T,N) = gI (B,T,H) @ W_in^T.
+ * MmBackward of spiking_layers.py:163/233 w.r.t. `inputs`; layer l+1 hands gX down as the g_Z seed of layer l.
+ * gI is the gradient w.r.t. the input current that snnk_backward leaves in its workspace (sum of the two tf32
+ * planes in tensor-core mode).
+ */
+int snnk_input_grad(const SnnkDesc* d, const float* gI, const float* W_in, float* gX, snnk_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,7 @@ _SIGNATURES = {
 	"snnk_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(SnnkDesc)]),
 	"snnk_forward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 18 + [ctypes.c_size_t, _p]),
 	"snnk_head_nll": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _p, _p, _p, _p, _p, _p]),
+	"snnk_input_grad": (ctypes.c_int, [ctypes.POINTER(SnnkDesc), _p, _p, _p, _p]),
 	"snnk_backward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 20 + [ctypes.c_size_t, _p]),
 }
 EXPORTS = tuple(_SIGNATURES)
@@ -101,7 +102,7 @@ def lib() -> ctypes.CDLL:
 	return _lib
 
 
-SNNK_K_COUNT = 10
+SNNK_K_COUNT = 11
 
 
 class kernel_profile:

@@ -88,6 +88,70 @@ __global__ void __launch_bounds__(kGemmThreads) k_proj_simt(const float* __restr
     }
 }
 
+// ---- input gradient (stacked hidden layers): gX[r][n] = sum_i gI[r][i] * W_in[n][i] ----------------------------
+// MmBackward of spiking_layers.py:163/233 w.r.t. its input: what layer l+1 hands down to the spikes of layer l.
+// A = gI (M x K, K = H of this layer), W_in is (Nn x K) row-major and used transposed; any Nn (guarded).
+__global__ void __launch_bounds__(kGemmThreads) k_input_grad_simt(const float* __restrict__ A, const float* __restrict__ W_in,
+                                                                 float* __restrict__ C, int M, int K, int Nn)
+{
+    constexpr int BN = 64, TN = BN / 4, TMG = kGemmThreads / TN, TM = kGemmBM / TMG, LDA = kGemmBM + 4;
+    __shared__ __align__(16) float As[kGemmBK][LDA];
+    __shared__ __align__(16) float Bs[kGemmBK][BN];
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
+    const int tn = tid % TN, tm = tid / TN;
+    float acc[TM][4];
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const int arow = tid >> 1, akh = (tid & 1) * 8;
+    for (int k0 = 0; k0 < K; k0 += kGemmBK) {
+        {
+            const int r = r0 + arow;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + akh + j;
+                As[akh + j][arow] = (r < M && k < K) ? __ldg(A + (size_t)r * K + k) : 0.f;
+            }
+        }
+        for (int idx = tid; idx < kGemmBK * BN; idx += kGemmThreads) {
+            const int nn = idx / kGemmBK, kk = idx - nn * kGemmBK;      // k fastest: coalesced along a row of W_in
+            const int k = k0 + kk, n = n0 + nn;
+            Bs[kk][nn] = (k < K && n < Nn) ? __ldg(W_in + (size_t)n * K + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kGemmBK; ++kk) {
+            float av[TM];
+#pragma unroll
+            for (int q = 0; q < TM / 4; ++q) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][tm * TM + 4 * q]);
+                av[4 * q + 0] = a4.x; av[4 * q + 1] = a4.y; av[4 * q + 2] = a4.z; av[4 * q + 3] = a4.w;
+            }
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tn * 4]);
+#pragma unroll
+            for (int a = 0; a < TM; ++a) {
+                acc[a][0] = fmaf(av[a], b4.x, acc[a][0]);
+                acc[a][1] = fmaf(av[a], b4.y, acc[a][1]);
+                acc[a][2] = fmaf(av[a], b4.z, acc[a][2]);
+                acc[a][3] = fmaf(av[a], b4.w, acc[a][3]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < TM; ++a) {
+        const int r = r0 + tm * TM + a;
+        if (r >= M) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int n = n0 + tn * 4 + b;
+            if (n < Nn) C[(size_t)r * Nn + n] = acc[a][b];
+        }
+    }
+}
+
 // ---- weight gradients: split-K  C_part[s][m][n] = sum_{r in split s} A[r][m] * G[r][n] -------------------------
 struct WgradParams {
     int BT, T, N, H;            // rows r = b*T + t

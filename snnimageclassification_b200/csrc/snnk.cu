@@ -441,6 +441,7 @@ const char* snnk_kernel_name(int id)
     case SNNK_K_WGRAD: return "K4 k_wgrad (weight-gradient GEMM)";
     case SNNK_K_PROJ_FALLBACK: return "K1f k_proj_simt (gated fallback)";
     case SNNK_K_WGRAD_FALLBACK: return "K4f k_wgrad_simt (gated fallback)";
+    case SNNK_K_INPUT_GRAD: return "k_input_grad (stacked layers: dL/dx)";
     case SNNK_K_REDUCE_W: return "k_finalize_grads (all partial reductions)";
     default: return "?";
     }
@@ -609,6 +610,21 @@ int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labe
         k_head_nll<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
             B, O, logits, reinterpret_cast<const long long*>(labels), logp, loss, g_logits);
     }
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int snnk_input_grad(const SnnkDesc* d, const float* gI, const float* W_in, float* gX, snnk_stream_t stream)
+{
+    int rc = check_desc(d);
+    if (rc != SNNK_OK) return rc;
+    if (!gI || !W_in || !gX) return SNNK_ERR_ARG;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int M = d->B * d->T;
+    dim3 grid((M + kGemmBM - 1) / kGemmBM, (d->N + 63) / 64);
+    ProfScope ps(SNNK_K_INPUT_GRAD, st);
+    k_input_grad_simt<<<grid, kGemmThreads, 0, st>>>(gI, W_in, gX, M, d->H, d->N);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }

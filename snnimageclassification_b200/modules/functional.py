@@ -149,6 +149,20 @@ def run_backward(
 	return dict(dW_in=dW_in, dW_rec=dW_rec, dW_out=dW_out, db=db, gI=gI)
 
 
+def run_input_grad(c: LayerConsts, gI: torch.Tensor, W_in: torch.Tensor) -> torch.Tensor:
+	"""Calls ``snnk_input_grad``: gX (B,T,N) = gI (B,T,H) @ W_in^T  (W_in is (N,H))."""
+	lib = _cabi.lib()
+	B, T, H = gI.shape
+	N = W_in.shape[0]
+	desc = make_desc(c, B, T, N, H, 1, True)
+	gX = torch.empty((B, T, N), dtype=torch.float32, device=gI.device)
+	gI = gI.contiguous()
+	with torch.cuda.device(gI.device):
+		rc = lib.snnk_input_grad(ctypes.byref(desc), _cabi.ptr(gI), _cabi.ptr(W_in), _cabi.ptr(gX), _cabi.stream_ptr())
+	_cabi.check(rc, "snnk_input_grad")
+	return gX
+
+
 def run_head_nll(logits: torch.Tensor, labels: torch.Tensor, want_grad: bool = True):
 	"""Calls ``snnk_head_nll``.  Returns (loss (), logp (B,O), g_logits (B,O) | None)."""
 	lib = _cabi.lib()
@@ -177,6 +191,7 @@ class SpikingSequence(torch.autograd.Function):
 		Wi, Wr, M, Wo = _pad_hidden(H, Hp, Wi, Wr, M, Wo)
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=True)
 		ctx.consts, ctx.H, ctx.Hp = consts, H, Hp
+		ctx.Wi = Wi if ctx.needs_input_grad[1] else None      # stacked layers: the input is the spike trace below
 		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], out["Z"])
 		alif = consts.layer_type == _cabi.SNNK_ALIF
 		a = out["a"][..., :H] if alif else out["V"].new_zeros(())
@@ -196,7 +211,8 @@ class SpikingSequence(torch.autograd.Function):
 		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=g_V, g_Z=g_Z, Z=Z)
 		# (consts, x, W_in, W_rec, rec_mask, beta, W_out, b_out); beta gets no gradient -- the threshold input of
 		# the reference's spike function returns None (spike_funcs.py:62/79)
-		return (None, None, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
+		gX = run_input_grad(ctx.consts, g["gI"], ctx.Wi) if ctx.Wi is not None else None
+		return (None, gX, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
 			g["dW_out"][:H], g["db"])
 
 
@@ -213,6 +229,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=traces or need_grad)
 		loss, logp, g_logits = run_head_nll(out["logits"], labels, want_grad=need_grad)
 		ctx.consts, ctx.H = consts, H
+		ctx.Wi = Wi if ctx.needs_input_grad[1] else None
 		if need_grad:
 			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"], out["Z"])
 		empty = logp.new_zeros(())
@@ -227,5 +244,6 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		g = run_backward(
 			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=(g_logits * g_loss).contiguous(), tstar=tstar, Z=Z)
 		H = ctx.H
-		return (None, None, None, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
+		gX = run_input_grad(ctx.consts, g["gI"], ctx.Wi) if ctx.Wi is not None else None
+		return (None, gX, None, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
 			g["dW_out"][:H], g["db"], None)

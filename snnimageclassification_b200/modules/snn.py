@@ -198,21 +198,27 @@ class SNN(torch.nn.Module):
 		return inputs
 
 	# ---- the fused path -------------------------------------------------------------------------------------------
+	def _hidden_chain(self) -> List[Tuple[str, LIFLayer]]:
+		"""The spiking layers in execution order ("input", "hidden_0", ...; reference snn.py:103-128)."""
+		if not self.n_hidden_neurons:
+			raise NotImplementedError(
+				"the B200 path needs at least one hidden spiking layer (n_hidden_neurons=None is a readout-only model, "
+				"which no published configuration of the reference uses); there is no eager fallback")
+		chain = [(name, layer) for name, layer in self.layers.items() if name != "readout"]
+		for name, layer in chain:
+			if isinstance(layer, IzhikevichLayer) or not isinstance(layer, LIFLayer):
+				raise NotImplementedError(
+					f"{type(layer).__name__} is not supported by the B200 path (only LIF and ALIF are fused)")
+		return chain
+
 	def _hot_layers(self) -> Tuple[LIFLayer, ReadoutLayer]:
-		if len(self.n_hidden_neurons) != 1:
-			raise NotImplementedError(
-				"the B200 path fuses exactly one hidden spiking layer with the readout (every published configuration "
-				f"of the reference); n_hidden_neurons={list(self.n_hidden_neurons)} is not supported yet and there is "
-				"no eager fallback")
-		layer = self.layers["input"]
-		if isinstance(layer, IzhikevichLayer) or not isinstance(layer, LIFLayer):
-			raise NotImplementedError(
-				f"{type(layer).__name__} is not supported by the B200 path (only LIF and ALIF are fused)")
-		return layer, self.layers["readout"]
+		"""(last hidden layer, readout): the pair the fused recurrence + readout kernel runs."""
+		return self._hidden_chain()[-1][1], self.layers["readout"]
 
 	def refresh_constants(self):
 		"""Re-reads alpha/rho/theta/gamma/kappa from the layers (call after editing them by hand)."""
 		self._consts_cache = None
+		self._inner_cache = {}
 
 	def _consts(self) -> F_.LayerConsts:
 		if self._consts_cache is None:
@@ -220,28 +226,54 @@ class SNN(torch.nn.Module):
 			self._consts_cache = layer.snnk_consts(kappa=float(readout.kappa), tensor_core=self.tensor_core)
 		return self._consts_cache
 
+	@staticmethod
+	def _layer_weights(layer: LIFLayer):
+		beta = layer.beta.reshape(1) if isinstance(layer, ALIFLayer) else None
+		return layer.forward_weights, layer.recurrent_weights, layer.rec_mask, beta
+
 	def _weights(self):
 		layer, readout = self._hot_layers()
-		beta = layer.beta.reshape(1) if isinstance(layer, ALIFLayer) else None
-		return (
-			layer.forward_weights, layer.recurrent_weights, layer.rec_mask, beta, readout.forward_weights,
-			readout.bias_weights)
+		return (*self._layer_weights(layer), readout.forward_weights, readout.bias_weights)
+
+	def _run_inner_layers(self, x: torch.Tensor, hidden: Optional[dict] = None) -> torch.Tensor:
+		"""Stacked hidden layers (snn.py:116-128): every layer but the last runs the same fused kernels with a null
+		readout; its spike trace is the input of the next layer.  (Time-then-layer, as the reference loops, and
+		layer-then-time, as here, are the same computation: layer l at step t only sees layer l-1 at step t.)"""
+		if not hasattr(self, "_inner_cache"):
+			self._inner_cache = {}
+		for name, layer in self._hidden_chain()[:-1]:
+			if name not in self._inner_cache:
+				H = layer.output_size
+				self._inner_cache[name] = (
+					layer.snnk_consts(kappa=0.0, tensor_core=self.tensor_core),
+					torch.zeros((H, 1), dtype=torch.float32, device=self.device),
+					torch.zeros((1,), dtype=torch.float32, device=self.device))
+			consts, w0, b0 = self._inner_cache[name]
+			_, V, a, Z = F_.SpikingSequence.apply(consts, x, *self._layer_weights(layer), w0, b0)
+			if hidden is not None:
+				hidden[name] = (V, a, Z) if isinstance(layer, ALIFLayer) else (V, Z)
+			x = Z
+		return x
 
 	def forward(self, inputs):
-		"""-> (outputs_trace (B,T,O), {"input": (V,[a],Z), "readout": (y,)}), as reference snn.py:201-219."""
+		"""-> (outputs_trace (B,T,O), {"input": (V,[a],Z), ["hidden_i": ...], "readout": (y,)}), as snn.py:201-219."""
 		layer, _ = self._hot_layers()
 		inputs = self._format_inputs(self._encode_if_needed(inputs.to(self.device, non_blocking=True)))
+		hidden_states = {}
+		inputs = self._run_inner_layers(inputs, hidden_states)
 		y, V, a, Z = F_.SpikingSequence.apply(self._consts(), inputs, *self._weights())
-		hidden = (V, a, Z) if isinstance(layer, ALIFLayer) else (V, Z)
-		return y, {"input": hidden, "readout": (y,)}
+		hidden_states[self._hidden_chain()[-1][0]] = (V, a, Z) if isinstance(layer, ALIFLayer) else (V, Z)
+		hidden_states["readout"] = (y,)
+		return y, hidden_states
 
 	def _infer_logits(self, inputs: torch.Tensor) -> torch.Tensor:
-		"""Forward without materialising the hidden traces; the max over time comes out of the kernel."""
+		"""Forward without materialising the last layer's traces; the max over time comes out of the kernel."""
 		inputs = self._format_inputs(self._encode_if_needed(inputs))
+		inputs = self._run_inner_layers(inputs)
 		Wi, Wr, M, be, Wo, bo = (F_._c(w) for w in self._weights())
 		H = Wo.shape[0]
 		Wi, Wr, M, Wo = F_._pad_hidden(H, F_.padded_width(H), Wi, Wr, M, Wo)
-		return F_.run_forward(self._consts(), inputs, Wi, Wr, M, be, Wo, bo, traces=False)["logits"]
+		return F_.run_forward(self._consts(), F_._c(inputs), Wi, Wr, M, be, Wo, bo, traces=False)["logits"]
 
 	# ---- prediction heads (reference snn.py:221-259) --------------------------------------------------------------
 	def get_prediction_logits(self, inputs: torch.Tensor, re_outputs_trace: bool = True, re_hidden_states: bool = True):
@@ -381,7 +413,7 @@ class SNN(torch.nn.Module):
 		x = self._encode_if_needed(x_batch.to(self.device, non_blocking=True))
 		y = y_batch.to(self.device, non_blocking=True)
 		if criterion is None or self._is_plain_nll(criterion):
-			x = self._format_inputs(x)
+			x = self._run_inner_layers(self._format_inputs(x))
 			loss, *_ = F_.SpikingSequenceNLL.apply(self._consts(), x, y.long(), *self._weights(), traces)
 			return loss
 		log_p_y, out, h_states = self.get_prediction_log_proba(x, re_outputs_trace=True, re_hidden_states=True)

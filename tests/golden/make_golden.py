@@ -165,10 +165,59 @@ def init_fixture():
 	print("init fixture done")
 
 
-if __name__ == "__main__":
+def main():
 	encoder_fixture()
 	dynamics_fixture()
 	init_fixture()
+	stacked_fixture()
 	for f in sorted(os.listdir(HERE)):
 		if f.endswith(".npz"):
 			print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KB")
+
+
+def stacked_fixture():
+	"""Two stacked hidden layers (snn.py:116-128; train.py:72 shows the list form): state_dict, traces, loss, grads."""
+	out = {}
+	names = []
+	for name, layer, widths, rec in (("lif_32_64", LayerType.LIF, [32, 64], True), ("alif_64_32", LayerType.ALIF, [64, 32], True),
+			("alif_100_32_nonrec", LayerType.ALIF, [100, 32], False)):
+		torch.manual_seed(11)
+		kw = dict(learn_beta=False) if layer == LayerType.ALIF else {}
+		net = SNN(48, 10, widths, use_recurrent_connection=rec, int_time_steps=14, spike_func=SpikeFuncType.FastSigmoid,
+			hidden_layer_type=layer, device=torch.device("cpu"), **kw)
+		g = torch.Generator().manual_seed(3)
+		x = (torch.rand(4, 14, 48, generator=g) < (0.3 if layer == LayerType.ALIF else 0.12)).float()
+		labels = torch.randint(0, 10, (4,), generator=g)
+		net.train()
+		logp, y, hs = net.get_prediction_log_proba(x, re_outputs_trace=True, re_hidden_states=True)
+		loss = torch.nn.NLLLoss()(logp, labels)
+		net.zero_grad()
+		loss.backward()
+		out[f"{name}/x"] = x.numpy().astype(np.uint8)
+		out[f"{name}/labels"] = labels.numpy()
+		out[f"{name}/y"] = y.detach().numpy()
+		out[f"{name}/loss"] = np.float32(loss.item())
+		out[f"{name}/widths"] = np.array(widths)
+		out[f"{name}/flags"] = np.array([int(layer == LayerType.ALIF), int(rec)])
+		for lname, tr in hs.items():
+			out[f"{name}/Z/{lname}"] = tr[-1].detach().numpy().astype(np.float32)
+			out[f"{name}/V/{lname}"] = tr[0].detach().numpy()
+		keys = []
+		for k, v in net.state_dict().items():
+			out[f"{name}/sd/{k}"] = v.numpy()
+			keys.append(k)
+		out[f"{name}/keys"] = np.array(keys)
+		for k, p in net.named_parameters():
+			if p.grad is not None:
+				out[f"{name}/grad/{k}"] = p.grad.numpy()
+		names.append(name)
+		print(name, "mean rates", {k: float(v[-1].mean()) for k, v in hs.items() if k != "readout"})
+	out["names"] = np.array(names)
+	np.savez_compressed(os.path.join(HERE, "stacked_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+	if os.environ.get("SNN_GOLDEN_ONLY") == "stacked":
+		stacked_fixture()
+	else:
+		main()

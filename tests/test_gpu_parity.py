@@ -467,3 +467,47 @@ def test_hidden_widths_of_the_reference_sweeps(H):
 	for mine, theirs in ((L.forward_weights, port.W_in), (L.recurrent_weights, port.W_rec), (R.forward_weights, port.W_out),
 			(R.bias_weights, port.b_out)):
 		assert rel_err(npy(mine.grad), npy(theirs.grad)) <= 1e-4
+
+
+# ---- stacked hidden layers: the reference's own state_dict loaded into the B200 SNN ------------------------------------
+STACKED = [str(n) for n in load("stacked_golden.npz")["names"]]
+
+
+@pytest.mark.parametrize("name", STACKED)
+@pytest.mark.parametrize("tc", [False, True])
+def test_stacked_hidden_layers_vs_reference(name, tc):
+	"""n_hidden_neurons=[h1, h2] (snn.py:116-128): load the reference's checkpoint tensors by name, run the same
+	batch, compare every layer's raster, the output trace, the loss and every parameter gradient with the reference."""
+	z = load("stacked_golden.npz")
+	d = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "/")}
+	alif, rec = (int(v) for v in d["flags"])
+	widths = [int(v) for v in d["widths"]]
+	kw = dict(learn_beta=False) if alif else {}
+	net = SNN(48, 10, widths, use_recurrent_connection=bool(rec), int_time_steps=14, spike_func=SpikeFuncType.FastSigmoid,
+		hidden_layer_type=LayerType.ALIF if alif else LayerType.LIF, device=DEV, tensor_core=tc, **kw)
+	assert list(net.state_dict().keys()) == [str(k) for k in d["keys"]]
+	net.load_state_dict({str(k): torch.from_numpy(d[f"sd/{k}"]) for k in d["keys"]}, strict=True)
+	x = torch.from_numpy(d["x"].astype(np.float32))
+	labels = torch.from_numpy(d["labels"])
+	net.train()
+	logp, y, hs = net.get_prediction_log_proba(x, re_outputs_trace=True, re_hidden_states=True)
+	assert list(hs.keys()) == ["input", "hidden_0", "readout"]
+	for lname in ("input", "hidden_0"):
+		assert np.array_equal(npy(hs[lname][-1]), d[f"Z/{lname}"]), lname          # rasters identical
+		assert rel_err(npy(hs[lname][0]), d[f"V/{lname}"]) <= 1e-5, lname
+	assert rel_err(npy(y), d["y"]) <= 1e-5
+	loss = torch.nn.functional.nll_loss(logp, labels.to(DEV))
+	assert abs(loss.item() - float(d["loss"])) <= 1e-5 * abs(float(d["loss"]))
+	net.zero_grad()
+	loss.backward()
+	generic = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+	net.zero_grad()
+	net.batch_loss(x, labels).backward()                                              # fused head on the last layer
+	for k, p in net.named_parameters():
+		assert p.grad is not None, k
+		assert rel_err(npy(p.grad), d[f"grad/{k}"]) <= 1e-4, k
+		assert rel_err(npy(generic[k]), d[f"grad/{k}"]) <= 1e-4, k
+	with torch.no_grad():
+		net.eval()
+		lg = net.get_prediction_logits(x, re_outputs_trace=False, re_hidden_states=False)
+	assert rel_err(npy(lg), d["y"].max(axis=1)) <= 1e-5
