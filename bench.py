@@ -141,7 +141,7 @@ def main():
 		return
 
 	import torch.distributed as dist
-	from snnimageclassification_b200 import SNN, LayerType, SpikeFuncType, ToSpikes, _cabi
+	from snnimageclassification_b200 import SNN, FusedAdam, LayerType, SpikeFuncType, ToSpikes, _cabi
 	dev = torch.device("cuda", local_rank)
 	torch.cuda.set_device(dev)
 	_cabi.require_b200(dev)          # fails loudly: no fallback
@@ -152,7 +152,7 @@ def main():
 	enc = ToSpikes(T, use_periods=True)      # production encoder settings (tau = 0.02, datasets.py:21)
 	net = SNN(N, O, H, use_recurrent_connection=True, int_time_steps=T, spike_func=SpikeFuncType.FastSigmoid,
 		hidden_layer_type=LayerType.ALIF, device=dev, learn_beta=True, input_encoder=enc)
-	opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, fused=True, capturable=True)
+	opt = FusedAdam(net.parameters(), lr=1e-3, weight_decay=1e-5)    # torch.optim.Adam semantics, one libsnnk launch
 	crit = torch.nn.NLLLoss()
 	net.train()
 
@@ -259,7 +259,7 @@ def main():
 		"vs_baseline": None, "dtype": "f32", "data": "synthetic",
 		"config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
 			"l2": f"{N_POOL} rotating input batches ({N_POOL * B_PER_GPU * T * N * 4 >> 20} MiB) > 126 MB L2",
-			"optimizer": "Adam(lr=1e-3, weight_decay=1e-5), fused+capturable", "launch": "one CUDA graph per step"},
+			"optimizer": "Adam(lr=1e-3, weight_decay=1e-5) as snnk_adam_step", "launch": "one CUDA graph per step"},
 		"clocks": clocks,
 		"e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
 			"ms_per_step": ms_e2e / args.steps, "input": "pinned host images (B,784) fp32 + labels; GPU to_spikes",

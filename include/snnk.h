@@ -89,7 +89,7 @@ typedef struct SnnkDesc {
 enum {
     SNNK_K_ENCODE = 0, SNNK_K_PROJ = 1, SNNK_K_RECUR_FWD = 2, SNNK_K_HEAD = 3, SNNK_K_RECUR_BWD = 4,
     SNNK_K_REDUCE_OUT = 5, SNNK_K_WGRAD = 6, SNNK_K_REDUCE_W = 7, SNNK_K_PROJ_FALLBACK = 8,
-    SNNK_K_WGRAD_FALLBACK = 9, SNNK_K_INPUT_GRAD = 10, SNNK_K_COUNT = 11
+    SNNK_K_WGRAD_FALLBACK = 9, SNNK_K_INPUT_GRAD = 10, SNNK_K_ADAM = 11, SNNK_K_COUNT = 12
 };
 
 int snnk_abi_version(void);
@@ -171,8 +171,9 @@ int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labe
  * Reverse-time BPTT.  Replaces autograd's sweep for batch_loss.backward() (snn.py:413) over the graph
  * built by the forward loop, with the surrogate derivatives of spike_funcs.py:59-62 / :75-79.
  * Gradient seeds: either g_y (B,T,O) dense w.r.t. the output trace, or -- the fused-head form --
- * g_logits (B,O) with tstar (B,O) (the gradient lands on y[b,tstar[b,o],o]).  Exactly one of the
- * two forms must be given.  g_V, g_Z (B,T,H) are optional extra seeds on the hidden traces.
+ * g_logits (B,O) with tstar (B,O) (the gradient lands on y[b,tstar[b,o],o]), optionally multiplied by
+ * the device scalar g_scale (dL/dloss handed in by autograd; NULL = 1).  Exactly one of the two forms
+ * must be given.  g_V, g_Z (B,T,H) are optional extra seeds on the hidden traces.
  * V, a (ALIF), Z (B,T,H) and zbits are the traces the forward wrote (Z, the fp32 spike trace, is read by the
  * tensor-core weight-gradient GEMM only and may be NULL without SNNK_F_TENSOR_CORE).
  * Outputs: dW_in (N,H), dW_rec (H,H, masked; NULL iff !recurrent), dW_out (H,O), db (O); they are
@@ -184,9 +185,19 @@ int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labe
 int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const float* rec_mask,
                   const float* beta, const float* W_out, const float* Z0, const float* V,
                   const float* a, const float* Z, const uint32_t* zbits, const float* g_y, const float* g_logits,
-                  const int32_t* tstar, const float* g_V, const float* g_Z, float* dW_in,
+                  const int32_t* tstar, const float* g_scale, const float* g_V, const float* g_Z, float* dW_in,
                   float* dW_rec, float* dW_out, float* db, void* workspace, size_t workspace_bytes,
                   snnk_stream_t stream);
+
+/*
+ * Optimizer step of SNN._exec_batch (snn.py:414) for the reference's default optimizer, Adam with L2 weight decay
+ * (snn.py:299): torch.optim.Adam semantics (no amsgrad) over `count` <= 16 tensors in one launch.  params, grads,
+ * exp_avg, exp_avg_sq, steps are HOST arrays of device pointers; steps[k] is the float32 device scalar torch keeps
+ * per parameter when the optimizer is capturable (incremented here).  Graph-capturable.
+ */
+int snnk_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, float* const* steps, const int64_t* numel, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, snnk_stream_t stream);
 
 /*
  * Gradient w.r.t. the layer input, for stacked hidden layers (snn.py:116-128): gX (B,T,N) = gI (B,T,H) @ W_in^T.

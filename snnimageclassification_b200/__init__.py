@@ -15,6 +15,7 @@ CPU, eager-PyTorch or Triton fallback: without the built extension or off a B200
 """
 from ._cabi import build_extension  # noqa: F401
 from .datasets.datasets import DatasetId, ToSpikes  # noqa: F401
+from .modules.optim import FusedAdam  # noqa: F401
 from .modules.snn import SNN, LoadCheckpointMode  # noqa: F401
 from .modules.spike_funcs import (  # noqa: F401
 	HeavisidePhiApprox, HeavisideSigmoidApprox, SpikeFuncType, SpikeFuncType2Func, SpikeFunction)

@@ -77,7 +77,9 @@ _SIGNATURES = {
 	"snnk_forward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 18 + [ctypes.c_size_t, _p]),
 	"snnk_head_nll": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _p, _p, _p, _p, _p, _p]),
 	"snnk_input_grad": (ctypes.c_int, [ctypes.POINTER(SnnkDesc), _p, _p, _p, _p]),
-	"snnk_backward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 20 + [ctypes.c_size_t, _p]),
+	"snnk_backward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 21 + [ctypes.c_size_t, _p]),
+	"snnk_adam_step": (ctypes.c_int, [ctypes.c_int32, _p, _p, _p, _p, _p, _p, ctypes.c_float, ctypes.c_float,
+		ctypes.c_float, ctypes.c_float, ctypes.c_float, _p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
@@ -102,7 +104,7 @@ def lib() -> ctypes.CDLL:
 	return _lib
 
 
-SNNK_K_COUNT = 11
+SNNK_K_COUNT = 12
 
 
 class kernel_profile:

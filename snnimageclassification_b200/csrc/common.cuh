@@ -34,6 +34,7 @@ struct BwdParams {
     const float* V; const float* a; const uint32_t* zbits;
     const float* g_y;                               // (B,T,O) dense seeds, or null
     const float* g_logits; const int32_t* tstar;    // (B,O) sparse seeds, or null
+    const float* g_scale;                           // device scalar multiplying the sparse seeds (dL/dloss), or null
     const float* g_V; const float* g_Z;             // optional (B,T,H) seeds
     float* gI;          // (B,T,H)
     float* gI_lo;       // (B,T,H) or null: when set, gI receives trunc_tf32(gI) and gI_lo the exact remainder

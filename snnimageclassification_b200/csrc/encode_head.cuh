@@ -115,4 +115,43 @@ __global__ void __launch_bounds__(256) k_head_nll(int B, int O, const float* __r
     }
 }
 
+// ---- optimizer step of SNN._exec_batch (snn.py:414; the reference's default is Adam(lr, weight_decay=1e-5), :299) -----
+// torch.optim.Adam (no amsgrad, L2 weight decay) for up to kAdamMaxTensors parameter tensors in ONE launch; the
+// per-tensor step counters live on the device (float32, as torch keeps them when capturable) so the launch can sit
+// inside a captured CUDA graph.  Tensors whose gradient is absent (the never-trained beta) are simply not listed.
+constexpr int kAdamMaxTensors = 16;
+struct AdamTensors {
+    float* p[kAdamMaxTensors]; const float* g[kAdamMaxTensors]; float* m[kAdamMaxTensors]; float* v[kAdamMaxTensors];
+    float* step[kAdamMaxTensors]; long long n[kAdamMaxTensors]; long long start[kAdamMaxTensors + 1];
+    int count;
+};
+
+__global__ void __launch_bounds__(256) k_adam_step(const AdamTensors t, float lr, float beta1, float beta2, float eps,
+                                                  float weight_decay)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= t.start[t.count]) return;
+    int k = 0;
+    while (e >= t.start[k + 1]) ++k;
+    const long long i = e - t.start[k];
+    const float step = *t.step[k] + 1.0f;           // every thread reads the old counter; thread 0 of the tensor bumps it last
+    float g = t.g[k][i];
+    const float p = t.p[k][i];
+    g = fmaf(weight_decay, p, g);
+    const float m = fmaf(1.0f - beta1, g - t.m[k][i], t.m[k][i]);
+    const float v = fmaf(1.0f - beta2, g * g, beta2 * t.v[k][i]);
+    t.m[k][i] = m;
+    t.v[k][i] = v;
+    const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
+    const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+    t.p[k][i] = p - (lr / bc1) * (m / denom);
+}
+
+// bumps the step counters after k_adam_step has read them (separate tiny launch: no intra-grid ordering needed)
+__global__ void k_adam_bump(const AdamTensors t)
+{
+    const int k = threadIdx.x;
+    if (k < t.count) *t.step[k] += 1.0f;
+}
+
 }  // namespace snnk

@@ -231,11 +231,12 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_bwd_gen(const BwdParam
             if (b0 + r < B) s_gy[(r * T + t) * kOMax + c] = __ldg(p.g_y + (size_t)(b0 + r) * T * O + rem);
         }
     } else {
+        const float scale = p.g_scale ? __ldg(p.g_scale) : 1.0f;
         for (int idx = tid; idx < R * O; idx += BD) {
             const int r = idx / O, c = idx - r * O;
             if (b0 + r < B) {
                 const int ts = __ldg(p.tstar + (size_t)(b0 + r) * O + c);
-                s_gy[(r * T + ts) * kOMax + c] = __ldg(p.g_logits + (size_t)(b0 + r) * O + c);
+                s_gy[(r * T + ts) * kOMax + c] = __fmul_rn(__ldg(p.g_logits + (size_t)(b0 + r) * O + c), scale);
             }
         }
     }

@@ -442,6 +442,7 @@ const char* snnk_kernel_name(int id)
     case SNNK_K_PROJ_FALLBACK: return "K1f k_proj_simt (gated fallback)";
     case SNNK_K_WGRAD_FALLBACK: return "K4f k_wgrad_simt (gated fallback)";
     case SNNK_K_INPUT_GRAD: return "k_input_grad (stacked layers: dL/dx)";
+    case SNNK_K_ADAM: return "k_adam_step (optimizer)";
     case SNNK_K_REDUCE_W: return "k_finalize_grads (all partial reductions)";
     default: return "?";
     }
@@ -614,6 +615,31 @@ int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labe
     return SNNK_OK;
 }
 
+int snnk_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, float* const* steps, const int64_t* numel, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, snnk_stream_t stream)
+{
+    if (count < 0 || count > kAdamMaxTensors) return SNNK_ERR_SHAPE;
+    if (count == 0) return SNNK_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !steps || !numel) return SNNK_ERR_ARG;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    AdamTensors t{};
+    t.count = count;
+    long long total = 0;
+    for (int k = 0; k < count; ++k) {
+        if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k] || !steps[k] || numel[k] < 0) return SNNK_ERR_ARG;
+        t.p[k] = params[k]; t.g[k] = grads[k]; t.m[k] = exp_avg[k]; t.v[k] = exp_avg_sq[k]; t.step[k] = steps[k];
+        t.n[k] = numel[k]; t.start[k] = total; total += numel[k];
+    }
+    t.start[count] = total;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ProfScope ps(SNNK_K_ADAM, st);
+    k_adam_step<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t, lr, beta1, beta2, eps, weight_decay);
+    k_adam_bump<<<1, 32, 0, st>>>(t);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
 int snnk_input_grad(const SnnkDesc* d, const float* gI, const float* W_in, float* gX, snnk_stream_t stream)
 {
     int rc = check_desc(d);
@@ -631,8 +657,8 @@ int snnk_input_grad(const SnnkDesc* d, const float* gI, const float* W_in, float
 
 int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const float* rec_mask, const float* beta,
                   const float* W_out, const float* Z0, const float* V, const float* a, const float* Z,
-                  const uint32_t* zbits, const float* g_y, const float* g_logits, const int32_t* tstar, const float* g_V,
-                  const float* g_Z, float* dW_in, float* dW_rec, float* dW_out, float* db, void* workspace,
+                  const uint32_t* zbits, const float* g_y, const float* g_logits, const int32_t* tstar, const float* g_scale,
+                  const float* g_V, const float* g_Z, float* dW_in, float* dW_rec, float* dW_out, float* db, void* workspace,
                   size_t workspace_bytes, snnk_stream_t stream)
 {
     int rc = check_desc(d);
@@ -668,7 +694,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     bp.alpha = d->alpha; bp.theta = d->theta; bp.gamma = d->gamma; bp.kappa = d->kappa;
     bp.W_effT = W_effT; bp.beta = beta; bp.W_out = W_out; bp.Z0 = Z0;
     bp.V = V; bp.a = a; bp.zbits = zbits; bp.g_y = g_y; bp.g_logits = dense ? nullptr : g_logits;
-    bp.tstar = dense ? nullptr : tstar; bp.g_V = g_V; bp.g_Z = g_Z;
+    bp.tstar = dense ? nullptr : tstar; bp.g_scale = g_scale; bp.g_V = g_V; bp.g_Z = g_Z;
     float* gI_lo = pl.tc ? reinterpret_cast<float*>(ws + pl.off_gIlo) : nullptr;
     bp.gI = gI; bp.gI_lo = gI_lo; bp.part_wout = pwout; bp.part_db = pdb;
     if (pl.wide) {

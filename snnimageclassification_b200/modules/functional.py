@@ -120,9 +120,10 @@ def run_forward(
 
 def run_backward(
 		c: LayerConsts, x, W_rec, rec_mask, beta, W_out, V, a, zbits, g_y=None, g_logits=None, tstar=None,
-		g_V=None, g_Z=None, Z0=None, Z=None,
+		g_V=None, g_Z=None, Z0=None, Z=None, g_scale=None,
 ):
-	"""Calls ``snnk_backward``.  Returns dict(dW_in, dW_rec, dW_out, db, gI)."""
+	"""Calls ``snnk_backward``.  Returns dict(dW_in, dW_rec, dW_out, db, gI) -- ``gI`` is a zero-argument callable
+	(the tensor-core mode stores it as two planes; summing them is only worth it when somebody asks)."""
 	lib = _cabi.lib()
 	B, T, N = x.shape
 	H, O = W_out.shape
@@ -138,14 +139,18 @@ def run_backward(
 		rc = lib.snnk_backward(
 			ctypes.byref(desc), _cabi.ptr(x), _cabi.ptr(W_rec), _cabi.ptr(rec_mask), _cabi.ptr(beta),
 			_cabi.ptr(W_out), _cabi.ptr(Z0), _cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(g_y),
-			_cabi.ptr(g_logits), _cabi.ptr(tstar), _cabi.ptr(g_V), _cabi.ptr(g_Z), _cabi.ptr(dW_in),
+			_cabi.ptr(g_logits), _cabi.ptr(tstar), _cabi.ptr(g_scale), _cabi.ptr(g_V), _cabi.ptr(g_Z), _cabi.ptr(dW_in),
 			_cabi.ptr(dW_rec), _cabi.ptr(dW_out), _cabi.ptr(db), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr())
 	_cabi.check(rc, "snnk_backward")
 	n = B * T * H * 4
-	gI = ws[:n].view(torch.float32).view(B, T, H)
-	if c.tensor_core and N % 4 == 0:   # stored as two tf32 planes (high, exact remainder); see include/snnk.h
+	planes = c.tensor_core and N % 4 == 0   # stored as two tf32 planes (high, exact remainder); see include/snnk.h
+
+	def gI():
+		hi = ws[:n].view(torch.float32).view(B, T, H)
+		if not planes:
+			return hi
 		off = (n + 255) // 256 * 256
-		gI = gI + ws[off: off + n].view(torch.float32).view(B, T, H)
+		return hi + ws[off: off + n].view(torch.float32).view(B, T, H)
 	return dict(dW_in=dW_in, dW_rec=dW_rec, dW_out=dW_out, db=db, gI=gI)
 
 
@@ -191,6 +196,7 @@ class SpikingSequence(torch.autograd.Function):
 		Wi, Wr, M, Wo = _pad_hidden(H, Hp, Wi, Wr, M, Wo)
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=True)
 		ctx.consts, ctx.H, ctx.Hp = consts, H, Hp
+		ctx.set_materialize_grads(False)                     # absent seeds stay None instead of (B,T,H) zero fills
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None      # stacked layers: the input is the spike trace below
 		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], out["Z"])
 		alif = consts.layer_type == _cabi.SNNK_ALIF
@@ -211,7 +217,7 @@ class SpikingSequence(torch.autograd.Function):
 		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=g_V, g_Z=g_Z, Z=Z)
 		# (consts, x, W_in, W_rec, rec_mask, beta, W_out, b_out); beta gets no gradient -- the threshold input of
 		# the reference's spike function returns None (spike_funcs.py:62/79)
-		gX = run_input_grad(ctx.consts, g["gI"], ctx.Wi) if ctx.Wi is not None else None
+		gX = run_input_grad(ctx.consts, g["gI"](), ctx.Wi) if ctx.Wi is not None else None
 		return (None, gX, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
 			g["dW_out"][:H], g["db"])
 
@@ -229,6 +235,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=traces or need_grad)
 		loss, logp, g_logits = run_head_nll(out["logits"], labels, want_grad=need_grad)
 		ctx.consts, ctx.H = consts, H
+		ctx.set_materialize_grads(False)
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None
 		if need_grad:
 			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"], out["Z"])
@@ -241,9 +248,12 @@ class SpikingSequenceNLL(torch.autograd.Function):
 	@staticmethod
 	def backward(ctx, g_loss, *_):
 		xc, Wr, M, be, Wo, V, a, zbits, g_logits, tstar, Z = ctx.saved_tensors
+		if g_loss is None:
+			return (None,) * 10
 		g = run_backward(
-			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=(g_logits * g_loss).contiguous(), tstar=tstar, Z=Z)
+			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=g_logits, tstar=tstar, Z=Z,
+			g_scale=g_loss.detach().float().reshape(1))
 		H = ctx.H
-		gX = run_input_grad(ctx.consts, g["gI"], ctx.Wi) if ctx.Wi is not None else None
+		gX = run_input_grad(ctx.consts, g["gI"](), ctx.Wi) if ctx.Wi is not None else None
 		return (None, gX, None, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
 			g["dW_out"][:H], g["db"], None)

@@ -335,9 +335,12 @@ class SNN(torch.nn.Module):
 			criterion = nn.NLLLoss()
 		if optimizer is None:
 			# same hyper-parameters as the reference (snn.py:299); on the GPU the multi-tensor capturable variant is
-			# used so that the step can live inside the captured training graph
-			extra = dict(fused=True, capturable=True) if self.device.type == "cuda" else {}
-			optimizer = torch.optim.Adam(self.parameters(), lr=lr, weight_decay=1e-5, **extra)
+			# (libsnnk's one-launch step) is used so that the step can live inside the captured training graph
+			if self.device.type == "cuda":
+				from .optim import FusedAdam
+				optimizer = FusedAdam(self.parameters(), lr=lr, weight_decay=1e-5)
+			else:
+				optimizer = torch.optim.Adam(self.parameters(), lr=lr, weight_decay=1e-5)
 
 		start_epoch = 0
 		if load_checkpoint_mode is None:

@@ -163,7 +163,7 @@ def test_forward_backward_vs_reference_and_oracle(name):
 		kw = dict(g_logits=g_logits, tstar=out["tstar"]) if mode == "sparse" else dict(g_y=cu(h["g_y"]))
 		g = F_.run_backward(_consts(cfg), cu(x), cu(d.get("W_rec")), cu(d.get("rec_mask")), beta, cu(d["W_out"]),
 			out["V"], out["a"], out["zbits"], **kw)
-		assert rel_err(npy(g["gI"]), gref["gI"]) <= 1e-5, mode
+		assert rel_err(npy(g["gI"]()), gref["gI"]) <= 1e-5, mode
 		for k in ("dW_in", "dW_out", "db") + (("dW_rec",) if cfg.recurrent else ()):
 			assert rel_err(npy(g[k]), d[k]) <= 1e-4, (mode, k)       # vs the reference's autograd
 			assert rel_err(npy(g[k]), gref[k]) <= 1e-5, (mode, k)     # vs the oracle
@@ -198,7 +198,7 @@ def test_baseline_sized_batch_vs_oracle(layer, rec, phi, H):
 	g = F_.run_backward(_consts(cfg), cu(x), cu(W_rec), cu(mask), beta, cu(W_out), out["V"], out["a"], out["zbits"],
 		g_logits=g_logits, tstar=out["tstar"])
 	gref = oracle.backward(cfg, x, W_rec, mask, W_out, f["V"], f["a"], f["Z"], h["g_y"])
-	assert rel_err(npy(g["gI"]), gref["gI"]) <= 1e-5
+	assert rel_err(npy(g["gI"]()), gref["gI"]) <= 1e-5
 	for k in ("dW_in", "dW_out", "db") + (("dW_rec",) if rec else ()):
 		assert rel_err(npy(g[k]), gref[k]) <= 1e-4, k
 	# inference mode (no traces) gives the same logits
@@ -253,7 +253,7 @@ def test_initial_state_and_hidden_trace_seeds():
 		g_y=cu(g_y), g_V=cu(g_V), g_Z=cu(g_Z), Z0=cu(Z0))
 	gref = oracle.backward(cfg, x, W_rec, None, W_out, f["V"], f["a"], f["Z"], g_y, Z0=Z0, g_Vs=g_V, g_Zs=g_Z)
 	for k in ("gI", "dW_in", "dW_rec", "dW_out", "db"):
-		assert rel_err(npy(g[k]), gref[k]) <= 1e-5, k
+		assert rel_err(npy(g[k]() if callable(g[k]) else g[k]), gref[k]) <= 1e-5, k
 
 
 # ---- the reference-facing Python API ---------------------------------------------------------------------------------
@@ -429,7 +429,7 @@ def test_wide_hidden_vs_oracle(H, B, T, N, layer, rec):
 			cfg.kappa, tensor_core=tc)
 		g = F_.run_backward(c, cu(x), cu(W_rec), cu(mask), beta, cu(W_out), out["V"], out["a"], out["zbits"],
 			g_logits=g_logits, tstar=out["tstar"], Z=out["Z"])
-		assert rel_err(npy(g["gI"]), gref["gI"]) <= 1e-5, tc
+		assert rel_err(npy(g["gI"]()), gref["gI"]) <= 1e-5, tc
 		for k in ("dW_in", "dW_out", "db") + (("dW_rec",) if rec else ()):
 			assert rel_err(npy(g[k]), gref[k]) <= 1e-4, (tc, k)
 	# tensor-core projection on the wide path
@@ -511,3 +511,29 @@ def test_stacked_hidden_layers_vs_reference(name, tc):
 		net.eval()
 		lg = net.get_prediction_logits(x, re_outputs_trace=False, re_hidden_states=False)
 	assert rel_err(npy(lg), d["y"].max(axis=1)) <= 1e-5
+
+
+def test_fused_adam_matches_torch_adam():
+	"""snnk_adam_step == torch.optim.Adam(lr, weight_decay=1e-5) (snn.py:299); parameters without gradient are skipped;
+	the state_dict is interchangeable."""
+	from snnimageclassification_b200 import FusedAdam
+	g = torch.Generator().manual_seed(0)
+	shapes = [(784, 128), (128, 128), (), (128, 10), (10,)]
+	ref_p = [torch.randn(s, generator=g).to(DEV).requires_grad_() for s in shapes]
+	my_p = [p.detach().clone().requires_grad_() for p in ref_p]
+	ref = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=1e-5)
+	mine = FusedAdam(my_p, lr=1e-3, weight_decay=1e-5)
+	for it in range(6):
+		for k, (a, b) in enumerate(zip(ref_p, my_p)):
+			if k == 2:
+				continue                      # the never-trained beta: grad stays None
+			gr = torch.randn(a.shape, generator=g).to(DEV) * (10.0 if it == 3 else 1.0)
+			a.grad, b.grad = gr.clone(), gr.clone()
+		ref.step(); mine.step()
+	for a, b in zip(ref_p, my_p):
+		assert rel_err(npy(b), npy(a)) <= 1e-6
+	assert torch.equal(ref_p[2], my_p[2])
+	sd = mine.state_dict()
+	assert float(sd["state"][0]["step"]) == 6.0 and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+	other = torch.optim.Adam([p.detach().clone().requires_grad_() for p in my_p], lr=1e-3, weight_decay=1e-5)
+	other.load_state_dict(sd)                 # checkpoints interchange with the reference's optimizer

@@ -64,7 +64,7 @@ def test_tensor_core_matches_simt(B, T, N, H, rec, layer):
 	loss, logp, gl = F_.run_head_nll(f0["logits"], d["labels"])
 	kw = dict(g_logits=gl, tstar=f0["tstar"])
 	g0, g1 = _bwd(d, consts(False), f0, **kw), _bwd(d, consts(True), f0, **kw)
-	assert torch.equal(g0["gI"], g1["gI"])          # the two tf32 planes of gI sum back to gI exactly
+	assert torch.equal(g0["gI"](), g1["gI"]())          # the two tf32 planes of gI sum back to gI exactly
 	for k in ("dW_in", "dW_out", "db") + (("dW_rec",) if rec else ()):
 		assert rel_err(npy(g1[k]), npy(g0[k])) <= 1e-5, k
 	if rec:

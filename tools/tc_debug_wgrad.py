@@ -20,7 +20,7 @@ def consts(tc): return F_.LayerConsts(1,0,True,0.95,0.99,0.03,0.3,0.9,tensor_cor
 g0 = F_.run_backward(consts(False), x, W_rec, mask, beta, W_out, V, a, zbits, g_y=g_y, Z=Z)
 g1 = F_.run_backward(consts(True), x, W_rec, mask, beta, W_out, V, a, zbits, g_y=g_y, Z=Z)
 torch.cuda.synchronize()
-gI = g0["gI"].double().reshape(B*T, H)
+gI = g0["gI"]().double().reshape(B*T, H)
 exp_in = x.double().reshape(B*T, N).t() @ gI
 Zs = torch.cat([torch.zeros(B,1,H,device=dev), Z[:,:-1]],1).double().reshape(B*T,H)
 exp_rec = (Zs.t() @ gI) * mask.double()
@@ -36,7 +36,7 @@ for name, got, exp in (("dW_in", g1["dW_in"], exp_in), ("dW_rec", g1["dW_rec"], 
 		nzr = (got.abs().sum(1) > 0).nonzero().flatten()[:20].tolist(); nzc = (got.abs().sum(0) > 0).nonzero().flatten()[:20].tolist()
 		print("   nonzero rows", nzr, "cols", nzc)
 
-gI32 = g0["gI"].reshape(B*T, H)
+gI32 = g0["gI"]().reshape(B*T, H)
 hi = (gI32.view(torch.int32) & -8192).view(torch.float32).double()
 lo = gI.double() - hi
 X = x.double().reshape(B*T, N)
