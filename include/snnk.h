@@ -67,6 +67,10 @@ enum {
                                   inputs; the library falls back to the fp32 SIMT GEMM when x is not
                                   exactly representable) */
 
+#define SNNK_F_INPUT_BINARY 0x4u /* the caller guarantees x is exactly {0,1} (its own encoder's output, or the
+                                  spike trace of the layer below): the tensor-core kernels skip their on-device
+                                  exactness check and the gated fp32 fallback launches */
+
 /* Geometry and constants of one hidden spiking layer + leaky readout. */
 typedef struct SnnkDesc {
     int32_t B;          /* batch rows (independent)                           */

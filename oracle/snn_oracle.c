@@ -20,7 +20,7 @@
  * Summation orders (the reference leaves them to the BLAS; we fix them so the
  * CUDA kernels can be compared bit for bit):
  *   - input projection  : ascending k, one accumulator, fmaf
- *   - recurrent matvec  : eight accumulators over k mod 8, fmaf, ((s0+s1)+(s2+s3))+((s4+s5)+(s6+s7))
+ *   - recurrent matvec  : sixteen accumulators over k mod 16, fmaf, balanced tree over adjacent accumulators
  *   - readout matvec    : ascending j, one accumulator
  */
 #include <math.h>
@@ -144,13 +144,17 @@ int snn_oracle_encode_f32(const float* x, int64_t n_items, int64_t n_pix, int32_
 /* :229-243 (ALIF) and :402-408 (readout).                                   */
 /* ------------------------------------------------------------------------ */
 
-static float dot_rec8(const float* w_col, int stride, const float* z, int H)
+static float dot_rec16(const float* w_col, int stride, const float* z, int H)
 {
-    /* sum_k w[k*stride] * z[k], eight accumulators over k mod 8 (what two rounds of the packed FFMA2 hold) */
-    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < H; k += 8)
-        for (int j = 0; j < 8; ++j) s[j] = fmaf(w_col[(k + j) * stride], z[k + j], s[j]);
-    return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    /* sum_k w[k*stride] * z[k]: sixteen accumulators over k mod 16 (the lanes of eight packed FFMA2 registers),
+     * combined as a balanced tree over adjacent accumulators */
+    float s[16];
+    for (int j = 0; j < 16; ++j) s[j] = 0.f;
+    for (int k = 0; k < H; k += 16)
+        for (int j = 0; j < 16; ++j) s[j] = fmaf(w_col[(k + j) * stride], z[k + j], s[j]);
+    float lo = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    float hi = ((s[8] + s[9]) + (s[10] + s[11])) + ((s[12] + s[13]) + (s[14] + s[15]));
+    return lo + hi;
 }
 
 /* x (B,T,N); W_in (N,H); W_rec (H,H) raw, rec_mask (H,H) or NULL (= ones);
@@ -163,7 +167,7 @@ int snn_oracle_forward(const OracleCfg* c, const float* x, const float* W_in, co
                        float* a, float* Z, float* y)
 {
     const int B = c->B, T = c->T, N = c->N, H = c->H, O = c->O;
-    if (H % 8) return -2;
+    if (H % 16) return -2;
     float* Weff = NULL;
     if (c->recurrent) {
         Weff = (float*)malloc(sizeof(float) * (size_t)H * H);
@@ -197,7 +201,7 @@ int snn_oracle_forward(const OracleCfg* c, const float* x, const float* W_in, co
             for (int i = 0; i < H; ++i) {
                 float t1 = c->alpha * vprev[i];                  /* :169/239 */
                 float t2 = t1 + cur[i];
-                float t3 = c->recurrent ? t2 + dot_rec8(Weff + i, H, zprev, H) : t2 + 0.0f;
+                float t3 = c->recurrent ? t2 + dot_rec16(Weff + i, H, zprev, H) : t2 + 0.0f;
                 float v = t3 * (1.0f - zprev[i]);
                 float thr = c->theta;
                 if (c->layer_type == 1) {
@@ -333,7 +337,7 @@ int snn_oracle_backward(const OracleCfg* c, const float* x, const float* W_rec,
             for (int i = 0; i < H; ++i) {
                 float s = 0.f;
                 for (int o = 0; o < O; ++o) s = fmaf(gy[o], W_out[(size_t)i * O + o], s);
-                if (c->recurrent) s += dot_rec8(Weff + (size_t)i * H, 1, gi_next, H);
+                if (c->recurrent) s += dot_rec16(Weff + (size_t)i * H, 1, gi_next, H);
                 if (g_Zs) s += g_Zs[row + i];
                 float thr = c->theta;
                 if (c->layer_type == 1) thr = c->theta + c->beta * a[row + i];

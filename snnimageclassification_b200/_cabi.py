@@ -20,7 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "snnk.h")
 SNNK_LIF, SNNK_ALIF = 0, 1
 SNNK_FAST_SIGMOID, SNNK_PHI = 0, 1
 SNNK_F32, SNNK_F64, SNNK_U8, SNNK_I64 = 0, 1, 2, 3
-SNNK_F_TRACES, SNNK_F_TENSOR_CORE = 0x1, 0x2
+SNNK_F_TRACES, SNNK_F_TENSOR_CORE, SNNK_F_INPUT_BINARY = 0x1, 0x2, 0x4
 
 NVCC_FLAGS = [
 	"-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

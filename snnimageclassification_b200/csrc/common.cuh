@@ -67,24 +67,28 @@ __device__ __forceinline__ float surrogate_grad(int kind, float gamma, float v, 
     return __fmul_rn(__fdiv_rn(gamma, te), r);
 }
 
-// sum_k w[k] * z[k] with eight accumulators over k mod 8 (the order oracle/snn_oracle.c fixes), held as four
-// float2 and advanced with the packed FFMA2 of sm_100: H/2 FMA instructions instead of H.  Each lane of an
-// FFMA2 is an independent IEEE fma, so the result is bit-identical to eight scalar fmaf chains.
+// sum_k w[k] * z[k] with sixteen accumulators over k mod 16 (the order oracle/snn_oracle.c fixes), held as eight
+// float2 and advanced with the packed FFMA2 of sm_100: H/2 FMA instructions instead of H, and eight independent
+// dependency chains per warp so the FMA latency is covered without help from other warps.  Each lane of an FFMA2
+// is an independent IEEE fma, so the result is bit-identical to sixteen scalar fmaf chains.
 template <int H>
-__device__ __forceinline__ float dot_rec8(const float (&w)[H], const float4* __restrict__ zv)
+__device__ __forceinline__ float dot_rec16(const float (&w)[H], const float4* __restrict__ zv)
 {
-    float2 acc[4];
+    float2 acc[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
+    for (int q = 0; q < 8; ++q) acc[q] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < H / 4; ++j) {
         const float4 z = zv[j];
-        const int k = 4 * j, q = 2 * (j & 1);
+        const int k = 4 * j, q = 2 * (j & 3);
         acc[q] = __ffma2_rn(make_float2(w[k], w[k + 1]), make_float2(z.x, z.y), acc[q]);
         acc[q + 1] = __ffma2_rn(make_float2(w[k + 2], w[k + 3]), make_float2(z.z, z.w), acc[q + 1]);
     }
-    return __fadd_rn(__fadd_rn(__fadd_rn(acc[0].x, acc[0].y), __fadd_rn(acc[1].x, acc[1].y)),
-                     __fadd_rn(__fadd_rn(acc[2].x, acc[2].y), __fadd_rn(acc[3].x, acc[3].y)));
+    const float lo = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].x, acc[0].y), __fadd_rn(acc[1].x, acc[1].y)),
+                               __fadd_rn(__fadd_rn(acc[2].x, acc[2].y), __fadd_rn(acc[3].x, acc[3].y)));
+    const float hi = __fadd_rn(__fadd_rn(__fadd_rn(acc[4].x, acc[4].y), __fadd_rn(acc[5].x, acc[5].y)),
+                               __fadd_rn(__fadd_rn(acc[6].x, acc[6].y), __fadd_rn(acc[7].x, acc[7].y)));
+    return __fadd_rn(lo, hi);
 }
 
 }  // namespace snnk

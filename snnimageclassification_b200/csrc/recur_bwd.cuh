@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
 
     // row i of W_rec (.) rec_mask = column i of its transpose (k_prep_rec), staged by ONE bulk copy through shared
     // memory (the staging area aliases the loop buffers, which are initialised afterwards)
-    float w[REC ? H : 8];
+    float w[REC ? H : 16];
     if constexpr (REC) {
         float* s_t = reinterpret_cast<float*>(smem_raw);                        // [H][H]
         uint64_t* wbar = reinterpret_cast<uint64_t*>(s_t + H * H);
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
                     if constexpr (REC) {
                         const float4* gv4 =
                             reinterpret_cast<const float4*>(s_g + ((t + 1) & 1) * R * H + r * H);
-                        s = __fadd_rn(s, dot_rec8<REC ? H : 8>(w, gv4));   // gI_{t+1} (W_rec . M)^T
+                        s = __fadd_rn(s, dot_rec16<REC ? H : 16>(w, gv4));   // gI_{t+1} (W_rec . M)^T
                     }
                     const size_t o = ((size_t)(valid[r] ? b0 + r : 0) * T + t) * H + i;
                     if (p.g_Z && valid[r]) s = __fadd_rn(s, __ldg(p.g_Z + o));

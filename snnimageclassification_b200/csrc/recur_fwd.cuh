@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
     __syncthreads();   // barrier inits visible before anyone waits
 
     // column i of W_rec (.) rec_mask -> registers for the whole sequence
-    float w[REC ? H : 8];
+    float w[REC ? H : 16];
     if constexpr (REC) {
         tc::mbar_wait(s_bar + kRing, 0);
 #pragma unroll
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
             float rec = 0.0f;
             if constexpr (REC) {
                 const float4* zv = reinterpret_cast<const float4*>(s_z + ((t + 1) & 1) * R * H + r * H);
-                rec = dot_rec8<REC ? H : 8>(w, zv);
+                rec = dot_rec16<REC ? H : 16>(w, zv);
             }
             // V' = (alpha V + I_in + I_rec) (1 - Z.detach())     spiking_layers.py:169/239
             const float t1 = __fmul_rn(p.alpha, v[r]);

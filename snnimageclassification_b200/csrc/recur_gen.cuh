@@ -3,7 +3,7 @@
 // Same algorithm, same summation orders and therefore the same bits as recur_fwd.cuh / recur_bwd.cuh; what
 // changes is residency: an H x H fp32 recurrent matrix (4 MB at H = 1024) no longer fits in registers or
 // shared memory, so it is streamed from L2 once per step and per CTA and amortised over the R batch rows a
-// CTA owns (thread = neuron, R rows x 8 accumulation chains in registers, previous spike / gradient vector
+// CTA owns (thread = neuron, R rows, sixteen accumulation chains evaluated one after the other, previous spike / gradient vector
 // broadcast from shared memory as one LDS per k for all R rows).  The leaky readout and dW_out, which in the
 // narrow kernels ride along in registers / shared memory, become two small separate kernels here
 // (k_readout_scan, k_wout_grad).
@@ -20,7 +20,7 @@ constexpr int kGenMaxThreads = 1024;
 __host__ __device__ constexpr int gen_npt(int H) { return (H + kGenMaxThreads - 1) / kGenMaxThreads; }
 __host__ __device__ constexpr int gen_rows(int H) { return gen_npt(H) == 1 ? 4 : 2; }
 
-// acc[j][r] = sum over k = c, c+8, ... of Wm[k][i_j] * vec[k][r]   for one accumulation chain c
+// acc[j][r] = sum over k = c, c+16, ... of Wm[k][i_j] * vec[k][r]   for one accumulation chain c
 template <int NPT, int R>
 __device__ __forceinline__ void chain_dot(const float* __restrict__ Wm, const float* __restrict__ s_vec, int H, int BD,
                                           int tid, int c, float (&acc)[NPT][R])
@@ -30,7 +30,7 @@ __device__ __forceinline__ void chain_dot(const float* __restrict__ Wm, const fl
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
 #pragma unroll 4
-    for (int k = c; k < H; k += 8) {
+    for (int k = c; k < H; k += 16) {
         float z[R];
         if constexpr (R == 4) {
             const float4 z4 = *reinterpret_cast<const float4*>(s_vec + k * 4);
@@ -48,37 +48,51 @@ __device__ __forceinline__ void chain_dot(const float* __restrict__ Wm, const fl
     }
 }
 
-// Full dot product in the oracle's order: eight chains over k mod 8, combined ((s0+s1)+(s2+s3))+((s4+s5)+(s6+s7)).
+// Sum of the eight chains c0 .. c0+7 as the balanced tree ((s0+s1)+(s2+s3))+((s4+s5)+(s6+s7)).
 template <int NPT, int R>
-__device__ __forceinline__ void dot_rec8_gen(const float* __restrict__ Wm, const float* __restrict__ s_vec, int H, int BD,
-                                             int tid, float (&out)[NPT][R])
+__device__ __forceinline__ void tree8(const float* __restrict__ Wm, const float* __restrict__ s_vec, int H, int BD, int tid,
+                                      int c0, float (&out)[NPT][R])
 {
     float a[NPT][R], b[NPT][R], u[NPT][R];
-    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, 0, a);
-    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, 1, b);
+    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, c0 + 0, a);
+    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, c0 + 1, b);
 #pragma unroll
     for (int j = 0; j < NPT; ++j)
 #pragma unroll
-        for (int r = 0; r < R; ++r) u[j][r] = __fadd_rn(a[j][r], b[j][r]);               // s0+s1
-    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, 2, a);
-    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, 3, b);
+        for (int r = 0; r < R; ++r) u[j][r] = __fadd_rn(a[j][r], b[j][r]);
+    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, c0 + 2, a);
+    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, c0 + 3, b);
 #pragma unroll
     for (int j = 0; j < NPT; ++j)
 #pragma unroll
-        for (int r = 0; r < R; ++r) u[j][r] = __fadd_rn(u[j][r], __fadd_rn(a[j][r], b[j][r]));   // (s0+s1)+(s2+s3)
-    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, 4, a);
-    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, 5, b);
+        for (int r = 0; r < R; ++r) u[j][r] = __fadd_rn(u[j][r], __fadd_rn(a[j][r], b[j][r]));
+    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, c0 + 4, a);
+    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, c0 + 5, b);
 #pragma unroll
     for (int j = 0; j < NPT; ++j)
 #pragma unroll
-        for (int r = 0; r < R; ++r) out[j][r] = __fadd_rn(a[j][r], b[j][r]);             // s4+s5
-    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, 6, a);
-    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, 7, b);
+        for (int r = 0; r < R; ++r) out[j][r] = __fadd_rn(a[j][r], b[j][r]);
+    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, c0 + 6, a);
+    chain_dot<NPT, R>(Wm, s_vec, H, BD, tid, c0 + 7, b);
 #pragma unroll
     for (int j = 0; j < NPT; ++j)
 #pragma unroll
         for (int r = 0; r < R; ++r)
             out[j][r] = __fadd_rn(u[j][r], __fadd_rn(out[j][r], __fadd_rn(a[j][r], b[j][r])));
+}
+
+// Full dot product in the oracle's order: sixteen chains over k mod 16, balanced tree over adjacent chains.
+template <int NPT, int R>
+__device__ __forceinline__ void dot_rec16_gen(const float* __restrict__ Wm, const float* __restrict__ s_vec, int H, int BD,
+                                              int tid, float (&out)[NPT][R])
+{
+    float lo[NPT][R];
+    tree8<NPT, R>(Wm, s_vec, H, BD, tid, 0, lo);
+    tree8<NPT, R>(Wm, s_vec, H, BD, tid, 8, out);
+#pragma unroll
+    for (int j = 0; j < NPT; ++j)
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[j][r] = __fadd_rn(lo[j][r], out[j][r]);
 }
 
 // ---- forward --------------------------------------------------------------------------------------------------------
@@ -119,7 +133,7 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_fwd_gen(const FwdParam
                 cur[j][r] = valid[r] ? __ldg(p.I_in + ((size_t)(b0 + r) * T + t) * H + tid + j * BD) : 0.f;
         float rec[NPT][R];
         if constexpr (REC) {
-            dot_rec8_gen<NPT, R>(p.W_eff, s_z + ((t + 1) & 1) * H * R, H, BD, tid, rec);
+            dot_rec16_gen<NPT, R>(p.W_eff, s_z + ((t + 1) & 1) * H * R, H, BD, tid, rec);
         } else {
 #pragma unroll
             for (int j = 0; j < NPT; ++j)
@@ -268,7 +282,7 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_bwd_gen(const BwdParam
     for (int t = T - 1; t >= 0; --t) {
         float rec[NPT][R];
         if constexpr (REC) {
-            dot_rec8_gen<NPT, R>(p.W_effT, s_g + ((t + 1) & 1) * H * R, H, BD, tid, rec);
+            dot_rec16_gen<NPT, R>(p.W_effT, s_g + ((t + 1) & 1) * H * R, H, BD, tid, rec);
         } else {
 #pragma unroll
             for (int j = 0; j < NPT; ++j)

@@ -78,6 +78,7 @@ struct Plan {
     int S;            // split-K factor of the weight-gradient GEMM (splits are whole samples)
     int samples_per_split;
     bool tc;          // tcgen05 GEMMs eligible for this geometry (the flag asks for them and TMA can address x)
+    bool check;       // tensor-core path must verify on the device that x is tf32-exact (caller did not vouch)
     int kpad;         // K of the projection padded to the k-block
     bool wide;        // H > 128: generic recurrence kernels (recur_gen.cuh), N-tiled tensor-core GEMMs
     int tileN;        // N extent of one tensor-core tile
@@ -118,6 +119,7 @@ Plan make_plan(const SnnkDesc* d)
     p.m_total = d->N + (d->recurrent ? d->H : 0);
     // TMA needs 16-byte global strides: N % 4 == 0 (H is a multiple of 32 already)
     p.tc = (d->flags & SNNK_F_TENSOR_CORE) != 0 && d->N % 4 == 0;
+    p.check = p.tc && (d->flags & SNNK_F_INPUT_BINARY) == 0;
     p.kpad = (d->N + tc::kBlockK - 1) / tc::kBlockK * tc::kBlockK;
     int S;
     if (p.tc) {
@@ -187,7 +189,7 @@ template <int H>   // H = N extent of one CTA tile (the whole hidden width when 
 int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const float* W_in, float* I_in, float* planes,
                    unsigned int* flag, cudaStream_t st)
 {
-    constexpr int P = 3;
+    constexpr int P = 2;   // planes of W_in^T fed to the tensor pipe (k_split_w writes three)
     using Cfg = tc::ProjCfg<H, P>;
     const int M = d->B * d->T;
     const int Hf = d->H;
@@ -559,9 +561,11 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
         unsigned int* flag = nullptr;
         if (pl.tc) {
             char* ws = static_cast<char*>(workspace);
-            flag = reinterpret_cast<unsigned int*>(ws + pl.off_fflag);
             float* planes = reinterpret_cast<float*>(ws + pl.off_wplanes);
-            SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
+            if (pl.check) {
+                flag = reinterpret_cast<unsigned int*>(ws + pl.off_fflag);
+                SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
+            }
             switch (pl.tileN) {
             case 32: rc = launch_proj_tc<32>(d, pl, x, W_in, I_in, planes, flag, st); break;
             case 64: rc = launch_proj_tc<64>(d, pl, x, W_in, I_in, planes, flag, st); break;
@@ -569,11 +573,13 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
             }
             if (rc != SNNK_OK) return rc;
         }
-        dim3 grid((M + kGemmBM - 1) / kGemmBM, pl.ntiles);
-        ProfScope ps(pl.tc ? SNNK_K_PROJ_FALLBACK : SNNK_K_PROJ, st);
-        if (pl.BN == 64) k_proj_simt<64><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H, flag);
-        else k_proj_simt<32><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H, flag);
-        SNNK_CUDA(cudaGetLastError());
+        if (!pl.tc || pl.check) {
+            dim3 grid((M + kGemmBM - 1) / kGemmBM, pl.ntiles);
+            ProfScope ps(pl.tc ? SNNK_K_PROJ_FALLBACK : SNNK_K_PROJ, st);
+            if (pl.BN == 64) k_proj_simt<64><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H, flag);
+            else k_proj_simt<32><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H, flag);
+            SNNK_CUDA(cudaGetLastError());
+        }
     }
     // K2: fused recurrence + readout
     float* W_eff = nullptr;
@@ -712,8 +718,10 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     {
         unsigned int* flag = nullptr;
         if (pl.tc) {
-            flag = reinterpret_cast<unsigned int*>(ws + pl.off_flag);
-            SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
+            if (pl.check) {
+                flag = reinterpret_cast<unsigned int*>(ws + pl.off_flag);
+                SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
+            }
             switch (pl.tileN) {
             case 32: rc = launch_wgrad_tc<32>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
             case 64: rc = launch_wgrad_tc<64>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
@@ -726,13 +734,13 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         wp.mtiles_x = pl.mtiles_x; wp.rows_per_split = pl.samples_per_split * d->T;
         wp.x = x; wp.zbits = zbits; wp.Z0 = Z0; wp.gI = gI; wp.gI_lo = gI_lo; wp.run_if_flag = flag;
         wp.part = pw; wp.m_total = pl.m_total;
-        dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.ntiles, pl.S);
-        {
+        if (!pl.tc || pl.check) {
+            dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.ntiles, pl.S);
             ProfScope ps(pl.tc ? SNNK_K_WGRAD_FALLBACK : SNNK_K_WGRAD, st);
             if (pl.BN == 64) k_wgrad_simt<64><<<grid, kGemmThreads, 0, st>>>(wp);
             else k_wgrad_simt<32><<<grid, kGemmThreads, 0, st>>>(wp);
+            SNNK_CUDA(cudaGetLastError());
         }
-        SNNK_CUDA(cudaGetLastError());
         // every partial buffer (dW_in, dW_rec, dW_out, db) reduced by one launch
         FinalizeParams fz{};
         fz.pw = pw; fz.S = pl.S; fz.w_stride = (size_t)pl.m_total * d->H; fz.n_in = d->N * d->H;

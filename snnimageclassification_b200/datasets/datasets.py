@@ -127,6 +127,7 @@ class ToSpikes:
 			images = images.reshape(images.shape[0], int(np.prod(images.shape[1:])))
 		x2, _, _, _ = self._stage(images)
 		out, _ = self._run(x2, self.use_periods, out_dtype, want_periods=False)
+		out._snnk_binary = True    # exactly {0,1} by construction: lets the tensor-core kernels skip their input check
 		return out
 
 

@@ -36,8 +36,21 @@ class LayerConsts:
 	tensor_core: bool = False
 
 
-def make_desc(c: LayerConsts, B: int, T: int, N: int, H: int, O: int, traces: bool) -> _cabi.SnnkDesc:
-	flags = (_cabi.SNNK_F_TRACES if traces else 0) | (_cabi.SNNK_F_TENSOR_CORE if c.tensor_core else 0)
+BINARY_TAG = "_snnk_binary"   # python attribute on tensors known to hold exactly {0,1} (encoder output, spike traces)
+
+
+def mark_binary(t: torch.Tensor) -> torch.Tensor:
+	setattr(t, BINARY_TAG, True)
+	return t
+
+
+def is_binary(t) -> bool:
+	return bool(getattr(t, BINARY_TAG, False))
+
+
+def make_desc(c: LayerConsts, B: int, T: int, N: int, H: int, O: int, traces: bool, binary: bool = False) -> _cabi.SnnkDesc:
+	flags = (_cabi.SNNK_F_TRACES if traces else 0) | (_cabi.SNNK_F_TENSOR_CORE if c.tensor_core else 0) | (
+		_cabi.SNNK_F_INPUT_BINARY if binary else 0)
 	return _cabi.SnnkDesc(
 		B, T, N, H, O, c.layer_type, c.surrogate, int(c.recurrent), c.alpha, c.rho, c.theta, c.gamma, c.kappa, flags)
 
@@ -72,10 +85,13 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 	if t is None:
 		return None
-	t = t.detach()
-	if t.dtype != torch.float32:
-		t = t.float()
-	return t if t.is_contiguous() else t.contiguous()
+	r = t.detach()
+	if r.dtype != torch.float32:
+		r = r.float()
+	r = r if r.is_contiguous() else r.contiguous()
+	if is_binary(t):
+		mark_binary(r)
+	return r
 
 
 def run_forward(
@@ -89,7 +105,7 @@ def run_forward(
 	H, O = W_out.shape
 	if W_in.shape != (N, H):
 		raise RuntimeError(f"forward_weights has shape {tuple(W_in.shape)}, expected {(N, H)}")
-	desc = make_desc(c, B, T, N, H, O, traces)
+	desc = make_desc(c, B, T, N, H, O, traces, binary=is_binary(x))
 	dev = x.device
 	f32 = dict(dtype=torch.float32, device=dev)
 	alif = c.layer_type == _cabi.SNNK_ALIF
@@ -120,14 +136,14 @@ def run_forward(
 
 def run_backward(
 		c: LayerConsts, x, W_rec, rec_mask, beta, W_out, V, a, zbits, g_y=None, g_logits=None, tstar=None,
-		g_V=None, g_Z=None, Z0=None, Z=None, g_scale=None,
+		g_V=None, g_Z=None, Z0=None, Z=None, g_scale=None, binary_input: bool = False,
 ):
 	"""Calls ``snnk_backward``.  Returns dict(dW_in, dW_rec, dW_out, db, gI) -- ``gI`` is a zero-argument callable
 	(the tensor-core mode stores it as two planes; summing them is only worth it when somebody asks)."""
 	lib = _cabi.lib()
 	B, T, N = x.shape
 	H, O = W_out.shape
-	desc = make_desc(c, B, T, N, H, O, True)
+	desc = make_desc(c, B, T, N, H, O, True, binary=binary_input or is_binary(x))
 	dev = x.device
 	f32 = dict(dtype=torch.float32, device=dev)
 	dW_in = torch.empty((N, H), **f32)
@@ -197,6 +213,7 @@ class SpikingSequence(torch.autograd.Function):
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=True)
 		ctx.consts, ctx.H, ctx.Hp = consts, H, Hp
 		ctx.set_materialize_grads(False)                     # absent seeds stay None instead of (B,T,H) zero fills
+		ctx.binary = is_binary(xc)
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None      # stacked layers: the input is the spike trace below
 		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], out["Z"])
 		alif = consts.layer_type == _cabi.SNNK_ALIF
@@ -214,7 +231,8 @@ class SpikingSequence(torch.autograd.Function):
 		if Hp != H:
 			g_V = None if g_V is None else torch.nn.functional.pad(g_V, (0, Hp - H))
 			g_Z = None if g_Z is None else torch.nn.functional.pad(g_Z, (0, Hp - H))
-		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=g_V, g_Z=g_Z, Z=Z)
+		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=g_V, g_Z=g_Z, Z=Z,
+			binary_input=ctx.binary)
 		# (consts, x, W_in, W_rec, rec_mask, beta, W_out, b_out); beta gets no gradient -- the threshold input of
 		# the reference's spike function returns None (spike_funcs.py:62/79)
 		gX = run_input_grad(ctx.consts, g["gI"](), ctx.Wi) if ctx.Wi is not None else None
@@ -236,6 +254,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		loss, logp, g_logits = run_head_nll(out["logits"], labels, want_grad=need_grad)
 		ctx.consts, ctx.H = consts, H
 		ctx.set_materialize_grads(False)
+		ctx.binary = is_binary(xc)
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None
 		if need_grad:
 			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"], out["Z"])
@@ -252,7 +271,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 			return (None,) * 10
 		g = run_backward(
 			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=g_logits, tstar=tstar, Z=Z,
-			g_scale=g_loss.detach().float().reshape(1))
+			g_scale=g_loss.detach().float().reshape(1), binary_input=ctx.binary)
 		H = ctx.H
 		gX = run_input_grad(ctx.consts, g["gI"](), ctx.Wi) if ctx.Wi is not None else None
 		return (None, gX, None, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,

@@ -252,7 +252,7 @@ class SNN(torch.nn.Module):
 			_, V, a, Z = F_.SpikingSequence.apply(consts, x, *self._layer_weights(layer), w0, b0)
 			if hidden is not None:
 				hidden[name] = (V, a, Z) if isinstance(layer, ALIFLayer) else (V, Z)
-			x = Z
+			x = F_.mark_binary(Z)      # a spike trace is exactly {0,1}
 		return x
 
 	def forward(self, inputs):

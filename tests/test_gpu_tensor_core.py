@@ -164,3 +164,21 @@ def test_graphed_train_step_matches_eager():
 		assert abs(a - b) <= 1e-5 * abs(a)
 	for pe, pg in zip(eager.parameters(), graphed.parameters()):
 		assert rel_err(npy(pg), npy(pe)) <= 1e-5
+
+
+def test_binary_input_flag_skips_the_check_but_not_the_result():
+	"""SNNK_F_INPUT_BINARY (tensors tagged by the encoder / spike traces) gives bit-identical tensor-core results."""
+	d, consts = _setup(32, 50, 784, 128, 10, True, 1, 0.12)
+	f_checked = _fwd(d, consts(True))
+	xb = F_.mark_binary(d["x"].clone())
+	d2 = dict(d, x=xb)
+	f_tagged = _fwd(d2, consts(True))
+	for k in ("I_in", "V", "Z", "y"):
+		assert torch.equal(f_checked[k], f_tagged[k]), k
+	loss, logp, gl = F_.run_head_nll(f_checked["logits"], d["labels"])
+	g0 = _bwd(d, consts(True), f_checked, g_logits=gl, tstar=f_checked["tstar"])
+	g1 = _bwd(d2, consts(True), f_checked, g_logits=gl, tstar=f_checked["tstar"])
+	for k in ("dW_in", "dW_rec", "dW_out", "db"):
+		assert torch.equal(g0[k], g1[k]), k
+	from snnimageclassification_b200 import ToSpikes
+	assert F_.is_binary(ToSpikes(10, use_periods=True).encode_batch(torch.rand(4, 16)))
