@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -105,7 +106,7 @@ Plan make_plan(const SnnkDesc* d)
 {
     Plan p{};
     p.wide = d->H > 128;
-    p.R = p.wide ? gen_rows(d->H) : (d->B > 1024 ? 2 : 1);
+    p.R = p.wide ? gen_rows(d->H) : (d->B > 1024 ? 2 : 1);   // (R == 1 && B <= 1024 also selects the k-split forward kernel)
     p.grid_rows = (d->B + p.R - 1) / p.R;
     const int BT = d->B * d->T;
     p.tileN = p.wide ? 128 : d->H;
@@ -281,9 +282,31 @@ int launch_fwd_rec(const FwdParams& fp, bool rec, int grid, cudaStream_t st)
     return rec ? launch_fwd<H, R, true>(fp, grid, st) : launch_fwd<H, R, false>(fp, grid, st);
 }
 
+template <int H, bool REC>
+int launch_fwd_ks2(const FwdParams& fp, cudaStream_t st)
+{
+    const size_t smem = fwd_smem_bytes<H, 1>(fp.T, fp.O);
+    if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
+    auto kern = k_recur_fwd_ks2<H, REC>;
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { ProfScope ps(SNNK_K_RECUR_FWD, st); kern<<<fp.B, 2 * H, smem, st>>>(fp); }
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+// Two threads per neuron while the batch is small enough for the recurrence to be latency-bound (see
+// k_recur_fwd_ks2); SNNK_KSPLIT=0/1 overrides for experiments.
+bool use_ksplit(int B, int R)
+{
+    static const char* env = getenv("SNNK_KSPLIT");
+    if (env) return env[0] != '0';
+    return R == 1 && B <= 1024;
+}
+
 template <int H>
 int launch_fwd_r(const FwdParams& fp, bool rec, int R, int grid, cudaStream_t st)
 {
+    if (use_ksplit(fp.B, R)) return rec ? launch_fwd_ks2<H, true>(fp, st) : launch_fwd_ks2<H, false>(fp, st);
     return R == 1 ? launch_fwd_rec<H, 1>(fp, rec, grid, st) : launch_fwd_rec<H, 2>(fp, rec, grid, st);
 }
 
