@@ -16,6 +16,7 @@
 #include "recur_bwd.cuh"
 #include "recur_fwd.cuh"
 #include "recur_gen.cuh"
+#include "recur_mma.cuh"
 
 using namespace snnk;
 
@@ -290,6 +291,30 @@ int launch_fwd_ks2(const FwdParams& fp, cudaStream_t st)
     auto kern = k_recur_fwd_ks2<H, REC>;
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { ProfScope ps(SNNK_K_RECUR_FWD, st); kern<<<fp.B, 2 * H, smem, st>>>(fp); }
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+// Tensor-core recurrence (recur_mma.cuh): H = 128, selected by SNNK_F_TENSOR_CORE; SNNK_MMA_RECUR=0 keeps the SIMT kernel.
+bool use_mma_recur(const SnnkDesc* d)
+{
+    static const char* env = getenv("SNNK_MMA_RECUR");
+    if (env && env[0] == '0') return false;
+    return (d->flags & SNNK_F_TENSOR_CORE) != 0 && d->H == kMmaH;
+}
+
+int launch_fwd_mma(const FwdParams& fp, bool rec, cudaStream_t st)
+{
+    const size_t smem = fwd_mma_smem_bytes();
+    const int grid = (fp.B + kMmaRows - 1) / kMmaRows;
+    ProfScope ps(SNNK_K_RECUR_FWD, st);
+    if (rec) {
+        SNNK_CUDA(cudaFuncSetAttribute(k_recur_fwd_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_recur_fwd_mma<true><<<grid, kMmaThreads, smem, st>>>(fp);
+    } else {
+        SNNK_CUDA(cudaFuncSetAttribute(k_recur_fwd_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_recur_fwd_mma<false><<<grid, kMmaThreads, smem, st>>>(fp);
+    }
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -621,6 +646,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     fp.logits = logits; fp.tstar = tstar;
     const bool rec = d->recurrent != 0;
     if (pl.wide) return launch_fwd_wide(d, fp, rec, pl, st);
+    if (use_mma_recur(d)) return launch_fwd_mma(fp, rec, st);
     switch (d->H) {
     case 32: return launch_fwd_r<32>(fp, rec, pl.R, pl.grid_rows, st);
     case 64: return launch_fwd_r<64>(fp, rec, pl.R, pl.grid_rows, st);

@@ -182,3 +182,34 @@ def test_binary_input_flag_skips_the_check_but_not_the_result():
 		assert torch.equal(g0[k], g1[k]), k
 	from snnimageclassification_b200 import ToSpikes
 	assert F_.is_binary(ToSpikes(10, use_periods=True).encode_batch(torch.rand(4, 16)))
+
+
+@pytest.mark.parametrize("B,T,rec,layer", [(256, 100, True, 1), (37, 23, True, 0), (16, 5, False, 1), (300, 9, True, 1)])
+def test_mma_recurrence_self_consistency_and_vs_simt(B, T, rec, layer):
+	"""recur_mma.cuh (H = 128, tensor-core mode): internal consistency of everything it writes, and agreement with the
+	fp32 SIMT kernel on the samples that did not fork."""
+	d, consts = _setup(B, T, 784, 128, 10, rec, layer, 0.1 if layer else 0.03, seed=B)
+	f0, f1 = _fwd(d, consts(False)), _fwd(d, consts(True))
+	Z1 = f1["Z"]
+	# zbits == packed Z, logits == max_t y, tstar == first argmax, Z in {0,1}
+	zb = f1["zbits"].cpu().numpy().view(np.uint32)
+	bits = ((zb[..., :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(B, T, 128)
+	assert np.array_equal(bits, npy(Z1).astype(np.uint32))
+	assert torch.equal(f1["logits"], f1["y"].max(dim=1)[0])
+	assert torch.equal(f1["tstar"].long(), (f1["y"] == f1["logits"][:, None, :]).float().argmax(dim=1))
+	assert set(np.unique(npy(Z1))) <= {0.0, 1.0}
+	# V is consistent with Z inside the MMA kernel's own trace: Z_t = (V_t >= theta + beta a_t)
+	thr = consts(True).theta + (1.6 * f1["a"] if layer else 0.0)
+	assert torch.equal(Z1, (f1["V"] >= thr).float())
+	forked = (Z1 != f0["Z"]).flatten(1).any(dim=1)
+	assert forked.float().mean().item() <= 0.05
+	ok = ~forked
+	for k in ("V", "y") + (("a",) if layer else ()):
+		assert rel_err(npy(f1[k][ok]), npy(f0[k][ok])) <= 1e-5, k
+	same = (Z1 == f0["Z"]).float().mean().item()
+	if B * T * 128 >= 3_000_000:
+		assert same >= 0.9999, f"rasters only {same:.6f} identical to the fp32 kernel"
+	# inference mode (no traces) gives the same logits
+	c = consts(True)
+	o2 = F_.run_forward(c, d["x"], d["W_in"], d["W_rec"], d["mask"], d["beta"], d["W_out"], d["b_out"], traces=False)
+	assert torch.equal(o2["logits"], f1["logits"]) and torch.equal(o2["zbits"], f1["zbits"])
