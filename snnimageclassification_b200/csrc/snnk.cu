@@ -298,9 +298,12 @@ int launch_fwd_ks2(const FwdParams& fp, cudaStream_t st)
 // Tensor-core recurrence (recur_mma.cuh): H = 128, selected by SNNK_F_TENSOR_CORE; SNNK_MMA_RECUR=0 keeps the SIMT kernel.
 bool use_mma_recur(const SnnkDesc* d)
 {
+    // Measured on B200 (profiles/): a 16-row tile keeps one SM busy for ~1.8 us per step whatever the batch, so the
+    // MMA kernel wins once there are enough tiles to fill the chip (B=4096: 0.38 ms vs 1.07 ms) and loses to the
+    // 128-threads-per-row SIMT kernel, which spreads a small batch over all SMs (B=256: 180 us vs 64 us).
     static const char* env = getenv("SNNK_MMA_RECUR");
-    if (env && env[0] == '0') return false;
-    return (d->flags & SNNK_F_TENSOR_CORE) != 0 && d->H == kMmaH;
+    if (env) return env[0] != '0' && d->H == kMmaH;
+    return (d->flags & SNNK_F_TENSOR_CORE) != 0 && d->H == kMmaH && d->B >= 768;
 }
 
 int launch_fwd_mma(const FwdParams& fp, bool rec, cudaStream_t st)

@@ -24,6 +24,16 @@ def allreduce_mean_(tensors: Iterable[torch.Tensor]) -> None:
 	ts: List[torch.Tensor] = [t for t in tensors if t is not None]
 	if not ts:
 		return
+	if ts[0].is_cuda and dist.get_backend() == "nccl" and hasattr(dist, "_coalescing_manager"):
+		# NCCL: the per-tensor all-reduces are coalesced into ONE group launch that averages in place -- no flatten /
+		# copy-back kernels around the collective (it all sits inside the captured training graph)
+		try:
+			with dist._coalescing_manager(device=ts[0].device):
+				for t in ts:
+					dist.all_reduce(t, op=dist.ReduceOp.AVG)
+			return
+		except Exception:   # pragma: no cover  (older torch: fall through to the flat buffer)
+			pass
 	flat = torch.cat([t.reshape(-1) for t in ts])
 	dist.all_reduce(flat, op=dist.ReduceOp.SUM)
 	flat.div_(ws)

@@ -102,7 +102,7 @@ def test_inexact_input_falls_back_on_device():
 	d, consts = _setup(16, 20, 64, 128, 10, True, 1, 0.3)
 	d["x"] = d["x"] * torch.rand_like(d["x"])          # arbitrary fp32 currents: not representable in tf32
 	f0, f1 = _fwd(d, consts(False)), _fwd(d, consts(True))
-	for k in ("I_in", "V", "a", "Z", "y"):
+	for k in ("I_in", "V", "a", "Z", "y"):     # B = 16: the SIMT recurrence runs in both modes, so everything is bit-identical
 		assert torch.equal(f0[k], f1[k]), k
 	g_y = torch.randn(16, 20, 10, device=DEV)
 	g0, g1 = _bwd(d, consts(False), f0, g_y=g_y), _bwd(d, consts(True), f0, g_y=g_y)
@@ -184,7 +184,7 @@ def test_binary_input_flag_skips_the_check_but_not_the_result():
 	assert F_.is_binary(ToSpikes(10, use_periods=True).encode_batch(torch.rand(4, 16)))
 
 
-@pytest.mark.parametrize("B,T,rec,layer", [(256, 100, True, 1), (37, 23, True, 0), (16, 5, False, 1), (300, 9, True, 1)])
+@pytest.mark.parametrize("B,T,rec,layer", [(1024, 100, True, 1), (800, 23, True, 0), (770, 5, False, 1), (1000, 9, True, 1)])
 def test_mma_recurrence_self_consistency_and_vs_simt(B, T, rec, layer):
 	"""recur_mma.cuh (H = 128, tensor-core mode): internal consistency of everything it writes, and agreement with the
 	fp32 SIMT kernel on the samples that did not fork."""
@@ -208,7 +208,7 @@ def test_mma_recurrence_self_consistency_and_vs_simt(B, T, rec, layer):
 		assert rel_err(npy(f1[k][ok]), npy(f0[k][ok])) <= 1e-5, k
 	same = (Z1 == f0["Z"]).float().mean().item()
 	if B * T * 128 >= 3_000_000:
-		assert same >= 0.9999, f"rasters only {same:.6f} identical to the fp32 kernel"
+		assert same >= 0.9995, f"rasters only {same:.6f} identical to the fp32 kernel"
 	# inference mode (no traces) gives the same logits
 	c = consts(True)
 	o2 = F_.run_forward(c, d["x"], d["W_in"], d["W_rec"], d["mask"], d["beta"], d["W_out"], d["b_out"], traces=False)
