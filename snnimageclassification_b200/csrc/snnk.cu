@@ -107,7 +107,7 @@ Plan make_plan(const SnnkDesc* d)
 {
     Plan p{};
     p.wide = d->H > 128;
-    p.R = p.wide ? gen_rows(d->H) : (d->B > 1024 ? 2 : 1);   // (R == 1 && B <= 1024 also selects the k-split forward kernel)
+    p.R = p.wide ? gen_rows(d->H) : (d->B > 1024 ? 2 : 1);
     p.grid_rows = (d->B + p.R - 1) / p.R;
     const int BT = d->B * d->T;
     p.tileN = p.wide ? 128 : d->H;
@@ -322,13 +322,13 @@ int launch_fwd_mma(const FwdParams& fp, bool rec, cudaStream_t st)
     return SNNK_OK;
 }
 
-// Two threads per neuron while the batch is small enough for the recurrence to be latency-bound (see
-// k_recur_fwd_ks2); SNNK_KSPLIT=0/1 overrides for experiments.
+// k_recur_fwd_ks2 (two threads per neuron) is kept as an experiment, off unless SNNK_KSPLIT=1: measured on B200 it is
+// SLOWER than k_recur_fwd (76 us vs 65 us at B = 256) -- which is how the kernel turned out to be bound by the shared-
+// memory return path (every thread re-reads the spike vector), not by per-warp latency; see DESIGN.md.
 bool use_ksplit(int B, int R)
 {
     static const char* env = getenv("SNNK_KSPLIT");
-    if (env) return env[0] != '0';
-    return R == 1 && B <= 1024;
+    return env && env[0] == '1' && R == 1 && B <= 1024;
 }
 
 template <int H>
