@@ -153,6 +153,7 @@ def main():
 	net = SNN(N, O, H, use_recurrent_connection=True, int_time_steps=T, spike_func=SpikeFuncType.FastSigmoid,
 		hidden_layer_type=LayerType.ALIF, device=dev, learn_beta=True, input_encoder=enc)
 	opt = FusedAdam(net.parameters(), lr=1e-3, weight_decay=1e-5)    # torch.optim.Adam semantics, one libsnnk launch
+	dp_fused = world > 1 and os.environ.get("SNNK_DP_FUSED", "1") != "0" and opt.enable_data_parallel()
 	crit = torch.nn.NLLLoss()
 	net.train()
 
@@ -173,7 +174,7 @@ def main():
 		loss = net.batch_loss(rasters[i % N_POOL], labels_dev[i % N_POOL], crit)
 		opt.zero_grad()
 		loss.backward()
-		net._allreduce_gradients()
+		net._allreduce_gradients(opt)
 		opt.step()
 		return loss
 
@@ -259,7 +260,9 @@ def main():
 		"vs_baseline": None, "dtype": "f32", "data": "synthetic",
 		"config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
 			"l2": f"{N_POOL} rotating input batches ({N_POOL * B_PER_GPU * T * N * 4 >> 20} MiB) > 126 MB L2",
-			"optimizer": "Adam(lr=1e-3, weight_decay=1e-5) as snnk_adam_step", "launch": "one CUDA graph per step"},
+			"optimizer": "Adam(lr=1e-3, weight_decay=1e-5) as snnk_adam_step", "launch": "one CUDA graph per step",
+			"grad_exchange": ("none (1 rank)" if world == 1 else
+				"fused into snnk_adam_step_dp over NVLink peer memory" if dp_fused else "NCCL all-reduce (mean)")},
 		"clocks": clocks,
 		"e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
 			"ms_per_step": ms_e2e / args.steps, "input": "pinned host images (B,784) fp32 + labels; GPU to_spikes",

@@ -204,6 +204,25 @@ int snnk_adam_step(int32_t count, float* const* params, const float* const* grad
                    float beta2, float eps, float weight_decay, snnk_stream_t stream);
 
 /*
+ * Data-parallel form of snnk_adam_step (one process per GPU, batch rows sharded, weights replicated): the mean of
+ * the weight gradients over the ranks -- the single exchange step of SNN._exec_batch's path -- and
+ * the Adam update in ONE kernel over NVLink peer memory.  Every rank pushes its gradient into a slot of each
+ * peer's exchange buffer, publishes a flag, waits for its peers' flags and reduces the slots in rank order, so
+ * all ranks compute bit-identical means; grads[k] is overwritten with the mean (as after an all-reduce).
+ *   peer_buffers: HOST array of `world` device pointers; entry r is rank r's exchange buffer as mapped into this
+ *                 process (entry `rank` is the local one).  Each buffer holds snnk_adam_dp_buffer_bytes(world,
+ *                 sum(numel)) bytes of peer-accessible memory, zero-filled on every rank before the first call.
+ *   state:        4 zero-initialised uint32 in LOCAL device memory (epoch and grid counters; never reset them).
+ * All ranks must issue the same sequence of calls.  Graph-capturable; a peer that never arrives traps the kernel
+ * after 20 s (a sticky CUDA error) instead of hanging.
+ */
+int snnk_adam_dp_buffer_bytes(int32_t world, int64_t total_numel, size_t* bytes);
+int snnk_adam_step_dp(int32_t count, float* const* params, float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, float* const* steps, const int64_t* numel, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int32_t rank, int32_t world,
+                      void* const* peer_buffers, uint32_t* state, snnk_stream_t stream);
+
+/*
  * Gradient w.r.t. the layer input, for stacked hidden layers (snn.py:116-128): gX (B,T,N) = gI (B,T,H) @ W_in^T.
  * MmBackward of spiking_layers.py:163/233 w.r.t. `inputs`; layer l+1 hands gX down as the g_Z seed of layer l.
  * gI is the gradient w.r.t. the input current that snnk_backward leaves in its workspace (sum of the two tf32

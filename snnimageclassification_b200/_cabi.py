@@ -80,6 +80,9 @@ _SIGNATURES = {
 	"snnk_backward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 21 + [ctypes.c_size_t, _p]),
 	"snnk_adam_step": (ctypes.c_int, [ctypes.c_int32, _p, _p, _p, _p, _p, _p, ctypes.c_float, ctypes.c_float,
 		ctypes.c_float, ctypes.c_float, ctypes.c_float, _p]),
+	"snnk_adam_dp_buffer_bytes": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+	"snnk_adam_step_dp": (ctypes.c_int, [ctypes.c_int32, _p, _p, _p, _p, _p, _p, ctypes.c_float, ctypes.c_float,
+		ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_int32, _p, _p, _p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

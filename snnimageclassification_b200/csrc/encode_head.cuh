@@ -154,4 +154,112 @@ __global__ void k_adam_bump(const AdamTensors t)
     if (k < t.count) *t.step[k] += 1.0f;
 }
 
+// ---- data-parallel optimizer step: gradient exchange + mean + Adam in ONE kernel -------------------
+// The only exchange step of the path is the mean of the weight gradients over the ranks.  Instead of an NCCL
+// all-reduce followed by the optimizer launch, every rank PUSHES its gradient over NVLink straight into a slot of
+// each peer's exchange buffer (peer-mapped symmetric memory), raises a flag at each peer, waits for the peers' flags
+// in its own buffer and then reduces the `world` local slots in rank order (bit-identical on every rank, so the
+// replicated weights never diverge), stores the mean back as the gradient and applies Adam.
+//   exchange buffer per rank: [kDpFlagWords uint32 flags][2 parities][world slots][total floats]
+//   parity = epoch & 1: a rank can be one launch ahead of a peer (it cannot pass the next flag wait before the peer
+//   has left this one), so two buffers suffice; the epoch counter lives in `state` and survives graph replays.
+constexpr int kDpMaxWorld = 16;
+constexpr int kDpFlagWords = 64;    // 256 B: flag[r] = last epoch rank r has published into this buffer
+struct AdamDp {
+    float* slots[kDpMaxWorld];      // peer r's gradient slots (after its flag words), as mapped into this process
+    unsigned* flags[kDpMaxWorld];   // peer r's flag words
+    unsigned* state;                // local: [0] epoch, [1] arrive counter, [2] leave counter, [3] timeout marker
+    int rank, world;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_adam_step_dp(const AdamTensors t, const AdamDp dp, float lr, float beta1,
+                                                     float beta2, float eps, float weight_decay)
+{
+    const long long total = t.start[t.count];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned epoch = *(volatile unsigned*)(dp.state) + 1u;   // bumped by the last CTA to leave
+    const size_t par = (size_t)(epoch & 1u) * dp.world;
+
+    // 1. push the local gradient into slot `rank` of every rank's buffer (own included)
+    {
+        const size_t mine = (par + dp.rank) * (size_t)total;
+        int k = 0;
+        for (long long e = e0; e < total; e += stride) {
+            while (e >= t.start[k + 1]) ++k;
+            const float g = t.g[k][e - t.start[k]];
+            for (int r = 0; r < dp.world; ++r) dp.slots[r][mine + e] = g;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // 2. the last CTA to arrive publishes this rank's epoch at every peer ...
+        if (atomicAdd(dp.state + 1, 1u) == gridDim.x - 1) {
+            dp.state[1] = 0;
+            __threadfence_system();
+            for (int r = 0; r < dp.world; ++r) st_release_sys(dp.flags[r] + dp.rank, epoch);
+        }
+        // ... and every CTA waits until all ranks have published into the local buffer
+        const unsigned long long t0 = global_ns();
+        for (int r = 0; r < dp.world; ++r) {
+            while ((int)(ld_acquire_sys(dp.flags[dp.rank] + r) - epoch) < 0) {
+                if (global_ns() - t0 > 20000000000ull) {   // 20 s: a peer died -- fail loudly instead of hanging
+                    dp.state[3] = epoch;
+                    __threadfence_system();
+                    __trap();
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // 3. mean over the local slots in rank order, then Adam
+    {
+        const float inv = 1.0f / (float)dp.world;
+        const float* local = dp.slots[dp.rank];
+        int k = 0;
+        for (long long e = e0; e < total; e += stride) {
+            while (e >= t.start[k + 1]) ++k;
+            const long long i = e - t.start[k];
+            float g = 0.0f;
+            for (int r = 0; r < dp.world; ++r) g += __ldcg(local + (par + r) * (size_t)total + e);
+            g *= inv;
+            const_cast<float*>(t.g[k])[i] = g;      // the caller sees the averaged gradient, as after an all-reduce
+            const float step = *t.step[k] + 1.0f;
+            const float p = t.p[k][i];
+            g = fmaf(weight_decay, p, g);
+            const float m = fmaf(1.0f - beta1, g - t.m[k][i], t.m[k][i]);
+            const float v = fmaf(1.0f - beta2, g * g, beta2 * t.v[k][i]);
+            t.m[k][i] = m;
+            t.v[k][i] = v;
+            const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
+            const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+            t.p[k][i] = p - (lr / bc1) * (m / denom);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(dp.state + 2, 1u) == gridDim.x - 1) {
+        dp.state[2] = 0;
+        dp.state[0] = epoch;
+    }
+}
+
 }  // namespace snnk

@@ -68,6 +68,14 @@ int device_ok()
     return major == 10;
 }
 
+int sm_count()
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) return 1;
+    return n;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // How the batch is cut into CTAs and how the weight-gradient GEMM is split; shared by the workspace
@@ -693,6 +701,51 @@ int snnk_adam_step(int32_t count, float* const* params, const float* const* grad
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ProfScope ps(SNNK_K_ADAM, st);
     k_adam_step<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t, lr, beta1, beta2, eps, weight_decay);
+    k_adam_bump<<<1, 32, 0, st>>>(t);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int snnk_adam_dp_buffer_bytes(int32_t world, int64_t total_numel, size_t* bytes)
+{
+    if (!bytes) return SNNK_ERR_ARG;
+    if (world < 1 || world > kDpMaxWorld || total_numel < 0) return SNNK_ERR_SHAPE;
+    *bytes = (size_t)kDpFlagWords * sizeof(unsigned) + (size_t)2 * world * (size_t)total_numel * sizeof(float);
+    return SNNK_OK;
+}
+
+int snnk_adam_step_dp(int32_t count, float* const* params, float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, float* const* steps, const int64_t* numel, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int32_t rank, int32_t world, void* const* peer_buffers,
+                      uint32_t* state, snnk_stream_t stream)
+{
+    if (count < 0 || count > kAdamMaxTensors) return SNNK_ERR_SHAPE;
+    if (world < 1 || world > kDpMaxWorld || rank < 0 || rank >= world) return SNNK_ERR_SHAPE;
+    if (count == 0) return SNNK_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !steps || !numel || !peer_buffers || !state) return SNNK_ERR_ARG;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    AdamTensors t{};
+    t.count = count;
+    long long total = 0;
+    for (int k = 0; k < count; ++k) {
+        if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k] || !steps[k] || numel[k] < 0) return SNNK_ERR_ARG;
+        t.p[k] = params[k]; t.g[k] = grads[k]; t.m[k] = exp_avg[k]; t.v[k] = exp_avg_sq[k]; t.step[k] = steps[k];
+        t.n[k] = numel[k]; t.start[k] = total; total += numel[k];
+    }
+    t.start[count] = total;
+    AdamDp dp{};
+    dp.rank = rank; dp.world = world; dp.state = state;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_buffers[r]) return SNNK_ERR_ARG;
+        dp.flags[r] = static_cast<unsigned*>(peer_buffers[r]);
+        dp.slots[r] = reinterpret_cast<float*>(dp.flags[r] + kDpFlagWords);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ProfScope ps(SNNK_K_ADAM, st);
+    // every CTA waits on the peers' flags, so the whole grid must be co-resident: at most one CTA per SM
+    const long long want = (total + 255) / 256;
+    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sm_count());
+    k_adam_step_dp<<<grid, 256, 0, st>>>(t, dp, lr, beta1, beta2, eps, weight_decay);
     k_adam_bump<<<1, 32, 0, st>>>(t);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;

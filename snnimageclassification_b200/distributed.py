@@ -51,6 +51,26 @@ def _symm_allreduce_mean_(ts: List[torch.Tensor], ws: int) -> bool:
 		return False
 
 
+class PeerExchangeBuffer:
+	"""``nbytes`` of zero-filled device memory on every rank of ``group``, each rank's block mapped into every other
+	rank's address space (NVLink peer access through torch's symmetric-memory allocator -- plumbing only: the
+	kernels that read and write it are libsnnk's).  ``ptrs[r]`` is rank r's block as seen from this process."""
+
+	def __init__(self, nbytes: int, device: torch.device, group=None):
+		import torch.distributed._symmetric_memory as symm
+		group = group if group is not None else dist.group.WORLD
+		self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+		self.buf = symm.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+		self.buf.zero_()
+		torch.cuda.synchronize(device)
+		self.handle = symm.rendezvous(self.buf, group.group_name)
+		self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+		if len(self.ptrs) != self.world or self.ptrs[self.rank] != self.buf.data_ptr():
+			raise RuntimeError("symmetric-memory rendezvous returned an unexpected peer table")
+		dist.barrier(group)     # nobody pushes before every rank has zeroed its flags
+		torch.cuda.synchronize(device)
+
+
 def allreduce_mean_(tensors: Iterable[torch.Tensor]) -> None:
 	"""In-place mean over the ranks of every tensor in ``tensors`` with a single flat all-reduce."""
 	ws = world_size()

@@ -70,7 +70,7 @@ class GraphedTrainStep:
 		loss = net.batch_loss(self.x, self.y, self.criterion)
 		self.optimizer.zero_grad(set_to_none=True)
 		loss.backward()
-		net._allreduce_gradients()
+		net._allreduce_gradients(self.optimizer)
 		if self.step_in_graph:
 			self.optimizer.step()
 		return loss

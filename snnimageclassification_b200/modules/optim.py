@@ -5,6 +5,11 @@ It IS a ``torch.optim.Adam`` (same constructor, ``state_dict`` layout, per-param
 ``exp_avg_sq`` state), so the reference's checkpoints load into it and its own load into ``torch.optim.Adam``;
 only the arithmetic of ``step`` moves to libsnnk.  The step counters live on the device, which lets the whole
 training step sit inside one captured CUDA graph (modules/graphed.py).
+
+Data parallel (one process per GPU): after ``enable_data_parallel()`` the same launch also performs
+the path's only exchange step -- the mean of the weight gradients over the ranks -- by pushing the gradients through
+NVLink peer memory (``snnk_adam_step_dp``); ``reduces_gradients`` then tells ``SNN._exec_batch`` to skip its
+all-reduce.
 """
 from __future__ import annotations
 
@@ -18,6 +23,46 @@ from .. import _cabi
 class FusedAdam(torch.optim.Adam):
 	def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
 		super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, capturable=True, foreach=False)
+		self.reduces_gradients = False
+		self._dp_group = None
+		self._dp_ctx = {}
+
+	def enable_data_parallel(self, group=None) -> bool:
+		"""Fuse the cross-rank gradient mean into ``step()``.  Returns False (and leaves the optimizer as it was:
+		the caller keeps using the NCCL all-reduce) when there is a single rank, the backend is not NCCL or peer
+		memory cannot be mapped.  Every rank must call it, and ``step()``, the same number of times."""
+		import torch.distributed as dist
+		if not (dist.is_available() and dist.is_initialized()):
+			return False
+		group = group if group is not None else dist.group.WORLD
+		if dist.get_world_size(group) == 1 or dist.get_backend(group) != "nccl":
+			return False
+		if dist.get_world_size(group) > 16:
+			return False
+		try:
+			import torch.distributed._symmetric_memory  # noqa: F401
+		except Exception:
+			return False
+		self._dp_group = group
+		self.reduces_gradients = True
+		return True
+
+	def _dp_context(self, key, ps):
+		ctx = self._dp_ctx.get(key)
+		if ctx is None:
+			from ..distributed import PeerExchangeBuffer
+			if torch.cuda.is_current_stream_capturing():
+				raise RuntimeError("FusedAdam: the first data-parallel step() must run outside CUDA graph capture")
+			total = sum(p.numel() for p in ps)
+			nbytes = ctypes.c_size_t(0)
+			world = torch.distributed.get_world_size(self._dp_group)
+			_cabi.check(_cabi.lib().snnk_adam_dp_buffer_bytes(world, total, ctypes.byref(nbytes)), "snnk_adam_dp_buffer_bytes")
+			xbuf = PeerExchangeBuffer(nbytes.value, ps[0].device, self._dp_group)
+			state = torch.zeros(4, dtype=torch.int32, device=ps[0].device)
+			ctx = self._dp_ctx[key] = (xbuf, state, total)
+		if ctx[2] != sum(p.numel() for p in ps):
+			raise RuntimeError("FusedAdam: the set of parameters with gradients changed between data-parallel steps")
+		return ctx
 
 	@torch.no_grad()
 	def step(self, closure=None):
@@ -26,7 +71,7 @@ class FusedAdam(torch.optim.Adam):
 			with torch.enable_grad():
 				loss = closure()
 		lib = _cabi.lib()
-		for group in self.param_groups:
+		for gi, group in enumerate(self.param_groups):
 			ps, gs, ms, vs, ss = [], [], [], [], []
 			for p in group["params"]:
 				if p.grad is None:
@@ -38,6 +83,8 @@ class FusedAdam(torch.optim.Adam):
 					st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
 					st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
 					st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+				if self.reduces_gradients and not p.grad.is_contiguous():
+					p.grad = p.grad.contiguous()
 				g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
 				ps.append(p); gs.append(g); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"]); ss.append(st["step"])
 			lr = float(group["lr"]) if not torch.is_tensor(group["lr"]) else float(group["lr"].item())
@@ -48,8 +95,16 @@ class FusedAdam(torch.optim.Adam):
 				arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
 				numel = (ctypes.c_int64 * n)(*[p.numel() for p in ps[chunk]])
 				with torch.cuda.device(ps[k0].device):
-					rc = lib.snnk_adam_step(
-						n, arr(ps[chunk]), arr(gs[chunk]), arr(ms[chunk]), arr(vs[chunk]), arr(ss[chunk]), numel, lr, b1, b2,
-						float(group["eps"]), float(group["weight_decay"]), _cabi.stream_ptr())
+					if self.reduces_gradients:
+						xbuf, state, _ = self._dp_context((gi, k0), ps[chunk])
+						peers = (ctypes.c_void_p * xbuf.world)(*xbuf.ptrs)
+						rc = lib.snnk_adam_step_dp(
+							n, arr(ps[chunk]), arr(gs[chunk]), arr(ms[chunk]), arr(vs[chunk]), arr(ss[chunk]), numel, lr, b1,
+							b2, float(group["eps"]), float(group["weight_decay"]), xbuf.rank, xbuf.world, peers,
+							state.data_ptr(), _cabi.stream_ptr())
+					else:
+						rc = lib.snnk_adam_step(
+							n, arr(ps[chunk]), arr(gs[chunk]), arr(ms[chunk]), arr(vs[chunk]), arr(ss[chunk]), numel, lr, b1, b2,
+							float(group["eps"]), float(group["weight_decay"]), _cabi.stream_ptr())
 				_cabi.check(rc, "snnk_adam_step")
 		return loss

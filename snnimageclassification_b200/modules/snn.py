@@ -339,6 +339,8 @@ class SNN(torch.nn.Module):
 			if self.device.type == "cuda":
 				from .optim import FusedAdam
 				optimizer = FusedAdam(self.parameters(), lr=lr, weight_decay=1e-5)
+				if os.environ.get("SNNK_DP_FUSED", "1") != "0":
+					optimizer.enable_data_parallel()    # no-op on one rank: gradient mean rides in the Adam launch
 			else:
 				optimizer = torch.optim.Adam(self.parameters(), lr=lr, weight_decay=1e-5)
 
@@ -449,15 +451,18 @@ class SNN(torch.nn.Module):
 			batch_loss = self.batch_loss(x_batch, y_batch, criterion)
 			optimizer.zero_grad()
 			batch_loss.backward()
-			self._allreduce_gradients()
+			self._allreduce_gradients(optimizer)
 			optimizer.step()
 		else:
 			with torch.no_grad():
 				batch_loss = self.batch_loss(x_batch, y_batch, criterion)
 		return batch_loss.item()
 
-	def _allreduce_gradients(self):
-		"""Data-parallel training: average the (small) gradients over the ranks with one flat NCCL all-reduce."""
+	def _allreduce_gradients(self, optimizer=None):
+		"""Data-parallel training: average the (small) gradients over the ranks with one flat NCCL all-reduce --
+		unless the optimizer does the exchange itself (``FusedAdam.enable_data_parallel``)."""
+		if getattr(optimizer, "reduces_gradients", False):
+			return
 		from ..distributed import allreduce_mean_
 		allreduce_mean_(p.grad for p in self.parameters())
 
