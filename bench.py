@@ -202,6 +202,7 @@ def main():
 	sampler.start()
 	ms = timed(step_resident, args.steps)
 	clocks = sampler.stop()
+	timeline = opt.exchange_timeline()[0] if dp_fused else None     # last resident step, rank-local device clock
 	value = world * B_PER_GPU * args.steps / (ms * 1e-3)
 
 	# end to end through the public API: pinned host images -> H2D -> GPU encoder -> train step -> loss read-back
@@ -262,7 +263,9 @@ def main():
 			"l2": f"{N_POOL} rotating input batches ({N_POOL * B_PER_GPU * T * N * 4 >> 20} MiB) > 126 MB L2",
 			"optimizer": "Adam(lr=1e-3, weight_decay=1e-5) as snnk_adam_step", "launch": "one CUDA graph per step",
 			"grad_exchange": ("none (1 rank)" if world == 1 else
-				"fused into snnk_adam_step_dp over NVLink peer memory" if dp_fused else "NCCL all-reduce (mean)")},
+				"fused into snnk_adam_step_dp over NVLink peer memory" if dp_fused else "NCCL all-reduce (mean)"),
+			"exchange_timeline_us": ({k: round(v, 2) for k, v in zip(("push", "wait_peers", "reduce_adam"),
+				timeline)} if dp_fused else None)},
 		"clocks": clocks,
 		"e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
 			"ms_per_step": ms_e2e / args.steps, "input": "pinned host images (B,784) fp32 + labels; GPU to_spikes",

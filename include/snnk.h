@@ -212,7 +212,9 @@ int snnk_adam_step(int32_t count, float* const* params, const float* const* grad
  *   peer_buffers: HOST array of `world` device pointers; entry r is rank r's exchange buffer as mapped into this
  *                 process (entry `rank` is the local one).  Each buffer holds snnk_adam_dp_buffer_bytes(world,
  *                 sum(numel)) bytes of peer-accessible memory, zero-filled on every rank before the first call.
- *   state:        4 zero-initialised uint32 in LOCAL device memory (epoch and grid counters; never reset them).
+ *   state:        16 zero-initialised uint32 in LOCAL device memory: [0] epoch, [1..2] grid counters (never reset
+ *                 them), [3] timeout marker, [4..11] four uint64 %globaltimer stamps of the last launch (start,
+ *                 gradients pushed, all peers seen, done) for measuring the exchange.
  * All ranks must issue the same sequence of calls.  Graph-capturable; a peer that never arrives traps the kernel
  * after 20 s (a sticky CUDA error) instead of hanging.
  */

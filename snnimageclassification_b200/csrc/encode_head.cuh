@@ -168,7 +168,8 @@ constexpr int kDpFlagWords = 64;    // 256 B: flag[r] = last epoch rank r has pu
 struct AdamDp {
     float* slots[kDpMaxWorld];      // peer r's gradient slots (after its flag words), as mapped into this process
     unsigned* flags[kDpMaxWorld];   // peer r's flag words
-    unsigned* state;                // local: [0] epoch, [1] arrive counter, [2] leave counter, [3] timeout marker
+    unsigned* state;                // local: [0] epoch, [1] arrive counter, [2] leave counter, [3] timeout marker,
+                                    // [4..11] globaltimer ns of the last launch as seen by CTA 0: start, pushed, peers seen, done
     int rank, world;
 };
 
@@ -197,6 +198,9 @@ __global__ void __launch_bounds__(256) k_adam_step_dp(const AdamTensors t, const
     const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned epoch = *(volatile unsigned*)(dp.state) + 1u;   // bumped by the last CTA to leave
     const size_t par = (size_t)(epoch & 1u) * dp.world;
+    unsigned long long* stamp = reinterpret_cast<unsigned long long*>(dp.state + 4);
+    const bool scribe = blockIdx.x == 0 && threadIdx.x == 0;
+    if (scribe) stamp[0] = global_ns();
 
     // 1. push the local gradient into slot `rank` of every rank's buffer (own included)
     {
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(256) k_adam_step_dp(const AdamTensors t, const
     }
     __threadfence_system();
     __syncthreads();
+    if (scribe) stamp[1] = global_ns();
     if (threadIdx.x == 0) {
         // 2. the last CTA to arrive publishes this rank's epoch at every peer ...
         if (atomicAdd(dp.state + 1, 1u) == gridDim.x - 1) {
@@ -230,6 +235,7 @@ __global__ void __launch_bounds__(256) k_adam_step_dp(const AdamTensors t, const
         }
     }
     __syncthreads();
+    if (scribe) stamp[2] = global_ns();
 
     // 3. mean over the local slots in rank order, then Adam
     {
@@ -259,7 +265,9 @@ __global__ void __launch_bounds__(256) k_adam_step_dp(const AdamTensors t, const
     if (threadIdx.x == 0 && atomicAdd(dp.state + 2, 1u) == gridDim.x - 1) {
         dp.state[2] = 0;
         dp.state[0] = epoch;
+        for (int k = 0; k < t.count; ++k) *t.step[k] += 1.0f;   // every thread of the grid has read the old counters
     }
+    if (scribe) stamp[3] = global_ns();
 }
 
 }  // namespace snnk

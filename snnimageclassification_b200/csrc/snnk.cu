@@ -742,11 +742,11 @@ int snnk_adam_step_dp(int32_t count, float* const* params, float* const* grads, 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ProfScope ps(SNNK_K_ADAM, st);
-    // every CTA waits on the peers' flags, so the whole grid must be co-resident: at most one CTA per SM
+    // every CTA waits on the peers' flags, so the whole grid must be co-resident: 4 CTAs of 256 threads per SM (of the
+    // 8 that fit) -- one element per thread at the reference's layer sizes, so all remote stores are in flight at once
     const long long want = (total + 255) / 256;
-    const unsigned grid = (unsigned)std::min<long long>(want, (long long)sm_count());
+    const unsigned grid = (unsigned)std::min<long long>(want, 4ll * sm_count());
     k_adam_step_dp<<<grid, 256, 0, st>>>(t, dp, lr, beta1, beta2, eps, weight_decay);
-    k_adam_bump<<<1, 32, 0, st>>>(t);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }

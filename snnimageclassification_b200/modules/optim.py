@@ -47,6 +47,14 @@ class FusedAdam(torch.optim.Adam):
 		self.reduces_gradients = True
 		return True
 
+	def exchange_timeline(self):
+		"""[(push_us, wait_peers_us, reduce_adam_us)] of the LAST data-parallel launch of every chunk (device clock)."""
+		out = []
+		for xbuf, state, _ in self._dp_ctx.values():
+			t = state[4:12].cpu().view(torch.int64).tolist()
+			out.append(tuple((t[i + 1] - t[i]) / 1e3 for i in range(3)))
+		return out
+
 	def _dp_context(self, key, ps):
 		ctx = self._dp_ctx.get(key)
 		if ctx is None:
@@ -58,7 +66,7 @@ class FusedAdam(torch.optim.Adam):
 			world = torch.distributed.get_world_size(self._dp_group)
 			_cabi.check(_cabi.lib().snnk_adam_dp_buffer_bytes(world, total, ctypes.byref(nbytes)), "snnk_adam_dp_buffer_bytes")
 			xbuf = PeerExchangeBuffer(nbytes.value, ps[0].device, self._dp_group)
-			state = torch.zeros(4, dtype=torch.int32, device=ps[0].device)
+			state = torch.zeros(16, dtype=torch.int32, device=ps[0].device)
 			ctx = self._dp_ctx[key] = (xbuf, state, total)
 		if ctx[2] != sum(p.numel() for p in ps):
 			raise RuntimeError("FusedAdam: the set of parameters with gradients changed between data-parallel steps")

@@ -37,7 +37,7 @@ def test_adam_dp_single_rank_is_plain_adam():
 	_cabi.check(lib.snnk_adam_dp_buffer_bytes(1, total, ctypes.byref(nbytes)), "bytes")
 	assert nbytes.value == 256 + 2 * total * 4
 	xbuf = torch.zeros(nbytes.value // 4, dtype=torch.float32, device=DEV)
-	state = torch.zeros(4, dtype=torch.int32, device=DEV)
+	state = torch.zeros(16, dtype=torch.int32, device=DEV)
 	peers = (ctypes.c_void_p * 1)(xbuf.data_ptr())
 	for it in range(5):
 		G = [torch.randn(s, generator=g).to(DEV) for s in shapes]
@@ -51,7 +51,9 @@ def test_adam_dp_single_rank_is_plain_adam():
 			assert torch.equal(a, b)
 		for a, b in zip(G, G2):
 			assert torch.equal(a, b)
-	assert state.tolist() == [5, 0, 0, 0]
+	assert state[:4].tolist() == [5, 0, 0, 0]
+	stamps = state[4:12].cpu().view(torch.int64).tolist()
+	assert stamps[0] > 0 and stamps == sorted(stamps)
 	assert all(float(s) == 5.0 for s in s2)
 	# argument checks
 	assert lib.snnk_adam_step_dp(len(Q), _arr(Q), _arr(G2), _arr(m2), _arr(v2), _arr(s2), numel, 1e-2, 0.9, 0.999, 1e-8,
