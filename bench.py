@@ -202,7 +202,10 @@ def main():
 	sampler.start()
 	ms = timed(step_resident, args.steps)
 	clocks = sampler.stop()
-	timeline = opt.exchange_timeline()[0] if dp_fused else None     # last resident step, rank-local device clock
+	timeline = None
+	if dp_fused:     # last resident step on every rank, rank-local device clocks, us since kernel start
+		timeline = [None] * world
+		dist.all_gather_object(timeline, [round(v, 2) for v in opt.exchange_timeline()[0]])
 	value = world * B_PER_GPU * args.steps / (ms * 1e-3)
 
 	# end to end through the public API: pinned host images -> H2D -> GPU encoder -> train step -> loss read-back
@@ -264,8 +267,8 @@ def main():
 			"optimizer": "Adam(lr=1e-3, weight_decay=1e-5) as snnk_adam_step", "launch": "one CUDA graph per step",
 			"grad_exchange": ("none (1 rank)" if world == 1 else
 				"fused into snnk_adam_step_dp over NVLink peer memory" if dp_fused else "NCCL all-reduce (mean)"),
-			"exchange_timeline_us": ({k: round(v, 2) for k, v in zip(("push", "wait_peers", "reduce_adam"),
-				timeline)} if dp_fused else None)},
+			"exchange_timeline_us": ({"columns": ["stores_issued", "peers_seen", "done"], "per_rank": timeline}
+				if dp_fused else None)},
 		"clocks": clocks,
 		"e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
 			"ms_per_step": ms_e2e / args.steps, "input": "pinned host images (B,784) fp32 + labels; GPU to_spikes",

@@ -206,15 +206,16 @@ int snnk_adam_step(int32_t count, float* const* params, const float* const* grad
 /*
  * Data-parallel form of snnk_adam_step (one process per GPU, batch rows sharded, weights replicated): the mean of
  * the weight gradients over the ranks -- the single exchange step of SNN._exec_batch's path -- and
- * the Adam update in ONE kernel over NVLink peer memory.  Every rank pushes its gradient into a slot of each
- * peer's exchange buffer, publishes a flag, waits for its peers' flags and reduces the slots in rank order, so
- * all ranks compute bit-identical means; grads[k] is overwritten with the mean (as after an all-reduce).
+ * the Adam update in ONE kernel over NVLink peer memory.  The thread owning a gradient element stores it, tagged
+ * with the launch epoch in the same 8-byte word, into its rank's slot of every peer's exchange buffer, polls the
+ * peers' slots of its own buffer until the tags match and sums the values in rank order, so all ranks compute
+ * bit-identical means; grads[k] is overwritten with the mean (as after an all-reduce).
  *   peer_buffers: HOST array of `world` device pointers; entry r is rank r's exchange buffer as mapped into this
  *                 process (entry `rank` is the local one).  Each buffer holds snnk_adam_dp_buffer_bytes(world,
  *                 sum(numel)) bytes of peer-accessible memory, zero-filled on every rank before the first call.
- *   state:        16 zero-initialised uint32 in LOCAL device memory: [0] epoch, [1..2] grid counters (never reset
- *                 them), [3] timeout marker, [4..11] four uint64 %globaltimer stamps of the last launch (start,
- *                 gradients pushed, all peers seen, done) for measuring the exchange.
+ *   state:        16 zero-initialised uint32 in LOCAL device memory: [0] epoch and [2] grid counter (never reset
+ *                 them), [3] timeout marker, [4..11] four uint64 %globaltimer stamps of the last launch as seen by
+ *                 the first thread (start, stores issued, all peers seen, done) for measuring the exchange.
  * All ranks must issue the same sequence of calls.  Graph-capturable; a peer that never arrives traps the kernel
  * after 20 s (a sticky CUDA error) instead of hanging.
  */

@@ -156,32 +156,34 @@ __global__ void k_adam_bump(const AdamTensors t)
 
 // ---- data-parallel optimizer step: gradient exchange + mean + Adam in ONE kernel -------------------
 // The only exchange step of the path is the mean of the weight gradients over the ranks.  Instead of an NCCL
-// all-reduce followed by the optimizer launch, every rank PUSHES its gradient over NVLink straight into a slot of
-// each peer's exchange buffer (peer-mapped symmetric memory), raises a flag at each peer, waits for the peers' flags
-// in its own buffer and then reduces the `world` local slots in rank order (bit-identical on every rank, so the
-// replicated weights never diverge), stores the mean back as the gradient and applies Adam.
-//   exchange buffer per rank: [kDpFlagWords uint32 flags][2 parities][world slots][total floats]
-//   parity = epoch & 1: a rank can be one launch ahead of a peer (it cannot pass the next flag wait before the peer
-//   has left this one), so two buffers suffice; the epoch counter lives in `state` and survives graph replays.
+// all-reduce followed by the optimizer launch, the thread that owns gradient element e PUSHES it over NVLink straight
+// into slot `rank` of every peer's exchange buffer (peer-mapped symmetric memory) as one 8-byte word {value, epoch},
+// then polls the same element of the other ranks' slots in its OWN buffer until their epoch tags match, sums the
+// `world` values in rank order (bit-identical on every rank, so the replicated weights never diverge), stores the
+// mean back as the gradient and applies Adam.  A 64-bit store is single-copy atomic, so the tag that arrives with the
+// value IS the synchronisation: no flags, no memory fences (a system-scope fence behind remote stores was measured at
+// ~5 us, and the flag protocol needs three in a row), no grid-wide dependency -- the latency is one NVLink crossing.
+//   exchange buffer per rank: [2 parities][world slots][total] x uint64
+//   parity = epoch & 1: a rank can run at most one launch ahead of a peer (it needs the peer's values of launch e+1,
+//   which the peer sends after it finished reading launch e), so two buffers suffice; the epoch counter lives in
+//   `state` and survives graph replays.  Buffers start zeroed and epochs start at 1.
 constexpr int kDpMaxWorld = 16;
-constexpr int kDpFlagWords = 64;    // 256 B: flag[r] = last epoch rank r has published into this buffer
 struct AdamDp {
-    float* slots[kDpMaxWorld];      // peer r's gradient slots (after its flag words), as mapped into this process
-    unsigned* flags[kDpMaxWorld];   // peer r's flag words
-    unsigned* state;                // local: [0] epoch, [1] arrive counter, [2] leave counter, [3] timeout marker,
+    unsigned long long* slots[kDpMaxWorld];   // peer r's exchange buffer as mapped into this process
+    unsigned* state;                // local: [0] epoch, [1] unused, [2] leave counter, [3] timeout marker,
                                     // [4..11] globaltimer ns of the last launch as seen by CTA 0: start, pushed, peers seen, done
     int rank, world;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
 {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns()
 {
@@ -201,71 +203,59 @@ __global__ void __launch_bounds__(256) k_adam_step_dp(const AdamTensors t, const
     unsigned long long* stamp = reinterpret_cast<unsigned long long*>(dp.state + 4);
     const bool scribe = blockIdx.x == 0 && threadIdx.x == 0;
     if (scribe) stamp[0] = global_ns();
+    const unsigned long long tag = (unsigned long long)epoch << 32;
+    const size_t mine = (par + dp.rank) * (size_t)total;
+    const unsigned long long* local = dp.slots[dp.rank];
+    const float inv = 1.0f / (float)dp.world;
 
-    // 1. push the local gradient into slot `rank` of every rank's buffer (own included)
-    {
-        const size_t mine = (par + dp.rank) * (size_t)total;
-        int k = 0;
-        for (long long e = e0; e < total; e += stride) {
-            while (e >= t.start[k + 1]) ++k;
-            const float g = t.g[k][e - t.start[k]];
-            for (int r = 0; r < dp.world; ++r) dp.slots[r][mine + e] = g;
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (scribe) stamp[1] = global_ns();
-    if (threadIdx.x == 0) {
-        // 2. the last CTA to arrive publishes this rank's epoch at every peer ...
-        if (atomicAdd(dp.state + 1, 1u) == gridDim.x - 1) {
-            dp.state[1] = 0;
-            __threadfence_system();
-            for (int r = 0; r < dp.world; ++r) st_release_sys(dp.flags[r] + dp.rank, epoch);
-        }
-        // ... and every CTA waits until all ranks have published into the local buffer
-        const unsigned long long t0 = global_ns();
+    int k = 0;
+    for (long long e = e0; e < total; e += stride) {
+        while (e >= t.start[k + 1]) ++k;
+        const long long i = e - t.start[k];
+        const float g_own = t.g[k][i];
+        // 1. push {value, epoch} to every peer
+        const unsigned long long word = tag | (unsigned long long)__float_as_uint(g_own);
+        for (int r = 0; r < dp.world; ++r)
+            if (r != dp.rank) st_relaxed_sys(dp.slots[r] + mine + e, word);
+        if (scribe && e == e0) stamp[1] = global_ns();
+        // 2. gather the peers' values of this element from the local buffer, in rank order
+        float g = 0.0f;
+        unsigned long long t0 = 0;
         for (int r = 0; r < dp.world; ++r) {
-            while ((int)(ld_acquire_sys(dp.flags[dp.rank] + r) - epoch) < 0) {
-                if (global_ns() - t0 > 20000000000ull) {   // 20 s: a peer died -- fail loudly instead of hanging
+            if (r == dp.rank) { g += g_own; continue; }
+            const unsigned long long* src = local + (par + r) * (size_t)total + e;
+            unsigned long long w = ld_relaxed_sys(src);
+            while ((unsigned)(w >> 32) != epoch) {
+                if (t0 == 0) t0 = global_ns();
+                else if (global_ns() - t0 > 20000000000ull) {   // 20 s: a peer died -- fail loudly instead of hanging
                     dp.state[3] = epoch;
                     __threadfence_system();
                     __trap();
                 }
+                w = ld_relaxed_sys(src);
             }
+            g += __uint_as_float((unsigned)w);
         }
-    }
-    __syncthreads();
-    if (scribe) stamp[2] = global_ns();
-
-    // 3. mean over the local slots in rank order, then Adam
-    {
-        const float inv = 1.0f / (float)dp.world;
-        const float* local = dp.slots[dp.rank];
-        int k = 0;
-        for (long long e = e0; e < total; e += stride) {
-            while (e >= t.start[k + 1]) ++k;
-            const long long i = e - t.start[k];
-            float g = 0.0f;
-            for (int r = 0; r < dp.world; ++r) g += __ldcg(local + (par + r) * (size_t)total + e);
-            g *= inv;
-            const_cast<float*>(t.g[k])[i] = g;      // the caller sees the averaged gradient, as after an all-reduce
-            const float step = *t.step[k] + 1.0f;
-            const float p = t.p[k][i];
-            g = fmaf(weight_decay, p, g);
-            const float m = fmaf(1.0f - beta1, g - t.m[k][i], t.m[k][i]);
-            const float v = fmaf(1.0f - beta2, g * g, beta2 * t.v[k][i]);
-            t.m[k][i] = m;
-            t.v[k][i] = v;
-            const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
-            const float denom = sqrtf(v) / sqrtf(bc2) + eps;
-            t.p[k][i] = p - (lr / bc1) * (m / denom);
-        }
+        if (scribe && e == e0) stamp[2] = global_ns();
+        // 3. mean, then Adam
+        g *= inv;
+        const_cast<float*>(t.g[k])[i] = g;      // the caller sees the averaged gradient, as after an all-reduce
+        const float step = *t.step[k] + 1.0f;
+        const float p = t.p[k][i];
+        g = fmaf(weight_decay, p, g);
+        const float m = fmaf(1.0f - beta1, g - t.m[k][i], t.m[k][i]);
+        const float v = fmaf(1.0f - beta2, g * g, beta2 * t.v[k][i]);
+        t.m[k][i] = m;
+        t.v[k][i] = v;
+        const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
+        const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+        t.p[k][i] = p - (lr / bc1) * (m / denom);
     }
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(dp.state + 2, 1u) == gridDim.x - 1) {
         dp.state[2] = 0;
         dp.state[0] = epoch;
-        for (int k = 0; k < t.count; ++k) *t.step[k] += 1.0f;   // every thread of the grid has read the old counters
+        for (int kk = 0; kk < t.count; ++kk) *t.step[kk] += 1.0f;   // every thread of the grid has read the old counters
     }
     if (scribe) stamp[3] = global_ns();
 }

@@ -710,7 +710,7 @@ int snnk_adam_dp_buffer_bytes(int32_t world, int64_t total_numel, size_t* bytes)
 {
     if (!bytes) return SNNK_ERR_ARG;
     if (world < 1 || world > kDpMaxWorld || total_numel < 0) return SNNK_ERR_SHAPE;
-    *bytes = (size_t)kDpFlagWords * sizeof(unsigned) + (size_t)2 * world * (size_t)total_numel * sizeof(float);
+    *bytes = (size_t)2 * world * (size_t)total_numel * sizeof(unsigned long long);
     return SNNK_OK;
 }
 
@@ -737,15 +737,15 @@ int snnk_adam_step_dp(int32_t count, float* const* params, float* const* grads, 
     dp.rank = rank; dp.world = world; dp.state = state;
     for (int r = 0; r < world; ++r) {
         if (!peer_buffers[r]) return SNNK_ERR_ARG;
-        dp.flags[r] = static_cast<unsigned*>(peer_buffers[r]);
-        dp.slots[r] = reinterpret_cast<float*>(dp.flags[r] + kDpFlagWords);
+        if (reinterpret_cast<uintptr_t>(peer_buffers[r]) & 7) return SNNK_ERR_ARG;
+        dp.slots[r] = static_cast<unsigned long long*>(peer_buffers[r]);
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ProfScope ps(SNNK_K_ADAM, st);
-    // every CTA waits on the peers' flags, so the whole grid must be co-resident: 4 CTAs of 256 threads per SM (of the
-    // 8 that fit) -- one element per thread at the reference's layer sizes, so all remote stores are in flight at once
+    // one gradient element per thread: every remote store of the step is in flight at once.  Threads only wait for
+    // REMOTE data, never for another local CTA, so the grid need not be co-resident.
     const long long want = (total + 255) / 256;
-    const unsigned grid = (unsigned)std::min<long long>(want, 4ll * sm_count());
+    const unsigned grid = (unsigned)std::min<long long>(want, 8ll * sm_count());
     k_adam_step_dp<<<grid, 256, 0, st>>>(t, dp, lr, beta1, beta2, eps, weight_decay);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;

@@ -48,11 +48,12 @@ class FusedAdam(torch.optim.Adam):
 		return True
 
 	def exchange_timeline(self):
-		"""[(push_us, wait_peers_us, reduce_adam_us)] of the LAST data-parallel launch of every chunk (device clock)."""
+		"""Per chunk, microseconds of the LAST data-parallel launch on this rank's device clock, relative to kernel
+		start, as seen by the first thread: (stores issued, all peers' values seen, kernel done)."""
 		out = []
 		for xbuf, state, _ in self._dp_ctx.values():
 			t = state[4:12].cpu().view(torch.int64).tolist()
-			out.append(tuple((t[i + 1] - t[i]) / 1e3 for i in range(3)))
+			out.append(tuple((t[i] - t[0]) / 1e3 for i in (1, 2, 3)))
 		return out
 
 	def _dp_context(self, key, ps):

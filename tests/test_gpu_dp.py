@@ -35,7 +35,7 @@ def test_adam_dp_single_rank_is_plain_adam():
 	total = sum(p.numel() for p in P)
 	nbytes = ctypes.c_size_t(0)
 	_cabi.check(lib.snnk_adam_dp_buffer_bytes(1, total, ctypes.byref(nbytes)), "bytes")
-	assert nbytes.value == 256 + 2 * total * 4
+	assert nbytes.value == 2 * total * 8
 	xbuf = torch.zeros(nbytes.value // 4, dtype=torch.float32, device=DEV)
 	state = torch.zeros(16, dtype=torch.int32, device=DEV)
 	peers = (ctypes.c_void_p * 1)(xbuf.data_ptr())
