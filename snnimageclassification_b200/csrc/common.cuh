@@ -91,4 +91,55 @@ __device__ __forceinline__ float dot_rec16(const float (&w)[H], const float4* __
     return __fadd_rn(lo, hi);
 }
 
+// ---- column-blocked form of the same sum ----------------------------------------------------------------------------
+// dot_rec16 makes every thread read the whole broadcast vector (H/4 LDS.128 per row and step); at 128 threads per row
+// that is 64 KB of shared-memory return traffic per row-step, and the recurrence kernels were measured to be bound by
+// exactly that path, not by the FMAs.  Here the four lanes of a quad share the quad's four columns: lane g holds, for
+// EACH of the four columns, the weights of accumulation chains 4g..4g+3 (k mod 16 in [4g, 4g+4)), so it needs only
+// every fourth float4 of the vector (H/16 LDS.128 per row-step, a quarter of the traffic) for the same H FMAs.  The
+// partial q_g = (c_4g + c_4g+1) + (c_4g+2 + c_4g+3) of a column is a subtree of dot_rec16's summation tree
+// (lo = q0 + q1, hi = q2 + q3, sum = lo + hi), so three quad shuffles finish the tree and the result is bit-identical;
+// lane g ends up with the finished sum of column 4*(i/4)+g = i, its own neuron.
+template <int H>
+__device__ __forceinline__ void load_w_cb(float (&w)[H], const float* __restrict__ s_w, int i)
+{
+    const int g = i & 3, c0 = i & ~3;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+        for (int j = 0; j < H / 16; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[(ci * (H / 16) + j) * 4 + e] = s_w[(16 * j + 4 * g + e) * H + c0 + ci];
+}
+
+template <int H>
+__device__ __forceinline__ float dot_rec16_cb(const float (&w)[H], const float4* __restrict__ zv, int g)
+{
+    float2 acc[4][2];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) acc[ci][0] = acc[ci][1] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < H / 16; ++j) {
+        const float4 z = zv[4 * j + g];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+            const int o = (ci * (H / 16) + j) * 4;
+            acc[ci][0] = __ffma2_rn(make_float2(w[o], w[o + 1]), make_float2(z.x, z.y), acc[ci][0]);
+            acc[ci][1] = __ffma2_rn(make_float2(w[o + 2], w[o + 3]), make_float2(z.z, z.w), acc[ci][1]);
+        }
+    }
+    float q[4];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+        q[ci] = __fadd_rn(__fadd_rn(acc[ci][0].x, acc[ci][0].y), __fadd_rn(acc[ci][1].x, acc[ci][1].y));
+    // quad butterfly: (xor 1) lo = q0 + q1 on lanes 0,1 and hi = q2 + q3 on lanes 2,3; (xor 2) lo + hi
+    const bool odd = g & 1, upper = g & 2;
+    const float rA = __shfl_xor_sync(0xffffffffu, odd ? q[0] : q[1], 1);
+    const float rB = __shfl_xor_sync(0xffffffffu, odd ? q[2] : q[3], 1);
+    const float sA = odd ? __fadd_rn(rA, q[1]) : __fadd_rn(q[0], rA);     // columns 0 (even lanes) / 1 (odd lanes)
+    const float sB = odd ? __fadd_rn(rB, q[3]) : __fadd_rn(q[2], rB);     // columns 2 / 3
+    const float rC = __shfl_xor_sync(0xffffffffu, upper ? sA : sB, 2);
+    return upper ? __fadd_rn(rC, sB) : __fadd_rn(sA, rC);
+}
+
 }  // namespace snnk

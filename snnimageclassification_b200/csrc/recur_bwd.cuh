@@ -58,8 +58,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
         }
         __syncthreads();
         tc::mbar_wait(wbar, 0);
-#pragma unroll
-        for (int k = 0; k < H; ++k) w[k] = s_t[k * H + i];
+        load_w_cb<REC ? H : 16>(w, s_t, i);
         __syncthreads();
         if (i == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(wbar)) : "memory");
     }
@@ -184,7 +183,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
                     if constexpr (REC) {
                         const float4* gv4 =
                             reinterpret_cast<const float4*>(s_g + ((t + 1) & 1) * R * H + r * H);
-                        s = __fadd_rn(s, dot_rec16<REC ? H : 16>(w, gv4));   // gI_{t+1} (W_rec . M)^T
+                        s = __fadd_rn(s, dot_rec16_cb<REC ? H : 16>(w, gv4, i & 3));   // gI_{t+1} (W_rec . M)^T
                     }
                     const size_t o = ((size_t)(valid[r] ? b0 + r : 0) * T + t) * H + i;
                     if (p.g_Z && valid[r]) s = __fadd_rn(s, __ldg(p.g_Z + o));

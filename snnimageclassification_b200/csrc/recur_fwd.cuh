@@ -45,21 +45,29 @@ __device__ __forceinline__ void fwd_tail(const FwdParams& p, const uint32_t* s_m
     }
 
     // Leaky readout, spiking_layers.py:407:  y_t = kappa y_{t-1} + Z_t @ W_out + b.
-    // (A) s[t][c] = sum_j Z_t[j] W_out[j][c], ascending j, for all (t,c) in parallel
-    for (int idx = tid; idx < R * T * O; idx += nthr) {
-        const int r = idx / (T * O), rem = idx - r * (T * O);
-        const int t = rem / O, c = rem - t * O;
-        const uint32_t* mw = s_mask + (r * T + t) * W32;
-        float s = 0.f;
-        for (int wd = 0; wd < W32; ++wd) {
-            const uint32_t m = mw[wd];
-#pragma unroll 8
-            for (int l = 0; l < 32; ++l) {
-                const float wv = s_wout[(wd * 32 + l) * O + c];
-                s = __fadd_rn(s, ((m >> l) & 1u) ? wv : 0.f);
+    // (A) s[t][c] = sum_j Z_t[j] W_out[j][c], ascending j.  nthr / O threads per class, each holding its class's
+    // column of W_out in registers (the recurrent weights are dead by now) and walking its share of the T spike
+    // words with one predicated add per bit: adding w only where the bit is set equals adding (bit ? w : 0) for every
+    // bit, because the running sum is never -0.
+    {
+        const int tpc = nthr / O, c = tid / tpc, u = tid - c * tpc;
+        if (c < O) {
+            float wc[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) wc[j] = s_wout[j * O + c];
+            for (int rt = u; rt < R * T; rt += tpc) {
+                const uint32_t* mw = s_mask + rt * W32;
+                float sum = 0.f;
+#pragma unroll
+                for (int wd = 0; wd < W32; ++wd) {
+                    const uint32_t m = mw[wd];
+#pragma unroll
+                    for (int l = 0; l < 32; ++l)
+                        if (m & (1u << l)) sum = __fadd_rn(sum, wc[wd * 32 + l]);
+                }
+                s_s[rt * O + c] = sum;
             }
         }
-        s_s[idx] = s;
     }
     __syncthreads();
     // (B) the scan over t (sequential per (row, class)) + max over time, snn.py:228 (first max wins)
@@ -130,8 +138,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
     float w[REC ? H : 16];
     if constexpr (REC) {
         tc::mbar_wait(s_bar + kRing, 0);
-#pragma unroll
-        for (int k = 0; k < H; ++k) w[k] = s_w[k * H + i];
+        load_w_cb<REC ? H : 16>(w, s_w, i);
     }
     const float beta = (p.alif && p.beta) ? __ldg(p.beta) : 0.f;
 
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
             float rec = 0.0f;
             if constexpr (REC) {
                 const float4* zv = reinterpret_cast<const float4*>(s_z + ((t + 1) & 1) * R * H + r * H);
-                rec = dot_rec16<REC ? H : 16>(w, zv);
+                rec = dot_rec16_cb<REC ? H : 16>(w, zv, i & 3);
             }
             // V' = (alpha V + I_in + I_rec) (1 - Z.detach())     spiking_layers.py:169/239
             const float t1 = __fmul_rn(p.alpha, v[r]);
@@ -199,118 +206,9 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
     fwd_tail<H, R>(p, s_mask, s_wout, s_s, b0, i, H);
 }
 
-// ---- k-split variant for the latency-bound regime (few rows per SM) ------------------------------------------------
-// Two threads per neuron (adjacent lanes): lane h = 0 owns accumulation chains 0..7 (k mod 16 < 8), lane h = 1 chains
-// 8..15, i.e. exactly the `lo` and `hi` halves of the oracle's summation tree, so rec = lo + hi is bit-identical to
-// k_recur_fwd.  A row then runs on 8 warps instead of 4: each warp's dependent FFMA2/LDS chain is half as long and
-// an SM holding two rows has 16 warps to hide latency with instead of 8.  One batch row per CTA.
-template <int H, bool REC>
-__global__ void __launch_bounds__(2 * H, 2) k_recur_fwd_ks2(const FwdParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int W32 = H / 32, R = 1, NT = 2 * H, KH = H / 2;
-    const int T = p.T, O = p.O, B = p.B;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int h = lane & 1, i = warp * 16 + (lane >> 1);
-    const int b0 = blockIdx.x;
-
-    float* s_z = reinterpret_cast<float*>(smem_raw);
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_z + 2 * R * H);
-    float* s_wout = reinterpret_cast<float*>(s_mask + ((R * T * W32 + 3) & ~3));
-    float* s_s = s_wout + H * O;
-    float* s_in = s_wout + ((H * O + R * T * O + 3) & ~3);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_in + kRing * R * kChunk * H);
-    float* s_w = reinterpret_cast<float*>(s_bar + kRing + 2);
-
-    const int nchunks = (T + kChunk - 1) / kChunk;
-    auto issue_chunk = [&](int c) {
-        const int slot = c % kRing, t0 = c * kChunk;
-        const uint32_t bytes = (uint32_t)(min(kChunk, T - t0) * H * sizeof(float));
-        tc::mbar_expect_tx(s_bar + slot, bytes);
-        tc::bulk_g2s(s_in + (slot * kChunk) * H, p.I_in + ((size_t)b0 * T + t0) * H, bytes, s_bar + slot);
-    };
-    if (tid == 0) {
-        for (int s = 0; s <= kRing; ++s) tc::mbar_init(s_bar + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (REC) {
-            tc::mbar_expect_tx(s_bar + kRing, (uint32_t)(H * H * sizeof(float)));
-            tc::bulk_g2s(s_w, p.W_eff, (uint32_t)(H * H * sizeof(float)), s_bar + kRing);
-        }
-        for (int c = 0; c < kRing && c < nchunks; ++c) issue_chunk(c);
-    }
-    __syncthreads();
-
-    // this thread's half of column i: local index kk <-> k = 16*(kk/8) + 8*h + kk%8
-    float w[REC ? KH : 8];
-    if constexpr (REC) {
-        tc::mbar_wait(s_bar + kRing, 0);
-#pragma unroll
-        for (int kk = 0; kk < KH; ++kk) w[kk] = s_w[(16 * (kk / 8) + 8 * h + (kk % 8)) * H + i];
-    }
-    const float beta = (p.alif && p.beta) ? __ldg(p.beta) : 0.f;
-    float v = p.V0 ? p.V0[(size_t)b0 * H + i] : 0.f;
-    float a = p.a0 ? p.a0[(size_t)b0 * H + i] : 0.f;
-    float zp = p.Z0 ? p.Z0[(size_t)b0 * H + i] : 0.f;
-    if (REC && h == 0) s_z[H + i] = zp;
-    for (int idx = tid; idx < H * O; idx += NT) s_wout[idx] = __ldg(p.W_out + idx);
-    __syncthreads();
-
-    uint16_t* s_mask16 = reinterpret_cast<uint16_t*>(s_mask);
-    for (int t = 0; t < T; ++t) {
-        const int c = t / kChunk, tt = t - c * kChunk, slot = c % kRing;
-        if (tt == 0) {
-            if (!REC) __syncthreads();
-            if (tid == 0 && c >= 1 && c - 1 + kRing < nchunks) issue_chunk(c - 1 + kRing);
-            tc::mbar_wait(s_bar + slot, (c / kRing) & 1);
-        }
-        const float cur = s_in[(slot * kChunk + tt) * H + i];
-        float rec = 0.0f;
-        if constexpr (REC) {
-            const float4* zv = reinterpret_cast<const float4*>(s_z + ((t + 1) & 1) * H) + 2 * h;
-            float2 acc[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int m = 0; m < H / 16; ++m) {
-                const float4 z0 = zv[4 * m], z1 = zv[4 * m + 1];
-                acc[0] = __ffma2_rn(make_float2(w[8 * m + 0], w[8 * m + 1]), make_float2(z0.x, z0.y), acc[0]);
-                acc[1] = __ffma2_rn(make_float2(w[8 * m + 2], w[8 * m + 3]), make_float2(z0.z, z0.w), acc[1]);
-                acc[2] = __ffma2_rn(make_float2(w[8 * m + 4], w[8 * m + 5]), make_float2(z1.x, z1.y), acc[2]);
-                acc[3] = __ffma2_rn(make_float2(w[8 * m + 6], w[8 * m + 7]), make_float2(z1.z, z1.w), acc[3]);
-            }
-            const float mine = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].x, acc[0].y), __fadd_rn(acc[1].x, acc[1].y)),
-                                         __fadd_rn(__fadd_rn(acc[2].x, acc[2].y), __fadd_rn(acc[3].x, acc[3].y)));
-            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-            rec = __fadd_rn(h ? other : mine, h ? mine : other);      // lo + hi
-        }
-        const float t1 = __fmul_rn(p.alpha, v);
-        const float t2 = __fadd_rn(t1, cur);
-        const float t3 = __fadd_rn(t2, rec);
-        const float vn = __fmul_rn(t3, __fsub_rn(1.0f, zp));
-        float thr = p.theta;
-        if (p.alif) {
-            a = __fadd_rn(__fmul_rn(p.rho, a), zp);
-            thr = __fadd_rn(p.theta, __fmul_rn(beta, a));
-        }
-        const float zn = vn >= thr ? 1.0f : 0.0f;
-        if (p.traces) {
-            const size_t o = ((size_t)b0 * T + t) * H + i;
-            if (h == 0) { p.V[o] = vn; p.Z[o] = zn; }
-            else if (p.alif) p.a[o] = a;
-        }
-        unsigned m = __ballot_sync(0xffffffffu, zn != 0.f) & 0x55555555u;    // even lanes carry the 16 neurons
-        m = (m | (m >> 1)) & 0x33333333u;
-        m = (m | (m >> 2)) & 0x0F0F0F0Fu;
-        m = (m | (m >> 4)) & 0x00FF00FFu;
-        m = (m | (m >> 8)) & 0x0000FFFFu;
-        if (lane == 0) s_mask16[t * (H / 16) + warp] = (uint16_t)m;
-        if (REC && h == 0) s_z[(t & 1) * H + i] = zn;
-        v = vn;
-        zp = zn;
-        if (REC) __syncthreads();
-    }
-    __syncthreads();
-    fwd_tail<H, 1>(p, s_mask, s_wout, s_s, b0, tid, NT);
-}
+// A k-split variant (two, then eight lanes per neuron; 8 warps per row) was built and measured twice: 76 us and 74 us
+// against 65 us / 59 us for the kernel above at B = 256.  The step is bound by instruction issue (each SM sub-partition
+// runs its two warps at the 1-per-2-cycles rate of the FMA pipe), so spreading a row over more threads only adds the
+// duplicated tail and wider barriers; see DESIGN.md.
 
 }  // namespace snnk

@@ -291,18 +291,6 @@ int launch_fwd_rec(const FwdParams& fp, bool rec, int grid, cudaStream_t st)
     return rec ? launch_fwd<H, R, true>(fp, grid, st) : launch_fwd<H, R, false>(fp, grid, st);
 }
 
-template <int H, bool REC>
-int launch_fwd_ks2(const FwdParams& fp, cudaStream_t st)
-{
-    const size_t smem = fwd_smem_bytes<H, 1>(fp.T, fp.O);
-    if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
-    auto kern = k_recur_fwd_ks2<H, REC>;
-    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { ProfScope ps(SNNK_K_RECUR_FWD, st); kern<<<fp.B, 2 * H, smem, st>>>(fp); }
-    SNNK_CUDA(cudaGetLastError());
-    return SNNK_OK;
-}
-
 // Tensor-core recurrence (recur_mma.cuh): H = 128, selected by SNNK_F_TENSOR_CORE; SNNK_MMA_RECUR=0 keeps the SIMT kernel.
 bool use_mma_recur(const SnnkDesc* d)
 {
@@ -330,19 +318,9 @@ int launch_fwd_mma(const FwdParams& fp, bool rec, cudaStream_t st)
     return SNNK_OK;
 }
 
-// k_recur_fwd_ks2 (two threads per neuron) is kept as an experiment, off unless SNNK_KSPLIT=1: measured on B200 it is
-// SLOWER than k_recur_fwd (76 us vs 65 us at B = 256) -- which is how the kernel turned out to be bound by the shared-
-// memory return path (every thread re-reads the spike vector), not by per-warp latency; see DESIGN.md.
-bool use_ksplit(int B, int R)
-{
-    static const char* env = getenv("SNNK_KSPLIT");
-    return env && env[0] == '1' && R == 1 && B <= 1024;
-}
-
 template <int H>
 int launch_fwd_r(const FwdParams& fp, bool rec, int R, int grid, cudaStream_t st)
 {
-    if (use_ksplit(fp.B, R)) return rec ? launch_fwd_ks2<H, true>(fp, st) : launch_fwd_ks2<H, false>(fp, st);
     return R == 1 ? launch_fwd_rec<H, 1>(fp, rec, grid, st) : launch_fwd_rec<H, 2>(fp, rec, grid, st);
 }
 
