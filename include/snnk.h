@@ -128,6 +128,30 @@ int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, 
                 int32_t out_dtype, int64_t* periods, snnk_stream_t stream);
 
 /*
+ * Frame runs of an encoded batch ("frame-dedup fast path for production ToSpikes output").
+ * ToSpikes with the production tau = 0.02 (datasets.py:21) emits at most three distinct frames per item, so
+ * consecutive time steps mostly repeat the previous frame.  snnk_encode_runs is snnk_encode that also records
+ *   frame_changed (n_items, n_steps) uint8: 1 where frame t differs from frame t-1 (scratch owned by the caller)
+ *   run_table     int32, snnk_run_table_bytes(n_items, n_steps) bytes:
+ *                 [0] number of runs in the batch  [1] ok: 1 when that number fits the table's capacity
+ *                 [2] capacity = max(128, n_items*n_steps/4 rounded up to 128)  [3] 0
+ *                 [4 ..) for every dense row item*n_steps+t the index of its run; then capacity first-rows; then
+ *                 capacity run lengths.
+ * snnk_frame_runs builds the table from change flags the caller produced itself.  snnk_forward / snnk_backward
+ * take the table of THEIR input x (or NULL): with SNNK_F_TENSOR_CORE | SNNK_F_INPUT_BINARY and H <= 128 the input
+ * projection is then evaluated once per run and the dW_in contraction runs over runs instead of rows.  Whether
+ * that variant or the dense one executes is decided on the device from word [1]; both are always enqueued, so
+ * the call stays CUDA-graph capturable and a batch with too many runs silently takes the dense kernels.
+ */
+size_t snnk_run_table_bytes(int64_t n_items, int32_t n_steps);
+int snnk_frame_runs(int64_t n_items, int32_t n_steps, const uint8_t* frame_changed, int32_t* run_table,
+                    snnk_stream_t stream);
+int snnk_encode_runs(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps,
+                     double t_max, double tau, double thr, double eps, int32_t periodic, void* out,
+                     int32_t out_dtype, int64_t* periods, uint8_t* frame_changed, int32_t* run_table,
+                     snnk_stream_t stream);
+
+/*
  * SpikeFunction.apply used stand-alone (spike_funcs.py:12-29): out = (v >= thr) ? 1 : 0, and its surrogate
  * backward (spike_funcs.py:46-62 FastSigmoid, :65-79 Phi): g_in = g_out * sigma'(v, thr, gamma).  thr has n
  * elements or 1 (broadcast); gamma is a device scalar.  The threshold and gamma get no gradient.
@@ -161,7 +185,8 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
                  const float* rec_mask, const float* beta, const float* W_out, const float* b_out,
                  const float* V0, const float* a0, const float* Z0, float* V, float* a, float* Z,
                  uint32_t* zbits, float* y, float* logits, int32_t* tstar, void* workspace,
-                 size_t workspace_bytes, snnk_stream_t stream);
+                 size_t workspace_bytes, const int32_t* run_table,
+                 snnk_stream_t stream);
 
 /*
  * Fused head: log_softmax over the max-over-time logits (snn.py:258) + NLLLoss mean (snn.py:297)
@@ -191,7 +216,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
                   const float* a, const float* Z, const uint32_t* zbits, const float* g_y, const float* g_logits,
                   const int32_t* tstar, const float* g_scale, const float* g_V, const float* g_Z, float* dW_in,
                   float* dW_rec, float* dW_out, float* db, void* workspace, size_t workspace_bytes,
-                  snnk_stream_t stream);
+                  const int32_t* run_table, snnk_stream_t stream);
 
 /*
  * Optimizer step of SNN._exec_batch (snn.py:414) for the reference's default optimizer, Adam with L2 weight decay

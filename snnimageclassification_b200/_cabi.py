@@ -74,10 +74,15 @@ _SIGNATURES = {
 	"snnk_spike_backward": (ctypes.c_int, [ctypes.c_int32, _p, _p, _p, _p, ctypes.c_int64, ctypes.c_int64, _p, _p]),
 	"snnk_forward_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(SnnkDesc)]),
 	"snnk_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(SnnkDesc)]),
-	"snnk_forward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 18 + [ctypes.c_size_t, _p]),
+	"snnk_run_table_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32]),
+	"snnk_frame_runs": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, _p, _p, _p]),
+	"snnk_encode_runs": (ctypes.c_int, [
+		_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_double,
+		ctypes.c_double, ctypes.c_double, ctypes.c_int32, _p, ctypes.c_int32, _p, _p, _p, _p]),
+	"snnk_forward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 18 + [ctypes.c_size_t, _p, _p]),
 	"snnk_head_nll": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _p, _p, _p, _p, _p, _p]),
 	"snnk_input_grad": (ctypes.c_int, [ctypes.POINTER(SnnkDesc), _p, _p, _p, _p]),
-	"snnk_backward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 21 + [ctypes.c_size_t, _p]),
+	"snnk_backward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 21 + [ctypes.c_size_t, _p, _p]),
 	"snnk_adam_step": (ctypes.c_int, [ctypes.c_int32, _p, _p, _p, _p, _p, _p, ctypes.c_float, ctypes.c_float,
 		ctypes.c_float, ctypes.c_float, ctypes.c_float, _p]),
 	"snnk_adam_dp_buffer_bytes": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)]),

@@ -43,7 +43,7 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) k_encode(const TIn* __restrict__ x, long long n_items, long long n_pix,
                                                int n_steps, double t_max, double tau, double thr, double eps,
                                                int periodic, TOut* __restrict__ out,
-                                               long long* __restrict__ periods)
+                                               long long* __restrict__ periods, unsigned char* __restrict__ changed)
 {
     const long long pix = (long long)blockIdx.y * blockDim.x + threadIdx.x;
     const long long item = blockIdx.x;
@@ -51,16 +51,26 @@ __global__ void __launch_bounds__(256) k_encode(const TIn* __restrict__ x, long 
     const long long per = period_of(x[item * n_pix + pix], t_max, tau, thr, eps);
     if (periods) periods[item * n_pix + pix] = per;
     TOut* col = out + item * (long long)n_steps * n_pix + pix;
+    // changed[item][t] = 1 when frame t of the item differs from frame t-1 in at least one pixel (zeroed by the
+    // caller; every writer stores the same byte) -- the run table of the frame-dedup path is built from it
+    unsigned char* chg = changed ? changed + item * (long long)n_steps : nullptr;
     if (!periodic) {
-        for (int t = 0; t < n_steps; ++t) col[(long long)t * n_pix] = (TOut)((long long)t == per ? 1 : 0);
+        for (int t = 0; t < n_steps; ++t) {
+            const bool s = (long long)t == per;
+            col[(long long)t * n_pix] = (TOut)(s ? 1 : 0);
+            if (chg && t > 0 && (s || (long long)(t - 1) == per)) chg[t] = 1;
+        }
     } else {
         long long p = per > n_steps - 1 ? n_steps - 1 : per;
         p = p < 1 ? 1 : p;
         long long next = p;
+        bool prev = false;
         for (int t = 0; t < n_steps; ++t) {
             const bool s = (long long)t == next;
             if (s) next += p;
             col[(long long)t * n_pix] = (TOut)(s ? 1 : 0);
+            if (chg && t > 0 && s != prev) chg[t] = 1;
+            prev = s;
         }
     }
 }

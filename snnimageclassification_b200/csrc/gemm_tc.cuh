@@ -228,8 +228,17 @@ struct ProjCfg {
 template <int H, int P>
 __global__ void __launch_bounds__(kThreads, 1)
 k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, float* __restrict__ C,
-          int M, int kblocks, int ldc, unsigned int* __restrict__ inexact_flag)
+          int M, int kblocks, int ldc, unsigned int* __restrict__ inexact_flag, const int* __restrict__ run_table,
+          int run_variant)
 {
+    // frame-dedup gating (runs.cuh): run_variant 0 = dense kernel, skipped when the table says the compact kernels
+    // run; 1 = compact kernel over M = n_rows rows, skipped otherwise.  Decided before any barrier or TMEM allocation.
+    if (run_table) {
+        const int ok = run_table[1];
+        if (ok != run_variant) return;
+        if (run_variant == 1) M = min(M, run_table[0]);
+        if ((int)blockIdx.x * kBlockM >= M) return;
+    }
     // H is the N extent of this CTA's tile; blockIdx.y selects the tile, ldc is the full hidden width
     using Cfg = ProjCfg<H, P>;
     constexpr int kStages = Cfg::kStages;
@@ -379,6 +388,9 @@ struct WgradTcParams {
     int samples_per_split;
     float* part;               // [S][m_total][H]
     unsigned int* inexact_flag;   // raised when an x tile holds values that are not tf32-exact
+    const int* run_table;      // frame-dedup gating (runs.cuh) or null
+    int run_gate;              // the launch runs only when the table's ok word equals this (0: dense, 1: dedup variant)
+    int run_clip;              // 1: "samples" are slabs of T compact rows; only the first n_rows rows are contracted
 };
 
 template <int H, int P>
@@ -403,7 +415,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
     const int b_lo = blockIdx.y * p.samples_per_split;
     const int b_hi = min(b_lo + p.samples_per_split, p.B);
     const int tblocks = (p.T + kBlockK - 1) / kBlockK;
-    const int kblocks = (b_hi - b_lo) * tblocks;
+    int kblocks = (b_hi - b_lo) * tblocks;
+    if (p.run_table) {
+        if (p.run_table[1] != p.run_gate) return;
+        if (p.run_clip) {   // compact rows [b_lo * T, b_hi * T) clipped to n_rows, whole 32-row blocks
+            const int lo = b_lo * p.T, hi = min(b_hi * p.T, p.run_table[0]);
+            kblocks = hi > lo ? (hi - lo + kBlockK - 1) / kBlockK : 0;
+        }
+    }
     constexpr uint32_t kTmemCols = tmem_cols_for(H);
 
     if (warp == 0 && lane == 0) {

@@ -223,6 +223,8 @@ struct FinalizeParams {
     // (a) thread per element, few partials:  dW_in (n_in elements) then dW_rec (n_rec elements, masked)
     const float* pw; int S; size_t w_stride; int n_in; int n_rec; const float* rec_mask;
     float* dW_in; float* dW_rec;
+    // frame-dedup variant (runs.cuh): when run_table says ok, dW_rec comes from its own partial buffer instead
+    const int* run_table; const float* pw_rec; int S_rec; size_t rec_stride;
     // (b) warp per element, many partials:   dW_out (n_out elements, P_out partials) then db (n_b, P_b partials)
     const float* pwout; int P_out; int n_out; float* dW_out;
     const float* pdb; int P_b; int n_b; float* db;
@@ -252,7 +254,9 @@ __global__ void __launch_bounds__(256) k_finalize_grads(const FinalizeParams p)
             p.dW_in[e] = sum_partials_seq(p.pw + e, p.S, p.w_stride);
         } else if (e - p.n_in < p.n_rec) {
             const int r = e - p.n_in;
-            const float s = sum_partials_seq(p.pw + p.n_in + r, p.S, p.w_stride);
+            const bool compact = p.run_table && p.run_table[1] == 1;
+            const float s = compact ? sum_partials_seq(p.pw_rec + r, p.S_rec, p.rec_stride)
+                                    : sum_partials_seq(p.pw + p.n_in + r, p.S, p.w_stride);
             p.dW_rec[r] = p.rec_mask ? s * __ldg(p.rec_mask + r) : s;
         }
         return;

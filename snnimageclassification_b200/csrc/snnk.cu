@@ -17,6 +17,7 @@
 #include "recur_fwd.cuh"
 #include "recur_gen.cuh"
 #include "recur_mma.cuh"
+#include "runs.cuh"
 
 using namespace snnk;
 
@@ -97,6 +98,12 @@ struct Plan {
     size_t off_gI, off_gIlo, off_pwout, off_pdb, off_pw, off_flag, bwd_bytes;
     size_t off_wplanes, off_fflag, off_weff, fwd_bytes;
     size_t off_weffT, off_gyscan;
+    // frame-dedup variant (runs.cuh); eligible = tensor-core GEMMs on a non-wide layer
+    bool runs;            // workspace for the compact kernels is reserved
+    int run_Tp;           // compact rows per weight-gradient split ("pseudo sample"), multiple of 32
+    int run_rows;         // S * run_Tp >= run_cap(B*T): rows of the compact buffers
+    int S_rec, sps_rec;   // split of the dW_rec-only GEMM of the variant
+    size_t off_xu_f, off_iu, off_xu_b, off_gu, gu_plane, off_pwrec;
 };
 
 int check_desc(const SnnkDesc* d)
@@ -151,11 +158,27 @@ Plan make_plan(const SnnkDesc* d)
     p.off_flag = off;   off = align_up(off + 256, 256);
     p.off_weffT = off;  off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
     p.off_gyscan = off; off = align_up(off + (p.wide ? sizeof(float) * (size_t)BT * kOMax : 0), 256);
+    p.runs = p.tc && !p.wide;
+    if (p.runs) {
+        const int cap = run_cap(BT);
+        p.run_Tp = 32 * ((cap + 32 * p.S - 1) / (32 * p.S));
+        p.run_rows = (p.S * p.run_Tp + 127) / 128 * 128;
+        p.sps_rec = (d->B + 127) / 128;
+        p.S_rec = (d->B + p.sps_rec - 1) / p.sps_rec;
+        p.gu_plane = align_up(sizeof(float) * (size_t)p.run_rows * d->H, 256);
+        p.off_xu_b = off;  off = align_up(off + sizeof(float) * (size_t)p.run_rows * d->N, 256);
+        p.off_gu = off;    off = align_up(off + 2 * p.gu_plane, 256);
+        p.off_pwrec = off; off = align_up(off + (d->recurrent ? sizeof(float) * (size_t)p.S_rec * d->H * d->H : 0), 256);
+    }
     p.bwd_bytes = off;
     off = align_up(sizeof(float) * (size_t)BT * d->H, 256);
     p.off_wplanes = off; off = align_up(off + (p.tc ? sizeof(float) * 3 * (size_t)d->H * p.kpad : 0), 256);
     p.off_fflag = off;   off = align_up(off + 256, 256);
     p.off_weff = off;    off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
+    if (p.runs) {
+        p.off_xu_f = off; off = align_up(off + sizeof(float) * (size_t)p.run_rows * d->N, 256);
+        p.off_iu = off;   off = align_up(off + sizeof(float) * (size_t)p.run_rows * d->H, 256);
+    }
     p.fwd_bytes = off;
     return p;
 }
@@ -197,13 +220,15 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
 
 template <int H>   // H = N extent of one CTA tile (the whole hidden width when it is <= 128)
 int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const float* W_in, float* I_in, float* planes,
-                   unsigned int* flag, cudaStream_t st)
+                   unsigned int* flag, cudaStream_t st, const int* run_table = nullptr, int run_variant = 0)
 {
+    // run_variant 1: x / I_in are the compact buffers of the frame-dedup path (run_rows rows, the weight planes are
+    // already split); 0 with a table: the dense launch, which the kernel skips when the table says ok
     constexpr int P = 2;   // planes of W_in^T fed to the tensor pipe (k_split_w writes three)
     using Cfg = tc::ProjCfg<H, P>;
-    const int M = d->B * d->T;
+    const int M = run_variant == 1 ? pl.run_rows : d->B * d->T;
     const int Hf = d->H;
-    {
+    if (run_variant == 0) {
         const int n = Hf * pl.kpad;
         tc::k_split_w<<<(n + 255) / 256, 256, 0, st>>>(W_in, d->N, Hf, pl.kpad, planes);
         SNNK_CUDA(cudaGetLastError());
@@ -227,50 +252,69 @@ int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const floa
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     ProfScope ps(SNNK_K_PROJ, st);
     dim3 grid((M + tc::kBlockM - 1) / tc::kBlockM, Hf / H);
-    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mw, I_in, M, pl.kpad / tc::kBlockK, Hf, flag);
+    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mw, I_in, M, pl.kpad / tc::kBlockK, Hf, flag, run_table, run_variant);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
 
+// Geometry of one weight-gradient launch.  The dense launch contracts [x ; Z_{t-1}]^T gI over (B, T); the frame-dedup
+// variant (runs.cuh) splits it into an x-only launch over compact rows (S slabs of run_Tp rows standing in for samples)
+// and a Z-only launch over the dense rows with its own, finer split.
+struct WgradGeom {
+    const float* x; const float* Ztrace; const float* g_planes; size_t g_plane_stride;
+    int T, B, N;             // extents of the (N|H, T, B) operand views
+    int mtiles_x, mtiles_z, m_total, S, samples_per_split;
+    float* part; unsigned int* flag; const int* run_table; int run_gate, run_clip;
+};
+
 template <int H>
-int launch_wgrad_tc(const SnnkDesc* d, const Plan& pl, const float* x, const float* Ztrace, const float* gI_planes,
-                    float* part, unsigned int* flag, cudaStream_t st)
+int launch_wgrad_tc(const SnnkDesc* d, const WgradGeom& g, cudaStream_t st)
 {
     constexpr int P = 2;
     using Cfg = tc::WgradCfg<H, P>;
-    const cuuint64_t T = d->T, B = d->B, N = d->N, Hf = d->H;
+    const cuuint64_t T = g.T, B = g.B, N = g.N > 0 ? g.N : 4, Hf = d->H;
     CUtensorMap mx, mz, mg;
     {
         const cuuint64_t dims[3] = {N, T, B};
         const cuuint64_t str[2] = {N * 4, T * N * 4};
         const cuuint32_t box[3] = {32, tc::kBlockK, 1};
-        int rc = make_map(&mx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        int rc = make_map(&mx, g.x ? g.x : g.g_planes, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != SNNK_OK) return rc;
     }
     {
         const cuuint64_t dims[3] = {Hf, T, B};
         const cuuint64_t str[2] = {Hf * 4, T * Hf * 4};
         const cuuint32_t box[3] = {32, tc::kBlockK, 1};
-        int rc = make_map(&mz, Ztrace ? Ztrace : gI_planes, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        int rc = make_map(&mz, g.Ztrace ? g.Ztrace : g.g_planes, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != SNNK_OK) return rc;
     }
     {
         const cuuint64_t dims[4] = {Hf, T, B, (cuuint64_t)P};
-        const cuuint64_t str[3] = {Hf * 4, T * Hf * 4, (cuuint64_t)(pl.off_gIlo - pl.off_gI)};   // planes are 256-B aligned
+        const cuuint64_t str[3] = {Hf * 4, T * Hf * 4, (cuuint64_t)g.g_plane_stride};   // planes are 256-B aligned
         const cuuint32_t box[4] = {32, tc::kBlockK, 1, 1};
-        int rc = make_map(&mg, gI_planes, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        int rc = make_map(&mg, g.g_planes, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != SNNK_OK) return rc;
     }
     tc::WgradTcParams wp{};
-    wp.N = d->N; wp.T = d->T; wp.B = d->B; wp.mtiles_x = pl.mtiles_x; wp.m_total = pl.m_total; wp.H_full = d->H;
-    wp.samples_per_split = pl.samples_per_split; wp.part = part; wp.inexact_flag = flag;
+    wp.N = g.N; wp.T = g.T; wp.B = g.B; wp.mtiles_x = g.mtiles_x; wp.m_total = g.m_total; wp.H_full = d->H;
+    wp.samples_per_split = g.samples_per_split; wp.part = g.part; wp.inexact_flag = g.flag;
+    wp.run_table = g.run_table; wp.run_gate = g.run_gate; wp.run_clip = g.run_clip;
     auto kern = tc::k_wgrad_tc<H, P>;
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-    dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.S, d->H / H);
+    dim3 grid(g.mtiles_x + g.mtiles_z, g.S, d->H / H);
     ProfScope ps(SNNK_K_WGRAD, st);
     kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mz, mg, wp);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
+}
+
+int launch_wgrad_tc_any(const SnnkDesc* d, int tileN, const WgradGeom& g, cudaStream_t st)
+{
+    switch (tileN) {
+    case 32: return launch_wgrad_tc<32>(d, g, st);
+    case 64: return launch_wgrad_tc<64>(d, g, st);
+    default: return launch_wgrad_tc<128>(d, g, st);
+    }
 }
 
 template <int H, int R, bool REC>
@@ -419,23 +463,24 @@ int launch_bwd_wide(const SnnkDesc* d, const BwdParams& bp, bool rec, const Plan
 template <typename TIn>
 int launch_encode(const TIn* x, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max, double tau,
                   double thr, double eps, int32_t periodic, void* out, int32_t out_dtype, int64_t* periods,
-                  cudaStream_t st)
+                  unsigned char* chg, cudaStream_t st)
 {
     dim3 grid((unsigned)n_items, (unsigned)((n_pix + 255) / 256));
     long long* per = reinterpret_cast<long long*>(periods);
+    if (chg) SNNK_CUDA(cudaMemsetAsync(chg, 0, (size_t)n_items * n_steps, st));
     ProfScope ps(SNNK_K_ENCODE, st);
     switch (out_dtype) {
     case SNNK_F32:
         k_encode<TIn, float><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
-                                                  static_cast<float*>(out), per);
+                                                  static_cast<float*>(out), per, chg);
         break;
     case SNNK_F64:
         k_encode<TIn, double><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
-                                                   static_cast<double*>(out), per);
+                                                   static_cast<double*>(out), per, chg);
         break;
     case SNNK_U8:
         k_encode<TIn, uint8_t><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
-                                                    static_cast<uint8_t*>(out), per);
+                                                    static_cast<uint8_t*>(out), per, chg);
         break;
     default:
         return SNNK_ERR_ARG;
@@ -514,6 +559,22 @@ int snnk_profile_end(double* ms_total, int64_t* launches)
     return SNNK_OK;
 }
 
+static int encode_any(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max,
+                      double tau, double thr, double eps, int32_t periodic, void* out, int32_t out_dtype,
+                      int64_t* periods, unsigned char* chg, cudaStream_t st)
+{
+    if (x_dtype == SNNK_F32)
+        return launch_encode(static_cast<const float*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
+                             periodic, out, out_dtype, periods, chg, st);
+    if (x_dtype == SNNK_F64)
+        return launch_encode(static_cast<const double*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
+                             periodic, out, out_dtype, periods, chg, st);
+    if (x_dtype == SNNK_I64)
+        return launch_encode(static_cast<const long long*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
+                             periodic, out, out_dtype, periods, chg, st);
+    return SNNK_ERR_ARG;
+}
+
 int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max,
                 double tau, double thr, double eps, int32_t periodic, void* out, int32_t out_dtype,
                 int64_t* periods, snnk_stream_t stream)
@@ -522,17 +583,39 @@ int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, 
     if (n_items == 0 || n_pix == 0) return SNNK_OK;   /* empty batch: nothing to do (pointers may be NULL) */
     if (!x || !out) return SNNK_ERR_ARG;
     if (!device_ok()) return SNNK_ERR_DEVICE;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (x_dtype == SNNK_F32)
-        return launch_encode(static_cast<const float*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
-                             periodic, out, out_dtype, periods, st);
-    if (x_dtype == SNNK_F64)
-        return launch_encode(static_cast<const double*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
-                             periodic, out, out_dtype, periods, st);
-    if (x_dtype == SNNK_I64)
-        return launch_encode(static_cast<const long long*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
-                             periodic, out, out_dtype, periods, st);
-    return SNNK_ERR_ARG;
+    return encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, periods,
+                      nullptr, static_cast<cudaStream_t>(stream));
+}
+
+size_t snnk_run_table_bytes(int64_t n_items, int32_t n_steps)
+{
+    if (n_items <= 0 || n_steps <= 0 || n_items * n_steps >= (1ll << 31) / 4) return 0;
+    return sizeof(int32_t) * run_table_ints(n_items * n_steps);
+}
+
+int snnk_frame_runs(int64_t n_items, int32_t n_steps, const uint8_t* frame_changed, int32_t* run_table,
+                    snnk_stream_t stream)
+{
+    if (n_items <= 0 || n_steps <= 0 || n_items * n_steps >= (1ll << 31) / 4) return SNNK_ERR_SHAPE;
+    if (!frame_changed || !run_table) return SNNK_ERR_ARG;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    k_frame_runs<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>((int)n_items, n_steps, frame_changed, run_table);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int snnk_encode_runs(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max,
+                     double tau, double thr, double eps, int32_t periodic, void* out, int32_t out_dtype,
+                     int64_t* periods, uint8_t* frame_changed, int32_t* run_table, snnk_stream_t stream)
+{
+    if (n_items <= 0 || n_pix <= 0 || n_steps <= 0 || n_items > 0x7fffffffll || n_pix > 65535ll * 256) return SNNK_ERR_SHAPE;
+    if (n_items * n_steps >= (1ll << 31) / 4) return SNNK_ERR_SHAPE;
+    if (!x || !out || !frame_changed || !run_table) return SNNK_ERR_ARG;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    int rc = encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, periods,
+                        frame_changed, static_cast<cudaStream_t>(stream));
+    if (rc != SNNK_OK) return rc;
+    return snnk_frame_runs(n_items, n_steps, frame_changed, run_table, stream);
 }
 
 int snnk_spike_forward(const float* v, const float* thr, int64_t n, int64_t thr_n, float* out,
@@ -576,7 +659,7 @@ size_t snnk_backward_workspace_bytes(const SnnkDesc* d)
 int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec, const float* rec_mask,
                  const float* beta, const float* W_out, const float* b_out, const float* V0, const float* a0,
                  const float* Z0, float* V, float* a, float* Z, uint32_t* zbits, float* y, float* logits,
-                 int32_t* tstar, void* workspace, size_t workspace_bytes, snnk_stream_t stream)
+                 int32_t* tstar, void* workspace, size_t workspace_bytes, const int32_t* run_table, snnk_stream_t stream)
 {
     int rc = check_desc(d);
     if (rc != SNNK_OK) return rc;
@@ -603,12 +686,30 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
                 flag = reinterpret_cast<unsigned int*>(ws + pl.off_fflag);
                 SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
             }
+            // frame-dedup variant (runs.cuh): only for inputs the caller vouches to be the encoder's {0,1} raster
+            const int* runs = (pl.runs && !pl.check) ? run_table : nullptr;
             switch (pl.tileN) {
-            case 32: rc = launch_proj_tc<32>(d, pl, x, W_in, I_in, planes, flag, st); break;
-            case 64: rc = launch_proj_tc<64>(d, pl, x, W_in, I_in, planes, flag, st); break;
-            default: rc = launch_proj_tc<128>(d, pl, x, W_in, I_in, planes, flag, st); break;
+            case 32: rc = launch_proj_tc<32>(d, pl, x, W_in, I_in, planes, flag, st, runs, 0); break;
+            case 64: rc = launch_proj_tc<64>(d, pl, x, W_in, I_in, planes, flag, st, runs, 0); break;
+            default: rc = launch_proj_tc<128>(d, pl, x, W_in, I_in, planes, flag, st, runs, 0); break;
             }
             if (rc != SNNK_OK) return rc;
+            if (runs) {
+                float* Xu = reinterpret_cast<float*>(ws + pl.off_xu_f);
+                float* Iu = reinterpret_cast<float*>(ws + pl.off_iu);
+                ProfScope ps(SNNK_K_PROJ, st);
+                k_gather_rows<<<pl.run_rows, 256, 0, st>>>(x, runs, M, d->N, Xu);
+                SNNK_CUDA(cudaGetLastError());
+                switch (pl.tileN) {
+                case 32: rc = launch_proj_tc<32>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1); break;
+                case 64: rc = launch_proj_tc<64>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1); break;
+                default: rc = launch_proj_tc<128>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1); break;
+                }
+                if (rc != SNNK_OK) return rc;
+                const long long nthr = (long long)M * (d->H / 4);
+                k_expand_rows<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Iu, runs, M, d->H, I_in);
+                SNNK_CUDA(cudaGetLastError());
+            }
         }
         if (!pl.tc || pl.check) {
             dim3 grid((M + kGemmBM - 1) / kGemmBM, pl.ntiles);
@@ -748,7 +849,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
                   const float* W_out, const float* Z0, const float* V, const float* a, const float* Z,
                   const uint32_t* zbits, const float* g_y, const float* g_logits, const int32_t* tstar, const float* g_scale,
                   const float* g_V, const float* g_Z, float* dW_in, float* dW_rec, float* dW_out, float* db, void* workspace,
-                  size_t workspace_bytes, snnk_stream_t stream)
+                  size_t workspace_bytes, const int32_t* run_table, snnk_stream_t stream)
 {
     int rc = check_desc(d);
     if (rc != SNNK_OK) return rc;
@@ -805,12 +906,41 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
                 flag = reinterpret_cast<unsigned int*>(ws + pl.off_flag);
                 SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
             }
-            switch (pl.tileN) {
-            case 32: rc = launch_wgrad_tc<32>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
-            case 64: rc = launch_wgrad_tc<64>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
-            default: rc = launch_wgrad_tc<128>(d, pl, x, rec ? Z : nullptr, gI, pw, flag, st); break;
-            }
+            const int* runs = (pl.runs && !pl.check) ? run_table : nullptr;
+            WgradGeom g{};
+            g.x = x; g.Ztrace = rec ? Z : nullptr; g.g_planes = gI; g.g_plane_stride = pl.off_gIlo - pl.off_gI;
+            g.T = d->T; g.B = d->B; g.N = d->N; g.mtiles_x = pl.mtiles_x; g.mtiles_z = pl.mtiles_z; g.m_total = pl.m_total;
+            g.S = pl.S; g.samples_per_split = pl.samples_per_split; g.part = pw; g.flag = flag;
+            g.run_table = runs; g.run_gate = 0; g.run_clip = 0;
+            rc = launch_wgrad_tc_any(d, pl.tileN, g, st);
             if (rc != SNNK_OK) return rc;
+            if (runs) {
+                // dedup variant: run sums of gI, x-only GEMM over the compact rows, Z-only GEMM over the dense rows
+                float* Xu = reinterpret_cast<float*>(ws + pl.off_xu_b);
+                float* Gu = reinterpret_cast<float*>(ws + pl.off_gu);
+                float* Gu_lo = reinterpret_cast<float*>(ws + pl.off_gu + pl.gu_plane);
+                {
+                    ProfScope ps(SNNK_K_WGRAD, st);
+                    k_gather_rows<<<pl.run_rows, 256, 0, st>>>(x, runs, d->B * d->T, d->N, Xu);
+                    k_run_sum<<<pl.run_rows, 128, 0, st>>>(gI, gI_lo, runs, d->B * d->T, d->H, Gu, Gu_lo);
+                    SNNK_CUDA(cudaGetLastError());
+                }
+                WgradGeom ga{};
+                ga.x = Xu; ga.Ztrace = nullptr; ga.g_planes = Gu; ga.g_plane_stride = pl.gu_plane;
+                ga.T = pl.run_Tp; ga.B = pl.S; ga.N = d->N; ga.mtiles_x = pl.mtiles_x; ga.mtiles_z = 0; ga.m_total = pl.m_total;
+                ga.S = pl.S; ga.samples_per_split = 1; ga.part = pw; ga.flag = nullptr;
+                ga.run_table = runs; ga.run_gate = 1; ga.run_clip = 1;
+                rc = launch_wgrad_tc_any(d, pl.tileN, ga, st);
+                if (rc != SNNK_OK) return rc;
+                if (rec) {
+                    WgradGeom gb = g;
+                    gb.x = nullptr; gb.N = 0; gb.mtiles_x = 0; gb.m_total = d->H; gb.S = pl.S_rec;
+                    gb.samples_per_split = pl.sps_rec; gb.part = reinterpret_cast<float*>(ws + pl.off_pwrec); gb.flag = nullptr;
+                    gb.run_gate = 1; gb.run_clip = 0;
+                    rc = launch_wgrad_tc_any(d, pl.tileN, gb, st);
+                    if (rc != SNNK_OK) return rc;
+                }
+            }
         }
         WgradParams wp{};
         wp.BT = d->B * d->T; wp.T = d->T; wp.N = d->N; wp.H = d->H;
@@ -830,6 +960,10 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         fz.n_rec = rec ? d->H * d->H : 0; fz.rec_mask = rec_mask; fz.dW_in = dW_in; fz.dW_rec = dW_rec;
         fz.pwout = pwout; fz.P_out = pl.n_pwout; fz.n_out = d->H * d->O; fz.dW_out = dW_out;
         fz.pdb = pdb; fz.P_b = pl.n_pdb; fz.n_b = d->O; fz.db = db;
+        if (pl.tc && pl.runs && !pl.check && run_table && rec) {
+            fz.run_table = run_table; fz.pw_rec = reinterpret_cast<float*>(ws + pl.off_pwrec); fz.S_rec = pl.S_rec;
+            fz.rec_stride = (size_t)d->H * d->H;
+        }
         fz.blocks_a = (fz.n_in + fz.n_rec + 255) / 256;
         const int blocks_b = (fz.n_out + fz.n_b + 7) / 8;
         ProfScope ps2(SNNK_K_REDUCE_W, st);

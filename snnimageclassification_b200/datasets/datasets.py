@@ -121,13 +121,33 @@ class ToSpikes:
 		return out.cpu() if on_cpu else out
 
 	# ---- the batched GPU entry point ----------------------------------------------------------------------------------
-	def encode_batch(self, images: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-		"""images (B, n_pix) float32|float64 (any device) -> spike trains (B, n_steps, n_pix) on the GPU."""
+	def encode_batch(self, images: torch.Tensor, out_dtype: torch.dtype = torch.float32, frame_runs: bool = True) -> torch.Tensor:
+		"""images (B, n_pix) float32|float64 (any device) -> spike trains (B, n_steps, n_pix) on the GPU.
+
+		The result is tagged as exactly {0,1} (the tensor-core kernels then skip their input check) and, with
+		``frame_runs``, carries the batch's frame-run table (``snnk_encode_runs``): the production encoder repeats
+		the same frame over long stretches of time steps, which ``SNN`` exploits."""
 		if images.ndim != 2:
 			images = images.reshape(images.shape[0], int(np.prod(images.shape[1:])))
 		x2, _, _, _ = self._stage(images)
-		out, _ = self._run(x2, self.use_periods, out_dtype, want_periods=False)
-		out._snnk_binary = True    # exactly {0,1} by construction: lets the tensor-core kernels skip their input check
+		n_items, n_pix = x2.shape
+		nbytes = _cabi.lib().snnk_run_table_bytes(n_items, self.n_steps) if (frame_runs and n_items > 0 and n_pix > 0) else 0
+		if nbytes == 0:
+			out, _ = self._run(x2, self.use_periods, out_dtype, want_periods=False)
+			out._snnk_binary = True
+			return out
+		_cabi.require_b200(x2.device)
+		out = torch.empty((n_items, self.n_steps, n_pix), dtype=out_dtype, device=x2.device)
+		changed = torch.empty((n_items, self.n_steps), dtype=torch.uint8, device=x2.device)
+		table = torch.empty((nbytes // 4,), dtype=torch.int32, device=x2.device)
+		with torch.cuda.device(x2.device):
+			rc = _cabi.lib().snnk_encode_runs(
+				_cabi.ptr(x2), _DT[x2.dtype], n_items, n_pix, self.n_steps, float(self.t_max), float(self.tau),
+				float(self.thr), float(self.epsilon), int(self.use_periods), _cabi.ptr(out), _DT[out_dtype], None,
+				_cabi.ptr(changed), _cabi.ptr(table), _cabi.stream_ptr())
+		_cabi.check(rc, "snnk_encode_runs")
+		out._snnk_binary = True
+		out._snnk_runs = table
 		return out
 
 

@@ -39,13 +39,29 @@ class LayerConsts:
 BINARY_TAG = "_snnk_binary"   # python attribute on tensors known to hold exactly {0,1} (encoder output, spike traces)
 
 
-def mark_binary(t: torch.Tensor) -> torch.Tensor:
+RUNS_TAG = "_snnk_runs"       # python attribute: the int32 run table of an encoded batch (include/snnk.h, snnk_encode_runs)
+
+
+def mark_binary(t: torch.Tensor, runs: Optional[torch.Tensor] = None) -> torch.Tensor:
 	setattr(t, BINARY_TAG, True)
+	if runs is not None:
+		setattr(t, RUNS_TAG, runs)
 	return t
 
 
 def is_binary(t) -> bool:
 	return bool(getattr(t, BINARY_TAG, False))
+
+
+def get_runs(t) -> Optional[torch.Tensor]:
+	"""The frame-run table riding on an encoder output, if it still describes ``t`` (same rows, same device)."""
+	runs = getattr(t, RUNS_TAG, None)
+	if runs is None or not is_binary(t) or t.ndim != 3:
+		return None
+	need = _cabi.lib().snnk_run_table_bytes(t.shape[0], t.shape[1]) // 4
+	if runs.dtype != torch.int32 or runs.device != t.device or runs.numel() != need or need == 0:
+		return None
+	return runs
 
 
 def make_desc(c: LayerConsts, B: int, T: int, N: int, H: int, O: int, traces: bool, binary: bool = False) -> _cabi.SnnkDesc:
@@ -90,7 +106,7 @@ def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 		r = r.float()
 	r = r if r.is_contiguous() else r.contiguous()
 	if is_binary(t):
-		mark_binary(r)
+		mark_binary(r, getattr(t, RUNS_TAG, None))
 	return r
 
 
@@ -106,6 +122,7 @@ def run_forward(
 	if W_in.shape != (N, H):
 		raise RuntimeError(f"forward_weights has shape {tuple(W_in.shape)}, expected {(N, H)}")
 	desc = make_desc(c, B, T, N, H, O, traces, binary=is_binary(x))
+	runs = get_runs(x)
 	dev = x.device
 	f32 = dict(dtype=torch.float32, device=dev)
 	alif = c.layer_type == _cabi.SNNK_ALIF
@@ -128,7 +145,7 @@ def run_forward(
 			ctypes.byref(desc), _cabi.ptr(x), _cabi.ptr(W_in), _cabi.ptr(W_rec), _cabi.ptr(rec_mask),
 			_cabi.ptr(beta), _cabi.ptr(W_out), _cabi.ptr(b_out), _cabi.ptr(V0), _cabi.ptr(a0), _cabi.ptr(Z0),
 			_cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(y), _cabi.ptr(logits),
-			_cabi.ptr(tstar), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr())
+			_cabi.ptr(tstar), _cabi.ptr(ws), ws.numel(), _cabi.ptr(runs), _cabi.stream_ptr())
 	_cabi.check(rc, "snnk_forward")
 	I_in = ws[: B * T * H * 4].view(torch.float32).view(B, T, H)
 	return dict(y=y, V=V, a=a, Z=Z, zbits=zbits, logits=logits, tstar=tstar, I_in=I_in, desc=desc, Z0=Z0)
@@ -136,7 +153,7 @@ def run_forward(
 
 def run_backward(
 		c: LayerConsts, x, W_rec, rec_mask, beta, W_out, V, a, zbits, g_y=None, g_logits=None, tstar=None,
-		g_V=None, g_Z=None, Z0=None, Z=None, g_scale=None, binary_input: bool = False,
+		g_V=None, g_Z=None, Z0=None, Z=None, g_scale=None, binary_input: bool = False, runs=None,
 ):
 	"""Calls ``snnk_backward``.  Returns dict(dW_in, dW_rec, dW_out, db, gI) -- ``gI`` is a zero-argument callable
 	(the tensor-core mode stores it as two planes; summing them is only worth it when somebody asks)."""
@@ -156,7 +173,8 @@ def run_backward(
 			ctypes.byref(desc), _cabi.ptr(x), _cabi.ptr(W_rec), _cabi.ptr(rec_mask), _cabi.ptr(beta),
 			_cabi.ptr(W_out), _cabi.ptr(Z0), _cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(g_y),
 			_cabi.ptr(g_logits), _cabi.ptr(tstar), _cabi.ptr(g_scale), _cabi.ptr(g_V), _cabi.ptr(g_Z), _cabi.ptr(dW_in),
-			_cabi.ptr(dW_rec), _cabi.ptr(dW_out), _cabi.ptr(db), _cabi.ptr(ws), ws.numel(), _cabi.stream_ptr())
+			_cabi.ptr(dW_rec), _cabi.ptr(dW_out), _cabi.ptr(db), _cabi.ptr(ws), ws.numel(),
+			_cabi.ptr(runs if runs is not None else get_runs(x)), _cabi.stream_ptr())
 	_cabi.check(rc, "snnk_backward")
 	n = B * T * H * 4
 	planes = c.tensor_core and N % 4 == 0   # stored as two tf32 planes (high, exact remainder); see include/snnk.h
@@ -213,7 +231,7 @@ class SpikingSequence(torch.autograd.Function):
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=True)
 		ctx.consts, ctx.H, ctx.Hp = consts, H, Hp
 		ctx.set_materialize_grads(False)                     # absent seeds stay None instead of (B,T,H) zero fills
-		ctx.binary = is_binary(xc)
+		ctx.binary, ctx.runs = is_binary(xc), get_runs(xc)
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None      # stacked layers: the input is the spike trace below
 		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], out["Z"])
 		alif = consts.layer_type == _cabi.SNNK_ALIF
@@ -232,7 +250,7 @@ class SpikingSequence(torch.autograd.Function):
 			g_V = None if g_V is None else torch.nn.functional.pad(g_V, (0, Hp - H))
 			g_Z = None if g_Z is None else torch.nn.functional.pad(g_Z, (0, Hp - H))
 		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=g_V, g_Z=g_Z, Z=Z,
-			binary_input=ctx.binary)
+			binary_input=ctx.binary, runs=ctx.runs)
 		# (consts, x, W_in, W_rec, rec_mask, beta, W_out, b_out); beta gets no gradient -- the threshold input of
 		# the reference's spike function returns None (spike_funcs.py:62/79)
 		gX = run_input_grad(ctx.consts, g["gI"](), ctx.Wi) if ctx.Wi is not None else None
@@ -254,7 +272,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		loss, logp, g_logits = run_head_nll(out["logits"], labels, want_grad=need_grad)
 		ctx.consts, ctx.H = consts, H
 		ctx.set_materialize_grads(False)
-		ctx.binary = is_binary(xc)
+		ctx.binary, ctx.runs = is_binary(xc), get_runs(xc)
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None
 		if need_grad:
 			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"], out["Z"])
@@ -271,7 +289,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 			return (None,) * 10
 		g = run_backward(
 			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=g_logits, tstar=tstar, Z=Z,
-			g_scale=g_loss.detach().float().reshape(1), binary_input=ctx.binary)
+			g_scale=g_loss.detach().float().reshape(1), binary_input=ctx.binary, runs=ctx.runs)
 		H = ctx.H
 		gX = run_input_grad(ctx.consts, g["gI"](), ctx.Wi) if ctx.Wi is not None else None
 		return (None, gX, None, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
