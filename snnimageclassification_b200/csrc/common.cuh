@@ -7,6 +7,8 @@ namespace snnk {
 
 constexpr int kOMax = 16;   // readout units are padded to 16 lanes in shared memory / registers
 
+constexpr int kRunHdrInts = 4;   // header words of the frame-run table (runs.cuh)
+
 struct FwdParams {
     int B, T, H, O;
     int alif, traces;
@@ -22,6 +24,9 @@ struct FwdParams {
     float* y;               // (B,T,O)
     float* logits;          // (B,O)
     int32_t* tstar;         // (B,O)
+    // frame-dedup variant (runs.cuh): when the table says ok, the input current of step (b,t) is row
+    // table[4 + b*T + t] of the compact projection I_u instead of row b*T+t of I_in
+    const int* run_table; const float* I_u;
 };
 
 struct BwdParams {
@@ -40,6 +45,9 @@ struct BwdParams {
     float* gI_lo;       // (B,T,H) or null: when set, gI receives trunc_tf32(gI) and gI_lo the exact remainder
     float* part_wout;   // [grid][H][O]
     float* part_db;     // [grid*R][O]
+    // frame-dedup variant (runs.cuh): when the table says ok, the sweep also leaves the sum of gI over every run of
+    // equal input frames in Gu_hi / Gu_lo (two tf32 planes, compact rows) for the dW_in contraction
+    const int* run_table; float* Gu_hi; float* Gu_lo;
 };
 
 // W_rec (.) rec_mask (spiking_layers.py:165/235 re-multiplies the mask at every step) and its transpose, once per call.

@@ -216,7 +216,7 @@ __device__ __forceinline__ uint32_t scan_inexact(const void* tile, uint32_t byte
 
 // ---- K1 ------------------------------------------------------------------------------------------------------------
 // map_x : 2-D (K, M) fp32, box (32, 128), SWIZZLE_128B        -> A tile, K-major
-// map_w : 3-D (Kpad, H, P) fp32 tf32-planes of W_in^T, box (32, H, 1) -> B planes, K-major
+// planes: tf32-planes of W_in^T pre-tiled and pre-swizzled by k_split_w -> B planes, K-major, one bulk copy each
 template <int H, int P>
 struct ProjCfg {
     static constexpr uint32_t kBPlaneBytes = H * kBlockK * 4;
@@ -227,9 +227,9 @@ struct ProjCfg {
 
 template <int H, int P>
 __global__ void __launch_bounds__(kThreads, 1)
-k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, float* __restrict__ C,
+k_proj_tc(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ planes, float* __restrict__ C,
           int M, int kblocks, int ldc, unsigned int* __restrict__ inexact_flag, const int* __restrict__ run_table,
-          int run_variant)
+          int run_variant, const float* __restrict__ a_tiled)
 {
     // frame-dedup gating (runs.cuh): run_variant 0 = dense kernel, skipped when the table says the compact kernels
     // run; 1 = compact kernel over M = n_rows rows, skipped otherwise.  Decided before any barrier or TMEM allocation.
@@ -253,12 +253,15 @@ k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBlockM;
     const int n0 = blockIdx.y * H;
-    constexpr uint32_t kTmemCols = tmem_cols_for(H);
+    // The P weight planes sit back to back in the stage, i.e. they ARE one K-major B operand of N = P*H rows: one MMA
+    // per k-step computes a . p0 and a . p1 side by side in TMEM (a tf32 MMA of K = 8 costs the same ~150 cycles for
+    // N = 32 ... 256, so halving the instruction count halves the tile time); the epilogue adds the column groups.
+    static_assert(P * H <= 256, "UMMA N");
+    constexpr uint32_t kTmemCols = tmem_cols_for(P * H);
     const bool check = inexact_flag != nullptr;   // null: the caller vouches for {0,1} inputs (SNNK_F_INPUT_BINARY)
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_x);
-        prefetch_tmap(&map_w);
         for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, check ? 1 + 4 : 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -277,15 +280,20 @@ k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
                 mbar_wait(empty + s, ph ^ 1);
                 unsigned char* st = smem + (size_t)s * Cfg::kStageBytes;
                 mbar_expect_tx(full + s, Cfg::kStageBytes);
-                tma_load_2d(st, &map_x, full + s, kb * kBlockK, m0);
+                if (a_tiled)   // pre-tiled, pre-swizzled A (k_gather_rows_tiled): one contiguous 16 KB copy
+                    bulk_g2s(st, a_tiled + ((size_t)blockIdx.x * kblocks + kb) * (kBlockM * kBlockK), kATileBytes, full + s);
+                else
+                    tma_load_2d(st, &map_x, full + s, kb * kBlockK, m0);
 #pragma unroll
                 for (int p = 0; p < P; ++p)
-                    tma_load_3d(st + kATileBytes + p * Cfg::kBPlaneBytes, &map_w, full + s, kb * kBlockK, n0, p);
+                    bulk_g2s(st + kATileBytes + p * Cfg::kBPlaneBytes,
+                             planes + ((size_t)p * kblocks + kb) * ((size_t)ldc * kBlockK) + (size_t)n0 * kBlockK,
+                             Cfg::kBPlaneBytes, full + s);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(H, 0, 0);
+            constexpr uint32_t idesc = make_idesc_tf32(P * H, 0, 0);
             for (int kb = 0; kb < kblocks; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
@@ -296,11 +304,8 @@ k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
 #pragma unroll
                 for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                     const uint64_t adesc = make_smem_desc(a0 + kk * kUmmaK * 4, 16, 1024);
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const uint64_t bdesc = make_smem_desc(b0 + p * Cfg::kBPlaneBytes + kk * kUmmaK * 4, 16, 1024);
-                        umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | kk | p) != 0);
-                    }
+                    const uint64_t bdesc = make_smem_desc(b0 + kk * kUmmaK * 4, 16, 1024);
+                    umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | kk) != 0);
                 }
                 umma_commit(empty + s);      // frees the stage once the MMAs above have read it
             }
@@ -330,6 +335,13 @@ k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
         for (int c0 = 0; c0 < H; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c0, v);
+#pragma unroll
+            for (int p = 1; p < P; ++p) {
+                float u[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + p * H + c0, u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += u[j];
+            }
             if (row < M) {
                 float4* dst = reinterpret_cast<float4*>(C + (size_t)row * ldc + n0 + c0);
 #pragma unroll
@@ -342,7 +354,11 @@ k_proj_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// W_in (K,H) fp32 -> tf32 planes of its transpose: planes[p][h][k], k padded with zeros to Kpad.
+// W_in (K,H) fp32 -> tf32 planes of its transpose, stored the way the tensor pipe wants them in shared memory:
+// planes[p][kb][h][32] -- per k-block of 32 one K-major tile row of 128 B per hidden unit, its eight 16-byte chunks
+// permuted by (chunk ^ (h & 7)), i.e. exactly what a SWIZZLE_128B tensor-map load would have produced.  A CTA's B
+// operand of one k-block (hidden units n0 .. n0+H) is then ONE contiguous range, fetched by a single 1-D bulk copy
+// instead of a tensor-map box of H strided 128-byte rows (the TMA unit's request rate, not bytes, bounded the tile).
 // w = p0 + p1 + p2 exactly; the projection uses the first two planes (round-to-nearest split: the dropped
 // remainder is at most 2^-22 |w|, i.e. at the level of fp32's own rounding and ten times below the
 // tensor pipe's accumulation noise; see DESIGN.md "Numerics").
@@ -357,9 +373,12 @@ __global__ void __launch_bounds__(256) k_split_w(const float* __restrict__ W, in
     const float r = w - p0;             // exact
     const float p1 = rn_tf32(r);        // |w - p0 - p1| <= 2^-22 |w|
     const float p2 = (r - p1);          // exact remainder, itself tf32-representable: p0 + p1 + p2 == w
-    planes[idx] = p0;
-    planes[(size_t)H * Kpad + idx] = p1;
-    planes[2 * (size_t)H * Kpad + idx] = p2;
+    const int kb = k / kBlockK, kk = k - kb * kBlockK;
+    const size_t o = ((size_t)kb * H + h) * kBlockK + (size_t)((((kk >> 2) ^ (h & 7)) << 2) | (kk & 3));
+    const size_t plane = (size_t)H * Kpad;
+    planes[o] = p0;
+    planes[plane + o] = p1;
+    planes[2 * plane + o] = p2;
 }
 
 // ---- K4 ------------------------------------------------------------------------------------------------------------
@@ -390,7 +409,8 @@ struct WgradTcParams {
     unsigned int* inexact_flag;   // raised when an x tile holds values that are not tf32-exact
     const int* run_table;      // frame-dedup gating (runs.cuh) or null
     int run_gate;              // the launch runs only when the table's ok word equals this (0: dense, 1: dedup variant)
-    int run_clip;              // 1: "samples" are slabs of T compact rows; only the first n_rows rows are contracted
+    int run_clip;              // 1: one "sample" of T compact rows, 32-row blocks dealt round-robin to the splits, only
+                               //    the first n_rows rows are contracted
 };
 
 template <int H, int P>
@@ -418,12 +438,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
     int kblocks = (b_hi - b_lo) * tblocks;
     if (p.run_table) {
         if (p.run_table[1] != p.run_gate) return;
-        if (p.run_clip) {   // compact rows [b_lo * T, b_hi * T) clipped to n_rows, whole 32-row blocks
-            const int lo = b_lo * p.T, hi = min(b_hi * p.T, p.run_table[0]);
-            kblocks = hi > lo ? (hi - lo + kBlockK - 1) / kBlockK : 0;
+        if (p.run_clip) {   // compact rows: split y contracts the 32-row blocks y, y + S, y + 2S, ... below n_rows
+            const int nblk = (p.run_table[0] + kBlockK - 1) / kBlockK;
+            kblocks = (int)blockIdx.y < nblk ? (nblk - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y : 0;
         }
     }
-    constexpr uint32_t kTmemCols = tmem_cols_for(H);
+    // the P planes of gI are adjacent MN blocks of the stage: one B operand of N = P*H (see k_proj_tc)
+    static_assert(P * H <= 256, "UMMA N");
+    constexpr uint32_t kTmemCols = tmem_cols_for(P * H);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_x);
@@ -444,8 +466,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
             for (int kb = 0; kb < kblocks; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
-                const int b = b_lo + kb / tblocks;
-                const int t0 = (kb % tblocks) * kBlockK;
+                const int b = p.run_clip ? 0 : b_lo + kb / tblocks;
+                const int t0 = p.run_clip ? ((int)blockIdx.y + kb * (int)gridDim.y) * kBlockK : (kb % tblocks) * kBlockK;
                 mbar_wait(empty + s, ph ^ 1);
                 unsigned char* st = smem + (size_t)s * Cfg::kStageBytes;
                 mbar_expect_tx(full + s, Cfg::kStageBytes);
@@ -462,7 +484,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(H, 1, 1);
+            constexpr uint32_t idesc = make_idesc_tf32(P * H, 1, 1);
             for (int kb = 0; kb < kblocks; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
@@ -473,12 +495,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
 #pragma unroll
                 for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                     const uint64_t adesc = make_smem_desc(a0 + kk * 1024, Cfg::kBoxBytes, 512, kLayoutSw128Base32);
-#pragma unroll
-                    for (int pl = 0; pl < P; ++pl) {
-                        const uint64_t bdesc =
-                            make_smem_desc(b0 + pl * (H / 32) * Cfg::kBoxBytes + kk * 1024, Cfg::kBoxBytes, 512, kLayoutSw128Base32);
-                        umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | kk | pl) != 0);
-                    }
+                    const uint64_t bdesc = make_smem_desc(b0 + kk * 1024, Cfg::kBoxBytes, 512, kLayoutSw128Base32);
+                    umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | kk) != 0);
                 }
                 umma_commit(empty + s);
             }
@@ -512,6 +530,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CU
             float v[32];
             if (kblocks > 0) {
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c0, v);
+#pragma unroll
+                for (int pl = 1; pl < P; ++pl) {
+                    float u[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + pl * H + c0, u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += u[j];
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;

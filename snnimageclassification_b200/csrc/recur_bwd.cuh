@@ -29,7 +29,7 @@ constexpr size_t bwd_smem_bytes(int T, bool rec)
     // the spike-word region is padded to 16 bytes: s_gy behind it is read with float4 loads
     size_t loop = sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)((R * T * (H / 32) + 3) & ~3) +
                   sizeof(float) * (size_t)(R * T * kOMax) + 2 * sizeof(float) * (size_t)(kRing * R * kChunk * H) +
-                  sizeof(uint64_t) * kRing;
+                  sizeof(uint64_t) * kRing + sizeof(int) * (size_t)(R * T);   // + compact row of every step (run sums)
     size_t stage = rec ? sizeof(float) * (size_t)H * H + 16 : 0;   // weight staging + its mbarrier, prologue only
     return loop > stage ? loop : stage;
 }
@@ -69,6 +69,9 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
     float* s_v = s_gy + R * T * kOMax;                                           // [kRing][R][kChunk][H]  V trace ring
     float* s_a = s_v + kRing * R * kChunk * H;                                   // [kRing][R][kChunk][H]  a trace ring
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_a + kRing * R * kChunk * H); // [kRing]
+    uint32_t* s_start = reinterpret_cast<uint32_t*>(s_bar + kRing);              // [R][ceil(T/32)] run-start bits
+    const bool run_sums = p.run_table != nullptr && p.run_table[1] == 1;
+    const int TW = (T + 31) >> 5;
 
     // The saved traces are streamed backwards in time through the ring by 1-D bulk async copies; chunk k (in
     // processing order) covers forward chunk nchunks-1-k.  Thread 0 only.
@@ -103,6 +106,23 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
         const int r = idx / (T * W32), rem = idx - r * (T * W32);
         s_mask[idx] = (b0 + r < B) ? __ldg(p.zbits + (size_t)(b0 + r) * T * W32 + rem) : 0u;
     }
+    if (run_sums) {
+        // bit t of a row's word: step t is the first of its run of equal input frames (its compact row differs from t-1's)
+        for (int idx = i; idx < R * TW; idx += H) s_start[idx] = 0u;
+        __syncthreads();
+        for (int idx = i; idx < nvalid * T; idx += H) {
+            const int r = idx / T, t = idx - r * T;
+            const int* rc = p.run_table + kRunHdrInts + (size_t)(b0 + r) * T;
+            if (t == 0 || __ldg(rc + t) != __ldg(rc + t - 1)) atomicOr(s_start + r * TW + (t >> 5), 1u << (t & 31));
+        }
+        if (blockIdx.x == 0) {   // the weight-gradient GEMM contracts whole 32-row blocks: zero the tail of the last one
+            const int n_rows = p.run_table[0], n_pad = (n_rows + 31) & ~31;
+            for (int idx = i; idx < (n_pad - n_rows) * H; idx += H) {
+                p.Gu_hi[(size_t)n_rows * H + idx] = 0.f;
+                p.Gu_lo[(size_t)n_rows * H + idx] = 0.f;
+            }
+        }
+    }
     __syncthreads();
     if (p.g_y) {
         for (int idx = i; idx < R * T * O; idx += H) {
@@ -135,12 +155,17 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
     }
     __syncthreads();
 
-    float gv[R];
+    float gv[R], racc[R];
+    int crow[R];          // compact row of the run the sweep is in (run sums)
+    uint32_t sbits[R];    // run-start bits of the current 32-step window
     bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         gv[r] = 0.f;
+        racc[r] = 0.f;
         valid[r] = b0 + r < B;
+        crow[r] = (run_sums && valid[r]) ? __ldg(p.run_table + kRunHdrInts + (size_t)(b0 + r) * T + T - 1) : 0;
+        sbits[r] = 0u;
     }
 
     for (int t = T - 1; t >= 0; --t) {
@@ -205,6 +230,19 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
                         }
                     }
                     if (REC) s_g[(t & 1) * R * H + r * H + i] = gi;
+                    if (run_sums) {   // sum of gI over the run of equal input frames this step belongs to
+                        racc[r] = __fadd_rn(racc[r], gi);
+                        if (t == T - 1 || (t & 31) == 31) sbits[r] = s_start[r * TW + (t >> 5)];
+                        if ((sbits[r] >> (t & 31)) & 1u) {
+                            if (valid[r]) {
+                                const float hi = __uint_as_float(__float_as_uint(racc[r]) & 0xFFFFE000u);
+                                p.Gu_hi[(size_t)crow[r] * H + i] = hi;
+                                p.Gu_lo[(size_t)crow[r] * H + i] = __fsub_rn(racc[r], hi);
+                            }
+                            racc[r] = 0.f;
+                            --crow[r];
+                        }
+                    }
                 }
                 if (REC) __syncthreads();
             }
@@ -225,6 +263,7 @@ struct FinalizeParams {
     float* dW_in; float* dW_rec;
     // frame-dedup variant (runs.cuh): when run_table says ok, dW_rec comes from its own partial buffer instead
     const int* run_table; const float* pw_rec; int S_rec; size_t rec_stride;
+    int S_cmp;   // number of dW_in partials the compact GEMM wrote (same buffer and stride as the dense ones)
     // (b) warp per element, many partials:   dW_out (n_out elements, P_out partials) then db (n_b, P_b partials)
     const float* pwout; int P_out; int n_out; float* dW_out;
     const float* pdb; int P_b; int n_b; float* db;
@@ -250,12 +289,12 @@ __global__ void __launch_bounds__(256) k_finalize_grads(const FinalizeParams p)
 {
     if ((int)blockIdx.x < p.blocks_a) {
         const int e = blockIdx.x * blockDim.x + threadIdx.x;
+        const bool compact = p.run_table && p.run_table[1] == 1;
         if (e < p.n_in) {
-            p.dW_in[e] = sum_partials_seq(p.pw + e, p.S, p.w_stride);
+            p.dW_in[e] = sum_partials_seq(p.pw + e, compact ? p.S_cmp : p.S, p.w_stride);
         } else if (e - p.n_in < p.n_rec) {
             const int r = e - p.n_in;
-            const bool compact = p.run_table && p.run_table[1] == 1;
-            const float s = compact ? sum_partials_seq(p.pw_rec + r, p.S_rec, p.rec_stride)
+            const float s = (compact && p.pw_rec) ? sum_partials_seq(p.pw_rec + r, p.S_rec, p.rec_stride)
                                     : sum_partials_seq(p.pw + p.n_in + r, p.S, p.w_stride);
             p.dW_rec[r] = p.rec_mask ? s * __ldg(p.rec_mask + r) : s;
         }

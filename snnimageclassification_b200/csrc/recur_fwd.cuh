@@ -27,7 +27,8 @@ constexpr size_t fwd_smem_bytes(int T, int O)
 {
     return sizeof(float) * (size_t)(2 * R * H) + sizeof(uint32_t) * (size_t)((R * T * (H / 32) + 3) & ~3) +
            sizeof(float) * (size_t)((H * O + R * T * O + 3) & ~3) + sizeof(float) * (size_t)(kRing * R * kChunk * H) +
-           sizeof(uint64_t) * (kRing + 2) + sizeof(float) * (size_t)H * H;   // + staging of the recurrent matrix
+           sizeof(uint64_t) * (kRing + 2) + sizeof(float) * (size_t)H * H +   // + staging of the recurrent matrix
+           sizeof(int) * (size_t)((R * T + 3) & ~3);                          // + compact row of every step (runs.cuh)
 }
 
 // Epilogue shared by the forward kernels: bit-packed raster out, leaky readout (spiking_layers.py:407) and max over
@@ -112,17 +113,31 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
     float* s_in = s_wout + ((H * O + R * T * O + 3) & ~3);                          // [kRing][R][kChunk][H], 16-B aligned
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_in + kRing * R * kChunk * H);   // [kRing] + 1 for the weights
     float* s_w = reinterpret_cast<float*>(s_bar + kRing + 2);                       // [H][H] staging (16-B aligned), prologue only
+    int* s_r2c = reinterpret_cast<int*>(s_w + H * H);                               // [R][T] compact row of (row, t)
 
+    // frame-dedup variant: the projection was evaluated once per run of equal frames; every step fetches its run's row
+    const bool compact = p.run_table != nullptr && p.run_table[1] == 1;
     const int nchunks = (T + kChunk - 1) / kChunk;
     // bulk copy of chunk c (kChunk consecutive steps of every valid row) into ring slot c % kRing; thread 0 only
     auto issue_chunk = [&](int c) {
         const int slot = c % kRing, t0 = c * kChunk;
-        const uint32_t bytes = (uint32_t)(min(kChunk, T - t0) * H * sizeof(float));
+        const int nt = min(kChunk, T - t0);
+        const uint32_t bytes = (uint32_t)(nt * H * sizeof(float));
         tc::mbar_expect_tx(s_bar + slot, bytes * nvalid);
-        for (int r = 0; r < nvalid; ++r)
-            tc::bulk_g2s(s_in + ((slot * R + r) * kChunk) * H, p.I_in + ((size_t)(b0 + r) * T + t0) * H, bytes,
-                         s_bar + slot);
+        if (!compact) {
+            for (int r = 0; r < nvalid; ++r)
+                tc::bulk_g2s(s_in + ((slot * R + r) * kChunk) * H, p.I_in + ((size_t)(b0 + r) * T + t0) * H, bytes,
+                             s_bar + slot);
+        } else {
+            for (int r = 0; r < nvalid; ++r)
+                for (int tt = 0; tt < nt; ++tt)
+                    tc::bulk_g2s(s_in + ((slot * R + r) * kChunk + tt) * H, p.I_u + (size_t)s_r2c[r * T + t0 + tt] * H,
+                                 (uint32_t)(H * sizeof(float)), s_bar + slot);
+        }
     };
+    if (compact)
+        for (int idx = i; idx < nvalid * T; idx += H)
+            s_r2c[idx] = __ldg(p.run_table + kRunHdrInts + (size_t)b0 * T + idx);   // rows b0.. are consecutive
     if (i == 0) {
         for (int s = 0; s <= kRing; ++s) tc::mbar_init(s_bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -130,9 +145,10 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
             tc::mbar_expect_tx(s_bar + kRing, (uint32_t)(H * H * sizeof(float)));
             tc::bulk_g2s(s_w, p.W_eff, (uint32_t)(H * H * sizeof(float)), s_bar + kRing);
         }
-        for (int c = 0; c < kRing && c < nchunks; ++c) issue_chunk(c);
     }
-    __syncthreads();   // barrier inits visible before anyone waits
+    __syncthreads();   // barrier inits (and the compact-row table) visible before anyone issues or waits
+    if (i == 0)
+        for (int c = 0; c < kRing && c < nchunks; ++c) issue_chunk(c);
 
     // column i of W_rec (.) rec_mask -> registers for the whole sequence
     float w[REC ? H : 16];

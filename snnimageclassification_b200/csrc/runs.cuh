@@ -18,7 +18,7 @@
 
 namespace snnk {
 
-constexpr int kRunHdr = 4;
+constexpr int kRunHdr = kRunHdrInts;
 __host__ __device__ inline int run_cap(long long BT)
 {
     long long c = (BT / 4 + 127) / 128 * 128;
@@ -26,52 +26,75 @@ __host__ __device__ inline int run_cap(long long BT)
 }
 __host__ __device__ inline size_t run_table_ints(long long BT) { return (size_t)kRunHdr + (size_t)BT + 2 * (size_t)run_cap(BT); }
 
-// One CTA: each thread owns a contiguous chunk of samples, counts their runs, a block scan gives its first compact
-// row, a second pass writes the table.  B*T bytes are read twice; the kernel runs once per encoded batch.
+// One CTA of 32 warps.  (1) warp per sample: run count from ballots over the change flags; (2) block scan of the
+// counts -> first compact row of every sample (scratch: the table's own run-length area, cap >= B ints, written last);
+// (3) warp per sample again: compact row of every step by a ballot prefix, and the first rows; (4) run lengths from
+// consecutive first rows.  A geometry whose scratch does not fit (T < 4 with B > 128) is marked not ok: dense kernels.
 __global__ void __launch_bounds__(1024) k_frame_runs(int B, int T, const unsigned char* __restrict__ changed,
                                                     int* __restrict__ table)
 {
-    __shared__ int s_cnt[1024];
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int per = (B + nthr - 1) / nthr;
-    const int b_lo = min(tid * per, B), b_hi = min(b_lo + per, B);
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
     const int cap = run_cap((long long)B * T);
     int* row2c = table + kRunHdr;
     int* rep = row2c + (size_t)B * T;
     int* len = rep + cap;
-    int mine = 0;
-    for (int b = b_lo; b < b_hi; ++b) {
-        const unsigned char* c = changed + (size_t)b * T;
-        int n = 1;
-        for (int t = 1; t < T; ++t) n += c[t] != 0;
-        mine += n;
+    int* base = len;
+    if (cap < B) {
+        if (tid == 0) { table[0] = B * T; table[1] = 0; table[2] = cap; table[3] = 0; }
+        return;
     }
-    s_cnt[tid] = mine;
-    __syncthreads();
-    // inclusive Hillis-Steele scan over the threads
-    for (int o = 1; o < nthr; o <<= 1) {
-        const int v = tid >= o ? s_cnt[tid - o] : 0;
-        __syncthreads();
-        s_cnt[tid] += v;
-        __syncthreads();
-    }
-    int r = s_cnt[tid] - mine;
-    for (int b = b_lo; b < b_hi; ++b) {
+    for (int b = warp; b < B; b += nwarp) {
         const unsigned char* c = changed + (size_t)b * T;
-        int start = 0;
-        for (int t = 0; t < T; ++t) {
-            if (t > 0 && c[t] != 0) {
-                if (r < cap) { rep[r] = b * T + start; len[r] = t - start; }
-                ++r;
-                start = t;
-            }
-            row2c[(size_t)b * T + t] = r;
+        int n = 0;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            const bool f = t < T && (t == 0 || c[t] != 0);
+            n += __popc(__ballot_sync(0xffffffffu, f));
         }
-        if (r < cap) { rep[r] = b * T + start; len[r] = T - start; }
-        ++r;
+        if (lane == 0) base[b] = n;
     }
-    if (tid == nthr - 1) {
-        const int total = s_cnt[tid];
+    __syncthreads();
+    // exclusive scan of the counts: every thread sums a contiguous chunk, Hillis-Steele over the chunk sums
+    const int per = (B + nthr - 1) / nthr;
+    const int lo = min(tid * per, B), hi = min(lo + per, B);
+    int mine = 0;
+    for (int b = lo; b < hi; ++b) mine += base[b];
+    s_part[tid] = mine;
+    __syncthreads();
+    for (int o = 1; o < nthr; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    const int total = s_part[nthr - 1];
+    int run = s_part[tid] - mine;
+    for (int b = lo; b < hi; ++b) { const int n = base[b]; base[b] = run; run += n; }
+    __syncthreads();
+    for (int b = warp; b < B; b += nwarp) {
+        const unsigned char* c = changed + (size_t)b * T;
+        int r = base[b] - 1;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            const bool f = t < T && (t == 0 || c[t] != 0);
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            const int r_t = r + __popc(m & (0xffffffffu >> (31 - lane)));
+            if (t < T) {
+                row2c[(size_t)b * T + t] = r_t;
+                if (f && r_t < cap) rep[r_t] = b * T + t;
+            }
+            r += __popc(m);
+        }
+    }
+    __syncthreads();
+    const int n = min(total, cap);
+    for (int r = tid; r < n; r += nthr) {
+        const int row = rep[r], b = row / T;
+        const int nxt = (r + 1 < n && rep[r + 1] / T == b) ? rep[r + 1] : (b + 1) * T;
+        len[r] = nxt - row;     // (the last stored run of an overfull table may be cut short: the table is not ok then)
+    }
+    if (tid == 0) {
         table[0] = total;
         table[1] = total <= cap ? 1 : 0;
         table[2] = cap;
@@ -80,20 +103,44 @@ __global__ void __launch_bounds__(1024) k_frame_runs(int B, int T, const unsigne
 }
 
 // X_u[r] = X[rep[r]] for r < n_rows; rows up to the next multiple of 32 are zero-filled (the weight-gradient GEMM
-// contracts over whole 32-row blocks).  One CTA per compact row, N/4 float4 per row.
+// contracts over whole 32-row blocks).  CTAs stride over the compact rows, N/4 float4 per row.
 __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ X, const int* __restrict__ table, int BT,
                                                     int N, float* __restrict__ Xu)
 {
     if (table[1] != 1) return;
-    const int n_rows = table[0], r = blockIdx.x;
-    if (r >= ((n_rows + 31) & ~31)) return;
-    float4* dst = reinterpret_cast<float4*>(Xu + (size_t)r * N);
-    if (r < n_rows) {
-        const int* rep = table + kRunHdr + BT;
+    const int n_rows = table[0], n_pad = (n_rows + 31) & ~31;
+    const int* rep = table + kRunHdr + BT;
+    for (int r = blockIdx.x; r < n_pad; r += gridDim.x) {
+        float4* dst = reinterpret_cast<float4*>(Xu + (size_t)r * N);
+        if (r < n_rows) {
+            const float4* src = reinterpret_cast<const float4*>(X + (size_t)rep[r] * N);
+            for (int i = threadIdx.x; i < N / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        } else {
+            for (int i = threadIdx.x; i < N / 4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// The same gather for the projection: X_u is written as the K-major, 128B-swizzled shared-memory tiles the tensor pipe
+// consumes ([row tile of 128][k-block of 32][row][32 floats], 16-byte chunks permuted by chunk ^ (row & 7), k padded
+// with zeros to Kpad), so that the projection kernel fetches an A tile with ONE contiguous 16 KB bulk copy instead of
+// a tensor-map box of 128 strided 128-byte rows.
+__global__ void __launch_bounds__(256) k_gather_rows_tiled(const float* __restrict__ X, const int* __restrict__ table,
+                                                          int BT, int N, int Kpad, float* __restrict__ Xt)
+{
+    if (table[1] != 1) return;
+    const int n_rows = table[0];
+    const int* rep = table + kRunHdr + BT;
+    const int kblocks = Kpad / 32;
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
         const float4* src = reinterpret_cast<const float4*>(X + (size_t)rep[r] * N);
-        for (int i = threadIdx.x; i < N / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-    } else {
-        for (int i = threadIdx.x; i < N / 4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int mt = r >> 7, rr = r & 127;
+        for (int c4 = threadIdx.x; c4 < Kpad / 4; c4 += blockDim.x) {
+            const float4 v = 4 * c4 < N ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int kb = c4 >> 3, c = c4 & 7;
+            float* tile = Xt + ((size_t)mt * kblocks + kb) * (128 * 32);
+            reinterpret_cast<float4*>(tile + rr * 32)[c ^ (rr & 7)] = v;
+        }
     }
 }
 
@@ -111,37 +158,6 @@ __global__ void __launch_bounds__(256) k_expand_rows(const float* __restrict__ I
     reinterpret_cast<float4*>(I_in + (size_t)row * H)[q] = __ldg(reinterpret_cast<const float4*>(Iu + (size_t)r * H) + q);
 }
 
-// G_u[r] = sum over the rows of run r of gI (= hi + lo plane), re-split into two tf32 planes; zero rows up to the
-// next multiple of 32.  One thread per (compact row, neuron), ascending t.
-__global__ void __launch_bounds__(128) k_run_sum(const float* __restrict__ g_hi, const float* __restrict__ g_lo,
-                                                const int* __restrict__ table, int BT, int H, float* __restrict__ Gu_hi,
-                                                float* __restrict__ Gu_lo)
-{
-    if (table[1] != 1) return;
-    const int n_rows = table[0], r = blockIdx.x;
-    if (r >= ((n_rows + 31) & ~31)) return;
-    for (int h = threadIdx.x; h < H; h += blockDim.x) {
-        float s = 0.f;
-        if (r < n_rows) {
-            const int cap = table[2];
-            const int* rep = table + kRunHdr + BT;
-            const int row = rep[r], n = rep[cap + r];
-            const float* ph = g_hi + (size_t)row * H + h;
-            const float* pl = g_lo + (size_t)row * H + h;
-            int j = 0;
-            for (; j + 4 <= n; j += 4) {
-                float a[4], b[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { a[u] = __ldg(ph + (size_t)(j + u) * H); b[u] = __ldg(pl + (size_t)(j + u) * H); }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) s += a[u] + b[u];
-            }
-            for (; j < n; ++j) s += __ldg(ph + (size_t)j * H) + __ldg(pl + (size_t)j * H);
-        }
-        const float hi = __uint_as_float(__float_as_uint(s) & 0xFFFFE000u);
-        Gu_hi[(size_t)r * H + h] = hi;
-        Gu_lo[(size_t)r * H + h] = s - hi;
-    }
-}
+// The run sums of gI (compact rows of the dW_in contraction) are produced by the BPTT sweep itself: recur_bwd.cuh.
 
 }  // namespace snnk

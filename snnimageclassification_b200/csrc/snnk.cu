@@ -100,9 +100,9 @@ struct Plan {
     size_t off_weffT, off_gyscan;
     // frame-dedup variant (runs.cuh); eligible = tensor-core GEMMs on a non-wide layer
     bool runs;            // workspace for the compact kernels is reserved
-    int run_Tp;           // compact rows per weight-gradient split ("pseudo sample"), multiple of 32
-    int run_rows;         // S * run_Tp >= run_cap(B*T): rows of the compact buffers
+    int run_rows;         // rows of the compact buffers: run_cap(B*T) rounded up to whole 128-row tiles
     int S_rec, sps_rec;   // split of the dW_rec-only GEMM of the variant
+    int S_cmp;            // split of the dW_in GEMM over compact rows (few 32-row blocks: a handful of splits)
     size_t off_xu_f, off_iu, off_xu_b, off_gu, gu_plane, off_pwrec;
 };
 
@@ -161,10 +161,10 @@ Plan make_plan(const SnnkDesc* d)
     p.runs = p.tc && !p.wide;
     if (p.runs) {
         const int cap = run_cap(BT);
-        p.run_Tp = 32 * ((cap + 32 * p.S - 1) / (32 * p.S));
-        p.run_rows = (p.S * p.run_Tp + 127) / 128 * 128;
+        p.run_rows = (cap + 127) / 128 * 128;
         p.sps_rec = (d->B + 127) / 128;
         p.S_rec = (d->B + p.sps_rec - 1) / p.sps_rec;
+        p.S_cmp = p.S < 8 ? p.S : 8;
         p.gu_plane = align_up(sizeof(float) * (size_t)p.run_rows * d->H, 256);
         p.off_xu_b = off;  off = align_up(off + sizeof(float) * (size_t)p.run_rows * d->N, 256);
         p.off_gu = off;    off = align_up(off + 2 * p.gu_plane, 256);
@@ -176,7 +176,7 @@ Plan make_plan(const SnnkDesc* d)
     p.off_fflag = off;   off = align_up(off + 256, 256);
     p.off_weff = off;    off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
     if (p.runs) {
-        p.off_xu_f = off; off = align_up(off + sizeof(float) * (size_t)p.run_rows * d->N, 256);
+        p.off_xu_f = off; off = align_up(off + sizeof(float) * (size_t)p.run_rows * p.kpad, 1024);   // tiled, k padded
         p.off_iu = off;   off = align_up(off + sizeof(float) * (size_t)p.run_rows * d->H, 256);
     }
     p.fwd_bytes = off;
@@ -233,7 +233,7 @@ int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const floa
         tc::k_split_w<<<(n + 255) / 256, 256, 0, st>>>(W_in, d->N, Hf, pl.kpad, planes);
         SNNK_CUDA(cudaGetLastError());
     }
-    CUtensorMap mx, mw;
+    CUtensorMap mx;
     {
         const cuuint64_t dims[2] = {(cuuint64_t)d->N, (cuuint64_t)M};
         const cuuint64_t str[1] = {(cuuint64_t)d->N * 4};
@@ -241,18 +241,12 @@ int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const floa
         int rc = make_map(&mx, x, 2, dims, str, box);
         if (rc != SNNK_OK) return rc;
     }
-    {
-        const cuuint64_t dims[3] = {(cuuint64_t)pl.kpad, (cuuint64_t)Hf, 3};
-        const cuuint64_t str[2] = {(cuuint64_t)pl.kpad * 4, (cuuint64_t)pl.kpad * 4 * Hf};
-        const cuuint32_t box[3] = {tc::kBlockK, (cuuint32_t)H, 1};
-        int rc = make_map(&mw, planes, 3, dims, str, box);
-        if (rc != SNNK_OK) return rc;
-    }
     auto kern = tc::k_proj_tc<H, P>;
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     ProfScope ps(SNNK_K_PROJ, st);
     dim3 grid((M + tc::kBlockM - 1) / tc::kBlockM, Hf / H);
-    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mw, I_in, M, pl.kpad / tc::kBlockK, Hf, flag, run_table, run_variant);
+    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, planes, I_in, M, pl.kpad / tc::kBlockK, Hf, flag, run_table, run_variant,
+                                                    run_variant == 1 ? x : nullptr);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -674,6 +668,8 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* I_in = static_cast<float*>(workspace);
 
+    const int* compact_table = nullptr;
+    const float* compact_rows = nullptr;
     // K1: input projection for all T steps at once.  Tensor-core path first (when asked for and addressable by
     // TMA); the fp32 SIMT kernel behind it only runs if x turned out not to be tf32-exact (device-side flag).
     {
@@ -698,17 +694,20 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
                 float* Xu = reinterpret_cast<float*>(ws + pl.off_xu_f);
                 float* Iu = reinterpret_cast<float*>(ws + pl.off_iu);
                 ProfScope ps(SNNK_K_PROJ, st);
-                k_gather_rows<<<pl.run_rows, 256, 0, st>>>(x, runs, M, d->N, Xu);
+                k_gather_rows_tiled<<<std::min(pl.run_rows, 8 * sm_count()), 256, 0, st>>>(x, runs, M, d->N, pl.kpad, Xu);
                 SNNK_CUDA(cudaGetLastError());
-                switch (pl.tileN) {
-                case 32: rc = launch_proj_tc<32>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1); break;
-                case 64: rc = launch_proj_tc<64>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1); break;
-                default: rc = launch_proj_tc<128>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1); break;
-                }
+                // few compact tiles: 32-column CTA tiles spread each over H/32 SMs (the tile time is bound by what one
+                // SM can pull in, two thirds of which are weight planes)
+                rc = launch_proj_tc<32>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1);
                 if (rc != SNNK_OK) return rc;
-                const long long nthr = (long long)M * (d->H / 4);
-                k_expand_rows<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Iu, runs, M, d->H, I_in);
-                SNNK_CUDA(cudaGetLastError());
+                if (pl.wide || use_mma_recur(d)) {   // k_recur_fwd fetches the compact rows itself
+                    const long long nthr = (long long)M * (d->H / 4);
+                    k_expand_rows<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Iu, runs, M, d->H, I_in);
+                    SNNK_CUDA(cudaGetLastError());
+                } else {
+                    compact_table = runs;
+                    compact_rows = Iu;
+                }
             }
         }
         if (!pl.tc || pl.check) {
@@ -734,6 +733,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     fp.I_in = I_in; fp.W_eff = W_eff; fp.beta = beta; fp.W_out = W_out; fp.b_out = b_out;
     fp.V0 = V0; fp.a0 = a0; fp.Z0 = Z0; fp.V = V; fp.a = a; fp.Z = Z; fp.zbits = zbits; fp.y = y;
     fp.logits = logits; fp.tstar = tstar;
+    fp.run_table = compact_table; fp.I_u = compact_rows;
     const bool rec = d->recurrent != 0;
     if (pl.wide) return launch_fwd_wide(d, fp, rec, pl, st);
     if (use_mma_recur(d)) return launch_fwd_mma(fp, rec, st);
@@ -887,6 +887,11 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     bp.tstar = dense ? nullptr : tstar; bp.g_scale = g_scale; bp.g_V = g_V; bp.g_Z = g_Z;
     float* gI_lo = pl.tc ? reinterpret_cast<float*>(ws + pl.off_gIlo) : nullptr;
     bp.gI = gI; bp.gI_lo = gI_lo; bp.part_wout = pwout; bp.part_db = pdb;
+    if (pl.tc && pl.runs && !pl.check && run_table) {
+        bp.run_table = run_table;
+        bp.Gu_hi = reinterpret_cast<float*>(ws + pl.off_gu);
+        bp.Gu_lo = reinterpret_cast<float*>(ws + pl.off_gu + pl.gu_plane);
+    }
     if (pl.wide) {
         rc = launch_bwd_wide(d, bp, rec, pl, reinterpret_cast<float*>(ws + pl.off_gyscan), zbits, st);
     } else {
@@ -918,17 +923,16 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
                 // dedup variant: run sums of gI, x-only GEMM over the compact rows, Z-only GEMM over the dense rows
                 float* Xu = reinterpret_cast<float*>(ws + pl.off_xu_b);
                 float* Gu = reinterpret_cast<float*>(ws + pl.off_gu);
-                float* Gu_lo = reinterpret_cast<float*>(ws + pl.off_gu + pl.gu_plane);
+                // (both planes of Gu, the run sums of gI, were written by the BPTT sweep: k_recur_bwd)
                 {
                     ProfScope ps(SNNK_K_WGRAD, st);
-                    k_gather_rows<<<pl.run_rows, 256, 0, st>>>(x, runs, d->B * d->T, d->N, Xu);
-                    k_run_sum<<<pl.run_rows, 128, 0, st>>>(gI, gI_lo, runs, d->B * d->T, d->H, Gu, Gu_lo);
+                    k_gather_rows<<<std::min(pl.run_rows, 8 * sm_count()), 256, 0, st>>>(x, runs, d->B * d->T, d->N, Xu);
                     SNNK_CUDA(cudaGetLastError());
                 }
                 WgradGeom ga{};
                 ga.x = Xu; ga.Ztrace = nullptr; ga.g_planes = Gu; ga.g_plane_stride = pl.gu_plane;
-                ga.T = pl.run_Tp; ga.B = pl.S; ga.N = d->N; ga.mtiles_x = pl.mtiles_x; ga.mtiles_z = 0; ga.m_total = pl.m_total;
-                ga.S = pl.S; ga.samples_per_split = 1; ga.part = pw; ga.flag = nullptr;
+                ga.T = pl.run_rows; ga.B = 1; ga.N = d->N; ga.mtiles_x = pl.mtiles_x; ga.mtiles_z = 0; ga.m_total = pl.m_total;
+                ga.S = pl.S_cmp; ga.samples_per_split = 1; ga.part = pw; ga.flag = nullptr;
                 ga.run_table = runs; ga.run_gate = 1; ga.run_clip = 1;
                 rc = launch_wgrad_tc_any(d, pl.tileN, ga, st);
                 if (rc != SNNK_OK) return rc;
@@ -964,6 +968,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
             fz.run_table = run_table; fz.pw_rec = reinterpret_cast<float*>(ws + pl.off_pwrec); fz.S_rec = pl.S_rec;
             fz.rec_stride = (size_t)d->H * d->H;
         }
+        if (pl.tc && pl.runs && !pl.check && run_table) { fz.run_table = run_table; fz.S_cmp = pl.S_cmp; }
         fz.blocks_a = (fz.n_in + fz.n_rec + 255) / 256;
         const int blocks_b = (fz.n_out + fz.n_b + 7) / 8;
         ProfScope ps2(SNNK_K_REDUCE_W, st);

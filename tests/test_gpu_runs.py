@@ -50,7 +50,8 @@ def test_run_table_matches_raster(tau, periodic, T):
 	assert np.array_equal(tab[4:4 + B * T], row2c)
 	n = min(len(rep), cap)
 	assert np.array_equal(tab[4 + B * T: 4 + B * T + n], rep[:n])
-	assert np.array_equal(tab[4 + B * T + cap: 4 + B * T + cap + n], ln[:n])
+	m = n if tab[1] else n - 1       # the last stored run of an overfull table may be cut short
+	assert np.array_equal(tab[4 + B * T + cap: 4 + B * T + cap + m], ln[:m])
 	# the raster itself is unchanged by recording the runs
 	plain = enc.encode_batch(_images(23, 196, 1).to(DEV), frame_runs=False)
 	assert torch.equal(plain, x) and get_runs(plain) is None
