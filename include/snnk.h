@@ -137,6 +137,9 @@ int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, 
  *                 [2] capacity = max(128, n_items*n_steps/4 rounded up to 128)  [3] 0
  *                 [4 ..) for every dense row item*n_steps+t the index of its run; then capacity first-rows; then
  *                 capacity run lengths.
+ * lazy != 0: `out` is only written where a consumer of the table will read it -- every row when the table is not
+ * ok, otherwise just the first row of every run (the rest of `out` stays uninitialised): for callers that hand
+ * `out` to snnk_forward / snnk_backward together with the table and to nobody else.
  * snnk_frame_runs builds the table from change flags the caller produced itself.  snnk_forward / snnk_backward
  * take the table of THEIR input x (or NULL): with SNNK_F_TENSOR_CORE | SNNK_F_INPUT_BINARY and H <= 128 the input
  * projection is then evaluated once per run and the dW_in contraction runs over runs instead of rows.  Whether
@@ -149,7 +152,7 @@ int snnk_frame_runs(int64_t n_items, int32_t n_steps, const uint8_t* frame_chang
 int snnk_encode_runs(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps,
                      double t_max, double tau, double thr, double eps, int32_t periodic, void* out,
                      int32_t out_dtype, int64_t* periods, uint8_t* frame_changed, int32_t* run_table,
-                     snnk_stream_t stream);
+                     int32_t lazy, snnk_stream_t stream);
 
 /*
  * SpikeFunction.apply used stand-alone (spike_funcs.py:12-29): out = (v >= thr) ? 1 : 0, and its surrogate

@@ -75,6 +75,72 @@ __global__ void __launch_bounds__(256) k_encode(const TIn* __restrict__ x, long 
     }
 }
 
+// ---- lazy raster (snnk_encode_runs with lazy != 0) ------------------------------------------------------------------
+// Pass A: the change flags alone, straight from the latency/period of every pixel -- no loop over time: a pixel of
+// period p >= 2 toggles at every multiple of p and one step later, a pixel of period 1 only at t = 1, a latency-coded
+// pixel at its firing time and one step later.  Same flags as k_encode records.
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_encode_flags(const TIn* __restrict__ x, long long n_items, long long n_pix,
+                                                     int n_steps, double t_max, double tau, double thr, double eps,
+                                                     int periodic, unsigned char* __restrict__ changed)
+{
+    const long long pix = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+    const long long item = blockIdx.x;
+    if (pix >= n_pix || item >= n_items) return;
+    const long long per = period_of(x[item * n_pix + pix], t_max, tau, thr, eps);
+    unsigned char* chg = changed + item * (long long)n_steps;
+    if (!periodic) {
+        if (per >= 0 && per < n_steps) {
+            if (per > 0) chg[per] = 1;
+            if (per + 1 < n_steps) chg[per + 1] = 1;
+        }
+    } else {
+        long long p = per > n_steps - 1 ? n_steps - 1 : per;
+        p = p < 1 ? 1 : p;
+        if (p == 1) {
+            if (n_steps > 1) chg[1] = 1;
+        } else {
+            for (long long t = p; t < n_steps; t += p) {
+                chg[t] = 1;
+                if (t + 1 < n_steps) chg[t + 1] = 1;
+            }
+        }
+    }
+}
+
+// Pass B, after k_frame_runs: the whole raster if the table is not ok (the dense kernels will read every row),
+// otherwise only the first row of every run -- the only rows the frame-dedup kernels ever read.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) k_encode_rows(const TIn* __restrict__ x, long long n_items, long long n_pix,
+                                                    int n_steps, double t_max, double tau, double thr, double eps,
+                                                    int periodic, TOut* __restrict__ out, const int* __restrict__ table)
+{
+    const long long pix = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+    const long long item = blockIdx.x;
+    if (pix >= n_pix || item >= n_items) return;
+    const long long per = period_of(x[item * n_pix + pix], t_max, tau, thr, eps);
+    long long p = per > n_steps - 1 ? n_steps - 1 : per;
+    p = p < 1 ? 1 : p;
+    TOut* col = out + item * (long long)n_steps * n_pix + pix;
+    if (table[1] != 1) {
+        long long next = periodic ? p : per;
+        for (int t = 0; t < n_steps; ++t) {
+            const bool s = (long long)t == next;
+            if (s && periodic) next += p;
+            col[(long long)t * n_pix] = (TOut)(s ? 1 : 0);
+        }
+        return;
+    }
+    const int* row2c = table + 4;
+    const int* rep = row2c + n_items * n_steps;
+    const int r0 = row2c[item * n_steps], r1 = row2c[item * n_steps + n_steps - 1];
+    for (int r = r0; r <= r1; ++r) {
+        const long long t = rep[r] - item * n_steps;
+        const bool s = periodic ? (t >= p && t % p == 0) : t == per;
+        col[t * n_pix] = (TOut)(s ? 1 : 0);
+    }
+}
+
 // ---- SpikeFunction.apply stand-alone (src/modules/spike_funcs.py:12-29, :46-62, :65-79) --------------------------
 // thr is a tensor of the same shape as v, or a single element (thr_n == 1) broadcast over it.
 __global__ void __launch_bounds__(256) k_spike_fwd(const float* __restrict__ v, const float* __restrict__ thr,

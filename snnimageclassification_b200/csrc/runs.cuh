@@ -26,65 +26,93 @@ __host__ __device__ inline int run_cap(long long BT)
 }
 __host__ __device__ inline size_t run_table_ints(long long BT) { return (size_t)kRunHdr + (size_t)BT + 2 * (size_t)run_cap(BT); }
 
-// One CTA of 32 warps.  (1) warp per sample: run count from ballots over the change flags; (2) block scan of the
-// counts -> first compact row of every sample (scratch: the table's own run-length area, cap >= B ints, written last);
-// (3) warp per sample again: compact row of every step by a ballot prefix, and the first rows; (4) run lengths from
-// consecutive first rows.  A geometry whose scratch does not fit (T < 4 with B > 128) is marked not ok: dense kernels.
+// One CTA of 32 warps.  (1) ballots over the change flags count the runs of every sample; (2) block scan of the counts
+// -> first compact row of every sample (in shared memory up to kRunSmemB samples, else in the table's own run-length
+// area, cap >= B ints, which is written last); (3) compact row of every step by a ballot prefix, and the first rows;
+// (4) run lengths from consecutive first rows.  The kernel is a chain of dependent global round trips, so each phase
+// issues all its loads before the first ballot.  A geometry whose scratch does not fit is marked not ok (dense kernels).
+constexpr int kRunSmemB = 4096;
 __global__ void __launch_bounds__(1024) k_frame_runs(int B, int T, const unsigned char* __restrict__ changed,
                                                     int* __restrict__ table)
 {
-    __shared__ int s_part[1024];
+    __shared__ int s_base[kRunSmemB];
+    __shared__ int s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
     const int cap = run_cap((long long)B * T);
     int* row2c = table + kRunHdr;
     int* rep = row2c + (size_t)B * T;
     int* len = rep + cap;
-    int* base = len;
-    if (cap < B) {
+    int* base = B <= kRunSmemB ? s_base : len;
+    if (B > kRunSmemB && cap < B) {
         if (tid == 0) { table[0] = B * T; table[1] = 0; table[2] = cap; table[3] = 0; }
         return;
     }
-    for (int b = warp; b < B; b += nwarp) {
-        const unsigned char* c = changed + (size_t)b * T;
-        int n = 0;
+    constexpr int kBatch = 8;
+    for (int b0 = warp * kBatch; b0 < B; b0 += nwarp * kBatch) {     // kBatch samples per pass, chunk by chunk
+        int n[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) n[q] = 0;
         for (int t0 = 0; t0 < T; t0 += 32) {
             const int t = t0 + lane;
-            const bool f = t < T && (t == 0 || c[t] != 0);
-            n += __popc(__ballot_sync(0xffffffffu, f));
+            bool f[kBatch];
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q)
+                f[q] = b0 + q < B && t < T && (t == 0 || changed[(size_t)(b0 + q) * T + t] != 0);
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) n[q] += __popc(__ballot_sync(0xffffffffu, f[q]));
         }
-        if (lane == 0) base[b] = n;
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q)
+            if (lane == q && b0 + q < B) base[b0 + q] = n[q];
     }
     __syncthreads();
-    // exclusive scan of the counts: every thread sums a contiguous chunk, Hillis-Steele over the chunk sums
+    // exclusive scan of the counts: contiguous chunk per thread, warp shuffle scan, scan of the 32 warp totals
     const int per = (B + nthr - 1) / nthr;
     const int lo = min(tid * per, B), hi = min(lo + per, B);
     int mine = 0;
     for (int b = lo; b < hi; ++b) mine += base[b];
-    s_part[tid] = mine;
-    __syncthreads();
-    for (int o = 1; o < nthr; o <<= 1) {
-        const int v = tid >= o ? s_part[tid - o] : 0;
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
-    const int total = s_part[nthr - 1];
-    int run = s_part[tid] - mine;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nwarp ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        s_warp[lane] = w;      // inclusive totals
+    }
+    __syncthreads();
+    const int total = s_warp[nwarp - 1];
+    int run = incl - mine + (warp > 0 ? s_warp[warp - 1] : 0);
     for (int b = lo; b < hi; ++b) { const int n = base[b]; base[b] = run; run += n; }
     __syncthreads();
-    for (int b = warp; b < B; b += nwarp) {
-        const unsigned char* c = changed + (size_t)b * T;
-        int r = base[b] - 1;
+    for (int b0 = warp * kBatch; b0 < B; b0 += nwarp * kBatch) {     // kBatch samples per pass, chunk by chunk
+        int r[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) r[q] = (b0 + q < B ? base[b0 + q] : 0) - 1;
         for (int t0 = 0; t0 < T; t0 += 32) {
             const int t = t0 + lane;
-            const bool f = t < T && (t == 0 || c[t] != 0);
-            const unsigned m = __ballot_sync(0xffffffffu, f);
-            const int r_t = r + __popc(m & (0xffffffffu >> (31 - lane)));
-            if (t < T) {
-                row2c[(size_t)b * T + t] = r_t;
-                if (f && r_t < cap) rep[r_t] = b * T + t;
+            bool f[kBatch];
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q)
+                f[q] = b0 + q < B && t < T && (t == 0 || changed[(size_t)(b0 + q) * T + t] != 0);
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+                const unsigned m = __ballot_sync(0xffffffffu, f[q]);
+                const int r_t = r[q] + __popc(m & (0xffffffffu >> (31 - lane)));
+                if (b0 + q < B && t < T) {
+                    row2c[(size_t)(b0 + q) * T + t] = r_t;
+                    if (f[q] && r_t < cap) rep[r_t] = (b0 + q) * T + t;
+                }
+                r[q] += __popc(m);
             }
-            r += __popc(m);
         }
     }
     __syncthreads();

@@ -454,27 +454,41 @@ int launch_bwd_wide(const SnnkDesc* d, const BwdParams& bp, bool rec, const Plan
                               : launch_bwd_wide_t<2, 2>(d, bp, rec, pl, gy_scan, zbits, st);
 }
 
+// pass 0: raster (+ change flags when chg != null)          k_encode
+// pass 1: change flags only                                  k_encode_flags   } lazy raster of snnk_encode_runs
+// pass 2: the rows the consumers of run_table will read      k_encode_rows    }
 template <typename TIn>
 int launch_encode(const TIn* x, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max, double tau,
                   double thr, double eps, int32_t periodic, void* out, int32_t out_dtype, int64_t* periods,
-                  unsigned char* chg, cudaStream_t st)
+                  unsigned char* chg, cudaStream_t st, int pass = 0, const int* run_table = nullptr)
 {
     dim3 grid((unsigned)n_items, (unsigned)((n_pix + 255) / 256));
     long long* per = reinterpret_cast<long long*>(periods);
-    if (chg) SNNK_CUDA(cudaMemsetAsync(chg, 0, (size_t)n_items * n_steps, st));
+    if (chg && pass != 2) SNNK_CUDA(cudaMemsetAsync(chg, 0, (size_t)n_items * n_steps, st));
     ProfScope ps(SNNK_K_ENCODE, st);
+    if (pass == 1) {
+        k_encode_flags<TIn><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, chg);
+        SNNK_CUDA(cudaGetLastError());
+        return SNNK_OK;
+    }
     switch (out_dtype) {
     case SNNK_F32:
-        k_encode<TIn, float><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
-                                                  static_cast<float*>(out), per, chg);
+        if (pass == 2) k_encode_rows<TIn, float><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                                      static_cast<float*>(out), run_table);
+        else k_encode<TIn, float><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                       static_cast<float*>(out), per, chg);
         break;
     case SNNK_F64:
-        k_encode<TIn, double><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
-                                                   static_cast<double*>(out), per, chg);
+        if (pass == 2) k_encode_rows<TIn, double><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                                       static_cast<double*>(out), run_table);
+        else k_encode<TIn, double><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                        static_cast<double*>(out), per, chg);
         break;
     case SNNK_U8:
-        k_encode<TIn, uint8_t><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
-                                                    static_cast<uint8_t*>(out), per, chg);
+        if (pass == 2) k_encode_rows<TIn, uint8_t><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                                        static_cast<uint8_t*>(out), run_table);
+        else k_encode<TIn, uint8_t><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                         static_cast<uint8_t*>(out), per, chg);
         break;
     default:
         return SNNK_ERR_ARG;
@@ -555,17 +569,17 @@ int snnk_profile_end(double* ms_total, int64_t* launches)
 
 static int encode_any(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max,
                       double tau, double thr, double eps, int32_t periodic, void* out, int32_t out_dtype,
-                      int64_t* periods, unsigned char* chg, cudaStream_t st)
+                      int64_t* periods, unsigned char* chg, cudaStream_t st, int pass = 0, const int* run_table = nullptr)
 {
     if (x_dtype == SNNK_F32)
         return launch_encode(static_cast<const float*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
-                             periodic, out, out_dtype, periods, chg, st);
+                             periodic, out, out_dtype, periods, chg, st, pass, run_table);
     if (x_dtype == SNNK_F64)
         return launch_encode(static_cast<const double*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
-                             periodic, out, out_dtype, periods, chg, st);
+                             periodic, out, out_dtype, periods, chg, st, pass, run_table);
     if (x_dtype == SNNK_I64)
         return launch_encode(static_cast<const long long*>(x), n_items, n_pix, n_steps, t_max, tau, thr, eps,
-                             periodic, out, out_dtype, periods, chg, st);
+                             periodic, out, out_dtype, periods, chg, st, pass, run_table);
     return SNNK_ERR_ARG;
 }
 
@@ -600,16 +614,27 @@ int snnk_frame_runs(int64_t n_items, int32_t n_steps, const uint8_t* frame_chang
 
 int snnk_encode_runs(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max,
                      double tau, double thr, double eps, int32_t periodic, void* out, int32_t out_dtype,
-                     int64_t* periods, uint8_t* frame_changed, int32_t* run_table, snnk_stream_t stream)
+                     int64_t* periods, uint8_t* frame_changed, int32_t* run_table, int32_t lazy, snnk_stream_t stream)
 {
     if (n_items <= 0 || n_pix <= 0 || n_steps <= 0 || n_items > 0x7fffffffll || n_pix > 65535ll * 256) return SNNK_ERR_SHAPE;
     if (n_items * n_steps >= (1ll << 31) / 4) return SNNK_ERR_SHAPE;
     if (!x || !out || !frame_changed || !run_table) return SNNK_ERR_ARG;
     if (!device_ok()) return SNNK_ERR_DEVICE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!lazy) {
+        int rc = encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, periods,
+                            frame_changed, st);
+        if (rc != SNNK_OK) return rc;
+        return snnk_frame_runs(n_items, n_steps, frame_changed, run_table, stream);
+    }
+    // lazy raster: flags -> run table -> only the rows the consumers of the table will read (all of them if not ok)
     int rc = encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, periods,
-                        frame_changed, static_cast<cudaStream_t>(stream));
+                        frame_changed, st, 1, nullptr);
     if (rc != SNNK_OK) return rc;
-    return snnk_frame_runs(n_items, n_steps, frame_changed, run_table, stream);
+    rc = snnk_frame_runs(n_items, n_steps, frame_changed, run_table, stream);
+    if (rc != SNNK_OK) return rc;
+    return encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, nullptr,
+                      frame_changed, st, 2, run_table);
 }
 
 int snnk_spike_forward(const float* v, const float* thr, int64_t n, int64_t thr_n, float* out,
@@ -693,9 +718,11 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
             if (runs) {
                 float* Xu = reinterpret_cast<float*>(ws + pl.off_xu_f);
                 float* Iu = reinterpret_cast<float*>(ws + pl.off_iu);
-                ProfScope ps(SNNK_K_PROJ, st);
-                k_gather_rows_tiled<<<std::min(pl.run_rows, 8 * sm_count()), 256, 0, st>>>(x, runs, M, d->N, pl.kpad, Xu);
-                SNNK_CUDA(cudaGetLastError());
+                {
+                    ProfScope ps(SNNK_K_PROJ, st);
+                    k_gather_rows_tiled<<<std::min(pl.run_rows, 8 * sm_count()), 256, 0, st>>>(x, runs, M, d->N, pl.kpad, Xu);
+                    SNNK_CUDA(cudaGetLastError());
+                }
                 // few compact tiles: 32-column CTA tiles spread each over H/32 SMs (the tile time is bound by what one
                 // SM can pull in, two thirds of which are weight planes)
                 rc = launch_proj_tc<32>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1);

@@ -121,12 +121,15 @@ class ToSpikes:
 		return out.cpu() if on_cpu else out
 
 	# ---- the batched GPU entry point ----------------------------------------------------------------------------------
-	def encode_batch(self, images: torch.Tensor, out_dtype: torch.dtype = torch.float32, frame_runs: bool = True) -> torch.Tensor:
+	def encode_batch(self, images: torch.Tensor, out_dtype: torch.dtype = torch.float32, frame_runs: bool = True,
+			lazy: bool = False) -> torch.Tensor:
 		"""images (B, n_pix) float32|float64 (any device) -> spike trains (B, n_steps, n_pix) on the GPU.
 
 		The result is tagged as exactly {0,1} (the tensor-core kernels then skip their input check) and, with
 		``frame_runs``, carries the batch's frame-run table (``snnk_encode_runs``): the production encoder repeats
-		the same frame over long stretches of time steps, which ``SNN`` exploits."""
+		the same frame over long stretches of time steps, which ``SNN`` exploits.  ``lazy`` (used by
+		``SNN`` for its own intermediate raster, never for a tensor handed to the user): rows that the kernels consuming
+		the table will not read are left unwritten."""
 		if images.ndim != 2:
 			images = images.reshape(images.shape[0], int(np.prod(images.shape[1:])))
 		x2, _, _, _ = self._stage(images)
@@ -144,7 +147,7 @@ class ToSpikes:
 			rc = _cabi.lib().snnk_encode_runs(
 				_cabi.ptr(x2), _DT[x2.dtype], n_items, n_pix, self.n_steps, float(self.t_max), float(self.tau),
 				float(self.thr), float(self.epsilon), int(self.use_periods), _cabi.ptr(out), _DT[out_dtype], None,
-				_cabi.ptr(changed), _cabi.ptr(table), _cabi.stream_ptr())
+				_cabi.ptr(changed), _cabi.ptr(table), int(bool(lazy)), _cabi.stream_ptr())
 		_cabi.check(rc, "snnk_encode_runs")
 		out._snnk_binary = True
 		out._snnk_runs = table

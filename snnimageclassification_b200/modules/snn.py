@@ -194,7 +194,14 @@ class SNN(torch.nn.Module):
 	def _encode_if_needed(self, inputs: torch.Tensor) -> torch.Tensor:
 		"""Image batches (B, F) are turned into spike trains on the GPU when an ``input_encoder`` was given."""
 		if self.input_encoder is not None and inputs.ndim == 2:
-			return self.input_encoder.encode_batch(inputs)
+			# the raster is an intermediate nobody but the first layer's kernels reads: with the frame-dedup variant
+			# active those read only the first row of every run, so the rest need not be written (lazy raster)
+			# (only where snnk_forward / snnk_backward take the variant: tensor-core GEMMs, first layer <= 128 wide,
+			# TMA-addressable input width -- include/snnk.h; otherwise the dense kernels read every row)
+			lazy = (self.tensor_core and self.input_encoder.n_steps == self.int_time_steps
+				and bool(self.n_hidden_neurons) and F_.padded_width(int(self.n_hidden_neurons[0])) <= 128
+				and inputs.shape[1] % 4 == 0 and os.environ.get("SNNK_LAZY_RASTER", "1") != "0")
+			return self.input_encoder.encode_batch(inputs, lazy=lazy)
 		return inputs
 
 	# ---- the fused path -------------------------------------------------------------------------------------------

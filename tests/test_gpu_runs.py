@@ -149,3 +149,30 @@ def test_dedup_in_graphed_step_and_fp32_mode():
 	a, _ = exact(x)
 	b, _ = exact(mark_binary(x.clone()))
 	assert torch.equal(a, b)
+
+
+def test_lazy_raster_training_matches_dense_raster():
+	"""SNN's own intermediate raster is written lazily (only the rows the dedup kernels read); training through
+	_exec_batch must not notice -- production encoder (dedup variant runs) and tau = 20 (table not ok: every row is
+	written and the dense kernels run), plus a wide first layer (variant not eligible: never lazy)."""
+	import os
+	from snnimageclassification_b200 import FusedAdam, LayerType, SNN, SpikeFuncType, ToSpikes
+	B, T, N = 32, 100, 784
+	imgs = [_images(B, N, 20 + i) for i in range(3)]
+	y = torch.randint(0, 10, (B,), generator=torch.Generator().manual_seed(8))
+	for tau, H in ((0.02, 128), (20.0, 128), (0.02, 256)):
+		enc = ToSpikes(T, tau=tau, use_periods=True)
+		res = {}
+		for lazy in ("1", "0"):
+			os.environ["SNNK_LAZY_RASTER"] = lazy
+			torch.manual_seed(0)
+			net = SNN(N, 10, H, use_recurrent_connection=True, int_time_steps=T, spike_func=SpikeFuncType.FastSigmoid,
+				hidden_layer_type=LayerType.ALIF, device=DEV, learn_beta=True, input_encoder=enc)
+			opt = FusedAdam(net.parameters(), lr=1e-3, weight_decay=1e-5)
+			net.train()
+			losses = [net._exec_batch(imgs[i % 3], y, torch.nn.NLLLoss(), opt) for i in range(4)]
+			res[lazy] = (losses, [p.detach().clone() for p in net.parameters()])
+		os.environ.pop("SNNK_LAZY_RASTER")
+		assert res["1"][0] == res["0"][0], (tau, H)
+		for a, b in zip(res["1"][1], res["0"][1]):
+			assert torch.equal(a, b), (tau, H)
