@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SNNK_ABI_VERSION 1
+#define SNNK_ABI_VERSION 2   /* 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp */
 
 typedef void* snnk_stream_t; /* cudaStream_t */
 
@@ -182,7 +182,9 @@ size_t snnk_backward_workspace_bytes(const SnnkDesc* d);
  *   zbits    (B,T,H/32) uint32, bit l of word w = spike of neuron 32*w+l; always written
  *   y        (B,T,O)  readout trace; logits (B,O) = max_t y, tstar (B,O) int32 = first argmax_t
  *   workspace: >= snnk_forward_workspace_bytes(); on return its first B*T*H floats hold the input
- *   current I_in = x @ W_in (exposed for tests)
+ *   current I_in = x @ W_in (exposed for tests) -- unless run_table was given and its ok word is set: the
+ *   projection then exists only for the first row of every run (compact rows further up in the workspace)
+ *   run_table: table of x from snnk_encode_runs / snnk_frame_runs, or NULL (see there)
  */
 int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec,
                  const float* rec_mask, const float* beta, const float* W_out, const float* b_out,

@@ -106,7 +106,7 @@ def lib() -> ctypes.CDLL:
 			fn = getattr(l, name)
 			fn.restype = res
 			fn.argtypes = args
-		if l.snnk_abi_version() != 1:
+		if l.snnk_abi_version() != 2:
 			raise RuntimeError("libsnnk.so ABI version mismatch; rebuild the extension")
 		_lib = l
 	return _lib
