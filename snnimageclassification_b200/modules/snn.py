@@ -99,6 +99,7 @@ class SNN(torch.nn.Module):
 		self.cuda_graphs = bool(kwargs.pop("cuda_graphs", os.environ.get("SNNK_CUDA_GRAPHS", "1") != "0"))
 		self._graphed_steps: Dict[Any, Any] = {}
 		self._graph_seen: Dict[Any, int] = {}
+		self.last_eval_accuracy = float("nan")     # accuracy counted by the latest eval-mode _exec_epoch
 		self.kwargs = kwargs
 
 		self.device = device
@@ -378,7 +379,7 @@ class SNN(torch.nn.Module):
 			unit="epoch", leave=p_bar_leave)
 		for epoch in p_bar:
 			epoch_loss = self._exec_phase(train_dataloader, val_dataloader, criterion, optimizer)
-			epoch_val_acc = self.compute_classification_accuracy(val_dataloader, verbose=False)
+			epoch_val_acc = self.last_eval_accuracy     # counted in the validation pass that produced the loss
 			self.loss_history.concat(epoch_loss)
 			is_best = epoch_loss["val"] < best_loss
 			self.save_checkpoint(optimizer, epoch, epoch_loss, is_best)
@@ -405,10 +406,24 @@ class SNN(torch.nn.Module):
 		return dict(train=train_loss, val=val_loss)
 
 	def _exec_epoch(self, dataloader, criterion, optimizer):
-		batch_losses = []
+		"""Mean batch loss of one pass over ``dataloader`` (reference snn.py:376-382), accumulated on the device in
+		float64 and read back once.  In eval mode the same pass also counts correct predictions
+		(``self.last_eval_accuracy``), which ``fit`` reports instead of running the validation set a second time."""
+		total = torch.zeros((), dtype=torch.float64, device=self.device)
+		correct = torch.zeros((), dtype=torch.float64, device=self.device)
+		n_batches = n_samples = 0
 		for x_batch, y_batch in dataloader:
-			batch_losses.append(self._exec_batch(x_batch, y_batch, criterion, optimizer))
-		return np.mean(batch_losses)
+			if self.training:
+				loss = self._exec_batch_device(x_batch, y_batch, criterion, optimizer)
+			else:
+				loss, c = self._eval_batch_device(x_batch, y_batch, criterion)
+				correct += c
+				n_samples += int(y_batch.shape[0])
+			total += loss.double()
+			n_batches += 1
+		if not self.training:
+			self.last_eval_accuracy = float(correct.item() / n_samples) if n_samples else float("nan")
+		return float(total.item() / n_batches) if n_batches else float("nan")
 
 	@staticmethod
 	def _is_plain_nll(criterion) -> bool:
@@ -445,15 +460,16 @@ class SNN(torch.nn.Module):
 			self._graphed_steps[key] = step
 		return step
 
-	def _exec_batch(self, x_batch, y_batch, criterion, optimizer):
-		"""forward (+ backward + optimizer step in train mode) -> python float (reference snn.py:384-415)."""
+	def _exec_batch_device(self, x_batch, y_batch, criterion, optimizer) -> torch.Tensor:
+		"""``_exec_batch`` without the host read-back: the batch loss as a 0-d device tensor (valid until the next
+		call).  The epoch loop accumulates these on the device and synchronises once per epoch."""
 		if self.training and self.cuda_graphs and self.device.type == "cuda":
 			key = (tuple(x_batch.shape), x_batch.dtype, tuple(y_batch.shape), y_batch.dtype, id(optimizer), id(criterion))
 			seen = self._graph_seen.get(key, 0)
 			self._graph_seen[key] = seen + 1
 			if seen >= 1:   # a geometry that repeats (every full batch of an epoch): capture once, replay afterwards
 				step = self.graphed_train_step(x_batch, y_batch, criterion, optimizer)
-				return step(x_batch, y_batch).item()
+				return step(x_batch, y_batch)
 		if self.training:
 			batch_loss = self.batch_loss(x_batch, y_batch, criterion)
 			optimizer.zero_grad()
@@ -463,7 +479,26 @@ class SNN(torch.nn.Module):
 		else:
 			with torch.no_grad():
 				batch_loss = self.batch_loss(x_batch, y_batch, criterion)
-		return batch_loss.item()
+		return batch_loss.detach()
+
+	def _exec_batch(self, x_batch, y_batch, criterion, optimizer):
+		"""forward (+ backward + optimizer step in train mode) -> python float (reference snn.py:384-415)."""
+		return self._exec_batch_device(x_batch, y_batch, criterion, optimizer).item()
+
+	def _eval_batch_device(self, x_batch, y_batch, criterion):
+		"""Validation batch in ONE pass: (loss, number of correct predictions) as device tensors.  The reference runs
+		the validation set twice per epoch (loss in ``_exec_phase``, accuracy in ``compute_classification_accuracy``,
+		snn.py:333-334); the fused head already yields the log-probabilities the accuracy needs."""
+		with torch.no_grad():
+			x = self._encode_if_needed(x_batch.to(self.device, non_blocking=True))
+			y = y_batch.to(self.device, non_blocking=True).long()
+			if criterion is None or self._is_plain_nll(criterion):
+				x = self._run_inner_layers(self._format_inputs(x))
+				loss, logp, *_ = F_.SpikingSequenceNLL.apply(self._consts(), x, y, *self._weights(), False)
+			else:
+				logp, out, h_states = self.get_prediction_log_proba(x, re_outputs_trace=True, re_hidden_states=True)
+				loss = criterion(logp, y)
+			return loss.detach(), torch.eq(torch.argmax(logp, dim=-1), y).sum()
 
 	def _allreduce_gradients(self, optimizer=None):
 		"""Data-parallel training: average the (small) gradients over the ranks with one flat NCCL all-reduce --
@@ -524,14 +559,23 @@ class SNN(torch.nn.Module):
 		with open(self.checkpoints_meta_path, "r+") as jsonFile:
 			meta: dict = json.load(jsonFile)
 		for path in meta[SNN.CHECKPOINT_EPOCHS_KEY].values():
-			history.concat(torch.load(path, map_location=self.device, weights_only=False)[SNN.CHECKPOINT_LOSS_KEY])
+			history.concat(self._load_file(path)[SNN.CHECKPOINT_LOSS_KEY])
 		return history
+
+	def _load_file(self, path: str) -> dict:
+		"""Checkpoints written here hold tensors and plain Python numbers only, so they load under torch's safe
+		``weights_only`` unpickler; files written by the reference (numpy scalars in the loss entry, snn.py:443-448,
+		which torch >= 2.6 refuses by default, :481) fall back to the full unpickler -- they are the user's own files."""
+		try:
+			return torch.load(path, map_location=self.device, weights_only=True)
+		except Exception:
+			return torch.load(path, map_location=self.device, weights_only=False)
 
 	def load_checkpoint(self, load_checkpoint_mode: LoadCheckpointMode = LoadCheckpointMode.BEST_EPOCH) -> dict:
 		with open(self.checkpoints_meta_path, "r+") as jsonFile:
 			info: dict = json.load(jsonFile)
 		path = self.get_save_path_from_checkpoints(info, load_checkpoint_mode)
-		checkpoint = torch.load(path, map_location=self.device, weights_only=False)
+		checkpoint = self._load_file(path)
 		self.load_state_dict(checkpoint[SNN.CHECKPOINT_STATE_DICT_KEY], strict=True)
 		return checkpoint
 

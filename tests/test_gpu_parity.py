@@ -390,7 +390,12 @@ def test_exec_batch_and_fit_on_synthetic_data(tmp_path):
 	assert len(hist["train"]) == 3 and hist["train"][-1] < first
 	acc = net.compute_classification_accuracy(train)
 	assert 0.0 <= acc <= 1.0
+	# the validation pass of the last epoch counted the same accuracy (one pass instead of the reference's two)
+	assert abs(net.last_eval_accuracy - acc) < 1e-12
 	assert (tmp_path / "ck" / "snn-epoch2.pth").exists()
+	# checkpoints written here load under torch's safe unpickler
+	ck = torch.load(tmp_path / "ck" / "snn-epoch2.pth", map_location="cpu", weights_only=True)
+	assert set(ck) >= {"epoch", "model_state_dict", "optimizer_state_dict"} or len(ck) >= 4
 	# resume: nothing left to do, history restored from the checkpoints
 	from snnimageclassification_b200 import LoadCheckpointMode
 	hist2 = net.fit(train, train, nb_epochs=3, load_checkpoint_mode=LoadCheckpointMode.LAST_EPOCH, verbose=False)
