@@ -305,8 +305,8 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the bench geometry (B = 256), ncu --set full
 NCU_TRAFFIC = {
-	"K3": (26.78e6, "profiles/r01_ncu_recur_cb_raw.csv"),
-	"K2": (13.51e6, "profiles/r01_ncu_recur_cb_raw.csv"),
+	"K3": (27.12e6, "profiles/r01_ncu_full_raw_final.csv"),
+	"K2": (27.99e6, "profiles/r01_ncu_full_raw_final.csv"),
 }
 
 
