@@ -40,12 +40,13 @@
 extern "C" {
 #endif
 
-#define SNNK_ABI_VERSION 2   /* 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp */
+#define SNNK_ABI_VERSION 3   /* 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
 
 typedef void* snnk_stream_t; /* cudaStream_t */
 
-/* LayerType, src/modules/spiking_layers.py:11-14 (Izhikevich is not on this path) */
-enum { SNNK_LIF = 0, SNNK_ALIF = 1 };
+/* LayerType, src/modules/spiking_layers.py:11-14.  SNNK_IZHIKEVICH (spiking_layers.py:246-353): H <= 128 only; the
+ * `a` trace and the a0 state hold the recovery variable u; V0 == NULL starts the membrane at v_rest (:309). */
+enum { SNNK_LIF = 0, SNNK_ALIF = 1, SNNK_IZHIKEVICH = 2 };
 /* SpikeFuncType, src/modules/spike_funcs.py:7-9 */
 enum { SNNK_FAST_SIGMOID = 0, SNNK_PHI = 1 };
 /* element types accepted by snnk_encode */
@@ -78,7 +79,7 @@ typedef struct SnnkDesc {
     int32_t N;          /* input features (784)                               */
     int32_t H;          /* hidden neurons                                     */
     int32_t O;          /* readout units (10); O <= 16                        */
-    int32_t layer_type; /* SNNK_LIF | SNNK_ALIF                               */
+    int32_t layer_type; /* SNNK_LIF | SNNK_ALIF | SNNK_IZHIKEVICH             */
     int32_t surrogate;  /* SNNK_FAST_SIGMOID | SNNK_PHI                       */
     int32_t recurrent;  /* use_recurrent_connection                           */
     float alpha;        /* exp(-dt/tau_m),  spiking_layers.py:119             */
@@ -87,6 +88,9 @@ typedef struct SnnkDesc {
     float gamma;        /* surrogate scale, spiking_layers.py:121             */
     float kappa;        /* exp(-dt/tau_out),spiking_layers.py:377             */
     uint32_t flags;     /* SNNK_F_*                                           */
+    /* SNNK_IZHIKEVICH only (ignored otherwise), spiking_layers.py:275-296: next_V = (V + dt (k (V - v_rest)(V - v_th)
+     * - u + I) / C)(1 - Z) + c Z;  next_u = u + dt a (b (V - v_rest) - u) + d Z;  spike at v_peak */
+    float dt, iz_C, iz_v_rest, iz_v_th, iz_k, iz_a, iz_b, iz_c, iz_d, iz_v_peak;
 } SnnkDesc;
 
 /* kernel groups reported by the optional profiler below */

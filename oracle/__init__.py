@@ -45,6 +45,9 @@ class _Cfg(ctypes.Structure):
 		("layer_type", ctypes.c_int32), ("surrogate", ctypes.c_int32), ("recurrent", ctypes.c_int32),
 		("alpha", ctypes.c_float), ("rho", ctypes.c_float), ("theta", ctypes.c_float),
 		("gamma", ctypes.c_float), ("kappa", ctypes.c_float), ("beta", ctypes.c_float),
+		("dt", ctypes.c_float), ("iz_C", ctypes.c_float), ("iz_vr", ctypes.c_float), ("iz_vth", ctypes.c_float),
+		("iz_k", ctypes.c_float), ("iz_a", ctypes.c_float), ("iz_b", ctypes.c_float), ("iz_c", ctypes.c_float),
+		("iz_d", ctypes.c_float), ("iz_vpeak", ctypes.c_float),
 	]
 
 
@@ -55,7 +58,7 @@ class OracleCfg:
 	N: int
 	H: int
 	O: int
-	layer_type: int = 1  # 0 LIF, 1 ALIF
+	layer_type: int = 1  # 0 LIF, 1 ALIF, 2 Izhikevich
 	surrogate: int = 0  # 0 FastSigmoid, 1 Phi
 	recurrent: int = 1
 	alpha: float = 0.0
@@ -64,11 +67,24 @@ class OracleCfg:
 	gamma: float = 1.0
 	kappa: float = 0.0
 	beta: float = 0.0
+	# Izhikevich constants (defaults of spiking_layers.py:287-296)
+	dt: float = 1e-3
+	iz_C: float = 100.0
+	iz_vr: float = -60.0
+	iz_vth: float = -40.0
+	iz_k: float = 0.7
+	iz_a: float = 0.03
+	iz_b: float = -2.0
+	iz_c: float = -50.0
+	iz_d: float = 100.0
+	iz_vpeak: float = 35.0
 
 	def c(self) -> _Cfg:
 		return _Cfg(
 			self.B, self.T, self.N, self.H, self.O, self.layer_type, self.surrogate, int(self.recurrent),
 			self.alpha, self.rho, self.theta, self.gamma, self.kappa, self.beta,
+			self.dt, self.iz_C, self.iz_vr, self.iz_vth, self.iz_k, self.iz_a, self.iz_b, self.iz_c, self.iz_d,
+			self.iz_vpeak,
 		)
 
 
@@ -135,6 +151,8 @@ def forward(cfg: OracleCfg, x, W_in, W_rec, rec_mask, W_out, b_out, V0=None, a0=
 	B, T, H, O = cfg.B, cfg.T, cfg.H, cfg.O
 	x, W_in, W_rec, rec_mask, W_out, b_out = map(_f32, (x, W_in, W_rec, rec_mask, W_out, b_out))
 	V0, a0, Z0 = map(_f32, (V0, a0, Z0))
+	if cfg.layer_type == 2 and V0 is None:     # IzhikevichLayer.create_empty_state: V starts at v_rest (spiking_layers.py:309)
+		V0 = np.full((B, H), cfg.iz_vr, np.float32)
 	out = {k: np.zeros((B, T, H), np.float32) for k in ("I_in", "V", "a", "Z")}
 	out["y"] = np.zeros((B, T, O), np.float32)
 	c = cfg.c()

@@ -30,10 +30,12 @@
 
 typedef struct {
     int32_t B, T, N, H, O;
-    int32_t layer_type; /* 0 = LIF, 1 = ALIF  (spiking_layers.py:11-14) */
+    int32_t layer_type; /* 0 = LIF, 1 = ALIF, 2 = Izhikevich  (spiking_layers.py:11-14) */
     int32_t surrogate;  /* 0 = FastSigmoid, 1 = Phi (spike_funcs.py:7-9) */
     int32_t recurrent;  /* use_recurrent_connection */
     float alpha, rho, theta, gamma, kappa, beta;
+    /* Izhikevich (spiking_layers.py:275-296): dt, C, v_rest, v_th, k, a, b, c, d, v_peak */
+    float dt, iz_C, iz_vr, iz_vth, iz_k, iz_a, iz_b, iz_c, iz_d, iz_vpeak;
 } OracleCfg;
 
 /* ------------------------------------------------------------------------ */
@@ -198,6 +200,29 @@ int snn_oracle_forward(const OracleCfg* c, const float* x, const float* W_in, co
                 cur[i] = s;
                 if (I_in) I_in[row + i] = s;
             }
+            if (c->layer_type == 2) {
+                /* IzhikevichLayer.forward, spiking_layers.py:330-353; the trace `a` holds the recovery variable u */
+                for (int i = 0; i < H; ++i) {
+                    float I = c->recurrent ? cur[i] + dot_rec16(Weff + i, H, zprev, H) : cur[i] + 0.0f;   /* :344 */
+                    float d1 = vprev[i] - c->iz_vr;
+                    float d2 = vprev[i] - c->iz_vth;
+                    float q = (c->iz_k * d1) * d2;               /* :345 */
+                    q = q - aprev[i];
+                    float dV = q + I;
+                    float inc = (c->dt * dV) / c->iz_C;          /* :346 */
+                    float v = (vprev[i] + inc) * (1.0f - zprev[i]);
+                    v = v + c->iz_c * zprev[i];
+                    float du = c->iz_a * (c->iz_b * d1 - aprev[i]);                                        /* :347 */
+                    float un = (aprev[i] + c->dt * du) + c->iz_d * zprev[i];                               /* :348 */
+                    float z = v >= c->iz_vpeak ? 1.0f : 0.0f;    /* :349 */
+                    V[row + i] = v;
+                    if (a) a[row + i] = un;
+                    Z[row + i] = z;
+                    vprev[i] = v;
+                    aprev[i] = un;
+                    cur[i] = z;
+                }
+            } else
             for (int i = 0; i < H; ++i) {
                 float t1 = c->alpha * vprev[i];                  /* :169/239 */
                 float t2 = t1 + cur[i];
@@ -317,6 +342,7 @@ int snn_oracle_backward(const OracleCfg* c, const float* x, const float* W_rec,
     float* Weff = (float*)calloc((size_t)H * H, sizeof(float));
     float* gy = (float*)calloc((size_t)O, sizeof(float));
     float* gv = (float*)calloc((size_t)H, sizeof(float));
+    float* gu = (float*)calloc((size_t)H, sizeof(float));     /* Izhikevich: adjoint of the recovery variable */
     float* gi_next = (float*)calloc((size_t)H, sizeof(float));
     float* gi = (float*)calloc((size_t)H, sizeof(float));
     if (!aWin || !aWrec || !aWout || !adb || !Weff || !gy || !gv || !gi_next || !gi) return -1;
@@ -325,7 +351,7 @@ int snn_oracle_backward(const OracleCfg* c, const float* x, const float* W_rec,
 
     for (int b = 0; b < B; ++b) {
         for (int o = 0; o < O; ++o) gy[o] = 0.f;
-        for (int i = 0; i < H; ++i) { gv[i] = 0.f; gi_next[i] = 0.f; }
+        for (int i = 0; i < H; ++i) { gv[i] = 0.f; gi_next[i] = 0.f; if (gu) gu[i] = 0.f; }
         for (int t = T - 1; t >= 0; --t) {
             size_t row = ((size_t)b * T + t) * H;
             const float* zt = Z + row;
@@ -339,6 +365,22 @@ int snn_oracle_backward(const OracleCfg* c, const float* x, const float* W_rec,
                 for (int o = 0; o < O; ++o) s = fmaf(gy[o], W_out[(size_t)i * O + o], s);
                 if (c->recurrent) s += dot_rec16(Weff + (size_t)i * H, 1, gi_next, H);
                 if (g_Zs) s += g_Zs[row + i];
+                if (c->layer_type == 2) {
+                    /* adjoint of spiking_layers.py:345-348 (reset factors detached, :343):
+                     *   dV'/dV = (1 + dt k ((V-vr) + (V-vth)) / C)(1-Z)   dV'/du = -(dt/C)(1-Z)   dV'/dI = (dt/C)(1-Z)
+                     *   du'/dV = dt a b                                    du'/du = 1 - dt a                          */
+                    float v = V[row + i];
+                    float sg = surrogate_grad(c, v, c->iz_vpeak);
+                    float dq = c->iz_k * ((v - c->iz_vr) + (v - c->iz_vth));
+                    float A = (1.0f + (c->dt * dq) / c->iz_C) * (1.0f - zt[i]);
+                    float dtC = c->dt / c->iz_C;
+                    float g = s * sg + gv[i] * A + gu[i] * (c->dt * c->iz_a * c->iz_b);
+                    if (g_Vs) g += g_Vs[row + i];
+                    float gun = gv[i] * (-dtC) * (1.0f - zt[i]) + gu[i] * (1.0f - c->dt * c->iz_a);
+                    gv[i] = g;
+                    gu[i] = gun;
+                    gi[i] = (g * dtC) * (1.0f - (zp ? zp[i] : 0.f));
+                } else {
                 float thr = c->theta;
                 if (c->layer_type == 1) thr = c->theta + c->beta * a[row + i];
                 float sg = surrogate_grad(c, V[row + i], thr);
@@ -347,6 +389,7 @@ int snn_oracle_backward(const OracleCfg* c, const float* x, const float* W_rec,
                 if (g_Vs) g += g_Vs[row + i];
                 gv[i] = g;
                 gi[i] = g * (1.0f - (zp ? zp[i] : 0.f));
+                }
                 if (gI) gI[row + i] = gi[i];
                 for (int o = 0; o < O; ++o) aWout[(size_t)i * O + o] += (double)zt[i] * gy[o];
             }
@@ -371,6 +414,6 @@ int snn_oracle_backward(const OracleCfg* c, const float* x, const float* W_rec,
     for (int i = 0; i < H * O; ++i) dW_out[i] = (float)aWout[i];
     for (int o = 0; o < O; ++o) db[o] = (float)adb[o];
     free(aWin); free(aWrec); free(aWout); free(adb); free(Weff); free(gy); free(gv);
-    free(gi_next); free(gi);
+    free(gi_next); free(gi); free(gu);
     return 0;
 }

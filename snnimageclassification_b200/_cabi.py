@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libsnnk.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "snnk.h")
 
-SNNK_LIF, SNNK_ALIF = 0, 1
+SNNK_LIF, SNNK_ALIF, SNNK_IZHIKEVICH = 0, 1, 2
 SNNK_FAST_SIGMOID, SNNK_PHI = 0, 1
 SNNK_F32, SNNK_F64, SNNK_U8, SNNK_I64 = 0, 1, 2, 3
 SNNK_F_TRACES, SNNK_F_TENSOR_CORE, SNNK_F_INPUT_BINARY = 0x1, 0x2, 0x4
@@ -36,6 +36,10 @@ class SnnkDesc(ctypes.Structure):
 		("recurrent", ctypes.c_int32), ("alpha", ctypes.c_float), ("rho", ctypes.c_float),
 		("theta", ctypes.c_float), ("gamma", ctypes.c_float), ("kappa", ctypes.c_float),
 		("flags", ctypes.c_uint32),
+		# SNNK_IZHIKEVICH only
+		("dt", ctypes.c_float), ("iz_C", ctypes.c_float), ("iz_v_rest", ctypes.c_float), ("iz_v_th", ctypes.c_float),
+		("iz_k", ctypes.c_float), ("iz_a", ctypes.c_float), ("iz_b", ctypes.c_float), ("iz_c", ctypes.c_float),
+		("iz_d", ctypes.c_float), ("iz_v_peak", ctypes.c_float),
 	]
 
 
@@ -106,7 +110,7 @@ def lib() -> ctypes.CDLL:
 			fn = getattr(l, name)
 			fn.restype = res
 			fn.argtypes = args
-		if l.snnk_abi_version() != 2:
+		if l.snnk_abi_version() != 3:
 			raise RuntimeError("libsnnk.so ABI version mismatch; rebuild the extension")
 		_lib = l
 	return _lib

@@ -9,6 +9,12 @@ constexpr int kOMax = 16;   // readout units are padded to 16 lanes in shared me
 
 constexpr int kRunHdrInts = 4;   // header words of the frame-run table (runs.cuh)
 
+// IzhikevichLayer constants (spiking_layers.py:275-296); on == 0 for LIF / ALIF
+struct IzhConsts {
+    int on;
+    float dt, C, vr, vth, k, a, b, c, d, vpeak;
+};
+
 struct FwdParams {
     int B, T, H, O;
     int alif, traces;
@@ -27,6 +33,7 @@ struct FwdParams {
     // frame-dedup variant (runs.cuh): when the table says ok, the input current of step (b,t) is row
     // table[4 + b*T + t] of the compact projection I_u instead of row b*T+t of I_in
     const int* run_table; const float* I_u;
+    IzhConsts iz;           // Izhikevich layer: the `a` trace / a0 state hold the recovery variable u
 };
 
 struct BwdParams {
@@ -48,6 +55,7 @@ struct BwdParams {
     // frame-dedup variant (runs.cuh): when the table says ok, the sweep also leaves the sum of gI over every run of
     // equal input frames in Gu_hi / Gu_lo (two tf32 planes, compact rows) for the dW_in contraction
     const int* run_table; float* Gu_hi; float* Gu_lo;
+    IzhConsts iz;
 };
 
 // W_rec (.) rec_mask (spiking_layers.py:165/235 re-multiplies the mask at every step) and its transpose, once per call.

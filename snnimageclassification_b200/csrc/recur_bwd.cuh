@@ -34,9 +34,11 @@ constexpr size_t bwd_smem_bytes(int T, bool rec)
     return loop > stage ? loop : stage;
 }
 
-template <int H, int R, bool REC>
+// MODE: 0 LIF, 1 ALIF, 2 Izhikevich; SURR: 0 FastSigmoid, 1 Phi -- compile-time for the same reason as in k_recur_fwd
+template <int H, int R, bool REC, int MODE = 1, int SURR = 0>
 __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
 {
+    constexpr bool IZH = MODE == 2, ALIF = MODE == 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W32 = H / 32;
     const int T = p.T, O = p.O, B = p.B;
@@ -79,11 +81,11 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
     auto issue_chunk = [&](int k) {
         const int slot = k % kRing, t0 = (nchunks - 1 - k) * kChunk;
         const uint32_t bytes = (uint32_t)(min(kChunk, T - t0) * H * sizeof(float));
-        tc::mbar_expect_tx(s_bar + slot, bytes * nvalid * (p.alif ? 2 : 1));
+        tc::mbar_expect_tx(s_bar + slot, bytes * nvalid * (ALIF ? 2 : 1));
         for (int r = 0; r < nvalid; ++r) {
             const size_t g = ((size_t)(b0 + r) * T + t0) * H;
             tc::bulk_g2s(s_v + ((slot * R + r) * kChunk) * H, p.V + g, bytes, s_bar + slot);
-            if (p.alif) tc::bulk_g2s(s_a + ((slot * R + r) * kChunk) * H, p.a + g, bytes, s_bar + slot);
+            if (ALIF) tc::bulk_g2s(s_a + ((slot * R + r) * kChunk) * H, p.a + g, bytes, s_bar + slot);
         }
     };
     if (i == 0) {   // the staging area above aliases the ring: the first copies start only now
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
         wo[c] = c < O ? __ldg(p.W_out + (size_t)i * O + c) : 0.f;
         dwo[c] = 0.f;
     }
-    const float beta = (p.alif && p.beta) ? __ldg(p.beta) : 0.f;
+    const float beta = (ALIF && p.beta) ? __ldg(p.beta) : 0.f;
 
     for (int idx = i; idx < 2 * R * H; idx += H) s_g[idx] = 0.f;
     for (int idx = i; idx < R * T * kOMax; idx += H) s_gy[idx] = 0.f;
@@ -155,13 +157,14 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
     }
     __syncthreads();
 
-    float gv[R], racc[R];
+    float gv[R], gu[R], racc[R];
     int crow[R];          // compact row of the run the sweep is in (run sums)
     uint32_t sbits[R];    // run-start bits of the current 32-step window
     bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         gv[r] = 0.f;
+        gu[r] = 0.f;      // Izhikevich: adjoint of the recovery variable
         racc[r] = 0.f;
         valid[r] = b0 + r < B;
         crow[r] = (run_sums && valid[r]) ? __ldg(p.run_table + kRunHdrInts + (size_t)(b0 + r) * T + T - 1) : 0;
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
                 for (int r = 0; r < R; ++r) {
                     const int o = ((slot * R + r) * kChunk + tt) * H + i;
                     vt[r] = valid[r] ? s_v[o] : 0.f;
-                    at[r] = (valid[r] && p.alif) ? s_a[o] : 0.f;
+                    at[r] = (valid[r] && ALIF) ? s_a[o] : 0.f;
                 }
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -212,14 +215,33 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
                     }
                     const size_t o = ((size_t)(valid[r] ? b0 + r : 0) * T + t) * H + i;
                     if (p.g_Z && valid[r]) s = __fadd_rn(s, __ldg(p.g_Z + o));
-                    float thr = p.theta;
-                    if (p.alif) thr = __fadd_rn(p.theta, __fmul_rn(beta, at[r]));
-                    const float sg = surrogate_grad(p.surrogate, p.gamma, vt[r], thr);
-                    const float carry = __fmul_rn(__fmul_rn(p.alpha, gv[r]), __fsub_rn(1.0f, zt));
-                    float g = __fadd_rn(__fmul_rn(s, sg), carry);
-                    if (p.g_V && valid[r]) g = __fadd_rn(g, __ldg(p.g_V + o));
+                    float g, gi_scale = 1.0f;
+                    if constexpr (IZH) {
+                        // adjoint of spiking_layers.py:345-348 (operation order of oracle/snn_oracle.c):
+                        //   dV'/dV = (1 + dt k ((V-vr) + (V-vth)) / C)(1-Z)   dV'/du = -(dt/C)(1-Z)   dV'/dI = (dt/C)(1-Z)
+                        //   du'/dV = dt a b                                    du'/du = 1 - dt a
+                        const float v = vt[r];
+                        const float sg = surrogate_grad(SURR, p.gamma, v, p.iz.vpeak);
+                        const float dq = __fmul_rn(p.iz.k, __fadd_rn(__fsub_rn(v, p.iz.vr), __fsub_rn(v, p.iz.vth)));
+                        const float A = __fmul_rn(__fadd_rn(1.0f, __fdiv_rn(__fmul_rn(p.iz.dt, dq), p.iz.C)), __fsub_rn(1.0f, zt));
+                        const float dtC = __fdiv_rn(p.iz.dt, p.iz.C);
+                        g = __fadd_rn(__fadd_rn(__fmul_rn(s, sg), __fmul_rn(gv[r], A)),
+                                      __fmul_rn(gu[r], __fmul_rn(__fmul_rn(p.iz.dt, p.iz.a), p.iz.b)));
+                        if (p.g_V && valid[r]) g = __fadd_rn(g, __ldg(p.g_V + o));
+                        gu[r] = __fadd_rn(__fmul_rn(__fmul_rn(gv[r], -dtC), __fsub_rn(1.0f, zt)),
+                                          __fmul_rn(gu[r], __fsub_rn(1.0f, __fmul_rn(p.iz.dt, p.iz.a))));
+                        gi_scale = dtC;
+                    } else {
+                        float thr = p.theta;
+                        if (ALIF) thr = __fadd_rn(p.theta, __fmul_rn(beta, at[r]));
+                        const float sg = surrogate_grad(SURR, p.gamma, vt[r], thr);
+                        const float carry = __fmul_rn(__fmul_rn(p.alpha, gv[r]), __fsub_rn(1.0f, zt));
+                        g = __fadd_rn(__fmul_rn(s, sg), carry);
+                        if (p.g_V && valid[r]) g = __fadd_rn(g, __ldg(p.g_V + o));
+                    }
                     gv[r] = g;
-                    const float gi = __fmul_rn(g, __fsub_rn(1.0f, zprev));
+                    const float gi = IZH ? __fmul_rn(__fmul_rn(g, gi_scale), __fsub_rn(1.0f, zprev))
+                                             : __fmul_rn(g, __fsub_rn(1.0f, zprev));
                     if (valid[r]) {
                         if (p.gI_lo) {   // tensor-core mode: exact two-plane tf32 split for the weight-gradient GEMM
                             const float hi = __uint_as_float(__float_as_uint(gi) & 0xFFFFE000u);

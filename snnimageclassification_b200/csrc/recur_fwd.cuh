@@ -96,9 +96,12 @@ __device__ __forceinline__ void fwd_tail(const FwdParams& p, const uint32_t* s_m
     }
 }
 
-template <int H, int R, bool REC>
+// MODE: 0 LIF, 1 ALIF, 2 Izhikevich -- compile-time, because a run-time branch on the layer type inside the step
+// loop measurably slows the issue-bound kernel (6 % for one extra uniform branch)
+template <int H, int R, bool REC, int MODE = 1>
 __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
 {
+    constexpr bool IZH = MODE == 2, ALIF = MODE == 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int W32 = H / 32;
     const int T = p.T, O = p.O, B = p.B;
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
         tc::mbar_wait(s_bar + kRing, 0);
         load_w_cb<REC ? H : 16>(w, s_w, i);
     }
-    const float beta = (p.alif && p.beta) ? __ldg(p.beta) : 0.f;
+    const float beta = (ALIF && p.beta) ? __ldg(p.beta) : 0.f;
 
     float v[R], a[R], zp[R];
     bool valid[R];
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
         const int b = b0 + r;
         valid[r] = b < B;
         const size_t s = (size_t)(valid[r] ? b : 0) * H + i;
-        v[r] = (valid[r] && p.V0) ? p.V0[s] : 0.f;
+        v[r] = (valid[r] && p.V0) ? p.V0[s] : (IZH ? p.iz.vr : 0.f);   // Izhikevich starts at v_rest (:309)
         a[r] = (valid[r] && p.a0) ? p.a0[s] : 0.f;
         zp[r] = (valid[r] && p.Z0) ? p.Z0[s] : 0.f;
         if (REC) s_z[1 * R * H + r * H + i] = zp[r];   // step 0 reads buffer (0+1)&1
@@ -193,21 +196,33 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
                 rec = dot_rec16_cb<REC ? H : 16>(w, zv, i & 3);
             }
             // V' = (alpha V + I_in + I_rec) (1 - Z.detach())     spiking_layers.py:169/239
-            const float t1 = __fmul_rn(p.alpha, v[r]);
-            const float t2 = __fadd_rn(t1, cur[r]);
-            const float t3 = __fadd_rn(t2, rec);
-            const float vn = __fmul_rn(t3, __fsub_rn(1.0f, zp[r]));
-            float thr = p.theta;
-            if (p.alif) {
-                a[r] = __fadd_rn(__fmul_rn(p.rho, a[r]), zp[r]);          // :240
-                thr = __fadd_rn(p.theta, __fmul_rn(beta, a[r]));          // :241
+            float vn, thr = p.theta;
+            if constexpr (IZH) {
+                // IzhikevichLayer.forward, spiking_layers.py:344-349 (same operation order as oracle/snn_oracle.c)
+                const float I = __fadd_rn(cur[r], rec);
+                const float d1 = __fsub_rn(v[r], p.iz.vr), d2 = __fsub_rn(v[r], p.iz.vth);
+                const float q = __fsub_rn(__fmul_rn(__fmul_rn(p.iz.k, d1), d2), a[r]);
+                const float inc = __fdiv_rn(__fmul_rn(p.iz.dt, __fadd_rn(q, I)), p.iz.C);
+                vn = __fadd_rn(__fmul_rn(__fadd_rn(v[r], inc), __fsub_rn(1.0f, zp[r])), __fmul_rn(p.iz.c, zp[r]));
+                const float du = __fmul_rn(p.iz.a, __fsub_rn(__fmul_rn(p.iz.b, d1), a[r]));
+                a[r] = __fadd_rn(__fadd_rn(a[r], __fmul_rn(p.iz.dt, du)), __fmul_rn(p.iz.d, zp[r]));
+                thr = p.iz.vpeak;
+            } else {
+                const float t1 = __fmul_rn(p.alpha, v[r]);
+                const float t2 = __fadd_rn(t1, cur[r]);
+                const float t3 = __fadd_rn(t2, rec);
+                vn = __fmul_rn(t3, __fsub_rn(1.0f, zp[r]));
+                if constexpr (ALIF) {
+                    a[r] = __fadd_rn(__fmul_rn(p.rho, a[r]), zp[r]);          // :240
+                    thr = __fadd_rn(p.theta, __fmul_rn(beta, a[r]));          // :241
+                }
             }
             const float zn = vn >= thr ? 1.0f : 0.0f;                     // spike_funcs.py:27-28
             if (p.traces && valid[r]) {
                 const size_t o = ((size_t)(b0 + r) * T + t) * H + i;
                 p.V[o] = vn;
                 p.Z[o] = zn;
-                if (p.alif) p.a[o] = a[r];
+                if (IZH || ALIF) p.a[o] = a[r];
             }
             const unsigned m = __ballot_sync(0xffffffffu, zn != 0.f);
             if (lane == 0) s_mask[(r * T + t) * W32 + warp] = m;

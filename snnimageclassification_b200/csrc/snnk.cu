@@ -110,12 +110,23 @@ int check_desc(const SnnkDesc* d)
 {
     if (!d) return SNNK_ERR_ARG;
     if (d->B <= 0 || d->T <= 0 || d->N <= 0 || d->H <= 0 || d->O <= 0) return SNNK_ERR_SHAPE;
-    if (d->layer_type != SNNK_LIF && d->layer_type != SNNK_ALIF) return SNNK_ERR_ARG;
+    if (d->layer_type != SNNK_LIF && d->layer_type != SNNK_ALIF && d->layer_type != SNNK_IZHIKEVICH) return SNNK_ERR_ARG;
+    if (d->layer_type == SNNK_IZHIKEVICH && d->H > 128) return SNNK_ERR_UNSUPPORTED;   // register-resident kernels only
+    if (d->layer_type == SNNK_IZHIKEVICH && !(d->iz_C != 0.0f)) return SNNK_ERR_ARG;
     if (d->surrogate != SNNK_FAST_SIGMOID && d->surrogate != SNNK_PHI) return SNNK_ERR_ARG;
     if (d->O > kOMax) return SNNK_ERR_SHAPE;
     if (d->H != 32 && d->H != 64 && d->H != 128 && !(d->H % 128 == 0 && d->H <= 2048)) return SNNK_ERR_UNSUPPORTED;
     if ((long long)d->B * d->T >= (1ll << 31) / 4) return SNNK_ERR_SHAPE;
     return SNNK_OK;
+}
+
+IzhConsts izh_consts(const SnnkDesc* d)
+{
+    IzhConsts z{};
+    z.on = d->layer_type == SNNK_IZHIKEVICH;
+    z.dt = d->dt; z.C = d->iz_C; z.vr = d->iz_v_rest; z.vth = d->iz_v_th; z.k = d->iz_k; z.a = d->iz_a; z.b = d->iz_b;
+    z.c = d->iz_c; z.d = d->iz_d; z.vpeak = d->iz_v_peak;
+    return z;
 }
 
 Plan make_plan(const SnnkDesc* d)
@@ -316,7 +327,8 @@ int launch_fwd(const FwdParams& fp, int grid, cudaStream_t st)
 {
     const size_t smem = fwd_smem_bytes<H, R>(fp.T, fp.O);
     if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
-    auto kern = k_recur_fwd<H, R, REC>;
+    // the Izhikevich body is a compile-time variant: a run-time branch in the step loop cost the LIF/ALIF kernels 6 %
+    auto kern = fp.iz.on ? k_recur_fwd<H, R, REC, 2> : (fp.alif ? k_recur_fwd<H, R, REC, 1> : k_recur_fwd<H, R, REC, 0>);
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { ProfScope ps(SNNK_K_RECUR_FWD, st); kern<<<grid, H, smem, st>>>(fp); }
     SNNK_CUDA(cudaGetLastError());
@@ -335,6 +347,7 @@ bool use_mma_recur(const SnnkDesc* d)
     // Measured on B200 (profiles/): a 16-row tile keeps one SM busy for ~1.8 us per step whatever the batch, so the
     // MMA kernel wins once there are enough tiles to fill the chip (B=4096: 0.38 ms vs 1.07 ms) and loses to the
     // 128-threads-per-row SIMT kernel, which spreads a small batch over all SMs (B=256: 180 us vs 64 us).
+    if (d->layer_type == SNNK_IZHIKEVICH) return false;   // the MMA recurrence implements the LIF / ALIF update only
     static const char* env = getenv("SNNK_MMA_RECUR");
     if (env) return env[0] != '0' && d->H == kMmaH;
     return (d->flags & SNNK_F_TENSOR_CORE) != 0 && d->H == kMmaH && d->B >= 768;
@@ -367,7 +380,16 @@ int launch_bwd(const BwdParams& bp, int grid, cudaStream_t st)
 {
     const size_t smem = bwd_smem_bytes<H, R>(bp.T, REC);
     if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
-    auto kern = k_recur_bwd<H, R, REC>;
+    const int mode = bp.iz.on ? 2 : (bp.alif ? 1 : 0);
+    void (*kern)(const BwdParams) = nullptr;
+    switch (mode * 2 + (bp.surrogate ? 1 : 0)) {
+    case 0: kern = k_recur_bwd<H, R, REC, 0, 0>; break;
+    case 1: kern = k_recur_bwd<H, R, REC, 0, 1>; break;
+    case 2: kern = k_recur_bwd<H, R, REC, 1, 0>; break;
+    case 3: kern = k_recur_bwd<H, R, REC, 1, 1>; break;
+    case 4: kern = k_recur_bwd<H, R, REC, 2, 0>; break;
+    default: kern = k_recur_bwd<H, R, REC, 2, 1>; break;
+    }
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { ProfScope ps(SNNK_K_RECUR_BWD, st); kern<<<grid, H, smem, st>>>(bp); }
     SNNK_CUDA(cudaGetLastError());
@@ -686,7 +708,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     if (d->recurrent && !W_rec) return SNNK_ERR_ARG;
     if (d->layer_type == SNNK_ALIF && !beta) return SNNK_ERR_ARG;
     const bool traces = (d->flags & SNNK_F_TRACES) != 0;
-    if (traces && (!V || !Z || (d->layer_type == SNNK_ALIF && !a))) return SNNK_ERR_ARG;
+    if (traces && (!V || !Z || (d->layer_type != SNNK_LIF && !a))) return SNNK_ERR_ARG;
     if (!device_ok()) return SNNK_ERR_DEVICE;
     const Plan pl = make_plan(d);
     if (workspace_bytes < pl.fwd_bytes) return SNNK_ERR_WORKSPACE;
@@ -756,6 +778,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     FwdParams fp{};
     fp.B = d->B; fp.T = d->T; fp.H = d->H; fp.O = d->O;
     fp.alif = d->layer_type == SNNK_ALIF; fp.traces = traces;
+    fp.iz = izh_consts(d);
     fp.alpha = d->alpha; fp.rho = d->rho; fp.theta = d->theta; fp.kappa = d->kappa;
     fp.I_in = I_in; fp.W_eff = W_eff; fp.beta = beta; fp.W_out = W_out; fp.b_out = b_out;
     fp.V0 = V0; fp.a0 = a0; fp.Z0 = Z0; fp.V = V; fp.a = a; fp.Z = Z; fp.zbits = zbits; fp.y = y;
@@ -908,6 +931,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     BwdParams bp{};
     bp.B = d->B; bp.T = d->T; bp.H = d->H; bp.O = d->O;
     bp.alif = d->layer_type == SNNK_ALIF; bp.surrogate = d->surrogate;
+    bp.iz = izh_consts(d);
     bp.alpha = d->alpha; bp.theta = d->theta; bp.gamma = d->gamma; bp.kappa = d->kappa;
     bp.W_effT = W_effT; bp.beta = beta; bp.W_out = W_out; bp.Z0 = Z0;
     bp.V = V; bp.a = a; bp.zbits = zbits; bp.g_y = g_y; bp.g_logits = dense ? nullptr : g_logits;

@@ -25,7 +25,7 @@ from .. import _cabi
 @dataclass(frozen=True)
 class LayerConsts:
 	"""Scalar constants of the hidden layer + readout (python floats, rounded to fp32 by the ABI struct)."""
-	layer_type: int      # _cabi.SNNK_LIF | SNNK_ALIF
+	layer_type: int      # _cabi.SNNK_LIF | SNNK_ALIF | SNNK_IZHIKEVICH
 	surrogate: int       # _cabi.SNNK_FAST_SIGMOID | SNNK_PHI
 	recurrent: bool
 	alpha: float
@@ -34,6 +34,7 @@ class LayerConsts:
 	gamma: float
 	kappa: float
 	tensor_core: bool = False
+	izh: Optional[Tuple[float, ...]] = None    # Izhikevich only: (dt, C, v_rest, v_th, k, a, b, c, d, v_peak)
 
 
 BINARY_TAG = "_snnk_binary"   # python attribute on tensors known to hold exactly {0,1} (encoder output, spike traces)
@@ -67,8 +68,10 @@ def get_runs(t) -> Optional[torch.Tensor]:
 def make_desc(c: LayerConsts, B: int, T: int, N: int, H: int, O: int, traces: bool, binary: bool = False) -> _cabi.SnnkDesc:
 	flags = (_cabi.SNNK_F_TRACES if traces else 0) | (_cabi.SNNK_F_TENSOR_CORE if c.tensor_core else 0) | (
 		_cabi.SNNK_F_INPUT_BINARY if binary else 0)
+	izh = tuple(c.izh) if c.izh is not None else (0.0,) * 10
 	return _cabi.SnnkDesc(
-		B, T, N, H, O, c.layer_type, c.surrogate, int(c.recurrent), c.alpha, c.rho, c.theta, c.gamma, c.kappa, flags)
+		B, T, N, H, O, c.layer_type, c.surrogate, int(c.recurrent), c.alpha, c.rho, c.theta, c.gamma, c.kappa, flags,
+		*izh)
 
 
 def padded_width(H: int) -> int:
@@ -125,7 +128,7 @@ def run_forward(
 	runs = get_runs(x)
 	dev = x.device
 	f32 = dict(dtype=torch.float32, device=dev)
-	alif = c.layer_type == _cabi.SNNK_ALIF
+	alif = c.layer_type != _cabi.SNNK_LIF     # three-state layers: ALIF (V, a, Z) and Izhikevich (V, u, Z)
 	V = torch.empty((B, T, H), **f32) if traces else None
 	Z = torch.empty((B, T, H), **f32) if traces else None
 	a = torch.empty((B, T, H), **f32) if (traces and alif) else None
@@ -234,7 +237,7 @@ class SpikingSequence(torch.autograd.Function):
 		ctx.binary, ctx.runs = is_binary(xc), get_runs(xc)
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None      # stacked layers: the input is the spike trace below
 		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], out["Z"])
-		alif = consts.layer_type == _cabi.SNNK_ALIF
+		alif = consts.layer_type != _cabi.SNNK_LIF
 		a = out["a"][..., :H] if alif else out["V"].new_zeros(())
 		ctx.mark_non_differentiable(a)
 		return out["y"], out["V"][..., :H], a, out["Z"][..., :H]

@@ -214,9 +214,9 @@ class SNN(torch.nn.Module):
 				"which no published configuration of the reference uses); there is no eager fallback")
 		chain = [(name, layer) for name, layer in self.layers.items() if name != "readout"]
 		for name, layer in chain:
-			if isinstance(layer, IzhikevichLayer) or not isinstance(layer, LIFLayer):
+			if not isinstance(layer, (LIFLayer, IzhikevichLayer)):
 				raise NotImplementedError(
-					f"{type(layer).__name__} is not supported by the B200 path (only LIF and ALIF are fused)")
+					f"{type(layer).__name__} is not supported by the B200 path (LIF, ALIF and Izhikevich are fused)")
 		return chain
 
 	def _hot_layers(self) -> Tuple[LIFLayer, ReadoutLayer]:
@@ -259,7 +259,7 @@ class SNN(torch.nn.Module):
 			consts, w0, b0 = self._inner_cache[name]
 			_, V, a, Z = F_.SpikingSequence.apply(consts, x, *self._layer_weights(layer), w0, b0)
 			if hidden is not None:
-				hidden[name] = (V, a, Z) if isinstance(layer, ALIFLayer) else (V, Z)
+				hidden[name] = (V, a, Z) if isinstance(layer, (ALIFLayer, IzhikevichLayer)) else (V, Z)
 			x = F_.mark_binary(Z)      # a spike trace is exactly {0,1}
 		return x
 
@@ -270,7 +270,7 @@ class SNN(torch.nn.Module):
 		hidden_states = {}
 		inputs = self._run_inner_layers(inputs, hidden_states)
 		y, V, a, Z = F_.SpikingSequence.apply(self._consts(), inputs, *self._weights())
-		hidden_states[self._hidden_chain()[-1][0]] = (V, a, Z) if isinstance(layer, ALIFLayer) else (V, Z)
+		hidden_states[self._hidden_chain()[-1][0]] = (V, a, Z) if isinstance(layer, (ALIFLayer, IzhikevichLayer)) else (V, Z)
 		hidden_states["readout"] = (y,)
 		return y, hidden_states
 

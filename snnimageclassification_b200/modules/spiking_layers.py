@@ -224,11 +224,12 @@ class ALIFLayer(LIFLayer):
 
 
 class IzhikevichLayer(RNNLayer):
-	"""Third LayerType member of the reference (spiking_layers.py:246-353).
+	"""Third LayerType member of the reference (spiking_layers.py:246-353), SURVEY.md 8f.3.
 
-	Not on the accelerated hot path: constructing it works (same parameters and defaults, so
-	checkpoints load), running it raises instead of silently falling back to eager PyTorch.
+	V' = (V + dt (k (V - v_rest)(V - v_th) - u + I) / C)(1 - Z) + c Z;  u' = u + dt a (b (V - v_rest) - u) + d Z;
+	Z' = H(V' - v_peak).  Same kernels as LIF/ALIF with a different elementwise body (hidden widths up to 128).
 	"""
+	SNNK_LAYER_TYPE = _cabi.SNNK_IZHIKEVICH
 
 	def __init__(self, input_size: int, output_size: int, use_recurrent_connection=True, use_rec_eye_mask=True,
 			spike_func: Type[SpikeFunction] = HeavisideSigmoidApprox, dt=1e-3, device=None, **kwargs):
@@ -241,14 +242,42 @@ class IzhikevichLayer(RNNLayer):
 		self.initialize_weights_()
 
 	def _set_default_kwargs(self):
+		# gamma: the reference's isinstance(<class>, HeavisideSigmoidApprox) test is never true, so 1.0 (:297-300)
 		for k, v in dict(C=100.0, v_rest=-60.0, v_th=-40.0, k=0.7, a=0.03, b=-2.0, c=-50.0, d=100.0,
 				v_peak=35.0, gamma=1.0).items():
 			self.kwargs.setdefault(k, v)
 
-	def forward(self, inputs: torch.Tensor, state=None):
-		raise NotImplementedError(
-			"LayerType.Izhikevich is not supported by the B200 path (only LIF and ALIF are fused); "
-			"there is no eager fallback")
+	def create_empty_state(self, batch_size: int = 1) -> Tuple[torch.Tensor, ...]:
+		"""(V = v_rest, u = 0, Z = 0), each (batch_size, output_size) (reference :308-328)."""
+		V, u, Z = self._zeros_state(batch_size, 3)
+		with torch.no_grad():
+			V += self.v_rest
+		return V, u, Z
+
+	def snnk_consts(self, kappa: float = 0.0, tensor_core: bool = False) -> F_.LayerConsts:
+		sid = getattr(self.spike_func, "SURROGATE_ID", None)
+		if sid is None:
+			raise RuntimeError(
+				f"spike function {self.spike_func!r} has no fused surrogate on the B200 path (supported: "
+				"HeavisideSigmoidApprox, HeavisidePhiApprox)")
+		if F_.padded_width(self.output_size) > 128:
+			raise NotImplementedError("IzhikevichLayer is fused for hidden widths up to 128 on the B200 path")
+		izh = tuple(float(v) for v in (self.dt, self.C, self.v_rest, self.v_th, self.k, self.a, self.b, self.c, self.d,
+			self.v_peak))
+		return F_.LayerConsts(
+			layer_type=self.SNNK_LAYER_TYPE, surrogate=sid, recurrent=bool(self.use_recurrent_connection),
+			alpha=0.0, rho=0.0, theta=float(self.v_peak), gamma=float(self.gamma), kappa=kappa, tensor_core=tensor_core,
+			izh=izh)
+
+	def _beta_tensor(self) -> Optional[torch.Tensor]:
+		return None
+
+	_step = LIFLayer._step
+
+	def forward(self, inputs: torch.Tensor, state: Tuple[torch.Tensor, ...] = None):
+		out = self._step(inputs, state)
+		next_V, next_u, next_Z = out["V"][:, 0], out["a"][:, 0], out["Z"][:, 0]
+		return next_Z, (next_V, next_u, next_Z)
 
 
 class ReadoutLayer(RNNLayer):

@@ -165,11 +165,67 @@ def init_fixture():
 	print("init fixture done")
 
 
+def izhikevich_fixture():
+	"""IzhikevichLayer (spiking_layers.py:246-353), the third LayerType member.  With the reference's default constants
+	(C=100, k=0.7, dt=1e-3) and N(0,1) weights the membrane barely leaves v_rest, so the cases use dt = 1.0 (the
+	millisecond units the constants come from) and scaled-up weights: every neuron spikes a few times in T steps."""
+	out = {}
+	names = []
+	i = 0
+	for sf in (SpikeFuncType.FastSigmoid, SpikeFuncType.Phi):
+		for rec in (False, True):
+			name = f"IZH_{sf.name}_rec{int(rec)}"
+			B, T, N, H, O = 3, 40, 48, 32, 10
+			torch.manual_seed(300 + i)
+			net = SNN(N, O, H, use_recurrent_connection=rec, int_time_steps=T, spike_func=sf,
+				hidden_layer_type=LayerType.Izhikevich, dt=1.0, device=torch.device("cpu"))
+			L, R = net.layers["input"], net.layers["readout"]
+			with torch.no_grad():
+				L.forward_weights.mul_(25.0).add_(20.0)
+				if rec:
+					L.recurrent_weights.mul_(10.0)
+			g = torch.Generator().manual_seed(301 + i)
+			x = (torch.rand(B, T, N, generator=g) < 0.2).float()
+			labels = torch.randint(0, O, (B,), generator=g)
+			net.train()
+			logp, y, hs = net.get_prediction_log_proba(x, re_outputs_trace=True, re_hidden_states=True)
+			loss = torch.nn.NLLLoss()(logp, labels)
+			net.zero_grad()
+			loss.backward()
+			V, u, Z = hs["input"]
+			d = dict(
+				x=x.numpy().astype(np.uint8), labels=labels.numpy(), W_in=L.forward_weights.detach().numpy(),
+				W_out=R.forward_weights.detach().numpy(), b_out=R.bias_weights.detach().numpy(),
+				V=V.detach().numpy(), u=u.detach().numpy(), Z=Z.detach().numpy().astype(np.uint8), y=y.detach().numpy(),
+				logp=logp.detach().numpy(), loss=np.float32(loss.item()),
+				dW_in=L.forward_weights.grad.numpy(), dW_out=R.forward_weights.grad.numpy(), db=R.bias_weights.grad.numpy(),
+				consts=np.array([float(L.dt), float(L.C), float(L.v_rest), float(L.v_th), float(L.k), float(L.a), float(L.b),
+					float(L.c), float(L.d), float(L.v_peak), float(L.gamma), float(R.kappa)], dtype=np.float32),
+				dims=np.array([B, T, N, H, O]), flags=np.array([int(sf == SpikeFuncType.Phi), int(rec)]),
+				spike_rate=np.float32(Z.detach().mean().item()),
+			)
+			if rec:
+				d["W_rec"] = L.recurrent_weights.detach().numpy()
+				d["rec_mask"] = L.rec_mask.numpy()
+				d["dW_rec"] = L.recurrent_weights.grad.numpy()
+			for k, v in d.items():
+				out[f"{name}/{k}"] = v
+			names.append(name)
+			print(name, "spike rate", float(d["spike_rate"]), "loss", float(d["loss"]), "|dW_in|max", float(np.abs(d["dW_in"]).max()))
+			i += 1
+	out["names"] = np.array(names)
+	np.savez_compressed(os.path.join(HERE, "izhikevich_golden.npz"), **out)
+
+
 def main():
+	if os.environ.get("SNN_GOLDEN_ONLY") == "izhikevich":
+		izhikevich_fixture()
+		return
 	encoder_fixture()
 	dynamics_fixture()
 	init_fixture()
 	stacked_fixture()
+	izhikevich_fixture()
 	for f in sorted(os.listdir(HERE)):
 		if f.endswith(".npz"):
 			print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KB")

@@ -27,12 +27,12 @@ def test_library_exports_every_declared_symbol():
 	for name in declared:
 		assert hasattr(lib, name), f"{name} declared in snnk.h but not exported by libsnnk.so"
 	assert sorted(_cabi.EXPORTS) == declared, "python binding and header disagree on the entry points"
-	assert _cabi.lib().snnk_abi_version() == 2
+	assert _cabi.lib().snnk_abi_version() == 3
 	assert b"sm_100" in _cabi.lib().snnk_strerror(-3)
 
 
 def test_desc_struct_matches_header_layout():
-	assert ctypes.sizeof(_cabi.SnnkDesc) == 14 * 4
+	assert ctypes.sizeof(_cabi.SnnkDesc) == 24 * 4
 	assert _cabi.SnnkDesc.alpha.offset == 32 and _cabi.SnnkDesc.flags.offset == 52
 
 
@@ -90,8 +90,13 @@ def test_no_cpu_fallback():
 		with pytest.raises(RuntimeError, match="no CPU fallback"):
 			ToSpikes(10)(np.zeros(4))
 	izh = SNN(16, 10, 32, hidden_layer_type=LayerType.Izhikevich, device=CPU, int_time_steps=4)
-	with pytest.raises(NotImplementedError, match="not supported by the B200 path"):
+	with pytest.raises(RuntimeError, match="no CPU fallback"):
 		izh(torch.zeros(2, 4, 16))
+	wide = SNN(16, 10, 256, hidden_layer_type=LayerType.Izhikevich, device=CPU, int_time_steps=4)
+	with pytest.raises(NotImplementedError, match="up to 128"):
+		wide(torch.zeros(2, 4, 16))
+	V, u, Z = izh.layers["input"].create_empty_state(3)           # reference spiking_layers.py:308-328
+	assert float(V.min()) == float(V.max()) == -60.0 and float(u.abs().max()) == 0.0 and float(Z.abs().max()) == 0.0
 
 
 def test_format_inputs():

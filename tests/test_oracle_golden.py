@@ -149,3 +149,33 @@ def test_torch_port_matches_reference(name):
 		# reference quirk: the threshold input of the spike function gets no gradient, so beta.grad is None
 		assert int(d["beta_grad_is_none"]) == 1
 		assert net.beta.grad is None
+
+
+# ---- IzhikevichLayer (third LayerType member, spiking_layers.py:246-353) ---------------------------------------------
+def _izh_cfg(c):
+	from oracle import OracleCfg
+	B, T, N, H, O = (int(v) for v in c["dims"])
+	k = c["consts"]
+	return OracleCfg(B, T, N, H, O, layer_type=2, surrogate=int(c["flags"][0]), recurrent=int(c["flags"][1]),
+		gamma=float(k[10]), kappa=float(k[11]), dt=float(k[0]), iz_C=float(k[1]), iz_vr=float(k[2]), iz_vth=float(k[3]),
+		iz_k=float(k[4]), iz_a=float(k[5]), iz_b=float(k[6]), iz_c=float(k[7]), iz_d=float(k[8]), iz_vpeak=float(k[9]))
+
+
+@pytest.mark.parametrize("name", ["IZH_FastSigmoid_rec0", "IZH_FastSigmoid_rec1", "IZH_Phi_rec0", "IZH_Phi_rec1"])
+def test_oracle_izhikevich_matches_reference(name):
+	import oracle
+	z = load("izhikevich_golden.npz")
+	c = dynamics_case(z, name)
+	cfg = _izh_cfg(c)
+	x = c["x"].astype(np.float32)
+	f = oracle.forward(cfg, x, c["W_in"], c.get("W_rec"), c.get("rec_mask"), c["W_out"], c["b_out"])
+	assert float(c["spike_rate"]) > 0.01
+	assert np.array_equal(f["Z"].astype(np.uint8), c["Z"])
+	assert rel_err(f["V"], c["V"]) <= 1e-5 and rel_err(f["a"], c["u"]) <= 1e-5 and rel_err(f["y"], c["y"]) <= 1e-5
+	h = oracle.head(f["y"], c["labels"])
+	assert rel_err(h["logp"], c["logp"]) <= 1e-5 and abs(h["loss"] - float(c["loss"])) <= 1e-5 * abs(float(c["loss"]))
+	g = oracle.backward(cfg, x, c.get("W_rec"), c.get("rec_mask"), c["W_out"], f["V"], f["a"], f["Z"], h["g_y"])
+	assert rel_err(g["dW_in"], c["dW_in"]) <= 1e-4
+	assert rel_err(g["dW_out"], c["dW_out"]) <= 1e-4 and rel_err(g["db"], c["db"]) <= 1e-4
+	if cfg.recurrent:
+		assert rel_err(g["dW_rec"], c["dW_rec"]) <= 1e-4
