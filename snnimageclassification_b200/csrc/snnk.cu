@@ -60,6 +60,31 @@ struct ProfScope {
     ~ProfScope() { if (slot >= 0) cudaEventRecord(g_prof[slot].b, st); }
 };
 
+// Fork / join onto a helper stream (one per device, created on first use) so that two independent kernels of one call
+// overlap.  Event record / wait are legal during stream capture: the helper stream joins the capture and the graph
+// gets two parallel branches.  The call still returns with everything ordered behind the caller's stream.
+struct Fork {
+    cudaStream_t side = nullptr;
+    cudaEvent_t forked = nullptr, joined = nullptr;
+    bool ok = false;
+};
+Fork* fork_for_device()
+{
+    static Fork forks[64];
+    static const char* env = getenv("SNNK_FORK");
+    if (env && env[0] == '0') return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    Fork& f = forks[dev];
+    if (!f.ok) {
+        if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.forked, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.joined, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        f.ok = true;
+    }
+    return &f;
+}
+
 int device_ok()
 {
     int dev = 0;
@@ -231,7 +256,8 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
 
 template <int H>   // H = N extent of one CTA tile (the whole hidden width when it is <= 128)
 int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const float* W_in, float* I_in, float* planes,
-                   unsigned int* flag, cudaStream_t st, const int* run_table = nullptr, int run_variant = 0)
+                   unsigned int* flag, cudaStream_t st, const int* run_table = nullptr, int run_variant = 0,
+                   bool split = true)
 {
     // run_variant 1: x / I_in are the compact buffers of the frame-dedup path (run_rows rows, the weight planes are
     // already split); 0 with a table: the dense launch, which the kernel skips when the table says ok
@@ -239,7 +265,7 @@ int launch_proj_tc(const SnnkDesc* d, const Plan& pl, const float* x, const floa
     using Cfg = tc::ProjCfg<H, P>;
     const int M = run_variant == 1 ? pl.run_rows : d->B * d->T;
     const int Hf = d->H;
-    if (run_variant == 0) {
+    if (run_variant == 0 && split) {
         const int n = Hf * pl.kpad;
         tc::k_split_w<<<(n + 255) / 256, 256, 0, st>>>(W_in, d->N, Hf, pl.kpad, planes);
         SNNK_CUDA(cudaGetLastError());
@@ -717,6 +743,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
 
     const int* compact_table = nullptr;
     const float* compact_rows = nullptr;
+    Fork* fk = nullptr;
     // K1: input projection for all T steps at once.  Tensor-core path first (when asked for and addressable by
     // TMA); the fp32 SIMT kernel behind it only runs if x turned out not to be tf32-exact (device-side flag).
     {
@@ -731,10 +758,22 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
             }
             // frame-dedup variant (runs.cuh): only for inputs the caller vouches to be the encoder's {0,1} raster
             const int* runs = (pl.runs && !pl.check) ? run_table : nullptr;
+            // With a run table the dense launch (which skips itself when the table says ok) and the preparation of the
+            // recurrent matrix go onto a parallel branch beside gather + compact projection; joined before K2.
+            fk = (runs && !pl.wide) ? fork_for_device() : nullptr;
+            cudaStream_t st_d = st;
+            if (fk) {
+                const int n = d->H * pl.kpad;
+                tc::k_split_w<<<(n + 255) / 256, 256, 0, st>>>(W_in, d->N, d->H, pl.kpad, planes);
+                SNNK_CUDA(cudaGetLastError());
+                SNNK_CUDA(cudaEventRecord(fk->forked, st));
+                SNNK_CUDA(cudaStreamWaitEvent(fk->side, fk->forked, 0));
+                st_d = fk->side;
+            }
             switch (pl.tileN) {
-            case 32: rc = launch_proj_tc<32>(d, pl, x, W_in, I_in, planes, flag, st, runs, 0); break;
-            case 64: rc = launch_proj_tc<64>(d, pl, x, W_in, I_in, planes, flag, st, runs, 0); break;
-            default: rc = launch_proj_tc<128>(d, pl, x, W_in, I_in, planes, flag, st, runs, 0); break;
+            case 32: rc = launch_proj_tc<32>(d, pl, x, W_in, I_in, planes, flag, st_d, runs, 0, fk == nullptr); break;
+            case 64: rc = launch_proj_tc<64>(d, pl, x, W_in, I_in, planes, flag, st_d, runs, 0, fk == nullptr); break;
+            default: rc = launch_proj_tc<128>(d, pl, x, W_in, I_in, planes, flag, st_d, runs, 0, fk == nullptr); break;
             }
             if (rc != SNNK_OK) return rc;
             if (runs) {
@@ -772,8 +811,12 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     if (d->recurrent) {
         W_eff = reinterpret_cast<float*>(static_cast<char*>(workspace) + pl.off_weff);
         const int n = d->H * d->H;
-        k_prep_rec<<<(n + 255) / 256, 256, 0, st>>>(W_rec, rec_mask, d->H, W_eff, nullptr);
+        k_prep_rec<<<(n + 255) / 256, 256, 0, fk ? fk->side : st>>>(W_rec, rec_mask, d->H, W_eff, nullptr);
         SNNK_CUDA(cudaGetLastError());
+    }
+    if (fk) {
+        SNNK_CUDA(cudaEventRecord(fk->joined, fk->side));
+        SNNK_CUDA(cudaStreamWaitEvent(st, fk->joined, 0));
     }
     FwdParams fp{};
     fp.B = d->B; fp.T = d->T; fp.H = d->H; fp.O = d->O;
@@ -968,13 +1011,28 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
             g.T = d->T; g.B = d->B; g.N = d->N; g.mtiles_x = pl.mtiles_x; g.mtiles_z = pl.mtiles_z; g.m_total = pl.m_total;
             g.S = pl.S; g.samples_per_split = pl.samples_per_split; g.part = pw; g.flag = flag;
             g.run_table = runs; g.run_gate = 0; g.run_clip = 0;
-            rc = launch_wgrad_tc_any(d, pl.tileN, g, st);
+            Fork* fk = runs ? fork_for_device() : nullptr;
+            cudaStream_t st_b = st;
+            if (fk) {   // dense (self-skipping) launch + Z-only GEMM on a parallel branch beside gather + compact GEMM
+                SNNK_CUDA(cudaEventRecord(fk->forked, st));
+                SNNK_CUDA(cudaStreamWaitEvent(fk->side, fk->forked, 0));
+                st_b = fk->side;
+            }
+            rc = launch_wgrad_tc_any(d, pl.tileN, g, st_b);
             if (rc != SNNK_OK) return rc;
             if (runs) {
-                // dedup variant: run sums of gI, x-only GEMM over the compact rows, Z-only GEMM over the dense rows
+                // dedup variant: x-only GEMM over the compact rows (run sums of gI come from the BPTT sweep) and Z-only
+                // GEMM over the dense rows; the two are independent
                 float* Xu = reinterpret_cast<float*>(ws + pl.off_xu_b);
                 float* Gu = reinterpret_cast<float*>(ws + pl.off_gu);
-                // (both planes of Gu, the run sums of gI, were written by the BPTT sweep: k_recur_bwd)
+                if (rec) {
+                    WgradGeom gb = g;
+                    gb.x = nullptr; gb.N = 0; gb.mtiles_x = 0; gb.m_total = d->H; gb.S = pl.S_rec;
+                    gb.samples_per_split = pl.sps_rec; gb.part = reinterpret_cast<float*>(ws + pl.off_pwrec); gb.flag = nullptr;
+                    gb.run_gate = 1; gb.run_clip = 0;
+                    rc = launch_wgrad_tc_any(d, pl.tileN, gb, st_b);
+                    if (rc != SNNK_OK) return rc;
+                }
                 {
                     ProfScope ps(SNNK_K_WGRAD, st);
                     k_gather_rows<<<std::min(pl.run_rows, 8 * sm_count()), 256, 0, st>>>(x, runs, d->B * d->T, d->N, Xu);
@@ -987,13 +1045,9 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
                 ga.run_table = runs; ga.run_gate = 1; ga.run_clip = 1;
                 rc = launch_wgrad_tc_any(d, pl.tileN, ga, st);
                 if (rc != SNNK_OK) return rc;
-                if (rec) {
-                    WgradGeom gb = g;
-                    gb.x = nullptr; gb.N = 0; gb.mtiles_x = 0; gb.m_total = d->H; gb.S = pl.S_rec;
-                    gb.samples_per_split = pl.sps_rec; gb.part = reinterpret_cast<float*>(ws + pl.off_pwrec); gb.flag = nullptr;
-                    gb.run_gate = 1; gb.run_clip = 0;
-                    rc = launch_wgrad_tc_any(d, pl.tileN, gb, st);
-                    if (rc != SNNK_OK) return rc;
+                if (fk) {
+                    SNNK_CUDA(cudaEventRecord(fk->joined, fk->side));
+                    SNNK_CUDA(cudaStreamWaitEvent(st, fk->joined, 0));
                 }
             }
         }
