@@ -97,6 +97,19 @@ def _pad_hidden(H: int, Hp: int, W_in, W_rec, rec_mask, W_out):
 		None if rec_mask is None else P(rec_mask, (0, pad, 0, pad)), P(W_out, (0, 0, 0, pad)))
 
 
+_CONST = {}
+
+
+def _const_scalar(value: float, device) -> torch.Tensor:
+	"""A cached 0-d fp32 constant per device: placeholders and the root gradient of ``loss.backward()`` would otherwise
+	each cost a fill kernel in every training step."""
+	key = (float(value), str(device))
+	t = _CONST.get(key)
+	if t is None:
+		t = _CONST[key] = torch.full((), float(value), dtype=torch.float32, device=device)
+	return t
+
+
 def _workspace(nbytes: int, device) -> torch.Tensor:
 	return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -238,7 +251,7 @@ class SpikingSequence(torch.autograd.Function):
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None      # stacked layers: the input is the spike trace below
 		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], out["Z"])
 		alif = consts.layer_type != _cabi.SNNK_LIF
-		a = out["a"][..., :H] if alif else out["V"].new_zeros(())
+		a = out["a"][..., :H] if alif else _const_scalar(0.0, out["V"].device)
 		ctx.mark_non_differentiable(a)
 		return out["y"], out["V"][..., :H], a, out["Z"][..., :H]
 
@@ -279,7 +292,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None
 		if need_grad:
 			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"], out["Z"])
-		empty = logp.new_zeros(())
+		empty = _const_scalar(0.0, logp.device)
 		extras = tuple(
 			(out[k] if k == "y" else out[k][..., :H]) if out[k] is not None else empty for k in ("y", "V", "a", "Z"))
 		ctx.mark_non_differentiable(logp, *extras)

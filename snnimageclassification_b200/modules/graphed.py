@@ -11,6 +11,8 @@ from typing import Optional
 
 import torch
 
+from .functional import _const_scalar
+
 
 def _optimizer_is_capturable(optimizer) -> bool:
 	groups = getattr(optimizer, "param_groups", None)
@@ -69,7 +71,7 @@ class GraphedTrainStep:
 		net = self.net
 		loss = net.batch_loss(self.x, self.y, self.criterion)
 		self.optimizer.zero_grad(set_to_none=True)
-		loss.backward()
+		loss.backward(gradient=_const_scalar(1.0, loss.device))     # cached root gradient: no ones_like fill per step
 		net._allreduce_gradients(self.optimizer)
 		if self.step_in_graph:
 			self.optimizer.step()
