@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SNNK_ABI_VERSION 3   /* 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
+#define SNNK_ABI_VERSION 4   /* 4: W_effT_out / W_effT_in; 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
 
 typedef void* snnk_stream_t; /* cudaStream_t */
 
@@ -189,12 +189,14 @@ size_t snnk_backward_workspace_bytes(const SnnkDesc* d);
  *   current I_in = x @ W_in (exposed for tests) -- unless run_table was given and its ok word is set: the
  *   projection then exists only for the first row of every run (compact rows further up in the workspace)
  *   run_table: table of x from snnk_encode_runs / snnk_frame_runs, or NULL (see there)
+ *   W_effT_out: optional (H,H): receives the transpose of W_rec (.) rec_mask, which snnk_backward of the same
+ *   weights accepts as W_effT_in and then need not prepare itself (one launch less on the training step)
  */
 int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec,
                  const float* rec_mask, const float* beta, const float* W_out, const float* b_out,
                  const float* V0, const float* a0, const float* Z0, float* V, float* a, float* Z,
                  uint32_t* zbits, float* y, float* logits, int32_t* tstar, void* workspace,
-                 size_t workspace_bytes, const int32_t* run_table,
+                 size_t workspace_bytes, const int32_t* run_table, float* W_effT_out,
                  snnk_stream_t stream);
 
 /*
@@ -225,7 +227,8 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
                   const float* a, const float* Z, const uint32_t* zbits, const float* g_y, const float* g_logits,
                   const int32_t* tstar, const float* g_scale, const float* g_V, const float* g_Z, float* dW_in,
                   float* dW_rec, float* dW_out, float* db, void* workspace, size_t workspace_bytes,
-                  const int32_t* run_table, snnk_stream_t stream);
+                  const int32_t* run_table, const float* W_effT_in,
+                  snnk_stream_t stream);
 
 /*
  * Optimizer step of SNN._exec_batch (snn.py:414) for the reference's default optimizer, Adam with L2 weight decay

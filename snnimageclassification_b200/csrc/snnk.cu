@@ -726,7 +726,8 @@ size_t snnk_backward_workspace_bytes(const SnnkDesc* d)
 int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec, const float* rec_mask,
                  const float* beta, const float* W_out, const float* b_out, const float* V0, const float* a0,
                  const float* Z0, float* V, float* a, float* Z, uint32_t* zbits, float* y, float* logits,
-                 int32_t* tstar, void* workspace, size_t workspace_bytes, const int32_t* run_table, snnk_stream_t stream)
+                 int32_t* tstar, void* workspace, size_t workspace_bytes, const int32_t* run_table, float* W_effT_out,
+                 snnk_stream_t stream)
 {
     int rc = check_desc(d);
     if (rc != SNNK_OK) return rc;
@@ -811,7 +812,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     if (d->recurrent) {
         W_eff = reinterpret_cast<float*>(static_cast<char*>(workspace) + pl.off_weff);
         const int n = d->H * d->H;
-        k_prep_rec<<<(n + 255) / 256, 256, 0, fk ? fk->side : st>>>(W_rec, rec_mask, d->H, W_eff, nullptr);
+        k_prep_rec<<<(n + 255) / 256, 256, 0, fk ? fk->side : st>>>(W_rec, rec_mask, d->H, W_eff, W_effT_out);
         SNNK_CUDA(cudaGetLastError());
     }
     if (fk) {
@@ -942,7 +943,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
                   const float* W_out, const float* Z0, const float* V, const float* a, const float* Z,
                   const uint32_t* zbits, const float* g_y, const float* g_logits, const int32_t* tstar, const float* g_scale,
                   const float* g_V, const float* g_Z, float* dW_in, float* dW_rec, float* dW_out, float* db, void* workspace,
-                  size_t workspace_bytes, const int32_t* run_table, snnk_stream_t stream)
+                  size_t workspace_bytes, const int32_t* run_table, const float* W_effT_in, snnk_stream_t stream)
 {
     int rc = check_desc(d);
     if (rc != SNNK_OK) return rc;
@@ -964,12 +965,15 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     const bool rec = d->recurrent != 0;
 
     // K3: reverse-time sweep
-    float* W_effT = nullptr;
-    if (rec) {
-        W_effT = reinterpret_cast<float*>(ws + pl.off_weffT);
+    const float* W_effT = nullptr;
+    if (rec && W_effT_in) {
+        W_effT = W_effT_in;      // prepared by snnk_forward of the same weights (its W_effT_out)
+    } else if (rec) {
+        float* wt = reinterpret_cast<float*>(ws + pl.off_weffT);
         const int n = d->H * d->H;
-        k_prep_rec<<<(n + 255) / 256, 256, 0, st>>>(W_rec, rec_mask, d->H, nullptr, W_effT);
+        k_prep_rec<<<(n + 255) / 256, 256, 0, st>>>(W_rec, rec_mask, d->H, nullptr, wt);
         SNNK_CUDA(cudaGetLastError());
+        W_effT = wt;
     }
     BwdParams bp{};
     bp.B = d->B; bp.T = d->T; bp.H = d->H; bp.O = d->O;

@@ -150,6 +150,8 @@ def run_forward(
 	logits = torch.empty((B, O), **f32)
 	tstar = torch.empty((B, O), dtype=torch.int32, device=dev)
 	ws = _workspace(lib.snnk_forward_workspace_bytes(ctypes.byref(desc)), dev)
+	# the transposed masked recurrent matrix the backward sweep needs is prepared here, off the critical path
+	W_effT = torch.empty((H, H), **f32) if (traces and W_rec is not None) else None
 	V0 = a0 = Z0 = None
 	if state is not None:
 		if alif:
@@ -161,15 +163,15 @@ def run_forward(
 			ctypes.byref(desc), _cabi.ptr(x), _cabi.ptr(W_in), _cabi.ptr(W_rec), _cabi.ptr(rec_mask),
 			_cabi.ptr(beta), _cabi.ptr(W_out), _cabi.ptr(b_out), _cabi.ptr(V0), _cabi.ptr(a0), _cabi.ptr(Z0),
 			_cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(y), _cabi.ptr(logits),
-			_cabi.ptr(tstar), _cabi.ptr(ws), ws.numel(), _cabi.ptr(runs), _cabi.stream_ptr())
+			_cabi.ptr(tstar), _cabi.ptr(ws), ws.numel(), _cabi.ptr(runs), _cabi.ptr(W_effT), _cabi.stream_ptr())
 	_cabi.check(rc, "snnk_forward")
 	I_in = ws[: B * T * H * 4].view(torch.float32).view(B, T, H)
-	return dict(y=y, V=V, a=a, Z=Z, zbits=zbits, logits=logits, tstar=tstar, I_in=I_in, desc=desc, Z0=Z0)
+	return dict(y=y, V=V, a=a, Z=Z, zbits=zbits, logits=logits, tstar=tstar, I_in=I_in, desc=desc, Z0=Z0, W_effT=W_effT)
 
 
 def run_backward(
 		c: LayerConsts, x, W_rec, rec_mask, beta, W_out, V, a, zbits, g_y=None, g_logits=None, tstar=None,
-		g_V=None, g_Z=None, Z0=None, Z=None, g_scale=None, binary_input: bool = False, runs=None,
+		g_V=None, g_Z=None, Z0=None, Z=None, g_scale=None, binary_input: bool = False, runs=None, W_effT=None,
 ):
 	"""Calls ``snnk_backward``.  Returns dict(dW_in, dW_rec, dW_out, db, gI) -- ``gI`` is a zero-argument callable
 	(the tensor-core mode stores it as two planes; summing them is only worth it when somebody asks)."""
@@ -190,7 +192,7 @@ def run_backward(
 			_cabi.ptr(W_out), _cabi.ptr(Z0), _cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(g_y),
 			_cabi.ptr(g_logits), _cabi.ptr(tstar), _cabi.ptr(g_scale), _cabi.ptr(g_V), _cabi.ptr(g_Z), _cabi.ptr(dW_in),
 			_cabi.ptr(dW_rec), _cabi.ptr(dW_out), _cabi.ptr(db), _cabi.ptr(ws), ws.numel(),
-			_cabi.ptr(runs if runs is not None else get_runs(x)), _cabi.stream_ptr())
+			_cabi.ptr(runs if runs is not None else get_runs(x)), _cabi.ptr(W_effT), _cabi.stream_ptr())
 	_cabi.check(rc, "snnk_backward")
 	n = B * T * H * 4
 	planes = c.tensor_core and N % 4 == 0   # stored as two tf32 planes (high, exact remainder); see include/snnk.h
@@ -247,7 +249,7 @@ class SpikingSequence(torch.autograd.Function):
 		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=True)
 		ctx.consts, ctx.H, ctx.Hp = consts, H, Hp
 		ctx.set_materialize_grads(False)                     # absent seeds stay None instead of (B,T,H) zero fills
-		ctx.binary, ctx.runs = is_binary(xc), get_runs(xc)
+		ctx.binary, ctx.runs, ctx.W_effT = is_binary(xc), get_runs(xc), out["W_effT"]
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None      # stacked layers: the input is the spike trace below
 		ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], out["Z"])
 		alif = consts.layer_type != _cabi.SNNK_LIF
@@ -266,7 +268,7 @@ class SpikingSequence(torch.autograd.Function):
 			g_V = None if g_V is None else torch.nn.functional.pad(g_V, (0, Hp - H))
 			g_Z = None if g_Z is None else torch.nn.functional.pad(g_Z, (0, Hp - H))
 		g = run_backward(ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_y=_c(g_y), g_V=g_V, g_Z=g_Z, Z=Z,
-			binary_input=ctx.binary, runs=ctx.runs)
+			binary_input=ctx.binary, runs=ctx.runs, W_effT=ctx.W_effT)
 		# (consts, x, W_in, W_rec, rec_mask, beta, W_out, b_out); beta gets no gradient -- the threshold input of
 		# the reference's spike function returns None (spike_funcs.py:62/79)
 		gX = run_input_grad(ctx.consts, g["gI"](), ctx.Wi) if ctx.Wi is not None else None
@@ -288,7 +290,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		loss, logp, g_logits = run_head_nll(out["logits"], labels, want_grad=need_grad)
 		ctx.consts, ctx.H = consts, H
 		ctx.set_materialize_grads(False)
-		ctx.binary, ctx.runs = is_binary(xc), get_runs(xc)
+		ctx.binary, ctx.runs, ctx.W_effT = is_binary(xc), get_runs(xc), out["W_effT"]
 		ctx.Wi = Wi if ctx.needs_input_grad[1] else None
 		if need_grad:
 			ctx.save_for_backward(xc, Wr, M, be, Wo, out["V"], out["a"], out["zbits"], g_logits, out["tstar"], out["Z"])
@@ -305,7 +307,7 @@ class SpikingSequenceNLL(torch.autograd.Function):
 			return (None,) * 10
 		g = run_backward(
 			ctx.consts, xc, Wr, M, be, Wo, V, a, zbits, g_logits=g_logits, tstar=tstar, Z=Z,
-			g_scale=g_loss.detach().float().reshape(1), binary_input=ctx.binary, runs=ctx.runs)
+			g_scale=g_loss.detach().float().reshape(1), binary_input=ctx.binary, runs=ctx.runs, W_effT=ctx.W_effT)
 		H = ctx.H
 		gX = run_input_grad(ctx.consts, g["gI"](), ctx.Wi) if ctx.Wi is not None else None
 		return (None, gX, None, g["dW_in"][:, :H], None if g["dW_rec"] is None else g["dW_rec"][:H, :H], None, None,
