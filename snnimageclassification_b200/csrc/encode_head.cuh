@@ -182,11 +182,15 @@ __global__ void __launch_bounds__(256) k_head_nll(int B, int O, const float* __r
             if (g_logits) g_logits[(size_t)b * O + c] = __fdiv_rn(expf(lp) - (c == lab ? 1.0f : 0.0f), (float)B);
         }
     }
-    s_part[threadIdx.x] = acc;
+    // fixed-shape reduction tree (shuffles inside a warp, then the warp sums in order): deterministic, and not a serial
+    // walk over 256 shared-memory words
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
-        for (int q = 0; q < (int)blockDim.x; ++q) s += s_part[q];
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += s_part[q];
         *loss = (float)(s / (double)B);
     }
 }

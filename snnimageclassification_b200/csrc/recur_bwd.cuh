@@ -294,8 +294,17 @@ struct FinalizeParams {
 
 __device__ __forceinline__ float sum_partials_seq(const float* __restrict__ base, int nparts, size_t stride)
 {
+    // ascending order, loads issued 32 (then 8) at a time: the dW_rec-only GEMM of the dedup variant leaves 128 partials
+    // and a chain of 8-load batches was the critical path of this kernel
     float s = 0.f;
     int q = 0;
+    for (; q + 32 <= nparts; q += 32) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __ldg(base + (size_t)(q + j) * stride);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s += v[j];
+    }
     for (; q + 8 <= nparts; q += 8) {
         float v[8];
 #pragma unroll
