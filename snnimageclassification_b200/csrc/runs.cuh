@@ -135,13 +135,18 @@ __global__ void __launch_bounds__(1024) k_frame_runs(int B, int T, const unsigne
 __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ X, const int* __restrict__ table, int BT,
                                                     int N, float* __restrict__ Xu)
 {
-    if (table[1] != 1) return;
-    const int n_rows = table[0], n_pad = (n_rows + 31) & ~31;
+    // header and the first-row index of this CTA's first compact row are independent loads (the index is inside the
+    // table whatever n_rows is): two dependent round trips instead of four on a latency-bound kernel
     const int* rep = table + kRunHdr + BT;
+    const int ok = table[1], n_rows = table[0], cap = table[2];
+    int first = (int)blockIdx.x < cap ? rep[blockIdx.x] : 0;
+    if (ok != 1) return;
+    const int n_pad = (n_rows + 31) & ~31;
     for (int r = blockIdx.x; r < n_pad; r += gridDim.x) {
         float4* dst = reinterpret_cast<float4*>(Xu + (size_t)r * N);
         if (r < n_rows) {
-            const float4* src = reinterpret_cast<const float4*>(X + (size_t)rep[r] * N);
+            const int row = r == (int)blockIdx.x ? first : rep[r];
+            const float4* src = reinterpret_cast<const float4*>(X + (size_t)row * N);
             for (int i = threadIdx.x; i < N / 4; i += blockDim.x) dst[i] = __ldg(src + i);
         } else {
             for (int i = threadIdx.x; i < N / 4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -156,12 +161,14 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ X
 __global__ void __launch_bounds__(256) k_gather_rows_tiled(const float* __restrict__ X, const int* __restrict__ table,
                                                           int BT, int N, int Kpad, float* __restrict__ Xt)
 {
-    if (table[1] != 1) return;
-    const int n_rows = table[0];
     const int* rep = table + kRunHdr + BT;
+    const int ok = table[1], n_rows = table[0], cap = table[2];
+    int first = (int)blockIdx.x < cap ? rep[blockIdx.x] : 0;      // independent of the header loads (see k_gather_rows)
+    if (ok != 1) return;
     const int kblocks = Kpad / 32;
     for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
-        const float4* src = reinterpret_cast<const float4*>(X + (size_t)rep[r] * N);
+        const int row = r == (int)blockIdx.x ? first : rep[r];
+        const float4* src = reinterpret_cast<const float4*>(X + (size_t)row * N);
         const int mt = r >> 7, rr = r & 127;
         for (int c4 = threadIdx.x; c4 < Kpad / 4; c4 += blockDim.x) {
             const float4 v = 4 * c4 < N ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);

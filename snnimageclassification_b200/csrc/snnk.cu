@@ -65,7 +65,7 @@ struct ProfScope {
 // gets two parallel branches.  The call still returns with everything ordered behind the caller's stream.
 struct Fork {
     cudaStream_t side = nullptr;
-    cudaEvent_t forked = nullptr, joined = nullptr;
+    cudaEvent_t forked = nullptr, joined = nullptr, mid = nullptr, forked2 = nullptr;
     bool ok = false;
 };
 Fork* fork_for_device()
@@ -80,6 +80,8 @@ Fork* fork_for_device()
         if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&f.forked, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&f.joined, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.forked2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         f.ok = true;
     }
     return &f;
@@ -763,13 +765,14 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
             // recurrent matrix go onto a parallel branch beside gather + compact projection; joined before K2.
             fk = (runs && !pl.wide) ? fork_for_device() : nullptr;
             cudaStream_t st_d = st;
-            if (fk) {
-                const int n = d->H * pl.kpad;
-                tc::k_split_w<<<(n + 255) / 256, 256, 0, st>>>(W_in, d->N, d->H, pl.kpad, planes);
-                SNNK_CUDA(cudaGetLastError());
+            if (fk) {   // side: weight planes -> [mid] -> dense launch, k_prep_rec;  main: gather -> wait mid -> compact GEMM
                 SNNK_CUDA(cudaEventRecord(fk->forked, st));
                 SNNK_CUDA(cudaStreamWaitEvent(fk->side, fk->forked, 0));
                 st_d = fk->side;
+                const int n = d->H * pl.kpad;
+                tc::k_split_w<<<(n + 255) / 256, 256, 0, st_d>>>(W_in, d->N, d->H, pl.kpad, planes);
+                SNNK_CUDA(cudaGetLastError());
+                SNNK_CUDA(cudaEventRecord(fk->mid, st_d));
             }
             switch (pl.tileN) {
             case 32: rc = launch_proj_tc<32>(d, pl, x, W_in, I_in, planes, flag, st_d, runs, 0, fk == nullptr); break;
@@ -787,6 +790,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
                 }
                 // few compact tiles: 32-column CTA tiles spread each over H/32 SMs (the tile time is bound by what one
                 // SM can pull in, two thirds of which are weight planes)
+                if (fk) SNNK_CUDA(cudaStreamWaitEvent(st, fk->mid, 0));
                 rc = launch_proj_tc<32>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1);
                 if (rc != SNNK_OK) return rc;
                 if (pl.wide || use_mma_recur(d)) {   // k_recur_fwd fetches the compact rows itself
@@ -964,6 +968,17 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     float* pw = reinterpret_cast<float*>(ws + pl.off_pw);
     const bool rec = d->recurrent != 0;
 
+    // dedup variant: the compact rows of x for the dW_in GEMM do not depend on the sweep -- gathered beside it
+    const int* runs_b = (pl.tc && pl.runs && !pl.check) ? run_table : nullptr;
+    Fork* fkb = runs_b ? fork_for_device() : nullptr;
+    if (fkb) {
+        SNNK_CUDA(cudaEventRecord(fkb->forked, st));
+        SNNK_CUDA(cudaStreamWaitEvent(fkb->side, fkb->forked, 0));
+        k_gather_rows<<<std::min(pl.run_rows, 8 * sm_count()), 256, 0, fkb->side>>>(
+            x, runs_b, d->B * d->T, d->N, reinterpret_cast<float*>(ws + pl.off_xu_b));
+        SNNK_CUDA(cudaGetLastError());
+        SNNK_CUDA(cudaEventRecord(fkb->mid, fkb->side));
+    }
     // K3: reverse-time sweep
     const float* W_effT = nullptr;
     if (rec && W_effT_in) {
@@ -1015,11 +1030,11 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
             g.T = d->T; g.B = d->B; g.N = d->N; g.mtiles_x = pl.mtiles_x; g.mtiles_z = pl.mtiles_z; g.m_total = pl.m_total;
             g.S = pl.S; g.samples_per_split = pl.samples_per_split; g.part = pw; g.flag = flag;
             g.run_table = runs; g.run_gate = 0; g.run_clip = 0;
-            Fork* fk = runs ? fork_for_device() : nullptr;
+            Fork* fk = runs ? fkb : nullptr;
             cudaStream_t st_b = st;
-            if (fk) {   // dense (self-skipping) launch + Z-only GEMM on a parallel branch beside gather + compact GEMM
-                SNNK_CUDA(cudaEventRecord(fk->forked, st));
-                SNNK_CUDA(cudaStreamWaitEvent(fk->side, fk->forked, 0));
+            if (fk) {   // dense (self-skipping) launch + Z-only GEMM on a parallel branch beside the compact GEMM
+                SNNK_CUDA(cudaEventRecord(fk->forked2, st));
+                SNNK_CUDA(cudaStreamWaitEvent(fk->side, fk->forked2, 0));
                 st_b = fk->side;
             }
             rc = launch_wgrad_tc_any(d, pl.tileN, g, st_b);
@@ -1037,10 +1052,12 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
                     rc = launch_wgrad_tc_any(d, pl.tileN, gb, st_b);
                     if (rc != SNNK_OK) return rc;
                 }
-                {
+                if (!fk) {
                     ProfScope ps(SNNK_K_WGRAD, st);
                     k_gather_rows<<<std::min(pl.run_rows, 8 * sm_count()), 256, 0, st>>>(x, runs, d->B * d->T, d->N, Xu);
                     SNNK_CUDA(cudaGetLastError());
+                } else {
+                    SNNK_CUDA(cudaStreamWaitEvent(st, fk->mid, 0));   // the gather issued beside the sweep
                 }
                 WgradGeom ga{};
                 ga.x = Xu; ga.Ztrace = nullptr; ga.g_planes = Gu; ga.g_plane_stride = pl.gu_plane;
