@@ -221,7 +221,8 @@ template <int H, int P>
 struct ProjCfg {
     static constexpr uint32_t kBPlaneBytes = H * kBlockK * 4;
     static constexpr uint32_t kStageBytes = kATileBytes + P * kBPlaneBytes;
-    static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
+    // the tile time is bytes in flight / latency: as many stages as shared memory holds (8 x 24 KB for 32-column tiles)
+    static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
     static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 256;
 };
 

@@ -7,6 +7,8 @@ input geometry and replays it: the host then does two small copies into static b
 """
 from __future__ import annotations
 
+import gc
+import weakref
 from typing import Optional
 
 import torch
@@ -29,7 +31,11 @@ class GraphedTrainStep:
 
 	def __init__(self, net, x_example: torch.Tensor, y_example: torch.Tensor, criterion, optimizer, warmup: int = 3,
 			static_inputs: bool = False):
-		self.net, self.optimizer, self.criterion = net, optimizer, criterion
+		# The network caches its graphed steps, so a strong reference back would be a cycle: a discarded network (and its
+		# CUDA graphs) would then be freed by the cyclic collector at an arbitrary later moment -- possibly in the middle
+		# of ANOTHER capture, which destroying a graph invalidates.  Weak reference + an explicit collection before capture.
+		self._net = weakref.ref(net)
+		self.optimizer, self.criterion = optimizer, criterion
 		dev = net.device
 		self.static_inputs = static_inputs
 		if static_inputs:
@@ -58,6 +64,7 @@ class GraphedTrainStep:
 		torch.cuda.synchronize(dev)
 
 		optimizer.zero_grad(set_to_none=True)
+		gc.collect()
 		self.graph = torch.cuda.CUDAGraph()
 		with torch.cuda.graph(self.graph):
 			self.loss = self._body()
@@ -66,6 +73,13 @@ class GraphedTrainStep:
 				p.copy_(s)
 		if saved_opt is not None:
 			_restore_state(optimizer, saved_opt)
+
+	@property
+	def net(self):
+		net = self._net()
+		if net is None:
+			raise RuntimeError("the network of this graphed training step no longer exists")
+		return net
 
 	def _body(self) -> torch.Tensor:
 		net = self.net
