@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
 						self.reasons.add(name)
 			except Exception:
 				pass
-			time.sleep(0.02)
+			time.sleep(0.001)      # the timed region is a few milliseconds long
 
 	def stop(self):
 		self._stop_evt.set()
@@ -125,8 +125,8 @@ def reference_arm(args, rank):
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument("--gpus", type=int, default=1)
-	ap.add_argument("--steps", type=int, default=50)
-	ap.add_argument("--warmup", type=int, default=10)
+	ap.add_argument("--steps", type=int, default=200)
+	ap.add_argument("--warmup", type=int, default=20)
 	ap.add_argument("--impl", default="native", choices=["native", "reference"])
 	ap.add_argument("--no-cpu-baseline", action="store_true")
 	ap.add_argument("--no-large-batch", action="store_true")
