@@ -137,3 +137,38 @@ def test_loss_history_and_temporal_filter():
 	# known answers of the reference's test/test_temporal_filter.py
 	x = torch.ones(1, 3, 1)
 	assert torch.allclose(batchwise_temporal_filter(x, 0.5), torch.tensor([[1.75]]))
+
+
+def test_host_side_size_queries():
+	"""Pure host entry points of the C ABI (no device needed): run-table and exchange-buffer sizes."""
+	lib = _cabi.lib()
+	B, T = 256, 100
+	cap = max(128, (B * T // 4 + 127) // 128 * 128)
+	assert lib.snnk_run_table_bytes(B, T) == 4 * (4 + B * T + 2 * cap)
+	assert lib.snnk_run_table_bytes(3, 5) == 4 * (4 + 15 + 2 * 128)
+	assert lib.snnk_run_table_bytes(0, 5) == 0 and lib.snnk_run_table_bytes(1 << 28, 100) == 0
+	n = ctypes.c_size_t(0)
+	assert lib.snnk_adam_dp_buffer_bytes(8, 118026, ctypes.byref(n)) == 0 and n.value == 2 * 8 * 118026 * 8
+	assert lib.snnk_adam_dp_buffer_bytes(17, 10, ctypes.byref(n)) != 0 and lib.snnk_adam_dp_buffer_bytes(0, 10, ctypes.byref(n)) != 0
+
+
+def test_fused_adam_data_parallel_needs_a_process_group():
+	from snnimageclassification_b200 import FusedAdam
+	p = torch.nn.Parameter(torch.zeros(4))
+	opt = FusedAdam([p], lr=1e-3)
+	assert opt.enable_data_parallel() is False and opt.reduces_gradients is False
+	p.grad = torch.ones(4)
+	with pytest.raises(RuntimeError, match="no CPU fallback"):
+		opt.step()
+
+
+def test_run_table_tag_is_validated():
+	from snnimageclassification_b200.modules.functional import get_runs, mark_binary
+	x = torch.zeros(2, 5, 8)
+	assert get_runs(x) is None
+	mark_binary(x, runs=torch.zeros(7, dtype=torch.int32))          # wrong size for (2, 5): ignored
+	assert get_runs(x) is None
+	need = _cabi.lib().snnk_run_table_bytes(2, 5) // 4
+	mark_binary(x, runs=torch.zeros(need, dtype=torch.int32))
+	assert get_runs(x) is not None
+	assert get_runs(mark_binary(torch.zeros(2, 5, 8), runs=torch.zeros(need, dtype=torch.int64))) is None
