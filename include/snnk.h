@@ -140,7 +140,7 @@ int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, 
  *                 [0] number of runs in the batch  [1] ok: 1 when that number fits the table's capacity
  *                 [2] capacity = max(128, n_items*n_steps/4 rounded up to 128)  [3] 0
  *                 [4 ..) for every dense row item*n_steps+t the index of its run; then capacity first-rows; then
- *                 capacity run lengths.
+ *                 capacity run lengths; then n_items words of scratch.
  * lazy != 0: `out` is only written where a consumer of the table will read it -- every row when the table is not
  * ok, otherwise just the first row of every run (the rest of `out` stays uninitialised): for callers that hand
  * `out` to snnk_forward / snnk_backward together with the table and to nobody else.

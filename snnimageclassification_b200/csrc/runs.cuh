@@ -24,7 +24,11 @@ __host__ __device__ inline int run_cap(long long BT)
     long long c = (BT / 4 + 127) / 128 * 128;
     return (int)(c < 128 ? 128 : c);
 }
-__host__ __device__ inline size_t run_table_ints(long long BT) { return (size_t)kRunHdr + (size_t)BT + 2 * (size_t)run_cap(BT); }
+// + one scratch word per sample behind the run lengths (run counts between the two kernels of the parallel build)
+__host__ __device__ inline size_t run_table_ints(long long B, long long T)
+{
+    return (size_t)kRunHdr + (size_t)(B * T) + 2 * (size_t)run_cap(B * T) + (size_t)B;
+}
 
 // One CTA of 32 warps.  (1) ballots over the change flags count the runs of every sample; (2) block scan of the counts
 // -> first compact row of every sample (in shared memory up to kRunSmemB samples, else in the table's own run-length
@@ -32,11 +36,14 @@ __host__ __device__ inline size_t run_table_ints(long long BT) { return (size_t)
 // (4) run lengths from consecutive first rows.  The kernel is a chain of dependent global round trips, so each phase
 // issues all its loads before the first ballot.  A geometry whose scratch does not fit is marked not ok (dense kernels).
 constexpr int kRunSmemB = 4096;
+constexpr int kRunMaskB = 1024;
 __global__ void __launch_bounds__(1024) k_frame_runs(int B, int T, const unsigned char* __restrict__ changed,
                                                     int* __restrict__ table)
 {
     __shared__ int s_base[kRunSmemB];
     __shared__ int s_warp[32];
+    __shared__ unsigned s_flag[kRunMaskB * 4];   // ballot words of the change flags (T <= 128, B <= kRunMaskB): phase 3
+                                                 // then needs no second trip to global memory
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
     const int cap = run_cap((long long)B * T);
     int* row2c = table + kRunHdr;
@@ -48,6 +55,7 @@ __global__ void __launch_bounds__(1024) k_frame_runs(int B, int T, const unsigne
         return;
     }
     constexpr int kBatch = 8;
+    const bool cached = T <= 128 && B <= kRunMaskB;
     for (int b0 = warp * kBatch; b0 < B; b0 += nwarp * kBatch) {     // kBatch samples per pass, chunk by chunk
         int n[kBatch];
 #pragma unroll
@@ -59,7 +67,11 @@ __global__ void __launch_bounds__(1024) k_frame_runs(int B, int T, const unsigne
             for (int q = 0; q < kBatch; ++q)
                 f[q] = b0 + q < B && t < T && (t == 0 || changed[(size_t)(b0 + q) * T + t] != 0);
 #pragma unroll
-            for (int q = 0; q < kBatch; ++q) n[q] += __popc(__ballot_sync(0xffffffffu, f[q]));
+            for (int q = 0; q < kBatch; ++q) {
+                const unsigned m = __ballot_sync(0xffffffffu, f[q]);
+                n[q] += __popc(m);
+                if (cached && lane == 0 && b0 + q < B) s_flag[(b0 + q) * 4 + (t0 >> 5)] = m;
+            }
         }
 #pragma unroll
         for (int q = 0; q < kBatch; ++q)
@@ -100,12 +112,21 @@ __global__ void __launch_bounds__(1024) k_frame_runs(int B, int T, const unsigne
         for (int t0 = 0; t0 < T; t0 += 32) {
             const int t = t0 + lane;
             bool f[kBatch];
+            unsigned mw[kBatch];
+            if (cached) {
 #pragma unroll
-            for (int q = 0; q < kBatch; ++q)
-                f[q] = b0 + q < B && t < T && (t == 0 || changed[(size_t)(b0 + q) * T + t] != 0);
+                for (int q = 0; q < kBatch; ++q) {
+                    mw[q] = b0 + q < B ? s_flag[(b0 + q) * 4 + (t0 >> 5)] : 0u;
+                    f[q] = (mw[q] >> lane) & 1u;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < kBatch; ++q)
+                    f[q] = b0 + q < B && t < T && (t == 0 || changed[(size_t)(b0 + q) * T + t] != 0);
+            }
 #pragma unroll
             for (int q = 0; q < kBatch; ++q) {
-                const unsigned m = __ballot_sync(0xffffffffu, f[q]);
+                const unsigned m = cached ? mw[q] : __ballot_sync(0xffffffffu, f[q]);
                 const int r_t = r[q] + __popc(m & (0xffffffffu >> (31 - lane)));
                 if (b0 + q < B && t < T) {
                     row2c[(size_t)(b0 + q) * T + t] = r_t;
@@ -127,6 +148,95 @@ __global__ void __launch_bounds__(1024) k_frame_runs(int B, int T, const unsigne
         table[1] = total <= cap ? 1 : 0;
         table[2] = cap;
         table[3] = 0;
+    }
+}
+
+// ---- parallel build for T <= 128 (the reference's T = 100): the single-CTA kernel above executes ~64 k warp
+// instructions on ONE SM (12 us); here a warp owns a sample, 8 samples per CTA, two launches.
+//   k_frame_counts: ballots of the change flags -> run count of every sample (scratch words behind the table)
+//   k_frame_fill  : every CTA sums the counts of the samples before its own (B small integers), then writes compact
+//                   rows, first rows and run lengths of its samples straight from the ballot words; the CTA that owns
+//                   the last sample writes the header.
+__global__ void __launch_bounds__(256) k_frame_counts(int B, int T, const unsigned char* __restrict__ changed,
+                                                     int* __restrict__ counts)
+{
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    bool f[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int t = 32 * c + lane;
+        f[c] = t < T && (t == 0 || changed[(size_t)b * T + t] != 0);
+    }
+    int n = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) n += __popc(__ballot_sync(0xffffffffu, f[c]));
+    if (lane == 0) counts[b] = n;
+}
+
+__global__ void __launch_bounds__(256) k_frame_fill(int B, int T, const unsigned char* __restrict__ changed,
+                                                   const int* __restrict__ counts, int* __restrict__ table)
+{
+    __shared__ int s_red[8];
+    __shared__ int s_cnt[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = blockIdx.x * 8, b = b0 + warp;
+    const int cap = run_cap((long long)B * T);
+    int* row2c = table + kRunHdr;
+    int* rep = row2c + (size_t)B * T;
+    int* len = rep + cap;
+    // this sample's flags (issued before the prefix sum: independent loads)
+    bool f[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int t = 32 * c + lane;
+        f[c] = b < B && t < T && (t == 0 || changed[(size_t)b * T + t] != 0);
+    }
+    // runs of all samples before this CTA's first one
+    int part = 0;
+    for (int q = tid; q < b0; q += 256) part += counts[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) { s_red[warp] = part; s_cnt[warp] = b < B ? counts[b] : 0; }
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) base += s_red[w];
+    for (int w = 0; w < warp; ++w) base += s_cnt[w];
+    unsigned m[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) m[c] = __ballot_sync(0xffffffffu, f[c]);
+    if (b < B) {
+        int r = base - 1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int t = 32 * c + lane;
+            const int r_t = r + __popc(m[c] & (0xffffffffu >> (31 - lane)));
+            if (t < T) {
+                row2c[(size_t)b * T + t] = r_t;
+                if (f[c] && r_t < cap) {
+                    // length of the run that starts here: distance to the next flag of this sample, or to T
+                    unsigned rest = lane < 31 ? (m[c] & (0xffffffffu << (lane + 1))) : 0u;
+                    int nxt = T;
+                    if (rest) nxt = 32 * c + __ffs(rest) - 1;
+                    else {
+#pragma unroll
+                        for (int c2 = 3; c2 >= 0; --c2)
+                            if (c2 > c && m[c2]) nxt = 32 * c2 + __ffs(m[c2]) - 1;
+                    }
+                    rep[r_t] = b * T + t;
+                    len[r_t] = nxt - t;
+                }
+            }
+            r += __popc(m[c]);
+        }
+        if (b == B - 1 && lane == 0) {
+            const int total = base + s_cnt[warp];
+            table[0] = total;
+            table[1] = total <= cap ? 1 : 0;
+            table[2] = cap;
+            table[3] = 0;
+        }
     }
 }
 

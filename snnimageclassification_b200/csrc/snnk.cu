@@ -648,7 +648,7 @@ int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, 
 size_t snnk_run_table_bytes(int64_t n_items, int32_t n_steps)
 {
     if (n_items <= 0 || n_steps <= 0 || n_items * n_steps >= (1ll << 31) / 4) return 0;
-    return sizeof(int32_t) * run_table_ints(n_items * n_steps);
+    return sizeof(int32_t) * run_table_ints(n_items, n_steps);
 }
 
 int snnk_frame_runs(int64_t n_items, int32_t n_steps, const uint8_t* frame_changed, int32_t* run_table,
@@ -657,7 +657,15 @@ int snnk_frame_runs(int64_t n_items, int32_t n_steps, const uint8_t* frame_chang
     if (n_items <= 0 || n_steps <= 0 || n_items * n_steps >= (1ll << 31) / 4) return SNNK_ERR_SHAPE;
     if (!frame_changed || !run_table) return SNNK_ERR_ARG;
     if (!device_ok()) return SNNK_ERR_DEVICE;
-    k_frame_runs<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>((int)n_items, n_steps, frame_changed, run_table);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_steps <= 128) {   // warp per sample, two launches spread over the chip (runs.cuh)
+        int* counts = run_table + kRunHdr + n_items * n_steps + 2 * (int64_t)run_cap(n_items * n_steps);
+        const unsigned grid = (unsigned)((n_items + 7) / 8);
+        k_frame_counts<<<grid, 256, 0, st>>>((int)n_items, n_steps, frame_changed, counts);
+        k_frame_fill<<<grid, 256, 0, st>>>((int)n_items, n_steps, frame_changed, counts, run_table);
+    } else {
+        k_frame_runs<<<1, 1024, 0, st>>>((int)n_items, n_steps, frame_changed, run_table);
+    }
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }

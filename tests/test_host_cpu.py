@@ -144,8 +144,8 @@ def test_host_side_size_queries():
 	lib = _cabi.lib()
 	B, T = 256, 100
 	cap = max(128, (B * T // 4 + 127) // 128 * 128)
-	assert lib.snnk_run_table_bytes(B, T) == 4 * (4 + B * T + 2 * cap)
-	assert lib.snnk_run_table_bytes(3, 5) == 4 * (4 + 15 + 2 * 128)
+	assert lib.snnk_run_table_bytes(B, T) == 4 * (4 + B * T + 2 * cap + B)
+	assert lib.snnk_run_table_bytes(3, 5) == 4 * (4 + 15 + 2 * 128 + 3)
 	assert lib.snnk_run_table_bytes(0, 5) == 0 and lib.snnk_run_table_bytes(1 << 28, 100) == 0
 	n = ctypes.c_size_t(0)
 	assert lib.snnk_adam_dp_buffer_bytes(8, 118026, ctypes.byref(n)) == 0 and n.value == 2 * 8 * 118026 * 8
