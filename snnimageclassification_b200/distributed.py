@@ -1,8 +1,10 @@
 """Data-parallel plumbing: one process per GPU, batch rows sharded, weights replicated.
 
 The spiking path has exactly one exchange step per training iteration: the mean of the (small) weight gradients
-over the ranks.  It is issued as ONE flat all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests); with equal
-shards and a mean-reduced local loss this reproduces the single-process full-batch gradient up to summation order.
+over the ranks.  With ``FusedAdam.enable_data_parallel()`` it happens inside the optimizer kernel over NVLink peer
+memory (``snnk_adam_step_dp``; ``PeerExchangeBuffer`` below supplies the peer-mapped buffers); for any other optimizer it
+is ONE coalesced all-reduce (NCCL on GPUs, gloo in the CPU tests).  With equal shards and a mean-reduced local loss this
+reproduces the single-process full-batch gradient up to summation order.
 """
 from __future__ import annotations
 
@@ -14,41 +16,6 @@ import torch.distributed as dist
 
 def world_size() -> int:
 	return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-
-
-_SYMM = {}
-
-
-def _symm_allreduce_mean_(ts: List[torch.Tensor], ws: int) -> bool:
-	"""One-shot all-reduce over NVLink peer memory (torch symmetric memory: every rank reads its peers' buffers
-	directly, no ring) -- lower latency than NCCL for the 0.5 MB gradient message.  Opt-in (SNNK_DP_SYMM=1)."""
-	import os
-	if os.environ.get("SNNK_DP_SYMM", "0") != "1":
-		return False
-	try:
-		import torch.distributed._symmetric_memory as symm
-		gname = dist.group.WORLD.group_name
-		n = sum(t.numel() for t in ts)
-		key = (n, ts[0].device)
-		buf = _SYMM.get(key)
-		if buf is None:
-			buf = symm.empty(n, dtype=torch.float32, device=ts[0].device)
-			symm.rendezvous(buf, gname)
-			_SYMM[key] = buf
-		flat = torch.cat([t.reshape(-1) for t in ts])
-		out = torch.ops.symm_mem.one_shot_all_reduce_copy(buf, flat, "sum", gname)
-		out.div_(ws)
-		off = 0
-		for t in ts:
-			k = t.numel()
-			t.copy_(out[off:off + k].view_as(t))
-			off += k
-		return True
-	except Exception as e:   # pragma: no cover
-		import warnings
-		warnings.warn(f"symmetric-memory all-reduce unavailable ({e!r}); using NCCL")
-		os.environ["SNNK_DP_SYMM"] = "0"
-		return False
 
 
 class PeerExchangeBuffer:
@@ -78,8 +45,6 @@ def allreduce_mean_(tensors: Iterable[torch.Tensor]) -> None:
 		return
 	ts: List[torch.Tensor] = [t for t in tensors if t is not None]
 	if not ts:
-		return
-	if ts[0].is_cuda and dist.get_backend() == "nccl" and _symm_allreduce_mean_(ts, ws):
 		return
 	if ts[0].is_cuda and dist.get_backend() == "nccl" and hasattr(dist, "_coalescing_manager"):
 		# NCCL: the per-tensor all-reduces are coalesced into ONE group launch that averages in place -- no flatten /

@@ -12,6 +12,8 @@ Outputs (committed):
                        reference's initial weights, forward traces, log-probabilities, loss and autograd
                        gradients from the reference's own SNN class.
   init_golden.npz      state_dict of reference SNNs built under torch.manual_seed (RNG-order parity).
+  stacked_golden.npz   Two stacked hidden layers: the reference's state_dict, traces, loss and gradients.
+  izhikevich_golden.npz  IzhikevichLayer x (rec|non-rec) x (FastSigmoid|Phi): traces (V, u, Z), loss, gradients.
 """
 import os
 import sys
