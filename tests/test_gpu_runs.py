@@ -72,7 +72,8 @@ def _step(net, x, y):
 
 
 @pytest.mark.parametrize("B,T,N,H,rec", [(64, 100, 784, 128, True), (37, 50, 196, 64, True), (16, 100, 784, 128, False),
-	(5, 7, 20, 32, True)])
+	(5, 7, 20, 32, True), (768, 16, 64, 128, True), (300, 130, 48, 128, True)])   # last two: MMA recurrence (expanded
+	# compact rows); T > 128 (single-CTA run-table build)
 def test_dedup_matches_dense(B, T, N, H, rec):
 	"""Production encoder (tau = 0.02, periodic): <= 3 runs per sample -> the compact kernels run.  The projection of a
 	run's first row is the same MMA sequence as in the dense kernel, so the forward pass is bit-identical; the weight
