@@ -245,6 +245,14 @@ def main():
 		step_e2e_raster(i)
 	ms_r = timed(step_e2e_raster, max(args.steps // 5, 3))
 	e2e_raster = world * B_PER_GPU * max(args.steps // 5, 3) / (ms_r * 1e-3)
+	# ... and from pinned host rasters in the bit-packed format (SNNK_BITS, 1/32 of the bytes; unpacked on the device)
+	host_bits = [enc.encode_batch_bits(pool_img[i].to(dev)).cpu().pin_memory() for i in range(2)]
+	def step_e2e_bits(i):
+		return net._exec_batch(host_bits[i % 2], pool_lab[i % 2], crit, opt)
+	for i in range(3):
+		step_e2e_bits(i)
+	ms_b = timed(step_e2e_bits, args.steps)
+	e2e_bits = world * B_PER_GPU * args.steps / (ms_b * 1e-3)
 	net.input_encoder = enc
 
 	# per-kernel CUDA-event timing (separate short loop, same process) -> roofline of the dominant kernel
@@ -296,7 +304,9 @@ def main():
 		"clocks": clocks,
 		"e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
 			"ms_per_step": ms_e2e / args.steps, "input": "pinned host images (B,784) fp32 + labels; GPU to_spikes",
-			"from_host_rasters": {"value": e2e_raster, "h2d_bytes_per_step": B_PER_GPU * T * N * 4 + B_PER_GPU * 8}},
+			"from_host_rasters": {"value": e2e_raster, "h2d_bytes_per_step": B_PER_GPU * T * N * 4 + B_PER_GPU * 8},
+			"from_host_bitpacked_rasters": {"value": e2e_bits,
+				"h2d_bytes_per_step": B_PER_GPU * T * ((N + 31) // 32) * 4 + B_PER_GPU * 8}},
 		"gpu_launches": int(round(launches_per_step * args.steps)),
 		"roofline": roofline, "cpu_baseline": cpu, "large_batch_kernels": big,
 	}))

@@ -50,7 +50,7 @@ enum { SNNK_LIF = 0, SNNK_ALIF = 1, SNNK_IZHIKEVICH = 2 };
 /* SpikeFuncType, src/modules/spike_funcs.py:7-9 */
 enum { SNNK_FAST_SIGMOID = 0, SNNK_PHI = 1 };
 /* element types accepted by snnk_encode */
-enum { SNNK_F32 = 0, SNNK_F64 = 1, SNNK_U8 = 2, SNNK_I64 = 3 };
+enum { SNNK_F32 = 0, SNNK_F64 = 1, SNNK_U8 = 2, SNNK_I64 = 3, SNNK_BITS = 4 };
 
 enum {
     SNNK_OK = 0,
@@ -123,13 +123,19 @@ int snnk_profile_end(double* ms_total, int64_t* launches);
  *   x    (n_items, n_pix)            x_dtype  SNNK_F32 | SNNK_F64 (arithmetic is done in that type, as numpy does)
  *                                    or SNNK_I64: x already holds firing times / periods, i.e. the call is
  *                                    firing_times_to_spikes (datasets.py:81-86) / firing_periods_to_spikes (:72-79)
- *   out  (n_items, n_steps, n_pix)   out_dtype SNNK_F32 | SNNK_F64 | SNNK_U8, values in {0,1}
+ *   out  (n_items, n_steps, n_pix)   out_dtype SNNK_F32 | SNNK_F64 | SNNK_U8, values in {0,1}; or SNNK_BITS:
+ *                                    (n_items, n_steps, ceil(n_pix/32)) uint32, bit l of word w = pixel 32 w + l --
+ *                                    the raster at 1/32 of its fp32 size for storage and host <-> device transport
+ *                                    (SURVEY.md 8f.1); snnk_unpack_raster turns it back into fp32 {0,1}
  *   periods (n_items, n_pix) int64, optional (may be NULL): pixels_to_firing_periods (datasets.py:42-54)
  *   periodic = use_periods (datasets.py:40)
  */
 int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps,
                 double t_max, double tau, double thr, double eps, int32_t periodic, void* out,
                 int32_t out_dtype, int64_t* periods, snnk_stream_t stream);
+
+/* bits (n_rows, ceil(n_pix/32)) uint32 -> out (n_rows, n_pix) fp32 {0,1}: the inverse of the SNNK_BITS raster format. */
+int snnk_unpack_raster(const uint32_t* bits, int64_t n_rows, int32_t n_pix, float* out, snnk_stream_t stream);
 
 /*
  * Frame runs of an encoded batch ("frame-dedup fast path for production ToSpikes output").

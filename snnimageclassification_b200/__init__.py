@@ -14,7 +14,7 @@ Every FLOP of the path runs in hand-written sm_100a CUDA kernels (csrc/, C ABI i
 CPU, eager-PyTorch or Triton fallback: without the built extension or off a B200 the compute calls raise.
 """
 from ._cabi import build_extension  # noqa: F401
-from .datasets.datasets import DatasetId, ToSpikes  # noqa: F401
+from .datasets.datasets import DatasetId, ToSpikes, unpack_raster  # noqa: F401
 from .modules.optim import FusedAdam  # noqa: F401
 from .modules.snn import SNN, LoadCheckpointMode  # noqa: F401
 from .modules.spike_funcs import (  # noqa: F401

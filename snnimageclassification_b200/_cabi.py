@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "snnk.h")
 
 SNNK_LIF, SNNK_ALIF, SNNK_IZHIKEVICH = 0, 1, 2
 SNNK_FAST_SIGMOID, SNNK_PHI = 0, 1
-SNNK_F32, SNNK_F64, SNNK_U8, SNNK_I64 = 0, 1, 2, 3
+SNNK_F32, SNNK_F64, SNNK_U8, SNNK_I64, SNNK_BITS = 0, 1, 2, 3, 4
 SNNK_F_TRACES, SNNK_F_TENSOR_CORE, SNNK_F_INPUT_BINARY = 0x1, 0x2, 0x4
 
 NVCC_FLAGS = [
@@ -78,6 +78,7 @@ _SIGNATURES = {
 	"snnk_spike_backward": (ctypes.c_int, [ctypes.c_int32, _p, _p, _p, _p, ctypes.c_int64, ctypes.c_int64, _p, _p]),
 	"snnk_forward_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(SnnkDesc)]),
 	"snnk_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(SnnkDesc)]),
+	"snnk_unpack_raster": (ctypes.c_int, [_p, ctypes.c_int64, ctypes.c_int32, _p, _p]),
 	"snnk_run_table_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32]),
 	"snnk_frame_runs": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, _p, _p, _p]),
 	"snnk_encode_runs": (ctypes.c_int, [

@@ -75,6 +75,45 @@ __global__ void __launch_bounds__(256) k_encode(const TIn* __restrict__ x, long 
     }
 }
 
+// ---- bit-packed raster: 32 pixels per uint32 word, bit l of word w = pixel 32 w + l -------------------
+// The same encoder with the time loop ending in a warp ballot instead of 32 stores: (n_items, n_steps, ceil(n_pix/32))
+// words -- 1/32 of the fp32 raster -- for rasters that are stored or moved (host <-> device) rather than consumed at once.
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_encode_bits(const TIn* __restrict__ x, long long n_items, long long n_pix,
+                                                    int n_steps, double t_max, double tau, double thr, double eps,
+                                                    int periodic, uint32_t* __restrict__ out)
+{
+    const long long pix = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+    const long long item = blockIdx.x;
+    const bool live = pix < n_pix;              // dead lanes keep taking part in the ballots
+    const int words = (int)((n_pix + 31) / 32);
+    const long long per = live ? period_of(x[item * n_pix + pix], t_max, tau, thr, eps) : -1;
+    long long p = per > n_steps - 1 ? n_steps - 1 : per;
+    p = p < 1 ? 1 : p;
+    long long next = periodic ? p : per;
+    uint32_t* row = out + item * (long long)n_steps * words + (pix >> 5);
+    const bool writer = (threadIdx.x & 31) == 0 && (pix >> 5) < words;
+    for (int t = 0; t < n_steps; ++t) {
+        const bool s = live && (long long)t == next;
+        if (s && periodic) next += p;
+        const unsigned m = __ballot_sync(0xffffffffu, s);
+        if (writer) row[(long long)t * words] = m;
+    }
+}
+
+// bits (n_rows, ceil(n_pix/32)) -> fp32 raster (n_rows, n_pix); one thread per output element, coalesced stores
+__global__ void __launch_bounds__(256) k_unpack_raster(const uint32_t* __restrict__ bits, long long n_rows, int n_pix,
+                                                      float* __restrict__ out)
+{
+    const int words = (n_pix + 31) / 32;
+    const long long total = n_rows * (long long)n_pix;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / n_pix;
+        const int c = (int)(e - r * n_pix);
+        out[e] = (float)((__ldg(bits + r * words + (c >> 5)) >> (c & 31)) & 1u);
+    }
+}
+
 // ---- lazy raster (snnk_encode_runs with lazy != 0) ------------------------------------------------------------------
 // Pass A: the change flags alone, straight from the latency/period of every pixel -- no loop over time: a pixel of
 // period p >= 2 toggles at every multiple of p and one step later, a pixel of period 1 only at t = 1, a latency-coded

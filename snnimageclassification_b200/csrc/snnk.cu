@@ -521,6 +521,13 @@ int launch_encode(const TIn* x, int64_t n_items, int64_t n_pix, int32_t n_steps,
         SNNK_CUDA(cudaGetLastError());
         return SNNK_OK;
     }
+    if (out_dtype == SNNK_BITS) {
+        if (pass != 0 || chg) return SNNK_ERR_ARG;      // the packed raster has no run-table / lazy form
+        k_encode_bits<TIn><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
+                                                static_cast<uint32_t*>(out));
+        SNNK_CUDA(cudaGetLastError());
+        return SNNK_OK;
+    }
     switch (out_dtype) {
     case SNNK_F32:
         if (pass == 2) k_encode_rows<TIn, float><<<grid, 256, 0, st>>>(x, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic,
@@ -643,6 +650,20 @@ int snnk_encode(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, 
     if (!device_ok()) return SNNK_ERR_DEVICE;
     return encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, periods,
                       nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int snnk_unpack_raster(const uint32_t* bits, int64_t n_rows, int32_t n_pix, float* out, snnk_stream_t stream)
+{
+    if (n_rows < 0 || n_pix <= 0) return SNNK_ERR_SHAPE;
+    if (n_rows == 0) return SNNK_OK;
+    if (!bits || !out) return SNNK_ERR_ARG;
+    if (!device_ok()) return SNNK_ERR_DEVICE;
+    const long long total = n_rows * (long long)n_pix;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 32ll * sm_count());
+    ProfScope ps(SNNK_K_ENCODE, static_cast<cudaStream_t>(stream));
+    k_unpack_raster<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, n_rows, n_pix, out);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
 }
 
 size_t snnk_run_table_bytes(int64_t n_items, int32_t n_steps)

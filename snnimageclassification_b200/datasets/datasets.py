@@ -123,6 +123,24 @@ class ToSpikes:
 		return out.cpu() if on_cpu else out
 
 	# ---- the batched GPU entry point ----------------------------------------------------------------------------------
+	def encode_batch_bits(self, images: torch.Tensor) -> torch.Tensor:
+		"""images (B, n_pix) -> the spike trains bit-packed: (B, n_steps, ceil(n_pix/32)) int32 on the GPU, bit l of
+		word w = pixel 32 w + l (``SNNK_BITS``).  1/32 of the fp32 raster: the format to store rasters in or to move them
+		between host and device; ``SNN`` accepts it directly (``unpack_raster`` is applied on the device)."""
+		if images.ndim != 2:
+			images = images.reshape(images.shape[0], int(np.prod(images.shape[1:])))
+		x2, _, _, _ = self._stage(images)
+		_cabi.require_b200(x2.device)
+		n_items, n_pix = x2.shape
+		out = torch.empty((n_items, self.n_steps, (n_pix + 31) // 32), dtype=torch.int32, device=x2.device)
+		with torch.cuda.device(x2.device):
+			rc = _cabi.lib().snnk_encode(
+				_cabi.ptr(x2), _DT[x2.dtype], n_items, n_pix, self.n_steps, float(self.t_max), float(self.tau),
+				float(self.thr), float(self.epsilon), int(self.use_periods), _cabi.ptr(out), _cabi.SNNK_BITS, None,
+				_cabi.stream_ptr())
+		_cabi.check(rc, "snnk_encode")
+		return out
+
 	def encode_batch(self, images: torch.Tensor, out_dtype: torch.dtype = torch.float32, frame_runs: bool = True,
 			lazy: bool = False) -> torch.Tensor:
 		"""images (B, n_pix) float32|float64 (any device) -> spike trains (B, n_steps, n_pix) on the GPU.
@@ -177,3 +195,18 @@ class SyntheticSpikeImages(torch.utils.data.Dataset):
 
 	def __getitem__(self, i):
 		return self.images[i], self.labels[i]
+
+
+def unpack_raster(bits: torch.Tensor, n_pix: int) -> torch.Tensor:
+	"""(..., ceil(n_pix/32)) int32 bit-packed raster on the GPU -> (..., n_pix) float32 {0,1}, tagged as exactly binary."""
+	if bits.dtype != torch.int32 or bits.shape[-1] != (n_pix + 31) // 32:
+		raise ValueError("expected an int32 tensor whose last dimension is ceil(n_pix / 32)")
+	_cabi.require_b200(bits.device)
+	b = bits.contiguous()
+	out = torch.empty(b.shape[:-1] + (n_pix,), dtype=torch.float32, device=b.device)
+	n_rows = int(np.prod(b.shape[:-1])) if b.ndim > 1 else 1
+	with torch.cuda.device(b.device):
+		rc = _cabi.lib().snnk_unpack_raster(_cabi.ptr(b), n_rows, n_pix, _cabi.ptr(out), _cabi.stream_ptr())
+	_cabi.check(rc, "snnk_unpack_raster")
+	out._snnk_binary = True
+	return out

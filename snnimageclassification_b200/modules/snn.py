@@ -193,7 +193,12 @@ class SNN(torch.nn.Module):
 		return inputs.float().contiguous()
 
 	def _encode_if_needed(self, inputs: torch.Tensor) -> torch.Tensor:
-		"""Image batches (B, F) are turned into spike trains on the GPU when an ``input_encoder`` was given."""
+		"""Image batches (B, F) are turned into spike trains on the GPU when an ``input_encoder`` was given; bit-packed
+		rasters (int32, last dimension ceil(F/32): ``ToSpikes.encode_batch_bits``) are unpacked on the device."""
+		if inputs.dtype == torch.int32 and inputs.ndim == 3 and inputs.shape[-1] == (self.input_size + 31) // 32 \
+				and inputs.shape[-1] != self.input_size:
+			from ..datasets.datasets import unpack_raster
+			return unpack_raster(inputs.to(self.device, non_blocking=True), self.input_size)
 		if self.input_encoder is not None and inputs.ndim == 2:
 			# the raster is an intermediate nobody but the first layer's kernels reads: with the frame-dedup variant
 			# active those read only the first row of every run, so the rest need not be written (lazy raster)

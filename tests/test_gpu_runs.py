@@ -177,3 +177,27 @@ def test_lazy_raster_training_matches_dense_raster():
 		assert res["1"][0] == res["0"][0], (tau, H)
 		for a, b in zip(res["1"][1], res["0"][1]):
 			assert torch.equal(a, b), (tau, H)
+
+
+@pytest.mark.parametrize("tau,periodic,N", [(0.02, True, 784), (20.0, True, 100), (20.0, False, 33)])
+def test_bit_packed_raster_format(tau, periodic, N):
+	"""SNNK_BITS: bit l of word w = pixel 32 w + l; unpacking gives the dense raster back; SNN takes the
+	packed raster directly and computes what it computes on the dense one."""
+	from snnimageclassification_b200 import LayerType, SNN, ToSpikes, unpack_raster
+	T, B = 24, 9
+	enc = ToSpikes(T, tau=tau, use_periods=periodic)
+	img = _images(B, N, 31).to(DEV)
+	dense = enc.encode_batch(img, frame_runs=False)
+	bits = enc.encode_batch_bits(img)
+	assert bits.dtype == torch.int32 and tuple(bits.shape) == (B, T, (N + 31) // 32)
+	d, w = npy(dense).astype(np.uint32), npy(bits).view(np.uint32)
+	ref = np.zeros_like(w)
+	for c in range(N):
+		ref[..., c // 32] |= d[..., c] << np.uint32(c % 32)
+	assert np.array_equal(w, ref)
+	assert torch.equal(unpack_raster(bits, N), dense)
+	torch.manual_seed(0)
+	net = SNN(N, 10, 32, int_time_steps=T, hidden_layer_type=LayerType.LIF, device=DEV, tensor_core=False)
+	a, _ = net(dense)
+	b, _ = net(bits.cpu())          # e.g. a packed raster coming from a host-side data loader
+	assert torch.equal(a, b)
