@@ -39,9 +39,26 @@ class FusedAdam(torch.optim.Adam):
 			return False
 		if dist.get_world_size(group) > 16:
 			return False
+		# Probe the peer mapping once, and agree on the outcome: either every rank exchanges through peer memory or every
+		# rank keeps the all-reduce (a mixed group would deadlock).
+		ok = 1
 		try:
-			import torch.distributed._symmetric_memory  # noqa: F401
+			from ..distributed import PeerExchangeBuffer
+			dev = next(p.device for g in self.param_groups for p in g["params"])
+			if dev.type != "cuda":
+				raise RuntimeError("parameters are not on a CUDA device")
+			PeerExchangeBuffer(256, dev, group)
+		except Exception as e:   # no peer access, no symmetric-memory allocator, ...
+			import warnings
+			warnings.warn(f"FusedAdam: peer-memory gradient exchange unavailable ({e!r}); keeping the NCCL all-reduce")
+			ok = 0
+		try:
+			flag = torch.tensor([ok], dtype=torch.int32, device=dev if ok else torch.device("cuda", torch.cuda.current_device()))
+			dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+			ok = int(flag.item())
 		except Exception:
+			ok = 0
+		if not ok:
 			return False
 		self._dp_group = group
 		self.reduces_gradients = True
