@@ -5,16 +5,19 @@
 //                dW_rec[j][n] = sum_r Z_{t-1}[r][j] gI[r][n]     (K4; MmBackward of the recurrent matmul)
 //
 // Numerics: kind::tf32 with fp32 accumulation in TMEM.  The spike operand (x, Z) is exactly {0,1}; the fp32
-// operand is split into tf32 planes whose sum is exact (W_in: 3 planes) or exact to 2^-22 (gI: 2 planes), so
-// every product is exact and only the accumulation order differs from the fp32 SIMT kernels.  x is read
-// straight from the user's fp32 tensor by TMA -- no conversion pass.  While the MMA pipeline runs, the
+// operand is split into tf32 planes whose sum is exact to 2^-22 (W_in: the first two of three round-to-nearest planes;
+// gI: truncated high plane + remainder), so every product is exact and only the accumulation order differs from
+// the fp32 SIMT kernels.  The planes of one operand sit back to back in shared memory and enter ONE MMA of N = 2H;
+// the epilogue adds the two TMEM column groups.  x is read straight from the user's fp32 tensor by TMA -- no
+// conversion pass.  While the MMA pipeline runs, the
 // otherwise idle epilogue warps check every x tile in shared memory for values that are not exactly
 // representable in tf32; if any is found a device flag is raised and the caller's fp32 SIMT kernel (which
 // is always launched behind this one and exits immediately when the flag is clear) recomputes the result.
 //
 // Structure (both kernels): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma
 // issuer, warps 2-5 = exactness check + epilogue (tcgen05.ld -> registers -> global).  smem ring of
-// kStages {A tile, B planes} with full/empty mbarriers; accumulator 128 x H fp32 in TMEM.
+// kStages {A tile, B planes} with full/empty mbarriers; accumulator 128 x 2H fp32 in TMEM.  Both kernels can be
+// gated on a frame-run table (runs.cuh): the launch returns at once unless the table's ok word asks for it.
 #pragma once
 #include <cuda.h>
 

@@ -11,11 +11,15 @@
 //   gV_t = gZ_t sigma'(V_t, A_t) + alpha gV_{t+1} (1 - Z_t)    [+ seed on V]
 //   gI_t = gV_t (1 - Z_{t-1})
 //
-// Same ownership as the forward kernel: one CTA = R batch rows, thread i = neuron i, ROW i of the
-// masked recurrent matrix in registers, gI_{t+1} broadcast from shared memory, one __syncthreads per
-// step.  dW_out and db are accumulated in registers / a pre-scan and leave as per-CTA partials (summed
-// in a fixed order by k_reduce_parts, so results are run-to-run deterministic); dW_in and dW_rec are
-// contractions over (batch x time) and belong to the weight-gradient GEMM (K4).
+// (Izhikevich, MODE = 2: the coupled (gV, gu) recurrence stated in the kernel body.)
+//
+// Same ownership as the forward kernel: one CTA = R batch rows, thread i = neuron i, the ROWS of the
+// masked recurrent matrix register-resident and column-blocked over lane quads (dot_rec16_cb on the
+// transpose), gI_{t+1} read from shared memory, one __syncthreads per step.  dW_out and db are
+// accumulated in registers / a pre-scan and leave as per-CTA partials (summed in a fixed order by
+// k_finalize_grads, so results are run-to-run deterministic); dW_in and dW_rec are contractions over
+// (batch x time) and belong to the weight-gradient GEMM (K4).  With a frame-run table the sweep also
+// leaves the sum of gI over every run of equal input frames (compact rows of the dW_in contraction).
 #pragma once
 #include "common.cuh"
 #include "gemm_tc.cuh"

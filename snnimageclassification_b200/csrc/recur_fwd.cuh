@@ -3,12 +3,15 @@
 // Replaces the time loop of SNN.forward (src/modules/snn.py:209-214) around LIFLayer/ALIFLayer.forward
 // (src/modules/spiking_layers.py:156-171, :229-243) and ReadoutLayer.forward (:402-408).
 //
+// IzhikevichLayer.forward (:330-353) is the MODE = 2 variant of the same kernel.
+//
 // One CTA owns R batch rows for all T steps (rows are independent, so there is no grid-wide sync).
 // Thread i owns hidden neuron i: its membrane/adaptation state lives in registers for the whole
-// sequence and column i of the masked recurrent matrix (H floats) is register-resident too, so one
-// step is H FFMAs against the previous spike vector broadcast from shared memory + the elementwise
-// update + one __syncthreads.  The input current of the row (a contiguous T x H block written by the
-// projection GEMM) is streamed through a shared-memory ring by 1-D bulk async copies (cp.async.bulk +
+// sequence.  The masked recurrent matrix is register-resident too, column-blocked over lane quads
+// (common.cuh, dot_rec16_cb): a step is H/2 packed FFMA2 against a quarter of the previous spike vector
+// read from shared memory, three quad shuffles, the elementwise update and one __syncthreads.  The input
+// current of the row (a contiguous T x H block written by the projection GEMM, or the compact rows of the
+// frame-dedup variant) is streamed through a shared-memory ring by 1-D bulk async copies (cp.async.bulk +
 // mbarrier), kChunk steps per copy and kRing copies in flight, so HBM/L2 latency never sits on the
 // step-to-step critical path.  Spikes are bit-packed with warp ballots; all T spike words stay in
 // shared memory, so the leaky readout (linear in the spikes) is evaluated after the loop instead of
