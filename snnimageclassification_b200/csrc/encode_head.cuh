@@ -245,32 +245,39 @@ struct AdamTensors {
     int count;
 };
 
+// CTAs that have finished the current k_adam_step launch; the last one bumps the step counters and resets it.  One
+// instance per device (module global); optimizer steps on one device are issued one after the other.
+__device__ unsigned int g_adam_done = 0;
+
 __global__ void __launch_bounds__(256) k_adam_step(const AdamTensors t, float lr, float beta1, float beta2, float eps,
                                                   float weight_decay)
 {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= t.start[t.count]) return;
-    int k = 0;
-    while (e >= t.start[k + 1]) ++k;
-    const long long i = e - t.start[k];
-    const float step = *t.step[k] + 1.0f;           // every thread reads the old counter; thread 0 of the tensor bumps it last
-    float g = t.g[k][i];
-    const float p = t.p[k][i];
-    g = fmaf(weight_decay, p, g);
-    const float m = fmaf(1.0f - beta1, g - t.m[k][i], t.m[k][i]);
-    const float v = fmaf(1.0f - beta2, g * g, beta2 * t.v[k][i]);
-    t.m[k][i] = m;
-    t.v[k][i] = v;
-    const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
-    const float denom = sqrtf(v) / sqrtf(bc2) + eps;
-    t.p[k][i] = p - (lr / bc1) * (m / denom);
-}
-
-// bumps the step counters after k_adam_step has read them (separate tiny launch: no intra-grid ordering needed)
-__global__ void k_adam_bump(const AdamTensors t)
-{
-    const int k = threadIdx.x;
-    if (k < t.count) *t.step[k] += 1.0f;
+    if (e < t.start[t.count]) {
+        int k = 0;
+        while (e >= t.start[k + 1]) ++k;
+        const long long i = e - t.start[k];
+        const float step = *t.step[k] + 1.0f;       // every thread reads the old counter; the last CTA out bumps it
+        float g = t.g[k][i];
+        const float p = t.p[k][i];
+        g = fmaf(weight_decay, p, g);
+        const float m = fmaf(1.0f - beta1, g - t.m[k][i], t.m[k][i]);
+        const float v = fmaf(1.0f - beta2, g * g, beta2 * t.v[k][i]);
+        t.m[k][i] = m;
+        t.v[k][i] = v;
+        const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
+        const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+        t.p[k][i] = p - (lr / bc1) * (m / denom);
+    }
+    // all reads of the step counters by this CTA are done once its threads pass the barrier
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&g_adam_done, 1u) == gridDim.x - 1) {
+            g_adam_done = 0;
+            for (int k = 0; k < t.count; ++k) *t.step[k] += 1.0f;
+        }
+    }
 }
 
 // ---- data-parallel optimizer step: gradient exchange + mean + Adam in ONE kernel -------------------

@@ -907,7 +907,6 @@ int snnk_adam_step(int32_t count, float* const* params, const float* const* grad
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ProfScope ps(SNNK_K_ADAM, st);
     k_adam_step<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t, lr, beta1, beta2, eps, weight_decay);
-    k_adam_bump<<<1, 32, 0, st>>>(t);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
