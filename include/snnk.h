@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SNNK_ABI_VERSION 4   /* 4: W_effT_out / W_effT_in; 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
+#define SNNK_ABI_VERSION 5   /* 5: loss mailbox of snnk_head_nll; 4: W_effT_out / W_effT_in; 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
 
 typedef void* snnk_stream_t; /* cudaStream_t */
 
@@ -209,9 +209,15 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
  * Fused head: log_softmax over the max-over-time logits (snn.py:258) + NLLLoss mean (snn.py:297)
  * and the gradient of that loss w.r.t. the logits.
  *   logits (B,O), labels (B) int64 -> logp (B,O), loss (1), g_logits (B,O) = (softmax - onehot)/B
+ *   loss_mailbox / mailbox_counter: both NULL, or: loss_mailbox is one 8-byte word of PINNED HOST memory (device-
+ *   accessible under unified addressing) and mailbox_counter a zero-initialised device word.  Every launch then also
+ *   stores ((++counter) << 32 | bits of loss) into the mailbox with a single store, so that the host can read the
+ *   step's loss (SNN._exec_batch returns it as a Python float, snn.py:415) by polling for the launch number it
+ *   expects -- no stream synchronisation, the backward pass may still be running.
  */
 int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labels, float* logp,
-                  float* loss, float* g_logits, snnk_stream_t stream);
+                  float* loss, float* g_logits, uint64_t* loss_mailbox, uint32_t* mailbox_counter,
+                  snnk_stream_t stream);
 
 /*
  * Reverse-time BPTT.  Replaces autograd's sweep for batch_loss.backward() (snn.py:413) over the graph

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(256) k_spike_bwd(int kind, const float* __rest
 // One CTA; B is a few thousand at most.  The loss is reduced in a fixed order (deterministic).
 __global__ void __launch_bounds__(256) k_head_nll(int B, int O, const float* __restrict__ logits,
                                                  const long long* __restrict__ labels, float* __restrict__ logp,
-                                                 float* __restrict__ loss, float* __restrict__ g_logits)
+                                                 float* __restrict__ loss, float* __restrict__ g_logits,
+                                                 unsigned long long* mailbox, unsigned int* counter)
 {
     __shared__ double s_part[256];
     double acc = 0.0;
@@ -230,7 +231,17 @@ __global__ void __launch_bounds__(256) k_head_nll(int B, int O, const float* __r
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += s_part[q];
-        *loss = (float)(s / (double)B);
+        const float lossf = (float)(s / (double)B);
+        *loss = lossf;
+        if (mailbox) {
+            // {launch number, loss} as ONE 8-byte store into pinned host memory: the host reads the step's loss by
+            // polling this word instead of synchronising with the stream, i.e. while the backward pass still runs
+            const unsigned int seq = *counter + 1u;
+            *counter = seq;
+            *reinterpret_cast<volatile unsigned long long*>(mailbox) =
+                (static_cast<unsigned long long>(seq) << 32) | __float_as_uint(lossf);
+            __threadfence_system();
+        }
     }
 }
 

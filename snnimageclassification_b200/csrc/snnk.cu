@@ -873,15 +873,17 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
 }
 
 int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labels, float* logp, float* loss,
-                  float* g_logits, snnk_stream_t stream)
+                  float* g_logits, uint64_t* loss_mailbox, uint32_t* mailbox_counter, snnk_stream_t stream)
 {
     if (!logits || !labels || !loss) return SNNK_ERR_ARG;
+    if ((loss_mailbox != nullptr) != (mailbox_counter != nullptr)) return SNNK_ERR_ARG;
     if (B <= 0 || O <= 0 || O > kOMax) return SNNK_ERR_SHAPE;
     if (!device_ok()) return SNNK_ERR_DEVICE;
     {
         ProfScope ps(SNNK_K_HEAD, static_cast<cudaStream_t>(stream));
         k_head_nll<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            B, O, logits, reinterpret_cast<const long long*>(labels), logp, loss, g_logits);
+            B, O, logits, reinterpret_cast<const long long*>(labels), logp, loss, g_logits,
+            reinterpret_cast<unsigned long long*>(loss_mailbox), mailbox_counter);
     }
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;

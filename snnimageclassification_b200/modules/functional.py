@@ -220,6 +220,11 @@ def run_input_grad(c: LayerConsts, gI: torch.Tensor, W_in: torch.Tensor) -> torc
 	return gX
 
 
+# (pinned host int64 word, device int32 counter) while a graphed training step is being built: the head kernel then
+# also posts the loss to the host word (include/snnk.h, snnk_head_nll); see modules/graphed.py
+LOSS_MAILBOX = None
+
+
 def run_head_nll(logits: torch.Tensor, labels: torch.Tensor, want_grad: bool = True):
 	"""Calls ``snnk_head_nll``.  Returns (loss (), logp (B,O), g_logits (B,O) | None)."""
 	lib = _cabi.lib()
@@ -229,9 +234,11 @@ def run_head_nll(logits: torch.Tensor, labels: torch.Tensor, want_grad: bool = T
 	logp = torch.empty_like(logits)
 	loss = torch.empty((), dtype=torch.float32, device=dev)
 	g = torch.empty_like(logits) if want_grad else None
+	box = LOSS_MAILBOX if (LOSS_MAILBOX is not None and LOSS_MAILBOX[1].device == dev) else None
 	with torch.cuda.device(dev):
 		rc = lib.snnk_head_nll(
 			B, O, _cabi.ptr(logits), _cabi.ptr(labels), _cabi.ptr(logp), _cabi.ptr(loss), _cabi.ptr(g),
+			ctypes.c_void_p(box[0].data_ptr()) if box else None, _cabi.ptr(box[1]) if box else None,
 			_cabi.stream_ptr())
 	_cabi.check(rc, "snnk_head_nll")
 	return loss, logp, g

@@ -11,8 +11,10 @@ import gc
 import weakref
 from typing import Optional
 
+import numpy as np
 import torch
 
+from . import functional as F_
 from .functional import _const_scalar
 
 
@@ -49,6 +51,14 @@ class GraphedTrainStep:
 			self.y.copy_(y_example, non_blocking=True)
 		self.step_in_graph = _optimizer_is_capturable(optimizer)
 		self.loss: Optional[torch.Tensor] = None
+		# Loss mailbox: the fused head posts {launch number, loss} into this pinned host word, so the host reads the
+		# loss of a replay by polling for its launch number -- it does not wait for the backward pass and can enqueue
+		# the next batch meanwhile (``wait_loss``).  Only the fused-head path (plain NLLLoss) posts.
+		self._mail = torch.zeros(1, dtype=torch.int64).pin_memory()
+		self._mail_np = self._mail.numpy().view(np.uint64)
+		self._mail_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+		self._expected = 0
+		self._posts = False
 
 		# Snapshot what the warm-up iterations would change: capture must not advance the training state.
 		params = [p for p in net.parameters()]
@@ -57,17 +67,23 @@ class GraphedTrainStep:
 
 		side = torch.cuda.Stream(device=dev)
 		side.wait_stream(torch.cuda.current_stream(dev))
-		with torch.cuda.stream(side):
-			for _ in range(warmup):
-				self._body()
-		torch.cuda.current_stream(dev).wait_stream(side)
-		torch.cuda.synchronize(dev)
+		F_.LOSS_MAILBOX = (self._mail, self._mail_counter)
+		try:
+			with torch.cuda.stream(side):
+				for _ in range(warmup):
+					self._body()
+			torch.cuda.current_stream(dev).wait_stream(side)
+			torch.cuda.synchronize(dev)
+			self._expected = int(self._mail_counter.item())       # launches so far (warm-up); 0 if the head never posted
+			self._posts = self._expected > 0
 
-		optimizer.zero_grad(set_to_none=True)
-		gc.collect()
-		self.graph = torch.cuda.CUDAGraph()
-		with torch.cuda.graph(self.graph):
-			self.loss = self._body()
+			optimizer.zero_grad(set_to_none=True)
+			gc.collect()
+			self.graph = torch.cuda.CUDAGraph()
+			with torch.cuda.graph(self.graph):
+				self.loss = self._body()
+		finally:
+			F_.LOSS_MAILBOX = None
 		with torch.no_grad():
 			for p, s in zip(params, saved_params):
 				p.copy_(s)
@@ -96,9 +112,21 @@ class GraphedTrainStep:
 			self.x.copy_(x, non_blocking=True)
 			self.y.copy_(y, non_blocking=True)
 		self.graph.replay()
+		self._expected = (self._expected + 1) & 0xFFFFFFFF
 		if not self.step_in_graph:
 			self.optimizer.step()
 		return self.loss
+
+	def wait_loss(self) -> float:
+		"""Python float of the latest replay's loss.  With the mailbox: polls the pinned host word for this replay's
+		launch number (the rest of the step may still be running); otherwise synchronises and reads the device scalar."""
+		if self._posts:
+			target, word = self._expected, self._mail_np
+			for _ in range(5_000_000):
+				w = int(word[0])
+				if (w >> 32) == target:
+					return float(np.uint32(w & 0xFFFFFFFF).view(np.float32))
+		return float(self.loss.item())
 
 
 def _clone_state(sd):

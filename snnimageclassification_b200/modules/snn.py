@@ -100,6 +100,7 @@ class SNN(torch.nn.Module):
 		self._graphed_steps: Dict[Any, Any] = {}
 		self._graph_seen: Dict[Any, int] = {}
 		self.last_eval_accuracy = float("nan")     # accuracy counted by the latest eval-mode _exec_epoch
+		self._last_graphed_step = None
 		self.kwargs = kwargs
 
 		self.device = device
@@ -474,7 +475,9 @@ class SNN(torch.nn.Module):
 			self._graph_seen[key] = seen + 1
 			if seen >= 1:   # a geometry that repeats (every full batch of an epoch): capture once, replay afterwards
 				step = self.graphed_train_step(x_batch, y_batch, criterion, optimizer)
+				self._last_graphed_step = step
 				return step(x_batch, y_batch)
+		self._last_graphed_step = None
 		if self.training:
 			batch_loss = self.batch_loss(x_batch, y_batch, criterion)
 			optimizer.zero_grad()
@@ -488,7 +491,11 @@ class SNN(torch.nn.Module):
 
 	def _exec_batch(self, x_batch, y_batch, criterion, optimizer):
 		"""forward (+ backward + optimizer step in train mode) -> python float (reference snn.py:384-415)."""
-		return self._exec_batch_device(x_batch, y_batch, criterion, optimizer).item()
+		loss = self._exec_batch_device(x_batch, y_batch, criterion, optimizer)
+		step = self._last_graphed_step
+		if step is not None and loss is step.loss:
+			return step.wait_loss()      # posted to pinned host memory by the head kernel: no stream synchronisation
+		return loss.item()
 
 	def _eval_batch_device(self, x_batch, y_batch, criterion):
 		"""Validation batch in ONE pass: (loss, number of correct predictions) as device tensors.  The reference runs
