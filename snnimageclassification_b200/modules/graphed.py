@@ -49,6 +49,15 @@ class GraphedTrainStep:
 			self.y = torch.empty(y_example.shape, dtype=y_example.dtype, device=dev)
 			self.x.copy_(x_example, non_blocking=True)
 			self.y.copy_(y_example, non_blocking=True)
+			# Host batches are staged through two device buffers on a copy stream: with the loss mailbox the caller is
+			# back with the next batch while this step's backward pass still runs, so its H2D copy overlaps that work;
+			# the compute stream then only does a device-to-device copy into the graph's input buffers.
+			self._copy_stream = torch.cuda.Stream(device=dev)
+			self._xs = [torch.empty_like(self.x) for _ in range(2)]
+			self._ys = [torch.empty_like(self.y) for _ in range(2)]
+			self._staged = [torch.cuda.Event() for _ in range(2)]
+			self._consumed = [torch.cuda.Event() for _ in range(2)]
+			self._flip = 0
 		self.step_in_graph = _optimizer_is_capturable(optimizer)
 		self.loss: Optional[torch.Tensor] = None
 		# Loss mailbox: the fused head posts {launch number, loss} into this pinned host word, so the host reads the
@@ -109,8 +118,23 @@ class GraphedTrainStep:
 
 	def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
 		if not self.static_inputs:
-			self.x.copy_(x, non_blocking=True)
-			self.y.copy_(y, non_blocking=True)
+			if x.is_cuda or y.is_cuda:     # device inputs are ordered on the compute stream: copy there
+				self.x.copy_(x, non_blocking=True)
+				self.y.copy_(y, non_blocking=True)
+			else:
+				k = self._flip
+				self._flip ^= 1
+				main = torch.cuda.current_stream(self.x.device)
+				cs = self._copy_stream
+				cs.wait_event(self._consumed[k])          # the compute stream has taken what was staged here two calls ago
+				with torch.cuda.stream(cs):
+					self._xs[k].copy_(x, non_blocking=True)
+					self._ys[k].copy_(y, non_blocking=True)
+					self._staged[k].record(cs)
+				main.wait_event(self._staged[k])
+				self.x.copy_(self._xs[k], non_blocking=True)
+				self.y.copy_(self._ys[k], non_blocking=True)
+				self._consumed[k].record(main)
 		self.graph.replay()
 		self._expected = (self._expected + 1) & 0xFFFFFFFF
 		if not self.step_in_graph:
