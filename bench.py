@@ -302,7 +302,8 @@ def main():
 			"exchange_timeline_us": ({"columns": ["stores_issued", "peers_seen", "done"], "per_rank": timeline}
 				if dp_fused else None)},
 		"clocks": clocks,
-		"e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+		"e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+			"readback": "the step's loss, posted by the head kernel as one 8-byte word into pinned host memory and polled by the host",
 			"ms_per_step": ms_e2e / args.steps, "input": "pinned host images (B,784) fp32 + labels; GPU to_spikes",
 			"from_host_rasters": {"value": e2e_raster, "h2d_bytes_per_step": B_PER_GPU * T * N * 4 + B_PER_GPU * 8},
 			"from_host_bitpacked_rasters": {"value": e2e_bits,
