@@ -54,7 +54,7 @@ SURROGATES = {0: _FastSigmoidSpike, 1: _PhiSpike}
 
 
 class TorchPortSNN:
-	"""One hidden LIF/ALIF layer + leaky readout (snn.py:201-219)."""
+	"""One hidden LIF (0) / ALIF (1) / Izhikevich (2) layer + leaky readout (snn.py:201-219)."""
 
 	def __init__(
 			self, N: int, H: int, O: int, T: int, layer_type: int = 1, surrogate: int = 0, recurrent: bool = True,
@@ -63,7 +63,13 @@ class TorchPortSNN:
 		self.N, self.H, self.O, self.T = N, H, O, T
 		self.layer_type, self.surrogate, self.recurrent = layer_type, surrogate, bool(recurrent)
 		# spiking_layers.py:124-130 / :201-210 / :380-381 defaults
-		if layer_type == 0:
+		self.dt = dt
+		# IzhikevichLayer constants, spiking_layers.py:287-300 (gamma 1.0: the never-true isinstance test)
+		self.iz = {k: torch.tensor(kw.get(k, v), dtype=torch.float32) for k, v in dict(
+			C=100.0, v_rest=-60.0, v_th=-40.0, k=0.7, a=0.03, b=-2.0, c=-50.0, d=100.0, v_peak=35.0).items()}
+		if layer_type == 2:
+			tau_m, theta, gamma = 10.0 * dt, 1.0, kw.get("gamma", 1.0)      # weights ~ N(0, 1) (spiking_layers.py:302-307)
+		elif layer_type == 0:
 			tau_m, theta, gamma = kw.get("tau_m", 10.0 * dt), kw.get("threshold", 1.0), kw.get("gamma", 1.0)
 		else:
 			tau_m, theta, gamma = kw.get("tau_m", 20.0 * dt), kw.get("threshold", 0.03), kw.get("gamma", 0.3)
@@ -108,6 +114,8 @@ class TorchPortSNN:
 		x = x.float()
 		spike = SURROGATES[self.surrogate].apply
 		V = torch.zeros(B, self.H, requires_grad=True)
+		if self.layer_type == 2:
+			V = (self.iz["v_rest"] * torch.ones(B, self.H)).requires_grad_()       # spiking_layers.py:309
 		a = torch.zeros(B, self.H, requires_grad=True)
 		Z = torch.zeros(B, self.H, requires_grad=True)
 		y = torch.zeros(B, self.O, requires_grad=True)
@@ -115,6 +123,17 @@ class TorchPortSNN:
 		for t in range(self.T):
 			cur = torch.matmul(x[:, t], self.W_in)                               # spiking_layers.py:163/233
 			rec = torch.matmul(Z, self.W_rec * self.rec_mask) if self.recurrent else 0.0  # :165/235
+			if self.layer_type == 2:                                                # spiking_layers.py:343-349
+				z, r = self.iz, Z.detach()
+				I = cur + rec
+				dVdt = z["k"] * (V - z["v_rest"]) * (V - z["v_th"]) - a + I
+				nV = (V + self.dt * dVdt / z["C"]) * (1.0 - r) + z["c"] * r
+				a = (a + self.dt * (z["a"] * (z["b"] * (V - z["v_rest"]) - a))) + z["d"] * r
+				V = nV
+				Z = spike(V, z["v_peak"], self.gamma)
+				y = self.kappa * y + torch.matmul(Z, self.W_out) + self.b_out
+				Vs.append(V); As.append(a); Zs.append(Z); ys.append(y)
+				continue
 			V = (self.alpha * V + cur + rec) * (1.0 - Z.detach())                  # :169/239
 			if self.layer_type == 1:
 				a = self.rho * a + Z                                                # :240
@@ -125,7 +144,7 @@ class TorchPortSNN:
 			y = self.kappa * y + torch.matmul(Z, self.W_out) + self.b_out          # :407
 			Vs.append(V); As.append(a); Zs.append(Z); ys.append(y)
 		st = lambda l: torch.stack(l, dim=1)  # noqa: E731  (snn.py:195-199, :218)
-		hidden = (st(Vs), st(As), st(Zs)) if self.layer_type == 1 else (st(Vs), st(Zs))
+		hidden = (st(Vs), st(As), st(Zs)) if self.layer_type != 0 else (st(Vs), st(Zs))
 		out = st(ys)
 		return out, {"input": hidden, "readout": (out,)}
 

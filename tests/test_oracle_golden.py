@@ -179,3 +179,24 @@ def test_oracle_izhikevich_matches_reference(name):
 	assert rel_err(g["dW_out"], c["dW_out"]) <= 1e-4 and rel_err(g["db"], c["db"]) <= 1e-4
 	if cfg.recurrent:
 		assert rel_err(g["dW_rec"], c["dW_rec"]) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["IZH_FastSigmoid_rec1", "IZH_Phi_rec0"])
+def test_torch_port_izhikevich_matches_reference(name):
+	z = load("izhikevich_golden.npz")
+	c = dynamics_case(z, name)
+	B, T, N, H, O = (int(v) for v in c["dims"])
+	k = c["consts"]
+	net = TorchPortSNN(N, H, O, T, layer_type=2, surrogate=int(c["flags"][0]), recurrent=bool(c["flags"][1]), dt=float(k[0]))
+	net.load(c["W_in"], c.get("W_rec"), c["W_out"], c["b_out"])
+	x = torch.from_numpy(c["x"].astype(np.float32))
+	logp, out, hs = net.log_proba(x)
+	V, u, Z = hs["input"]
+	assert np.array_equal(Z.detach().numpy().astype(np.uint8), c["Z"])
+	assert rel_err(V.detach().numpy(), c["V"]) <= 1e-5 and rel_err(u.detach().numpy(), c["u"]) <= 1e-5
+	loss = torch.nn.functional.nll_loss(logp, torch.from_numpy(c["labels"]))
+	loss.backward()
+	assert abs(float(loss) - float(c["loss"])) <= 1e-5 * abs(float(c["loss"]))
+	assert rel_err(net.W_in.grad.numpy(), c["dW_in"]) <= 1e-4 and rel_err(net.W_out.grad.numpy(), c["dW_out"]) <= 1e-4
+	if net.recurrent:
+		assert rel_err(net.W_rec.grad.numpy(), c["dW_rec"]) <= 1e-4
