@@ -284,6 +284,9 @@ def main():
 		if top.split()[0] in NCU_TRAFFIC:
 			roofline["traffic"], roofline["traffic_source"] = NCU_TRAFFIC[top.split()[0]]
 	launches_per_step = sum(v["launches_per_step"] for v in kern.values()) if kern else 0
+	# the profiler brackets the kernels that matter for time; three small helpers of a step carry no bracket:
+	# k_split_w, k_prep_rec (forward) and, with the dedup variant, the backward gather on the helper stream
+	launches_per_step += 2 + (1 if dedup["active"] else 0)
 	cpu = None
 	if world == 1 and not args.no_cpu_baseline:
 		r = cpu_reference_run(steps=40, warmup=2, budget_s=25.0)
