@@ -200,3 +200,76 @@ def test_torch_port_izhikevich_matches_reference(name):
 	assert rel_err(net.W_in.grad.numpy(), c["dW_in"]) <= 1e-4 and rel_err(net.W_out.grad.numpy(), c["dW_out"]) <= 1e-4
 	if net.recurrent:
 		assert rel_err(net.W_rec.grad.numpy(), c["dW_rec"]) <= 1e-4
+
+
+# ---- property checks of the encoder oracle against a second, numpy restatement of datasets.py:42-86 ------------------
+def _np_periods(x, t_max, tau, thr, eps):
+	x = np.asarray(x)
+	below = x < thr
+	xc = np.clip(x, thr + eps, 1e9)
+	T = tau * np.log(xc / (xc - thr))
+	T[below] = t_max
+	return T.astype(np.int64)
+
+
+def _np_periodic(per, n_steps):
+	p = np.clip(per, 1, n_steps - 1)
+	t = np.arange(n_steps)[:, None]
+	return ((t >= p[None, :]) & ((t - p[None, :]) % p[None, :] == 0)).astype(np.uint8)
+
+
+def _np_latency(per, n_steps):
+	t = np.arange(n_steps)[:, None]
+	return (t == per[None, :]).astype(np.uint8)
+
+
+def test_encoder_oracle_properties_float64():
+	from hypothesis import given, settings, strategies as st
+
+	@settings(max_examples=60, deadline=None)
+	@given(st.integers(0, 2**31 - 1), st.sampled_from([2, 10, 32, 100]), st.sampled_from([20.0, 0.02, 1.0]))
+	def check(seed, n_steps, tau):
+		rng = np.random.default_rng(seed)
+		x = rng.random(97)                      # float64: numpy's log is what the reference itself runs
+		x[rng.random(97) < 0.3] = 0.0
+		per = oracle.periods(x, n_steps, tau, 0.2, 1e-7)
+		assert np.array_equal(per, _np_periods(x, n_steps, tau, 0.2, 1e-7))
+		assert np.array_equal(oracle.raster(per[None], n_steps, True)[0], _np_periodic(per, n_steps))
+		assert np.array_equal(oracle.raster(per[None], n_steps, False)[0], _np_latency(per, n_steps))
+		r = oracle.raster(per[None], n_steps, True)[0].astype(np.int64)
+		p = np.clip(per, 1, n_steps - 1)
+		assert np.array_equal(r.sum(0), (n_steps - 1) // p)          # a pixel of period p fires floor((T-1)/p) times
+		assert r[0].sum() == 0                                        # never at t = 0 (p >= 1)
+	check()
+
+
+def test_dynamics_oracle_structural_properties():
+	"""Size-independent properties of the restated dynamics: batch rows are independent; zero input keeps a LIF layer
+	silent; the head's gradient w.r.t. the output trace is non-zero only at the (first) arg-max step of each class."""
+	rng = np.random.default_rng(5)
+	B, T, N, H, O = 6, 20, 24, 32, 10
+	cfg = OracleCfg(B, T, N, H, O, layer_type=1, surrogate=0, recurrent=1, alpha=0.95, rho=0.99, theta=0.03, gamma=0.3,
+		kappa=0.9, beta=0.01)
+	x = (rng.random((B, T, N)) < 0.2).astype(np.float32)
+	W_in = (rng.standard_normal((N, H)) * 0.03).astype(np.float32)
+	W_rec = (rng.standard_normal((H, H)) * 0.03).astype(np.float32)
+	mask = (1 - np.eye(H)).astype(np.float32)
+	W_out = rng.standard_normal((H, O)).astype(np.float32)
+	b = np.zeros(O, np.float32)
+	f = oracle.forward(cfg, x, W_in, W_rec, mask, W_out, b)
+	perm = rng.permutation(B)
+	fp = oracle.forward(cfg, x[perm], W_in, W_rec, mask, W_out, b)
+	for k in ("V", "a", "Z", "y"):
+		assert np.array_equal(fp[k], f[k][perm])
+	lif = OracleCfg(B, T, N, H, O, layer_type=0, surrogate=0, recurrent=1, alpha=0.9, theta=1.0, gamma=1.0, kappa=0.9)
+	z = oracle.forward(lif, np.zeros_like(x), W_in, W_rec, mask, W_out, b)
+	assert not z["Z"].any() and not z["V"].any() and not z["y"].any()
+	labels = rng.integers(0, O, B)
+	h = oracle.head(f["y"], labels)
+	assert np.allclose(np.exp(h["logp"]).sum(1), 1.0, atol=1e-6)
+	nz = h["g_y"] != 0
+	assert nz.sum(axis=1).max() <= 1                                  # at most one step per (sample, class)
+	bi, ti, ci = np.nonzero(nz)
+	assert np.array_equal(ti, h["tstar"][bi, ci])
+	assert np.array_equal(h["logits"], f["y"].max(axis=1))
+	assert np.array_equal(h["tstar"], f["y"].argmax(axis=1))           # first maximum wins (snn.py:228)
