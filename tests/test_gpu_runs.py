@@ -201,3 +201,29 @@ def test_bit_packed_raster_format(tau, periodic, N):
 	a, _ = net(dense)
 	b, _ = net(bits.cpu())          # e.g. a packed raster coming from a host-side data loader
 	assert torch.equal(a, b)
+
+
+def test_full_size_determinism_and_row_independence():
+	"""BASELINE configs[1] geometry (B = 256, T = 100, 784-128-10, production encoder, tensor-core + dedup kernels):
+	two identical training steps give bit-identical loss and gradients (every reduction has a fixed order), and
+	permuting the batch rows permutes the traces bit-exactly (rows never interact before the loss mean)."""
+	from snnimageclassification_b200 import ToSpikes
+	B, T, N, H = 256, 100, 784, 128
+	enc = ToSpikes(T, use_periods=True)
+	img = _images(B, N, 41)
+	y = torch.randint(0, 10, (B,), generator=torch.Generator().manual_seed(42)).to(DEV)
+	x = enc.encode_batch(img.to(DEV))
+	net = _net(N, H, T)
+	net.train()
+	l1, g1 = _step(net, x, y)
+	l2, g2 = _step(net, x, y)
+	assert l1 == l2
+	for k in g1:
+		assert torch.equal(g1[k], g2[k]), k
+	perm = torch.randperm(B, generator=torch.Generator().manual_seed(43))
+	xp = enc.encode_batch(img[perm].to(DEV))
+	out, hid = net(x)
+	outp, hidp = net(xp)
+	assert torch.equal(outp, out[perm.to(DEV)])
+	for u, v in zip(hidp["input"], hid["input"]):
+		assert torch.equal(u, v[perm.to(DEV)])
