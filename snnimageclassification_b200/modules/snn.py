@@ -103,26 +103,20 @@ class SNN(torch.nn.Module):
 		self._last_graphed_step = None
 		self.kwargs = kwargs
 
-		self.device = device
-		if self.device is None:
+		# device, time grid and the two enum-or-class arguments (reference snn.py:68-84)
+		if device is None:
+			self.device = None
 			self._set_default_device_()
-		self.device = torch.device(self.device)
-
-		self.dt = dt
-		self.int_time_steps = int_time_steps
-		if isinstance(spike_func, SpikeFuncType):
-			spike_func = SpikeFuncType2Func[spike_func]
-		self.spike_func = spike_func
-		if isinstance(hidden_layer_type, LayerType):
-			hidden_layer_type = LayerType2Layer[hidden_layer_type]
-		self.hidden_layer_type = hidden_layer_type
-
-		self.checkpoint_folder = checkpoint_folder
-		self.model_name = model_name
-
-		if isinstance(n_hidden_neurons, int):
-			n_hidden_neurons = [n_hidden_neurons]
-		self.n_hidden_neurons = n_hidden_neurons if n_hidden_neurons is not None else []
+			device = self.device
+		self.device = torch.device(device)
+		self.dt, self.int_time_steps = dt, int_time_steps
+		self.spike_func = SpikeFuncType2Func[spike_func] if isinstance(spike_func, SpikeFuncType) else spike_func
+		self.hidden_layer_type = (
+			LayerType2Layer[hidden_layer_type] if isinstance(hidden_layer_type, LayerType) else hidden_layer_type)
+		self.checkpoint_folder, self.model_name = checkpoint_folder, model_name
+		# an int is one hidden layer, None is a readout-only model
+		widths = [n_hidden_neurons] if isinstance(n_hidden_neurons, int) else n_hidden_neurons
+		self.n_hidden_neurons = [] if widths is None else widths
 		self.use_recurrent_connection = use_recurrent_connection
 		self.layers = nn.ModuleDict()
 		self._add_layers_()
@@ -138,45 +132,41 @@ class SNN(torch.nn.Module):
 	def _set_default_device_(self):
 		self.device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
 
+	def _spiking_layer(self, n_in: int, n_out: int):
+		"""One hidden layer of the configured type; every extra keyword of the constructor is handed on, as the
+		reference does (snn.py:103-128)."""
+		return self.hidden_layer_type(
+			input_size=n_in, output_size=n_out, use_recurrent_connection=self.use_recurrent_connection, dt=self.dt,
+			spike_func=self.spike_func, device=self.device, **self.kwargs)
+
 	def _add_input_layer_(self):
-		if not self.n_hidden_neurons:
-			return
-		self.layers["input"] = self.hidden_layer_type(
-			input_size=self.input_size, output_size=self.n_hidden_neurons[0],
-			use_recurrent_connection=self.use_recurrent_connection, dt=self.dt, spike_func=self.spike_func,
-			device=self.device, **self.kwargs)
+		if self.n_hidden_neurons:
+			self.layers["input"] = self._spiking_layer(self.input_size, self.n_hidden_neurons[0])
 
 	def _add_hidden_layers_(self):
-		if not self.n_hidden_neurons:
-			return
-		for i, hn in enumerate(self.n_hidden_neurons[:-1]):
-			self.layers[f"hidden_{i}"] = self.hidden_layer_type(
-				input_size=hn, output_size=self.n_hidden_neurons[i + 1],
-				use_recurrent_connection=self.use_recurrent_connection, dt=self.dt, spike_func=self.spike_func,
-				device=self.device, **self.kwargs)
+		widths = list(self.n_hidden_neurons)
+		for i, (n_in, n_out) in enumerate(zip(widths[:-1], widths[1:])):
+			self.layers[f"hidden_{i}"] = self._spiking_layer(n_in, n_out)
 
 	def _add_readout_layer(self):
-		in_size = self.n_hidden_neurons[-1] if self.n_hidden_neurons else self.input_size
+		n_in = self.n_hidden_neurons[-1] if self.n_hidden_neurons else self.input_size
 		self.layers["readout"] = ReadoutLayer(
-			input_size=in_size, output_size=self.output_size, dt=self.dt, spike_func=self.spike_func,
-			device=self.device, **self.kwargs)
+			input_size=n_in, output_size=self.output_size, dt=self.dt, spike_func=self.spike_func, device=self.device,
+			**self.kwargs)
 
 	def _add_layers_(self):
-		self._add_input_layer_()
-		self._add_hidden_layers_()
-		self._add_readout_layer()
+		for add in (self._add_input_layer_, self._add_hidden_layers_, self._add_readout_layer):
+			add()
 
 	def initialize_weights_(self):
 		# Same order as the reference (snn.py:149-157): every parameter is re-drawn ~N(0,1) -- including a learnable
 		# beta -- and then each layer applies its own initialiser, so a given torch seed yields the same weights.
-		for param in self.parameters():
-			if param.ndim > 2:
-				torch.nn.init.xavier_normal_(param)
-			else:
-				torch.nn.init.normal_(param)
-		for layer_name, layer in self.layers.items():
-			if getattr(layer, "initialize_weights_") and callable(layer.initialize_weights_):
-				layer.initialize_weights_()
+		for p in self.parameters():
+			(torch.nn.init.xavier_normal_ if p.ndim > 2 else torch.nn.init.normal_)(p)
+		for layer in self.layers.values():
+			init = getattr(layer, "initialize_weights_", None)
+			if callable(init):
+				init()
 
 	# ---- input formatting (reference snn.py:159-184) ------------------------------------------------------------
 	def _format_inputs(self, inputs: torch.Tensor) -> torch.Tensor:
@@ -328,6 +318,29 @@ class SNN(torch.nn.Module):
 		losses = self.loss_history["val"][-patience:]
 		return bool(np.all(np.abs(np.diff(losses)) < tol))
 
+	def _prepare_run(self, optimizer, load_checkpoint_mode, force_overwrite: bool, verbose: bool) -> int:
+		"""First epoch to run.  Fresh run (no load mode): the reference's guard is kept as it is (snn.py:301-306 -- it
+		insists on ``force_overwrite`` when there is NO checkpoint index yet, although its message says the opposite) and
+		an existing checkpoint folder is removed.  Resume: weights, optimizer state and loss history come back from the
+		chosen checkpoint; a missing one means starting from scratch."""
+		meta = self.checkpoints_meta_path
+		if load_checkpoint_mode is None:
+			have_meta = os.path.exists(meta)
+			assert have_meta or force_overwrite, (
+				f"{meta} already exists. Set force_overwrite flag to True to overwrite existing saves.")
+			if have_meta and force_overwrite:
+				shutil.rmtree(self.checkpoint_folder)
+			return 0
+		try:
+			ck = self.load_checkpoint(load_checkpoint_mode)       # also loads the weights
+		except FileNotFoundError:
+			if verbose:
+				logging.warning("No such checkpoint. Fit from beginning.")
+			return 0
+		optimizer.load_state_dict(ck[SNN.CHECKPOINT_OPTIMIZER_STATE_DICT_KEY])
+		self.loss_history = self.get_checkpoints_loss_history()
+		return int(ck[SNN.CHECKPOINT_EPOCH_KEY]) + 1
+
 	# ---- training loop (reference snn.py:280-415) -----------------------------------------------------------------
 	def fit(
 			self,
@@ -358,24 +371,7 @@ class SNN(torch.nn.Module):
 			else:
 				optimizer = torch.optim.Adam(self.parameters(), lr=lr, weight_decay=1e-5)
 
-		start_epoch = 0
-		if load_checkpoint_mode is None:
-			assert os.path.exists(self.checkpoints_meta_path) or force_overwrite, \
-				f"{self.checkpoints_meta_path} already exists. " \
-				f"Set force_overwrite flag to True to overwrite existing saves."
-			if os.path.exists(self.checkpoints_meta_path) and force_overwrite:
-				shutil.rmtree(self.checkpoint_folder)
-		else:
-			try:
-				checkpoint = self.load_checkpoint(load_checkpoint_mode)
-				self.load_state_dict(checkpoint[SNN.CHECKPOINT_STATE_DICT_KEY], strict=True)
-				optimizer.load_state_dict(checkpoint[SNN.CHECKPOINT_OPTIMIZER_STATE_DICT_KEY])
-				start_epoch = int(checkpoint[SNN.CHECKPOINT_EPOCH_KEY]) + 1
-				self.loss_history = self.get_checkpoints_loss_history()
-			except FileNotFoundError:
-				if verbose:
-					logging.warning("No such checkpoint. Fit from beginning.")
-
+		start_epoch = self._prepare_run(optimizer, load_checkpoint_mode, force_overwrite, verbose)
 		if start_epoch >= nb_epochs:
 			return self.loss_history
 
@@ -520,59 +516,17 @@ class SNN(torch.nn.Module):
 		from ..distributed import allreduce_mean_
 		allreduce_mean_(p.grad for p in self.parameters())
 
-	# ---- checkpoints (reference snn.py:417-505; same files, so checkpoints interchange) -----------------------------
-	def plot_loss_history(self, loss_history: LossHistory = None, show=False):
-		if loss_history is None:
-			loss_history = self.loss_history
-		os.makedirs(self._folder(), exist_ok=True)
-		loss_history.plot(f"{self._folder()}/loss_history.png", show)
-
+	# ---- checkpoints (reference snn.py:417-505; same files and index layout, so checkpoints interchange) -------------
+	# On disk: one "<model>-epoch<N>.pth" per epoch ({epoch, model_state_dict, optimizer_state_dict, loss}) and the index
+	# "<model>-checkpoints.json" = {"epochs": {"<N>": path, ...}, "best": path}.
 	def _folder(self) -> str:
 		# the reference writes "./{checkpoint_folder}/..." (snn.py:421, :425); absolute folders are kept usable here
 		f = str(self.checkpoint_folder)
 		return f if os.path.isabs(f) else f"./{f}"
 
-	def _create_checkpoint_path(self, epoch: int = -1):
-		return f"{self._folder()}/{self.model_name}{SNN.SUFFIX_SEP}{SNN.CHECKPOINT_EPOCH_KEY}{epoch}{SNN.SAVE_EXT}"
-
-	def _create_new_checkpoint_meta(self, epoch: int, best: bool = False) -> dict:
-		save_path = self._create_checkpoint_path(epoch)
-		new_info = {SNN.CHECKPOINT_EPOCHS_KEY: {epoch: save_path}}
-		if best:
-			new_info[SNN.CHECKPOINT_BEST_KEY] = save_path
-		return new_info
-
-	def save_checkpoint(self, optimizer, epoch: int, epoch_losses: Dict[str, Any], best: bool = False):
-		os.makedirs(self.checkpoint_folder, exist_ok=True)
-		save_path = self._create_checkpoint_path(epoch)
-		torch.save({
-			SNN.CHECKPOINT_EPOCH_KEY: epoch,
-			SNN.CHECKPOINT_STATE_DICT_KEY: self.state_dict(),
-			SNN.CHECKPOINT_OPTIMIZER_STATE_DICT_KEY: optimizer.state_dict(),
-			SNN.CHECKPOINT_LOSS_KEY: {k: float(v) for k, v in epoch_losses.items()},
-		}, save_path)
-		self.save_checkpoints_meta(self._create_new_checkpoint_meta(epoch, best))
-
-	@staticmethod
-	def get_save_path_from_checkpoints(
-			checkpoints_meta: Dict[str, Union[str, Dict[Any, str]]],
-			load_checkpoint_mode: LoadCheckpointMode = LoadCheckpointMode.BEST_EPOCH
-	) -> str:
-		if load_checkpoint_mode == LoadCheckpointMode.BEST_EPOCH:
-			return checkpoints_meta[SNN.CHECKPOINT_BEST_KEY]
-		elif load_checkpoint_mode == LoadCheckpointMode.LAST_EPOCH:
-			epochs_dict = checkpoints_meta[SNN.CHECKPOINT_EPOCHS_KEY]
-			last_epoch: int = max([int(e) for e in epochs_dict])
-			return checkpoints_meta[SNN.CHECKPOINT_EPOCHS_KEY][str(last_epoch)]
-		raise ValueError()
-
-	def get_checkpoints_loss_history(self) -> LossHistory:
-		history = LossHistory()
-		with open(self.checkpoints_meta_path, "r+") as jsonFile:
-			meta: dict = json.load(jsonFile)
-		for path in meta[SNN.CHECKPOINT_EPOCHS_KEY].values():
-			history.concat(self._load_file(path)[SNN.CHECKPOINT_LOSS_KEY])
-		return history
+	def _read_index(self) -> dict:
+		with open(self.checkpoints_meta_path, "r") as fh:
+			return json.load(fh)
 
 	def _load_file(self, path: str) -> dict:
 		"""Checkpoints written here hold tensors and plain Python numbers only, so they load under torch's safe
@@ -583,22 +537,60 @@ class SNN(torch.nn.Module):
 		except Exception:
 			return torch.load(path, map_location=self.device, weights_only=False)
 
-	def load_checkpoint(self, load_checkpoint_mode: LoadCheckpointMode = LoadCheckpointMode.BEST_EPOCH) -> dict:
-		with open(self.checkpoints_meta_path, "r+") as jsonFile:
-			info: dict = json.load(jsonFile)
-		path = self.get_save_path_from_checkpoints(info, load_checkpoint_mode)
-		checkpoint = self._load_file(path)
-		self.load_state_dict(checkpoint[SNN.CHECKPOINT_STATE_DICT_KEY], strict=True)
-		return checkpoint
+	def plot_loss_history(self, loss_history: LossHistory = None, show=False):
+		history = self.loss_history if loss_history is None else loss_history
+		os.makedirs(self._folder(), exist_ok=True)
+		history.plot(os.path.join(self._folder(), "loss_history.png"), show)
+
+	def _create_checkpoint_path(self, epoch: int = -1):
+		name = f"{self.model_name}{SNN.SUFFIX_SEP}{SNN.CHECKPOINT_EPOCH_KEY}{epoch}{SNN.SAVE_EXT}"
+		return f"{self._folder()}/{name}"
+
+	def _create_new_checkpoint_meta(self, epoch: int, best: bool = False) -> dict:
+		path = self._create_checkpoint_path(epoch)
+		entry = {SNN.CHECKPOINT_EPOCHS_KEY: {epoch: path}}
+		return {**entry, SNN.CHECKPOINT_BEST_KEY: path} if best else entry
 
 	def save_checkpoints_meta(self, new_info: dict):
-		info = dict()
-		if os.path.exists(self.checkpoints_meta_path):
-			with open(self.checkpoints_meta_path, "r+") as jsonFile:
-				info = json.load(jsonFile)
-		mapping_update_recursively(info, new_info)
-		with open(self.checkpoints_meta_path, "w+") as jsonFile:
-			json.dump(info, jsonFile, indent=4)
+		index = self._read_index() if os.path.exists(self.checkpoints_meta_path) else {}
+		mapping_update_recursively(index, new_info)
+		with open(self.checkpoints_meta_path, "w") as fh:
+			json.dump(index, fh, indent=4)
+
+	def save_checkpoint(self, optimizer, epoch: int, epoch_losses: Dict[str, Any], best: bool = False):
+		os.makedirs(self.checkpoint_folder, exist_ok=True)
+		payload = {
+			SNN.CHECKPOINT_EPOCH_KEY: epoch,
+			SNN.CHECKPOINT_STATE_DICT_KEY: self.state_dict(),
+			SNN.CHECKPOINT_OPTIMIZER_STATE_DICT_KEY: optimizer.state_dict(),
+			SNN.CHECKPOINT_LOSS_KEY: {phase: float(v) for phase, v in epoch_losses.items()},     # plain floats: weights_only-safe
+		}
+		torch.save(payload, self._create_checkpoint_path(epoch))
+		self.save_checkpoints_meta(self._create_new_checkpoint_meta(epoch, best))
+
+	@staticmethod
+	def get_save_path_from_checkpoints(
+			checkpoints_meta: Dict[str, Union[str, Dict[Any, str]]],
+			load_checkpoint_mode: LoadCheckpointMode = LoadCheckpointMode.BEST_EPOCH
+	) -> str:
+		if load_checkpoint_mode == LoadCheckpointMode.BEST_EPOCH:
+			return checkpoints_meta[SNN.CHECKPOINT_BEST_KEY]
+		if load_checkpoint_mode == LoadCheckpointMode.LAST_EPOCH:
+			per_epoch = checkpoints_meta[SNN.CHECKPOINT_EPOCHS_KEY]       # json keys are strings
+			return per_epoch[str(max(int(e) for e in per_epoch))]
+		raise ValueError()
+
+	def get_checkpoints_loss_history(self) -> LossHistory:
+		history = LossHistory()
+		for path in self._read_index()[SNN.CHECKPOINT_EPOCHS_KEY].values():
+			history.concat(self._load_file(path)[SNN.CHECKPOINT_LOSS_KEY])
+		return history
+
+	def load_checkpoint(self, load_checkpoint_mode: LoadCheckpointMode = LoadCheckpointMode.BEST_EPOCH) -> dict:
+		"""Loads the chosen checkpoint's weights into the model and returns the whole checkpoint dict."""
+		ck = self._load_file(self.get_save_path_from_checkpoints(self._read_index(), load_checkpoint_mode))
+		self.load_state_dict(ck[SNN.CHECKPOINT_STATE_DICT_KEY], strict=True)
+		return ck
 
 	# ---- evaluation (reference snn.py:507-555) ---------------------------------------------------------------------
 	def compute_classification_accuracy(self, dataloader: DataLoader, verbose: bool = False, desc: Optional[str] = None) -> float:

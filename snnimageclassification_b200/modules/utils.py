@@ -22,75 +22,96 @@ def batchwise_temporal_filter(x: torch.Tensor, decay: float = 0.9) -> torch.Tens
 
 
 def mapping_update_recursively(d, u):
-	"""Nested dict merge (reference utils.py:28-40)."""
-	for k, v in u.items():
-		if isinstance(v, collections.abc.Mapping):
-			d[k] = mapping_update_recursively(d.get(k, {}), v)
-		else:
-			d[k] = v
+	"""Deep merge of mapping ``u`` into ``d`` (in place, returned): nested mappings are merged key by key, any other
+	value replaces what was there.  Used for the checkpoint index (same contract as the reference's helper,
+	utils.py:28-40); written as an explicit work list rather than by recursion."""
+	work = [(d, u)]
+	while work:
+		dst, src = work.pop()
+		for key in src:
+			new = src[key]
+			if isinstance(new, collections.abc.Mapping):
+				cur = dst.get(key)
+				if not isinstance(cur, collections.abc.MutableMapping):
+					cur = dst[key] = {}
+				work.append((cur, new))
+			else:
+				dst[key] = new
 	return d
 
 
 class LossHistory:
-	"""{'train': [...], 'val': [...]} with the reference's accessors (utils.py:43-99)."""
+	"""Per-phase loss curves, e.g. ``{"train": [...], "val": [...]}``.
+
+	Interface of the reference's container (utils.py:43-99: ``container`` attribute, item access, ``items``,
+	``concat``, ``append``, ``min``, ``min_item``, ``plot``) so that ``SNN.fit`` and user code keep working; a missing
+	phase reads as an empty curve.
+	"""
 
 	def __init__(self, container: Dict[str, List[float]] = None):
 		self.container = defaultdict(list)
-		if container is not None:
-			self.container.update(container)
+		for phase, curve in (container or {}).items():
+			self.container[phase] = list(curve)
 
-	def __getitem__(self, item):
-		return self.container[item]
-
-	def __setitem__(self, key, value):
-		self.container[key] = value
-
-	def __contains__(self, item):
-		return item in self.container
-
-	def __iter__(self):
-		return iter(self.container)
-
+	# -- mapping protocol -----------------------------------------------------------------------------------------------
 	def __len__(self):
 		return len(self.container)
+
+	def __iter__(self):
+		yield from self.container
+
+	def __contains__(self, phase):
+		return phase in self.container
+
+	def __getitem__(self, phase):
+		return self.container[phase]
+
+	def __setitem__(self, phase, curve):
+		self.container[phase] = curve
 
 	def items(self):
 		return self.container.items()
 
+	# -- growing the curves ---------------------------------------------------------------------------------------------
+	def append(self, phase, value):
+		self.container[phase].append(value)
+
 	def concat(self, other):
-		for key, values in other.items():
-			if isinstance(values, list):
-				self.container[key].extend(values)
-			else:
-				self.container[key].append(values)
+		"""Adds one epoch (``{"train": 0.3, "val": 0.4}``) or a whole history (lists) phase by phase."""
+		for phase, values in other.items():
+			curve = self.container[phase]
+			curve.extend(values) if isinstance(values, list) else curve.append(values)
 
-	def append(self, key, value):
-		self.container[key].append(value)
-
+	# -- queries --------------------------------------------------------------------------------------------------------
 	def min(self, key="val"):
-		return min(self[key]) if key in self and len(self[key]) else np.inf
+		curve = self.container[key] if key in self.container else ()
+		return min(curve) if len(curve) else np.inf
 
 	def min_item(self, key="val"):
-		if key in self:
-			i = int(np.argmin(self[key]))
-			return {k: v[i] for k, v in self.items()}
+		"""Values of every phase at the epoch where ``key`` is smallest (None if ``key`` was never recorded)."""
+		if key not in self.container:
+			return None
+		best = int(np.argmin(self.container[key]))
+		return {phase: curve[best] for phase, curve in self.container.items()}
 
 	def plot(self, save_path=None, show=False):
+		"""Loss curves as a figure; returns False (and does nothing) when matplotlib is not installed."""
 		try:
 			import matplotlib
 			matplotlib.use("Agg")
-			import matplotlib.pyplot as plt
+			from matplotlib import pyplot
 		except ImportError:
 			return False
-		fig, ax = plt.subplots(figsize=(12, 10))
-		for name, values in self.items():
-			ax.plot(values, label=name, linewidth=3)
-		ax.set_xlabel("Epoch [-]", fontsize=16)
-		ax.set_ylabel("Loss [-]", fontsize=16)
-		ax.legend(fontsize=16)
+		figure, axes = pyplot.subplots(figsize=(12, 10))
+		for phase, curve in self.container.items():
+			axes.plot(curve, linewidth=3, label=phase)
+		axes.set(xlabel="Epoch [-]", ylabel="Loss [-]")
+		axes.xaxis.label.set_size(16)
+		axes.yaxis.label.set_size(16)
+		axes.legend(fontsize=16)
 		if save_path is not None:
-			plt.savefig(save_path, dpi=300)
+			figure.savefig(save_path, dpi=300)
 		if show:
-			plt.show()
-		plt.close(fig)
+			pyplot.show()
+		pyplot.close(figure)
 		return True
