@@ -328,7 +328,7 @@ class SNN(torch.nn.Module):
 			have_meta = os.path.exists(meta)
 			assert have_meta or force_overwrite, (
 				f"{meta} already exists. Set force_overwrite flag to True to overwrite existing saves.")
-			if have_meta and force_overwrite:
+			if have_meta and force_overwrite and self._is_writer():
 				shutil.rmtree(self.checkpoint_folder)
 			return 0
 		try:
@@ -524,6 +524,12 @@ class SNN(torch.nn.Module):
 		f = str(self.checkpoint_folder)
 		return f if os.path.isabs(f) else f"./{f}"
 
+	@staticmethod
+	def _is_writer() -> bool:
+		"""In a data-parallel run (one process per GPU, identical replicas) only rank 0 touches the checkpoint folder."""
+		import torch.distributed as dist
+		return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
 	def _read_index(self) -> dict:
 		with open(self.checkpoints_meta_path, "r") as fh:
 			return json.load(fh)
@@ -539,6 +545,8 @@ class SNN(torch.nn.Module):
 
 	def plot_loss_history(self, loss_history: LossHistory = None, show=False):
 		history = self.loss_history if loss_history is None else loss_history
+		if not self._is_writer():
+			return
 		os.makedirs(self._folder(), exist_ok=True)
 		history.plot(os.path.join(self._folder(), "loss_history.png"), show)
 
@@ -558,6 +566,8 @@ class SNN(torch.nn.Module):
 			json.dump(index, fh, indent=4)
 
 	def save_checkpoint(self, optimizer, epoch: int, epoch_losses: Dict[str, Any], best: bool = False):
+		if not self._is_writer():
+			return
 		os.makedirs(self.checkpoint_folder, exist_ok=True)
 		payload = {
 			SNN.CHECKPOINT_EPOCH_KEY: epoch,
