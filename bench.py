@@ -106,16 +106,24 @@ def cpu_reference_run(steps, warmup, budget_s=150.0):
 	return {"value": b * steps / dt, "ms_per_step": 1e3 * dt / steps, "cores": cores, "batch": b, "steps": steps}
 
 
+def base_config(world):
+	"""The keys both arms print (the driver compares them): what the workload IS, nothing about how an arm runs it."""
+	return {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
+		"l2": f"{N_POOL} rotating input batches ({N_POOL * B_PER_GPU * T * N * 4 >> 20} MiB) > 126 MB L2",
+		"optimizer": "Adam(lr=1e-3, weight_decay=1e-5)"}
+
+
 def reference_arm(args, rank):
 	if rank != 0:
 		return
+	world = int(os.environ.get("WORLD_SIZE", "1"))
 	r = cpu_reference_run(args.steps, max(args.warmup, 1))
 	sample = f"{r['steps']} train steps of batch {r['batch']} (of {B_PER_GPU}), T={T}, rasters resident in host memory"
 	print(json.dumps({
 		"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
 		"steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
 		"scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-		"config": {"workload": WORKLOAD, "batch_per_step": r["batch"]},
+		"config": base_config(world), "details": {"batch_per_step": r["batch"]},
 		"cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": sample},
 		"e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 	}))
@@ -296,9 +304,8 @@ def main():
 		"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
 		"warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
 		"vs_baseline": None, "dtype": "f32", "data": "synthetic",
-		"config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
-			"l2": f"{N_POOL} rotating input batches ({N_POOL * B_PER_GPU * T * N * 4 >> 20} MiB) > 126 MB L2",
-			"optimizer": "Adam(lr=1e-3, weight_decay=1e-5) as snnk_adam_step", "launch": "one CUDA graph per step",
+		"config": base_config(world),
+		"details": {"optimizer_kernel": "snnk_adam_step (one launch for all tensors)", "launch": "one CUDA graph per step",
 			"frame_dedup": dedup,
 			"grad_exchange": ("none (1 rank)" if world == 1 else
 				"fused into snnk_adam_step_dp over NVLink peer memory" if dp_fused else "NCCL all-reduce (mean)"),
@@ -317,11 +324,217 @@ def main():
 	finish(world)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at the bench geometry (B = 256), ncu --set full
-NCU_TRAFFIC = {
-	"K3": (27.12e6, "profiles/r01_ncu_full_raw_final.csv"),
-	"K2": (27.99e6, "profiles/r01_ncu_full_raw_final.csv"),
-}
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations (the headline above is configs[1]); one sub-object each under "configs".
+TRAIN_CONFIGS = [
+	dict(key="c1", name="LIF 784-128-10 non-recurrent, FastSigmoid, batch 256, MNIST-shaped periodic to_spikes",
+		H=128, layer="LIF", rec=False, ink=0.19, B=256, multi_gpu=False),
+	dict(key="c3", name="ALIF 784-64-10 non-recurrent, learn_beta, Fashion-MNIST-shaped (ink 0.5) periodic to_spikes, batch 256",
+		H=64, layer="ALIF", rec=False, ink=0.50, B=256, multi_gpu=False),
+	dict(key="c4", name="ALIF recurrent H=1024, learn_beta, batch 512 per GPU (4096 over 8 GPUs), data parallel",
+		H=1024, layer="ALIF", rec=True, ink=0.19, B=512, multi_gpu=True),
+]
+
+
+def load_peaks():
+	try:
+		pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+		return float(pk["hbm_gbs"]), float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0))), "measured"
+	except Exception:
+		return 6650.0, 1400.0, "fallback"
+
+
+def per_sample_work(Hh, rec, alif, train, traces=True, Tt=T):
+	"""Algorithmic FLOPs and HBM bytes per sample (SURVEY.md 8d): fwd 2T(NH + [rec]H^2 + HO), bwd 2T(NH + 2[rec]H^2 + 2HO);
+	bytes fwd = X + traces (s = 2 LIF, 3 ALIF) + y, the backward reads the same again."""
+	r = 1 if rec else 0
+	flops = 2 * Tt * (N * Hh + r * Hh * Hh + Hh * O)
+	byts = Tt * N * 4 + ((3 if alif else 2) * Tt * Hh * 4 if traces else 0) + Tt * O * 4
+	if train:
+		flops += 2 * Tt * (N * Hh + 2 * r * Hh * Hh + 2 * Hh * O)
+		byts *= 2
+	return flops, byts
+
+
+def step_roofline(value_per_gpu, Hh, rec, alif, train, traces=True, Tt=T):
+	"""Whole-step roofline of one configuration on one GPU: which of HBM or the (3 x BF16 split) tensor pipe bounds
+	the algorithmic work, and the fraction of that ceiling the measured throughput reaches."""
+	hbm, tf, src = load_peaks()
+	flops, byts = per_sample_work(Hh, rec, alif, train, traces, Tt)
+	ceil_hbm = hbm * 1e9 / byts
+	ceil_tc3 = tf * 1e12 / 3.0 / flops         # fp32-grade products on bf16 tensor cores cost three passes
+	if ceil_tc3 < ceil_hbm:
+		ach = value_per_gpu * flops * 3.0 / 1e12
+		return {"scope": "whole step", "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
+			"traffic": None, "peak_source": src, "note": "3xBF16-split FLOPs (fp32-grade products) against the sustained bf16 peak",
+			"ceiling_samples_per_s": ceil_tc3, "hbm_ceiling_samples_per_s": ceil_hbm}
+	ach = value_per_gpu * byts / 1e9
+	return {"scope": "whole step", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+		"traffic": None, "peak_source": src, "ceiling_samples_per_s": ceil_hbm, "tensor3x_ceiling_samples_per_s": ceil_tc3}
+
+
+def kernel_table(step_fn, iters=3):
+	from snnimageclassification_b200 import _cabi
+	for i in range(2):
+		step_fn(i)
+	torch.cuda.synchronize()
+	with _cabi.kernel_profile() as prof:
+		for i in range(iters):
+			step_fn(i)
+	return {name: round(ms / iters, 4) for name, (ms, n) in prof.result.items()}
+
+
+def run_train_config(spec, dev, world, rank, steps, warmup, timed, dp):
+	"""value / ms_per_step / roofline of one training configuration, measured exactly like the headline: rasters (with
+	their run tables) resident in HBM, rotating batches, one CUDA graph per step, CUDA events, max over ranks."""
+	from snnimageclassification_b200 import SNN, FusedAdam, LayerType, SpikeFuncType, ToSpikes
+	alif = spec["layer"] == "ALIF"
+	torch.manual_seed(0)
+	enc = ToSpikes(T, use_periods=True)
+	net = SNN(N, O, spec["H"], use_recurrent_connection=spec["rec"], int_time_steps=T, spike_func=SpikeFuncType.FastSigmoid,
+		hidden_layer_type=LayerType.ALIF if alif else LayerType.LIF, device=dev, **({"learn_beta": True} if alif else {}))
+	opt = FusedAdam(net.parameters(), lr=1e-3, weight_decay=1e-5)
+	if dp and world > 1:
+		opt.enable_data_parallel()
+	crit = torch.nn.NLLLoss()
+	net.train()
+	B = spec["B"]
+	pool = max(2, -(-(140 << 20) // (B * T * N * 4)))       # rotating batches > 126 MB of L2
+	xs, ys = [], []
+	g = torch.Generator().manual_seed(4242 + rank)
+	for i in range(pool):
+		img = (torch.randint(1, 256, (B, N), generator=g).float() / 255.0) * (torch.rand(B, N, generator=g) < spec["ink"])
+		xs.append(enc.encode_batch(img.to(dev)))
+		ys.append(torch.randint(0, O, (B,), generator=g).to(dev))
+	graphs = [net.graphed_train_step(xs[i], ys[i], crit, opt, static_inputs=True) for i in range(pool)]
+	def step(i):
+		return graphs[i % pool]()
+	for i in range(warmup):
+		step(i)
+	ms = timed(step, steps)
+	value = world * B * steps / (ms * 1e-3)
+	def eager(i):
+		loss = net.batch_loss(xs[i % pool], ys[i % pool], crit)
+		opt.zero_grad()
+		loss.backward()
+	kern = kernel_table(eager) if world == 1 else None
+	out = {"workload": spec["name"], "value": value, "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps,
+		"global_batch": world * B, "n_gpus": world, "roofline": step_roofline(value / world, spec["H"], spec["rec"], alif, True),
+		"kernel_ms_per_step_eager": kern}
+	del graphs, xs, ys, net, opt
+	torch.cuda.empty_cache()
+	return out
+
+
+def run_inference_sweep(dev, quick=False):
+	"""BASELINE configs[4]: inference only (no traces), batch 8192, H in {128, 512, 2048}, LIF / ALIF recurrent,
+	T in {2, 10, 32, 100} on encoder output, plus the spike-sparsity sweep on Bernoulli(p) rasters (H = 128, T = 100)."""
+	from snnimageclassification_b200 import SNN, LayerType, SpikeFuncType, ToSpikes
+	from snnimageclassification_b200.modules.functional import mark_binary
+	B = 8192
+	g = torch.Generator().manual_seed(99)
+	img = (torch.randint(1, 256, (B, N), generator=g).float() / 255.0) * (torch.rand(B, N, generator=g) < 0.19)
+	img = img.to(dev)
+	rows = []
+
+	def measure(net, x, iters):
+		net.eval()
+		with torch.no_grad():
+			for _ in range(2):
+				net.get_prediction_logits(x, re_outputs_trace=False, re_hidden_states=False)
+			e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+			torch.cuda.synchronize()
+			e0.record()
+			for _ in range(iters):
+				net.get_prediction_logits(x, re_outputs_trace=False, re_hidden_states=False)
+			e1.record()
+			torch.cuda.synchronize()
+		return e0.elapsed_time(e1) / iters
+
+	cases = [(Hh, layer, Tt) for Hh in (128, 512, 2048) for layer in ("LIF", "ALIF") for Tt in (2, 10, 32, 100)]
+	if quick:
+		cases = [c for c in cases if c[2] in (10, 100) and c[1] == "ALIF"]
+	for Hh, layer, Tt in cases:
+		alif = layer == "ALIF"
+		torch.manual_seed(0)
+		net = SNN(N, O, Hh, use_recurrent_connection=True, int_time_steps=Tt, spike_func=SpikeFuncType.FastSigmoid,
+			hidden_layer_type=LayerType.ALIF if alif else LayerType.LIF, device=dev, **({"learn_beta": True} if alif else {}))
+		x = ToSpikes(Tt, use_periods=True).encode_batch(img, frame_runs=False)      # (B,T,N) fp32 resident, > L2 from T = 10 on
+		ms = measure(net, x, 3 if Hh >= 512 and Tt >= 32 else 10)
+		v = B / (ms * 1e-3)
+		rows.append({"H": Hh, "layer": layer, "T": Tt, "input": "periodic to_spikes, ink 0.19", "ms": round(ms, 4), "value": v,
+			"roofline": step_roofline(v, Hh, True, alif, False, traces=False, Tt=Tt)})
+		del net, x
+		torch.cuda.empty_cache()
+	for p in (0.004, 0.01, 0.1, 0.4):
+		torch.manual_seed(0)
+		net = SNN(N, O, 128, use_recurrent_connection=True, int_time_steps=T, spike_func=SpikeFuncType.FastSigmoid,
+			hidden_layer_type=LayerType.ALIF, device=dev, learn_beta=True)
+		x = mark_binary((torch.rand(B, T, N, device=dev) < p).float())
+		ms = measure(net, x, 10)
+		v = B / (ms * 1e-3)
+		rows.append({"H": 128, "layer": "ALIF", "T": T, "input": f"Bernoulli({p})", "ms": round(ms, 4), "value": v,
+			"roofline": step_roofline(v, 128, True, True, False, traces=False)})
+		del net, x
+		torch.cuda.empty_cache()
+	best = max(rows, key=lambda r: r["value"])
+	return {"workload": "inference only (no traces), recurrent LIF/ALIF, batch 8192, 1 GPU; eager launches, rasters resident in HBM",
+		"unit": "samples/s", "value": next(r["value"] for r in rows if (r["H"], r["layer"], r["T"], r["input"][:3]) == (128, "ALIF", 100, "per")),
+		"value_of": "ALIF H=128, T=100", "sweep": rows, "best": {k: best[k] for k in ("H", "layer", "T", "input", "value")}}
+
+
+# ---- ncu evidence parsed from the committed summaries (never hand-copied numbers) --------------------------------------
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "": 1.0}
+
+
+def ncu_summary_rows(path):
+	"""Rows of an `ncu --page raw --csv` export (first row metric names, second row units) as dicts; values converted
+	to base units with the unit row (a Kbyte column read as bytes was a 1000x error in round 1)."""
+	import csv
+	try:
+		with open(path, newline="") as fh:
+			rows = list(csv.reader(fh))
+	except OSError:
+		return []
+	if len(rows) < 3:
+		return []
+	names, units = rows[0], rows[1]
+	out = []
+	for r in rows[2:]:
+		d = {}
+		for n, u, v in zip(names, units, r):
+			if n in ("Kernel Name", "Function Name"):
+				d["kernel"] = v
+				continue
+			try:
+				d[n] = float(v.replace(",", "")) * _UNIT.get(u, 1.0)
+			except ValueError:
+				d[n] = v
+		out.append(d)
+	return out
+
+
+NCU_SUMMARIES = ["profiles/r02_ncu_full_summary.csv", "profiles/r01_ncu_full_summary_final.csv"]
+KERNEL_REGEX = {"K1": "k_proj_tc", "K2": "k_recur_fwd", "K3": "k_recur_bwd", "K4": "k_wgrad_tc", "K5": "k_encode", "K6": "k_head_nll"}
+
+
+def ncu_evidence(kernel_key):
+	"""(dram traffic bytes per launch, shared-memory wavefronts per launch, source file) of the LONGEST launch of the
+	kernel family in the newest committed ncu summary that has it."""
+	pat = KERNEL_REGEX.get(kernel_key)
+	if not pat:
+		return None
+	for rel in NCU_SUMMARIES:
+		rows = [r for r in ncu_summary_rows(os.path.join(ROOT, rel)) if pat in str(r.get("kernel", ""))]
+		if rows:
+			r = max(rows, key=lambda q: q.get("gpu__time_duration.sum", 0.0))
+			return {"traffic": r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0),
+				"smem_wavefronts": r.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), "kernel": r["kernel"],
+				"ncu_duration_us": r.get("gpu__time_duration.sum", 0.0) * (1.0 if r.get("gpu__time_duration.sum", 0) > 1e3 else 1.0),
+				"source": rel}
+	return None
+
 
 
 def large_batch_rooflines(net, enc, dev, B=4096, iters=5):

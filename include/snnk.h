@@ -209,6 +209,9 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
  * Fused head: log_softmax over the max-over-time logits (snn.py:258) + NLLLoss mean (snn.py:297)
  * and the gradient of that loss w.r.t. the logits.
  *   logits (B,O), labels (B) int64 -> logp (B,O), loss (1), g_logits (B,O) = (softmax - onehot)/B
+ *   labels follow torch.nn.NLLLoss defaults: rows labelled -100 (ignore_index) are excluded from the mean (B becomes
+ *   the number of valid rows) and get a zero gradient; any other label outside [0, O) makes the loss and that row's
+ *   gradient NaN (torch raises a device-side assert there)
  *   loss_mailbox / mailbox_counter: both NULL, or: loss_mailbox is one 8-byte word of PINNED HOST memory (device-
  *   accessible under unified addressing) and mailbox_counter a zero-initialised device word.  Every launch then also
  *   stores ((++counter) << 32 | bits of loss) into the mailbox with a single store, so that the host can read the

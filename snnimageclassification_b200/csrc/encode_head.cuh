@@ -206,6 +206,28 @@ __global__ void __launch_bounds__(256) k_head_nll(int B, int O, const float* __r
                                                  unsigned long long* mailbox, unsigned int* counter)
 {
     __shared__ double s_part[256];
+    __shared__ int s_cnt[9];
+    // torch.nn.NLLLoss semantics for the labels (snn.py:297 uses the defaults): rows labelled ignore_index (-100) are
+    // left out of the mean and get a zero gradient; any other label outside [0, O) is an error -- torch raises, here
+    // the loss and that row's gradient become NaN so the mistake cannot pass silently
+    constexpr long long kIgnore = -100;
+    int nv = 0, nbad = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const long long l = labels[b];
+        nv += (l >= 0 && l < O);
+        nbad += (l != kIgnore && (l < 0 || l >= O));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = nv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += s_cnt[q];
+        s_cnt[8] = t;
+    }
+    const bool bad = __syncthreads_or(nbad != 0) != 0;
+    const int n_valid = s_cnt[8];      // == B for well-formed labels
     double acc = 0.0;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         float lg[kOMax];
@@ -214,12 +236,17 @@ __global__ void __launch_bounds__(256) k_head_nll(int B, int O, const float* __r
         float se = 0.f;
         for (int c = 0; c < O; ++c) se += expf(lg[c] - mx);
         const float lse = logf(se);
-        const int lab = (int)labels[b];
+        const long long lab = labels[b];
+        const bool row_ok = lab >= 0 && lab < O, row_bad = !row_ok && lab != kIgnore;
         for (int c = 0; c < O; ++c) {
             const float lp = (lg[c] - mx) - lse;
             if (logp) logp[(size_t)b * O + c] = lp;
             if (c == lab) acc += -(double)lp;
-            if (g_logits) g_logits[(size_t)b * O + c] = __fdiv_rn(expf(lp) - (c == lab ? 1.0f : 0.0f), (float)B);
+            if (g_logits) {
+                float g = row_ok ? __fdiv_rn(expf(lp) - (c == lab ? 1.0f : 0.0f), (float)n_valid) : 0.0f;
+                if (row_bad) g = __int_as_float(0x7fc00000);
+                g_logits[(size_t)b * O + c] = g;
+            }
         }
     }
     // fixed-shape reduction tree (shuffles inside a warp, then the warp sums in order): deterministic, and not a serial
@@ -231,7 +258,7 @@ __global__ void __launch_bounds__(256) k_head_nll(int B, int O, const float* __r
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += s_part[q];
-        const float lossf = (float)(s / (double)B);
+        const float lossf = bad ? __int_as_float(0x7fc00000) : (float)(s / (double)n_valid);
         *loss = lossf;
         if (mailbox) {
             // {launch number, loss} as ONE 8-byte store into pinned host memory: the host reads the step's loss by

@@ -376,7 +376,7 @@ bool use_mma_recur(const SnnkDesc* d)
     // MMA kernel wins once there are enough tiles to fill the chip (B=4096: 0.38 ms vs 1.07 ms) and loses to the
     // 128-threads-per-row SIMT kernel, which spreads a small batch over all SMs (B=256: 180 us vs 64 us).
     if (d->layer_type == SNNK_IZHIKEVICH) return false;   // the MMA recurrence implements the LIF / ALIF update only
-    static const char* env = getenv("SNNK_MMA_RECUR");
+    const char* env = getenv("SNNK_MMA_RECUR");   // read per call: tools/sanitize_run.py toggles it inside one process
     if (env) return env[0] != '0' && d->H == kMmaH;
     return (d->flags & SNNK_F_TENSOR_CORE) != 0 && d->H == kMmaH && d->B >= 768;
 }

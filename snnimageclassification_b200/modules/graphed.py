@@ -68,7 +68,19 @@ class GraphedTrainStep:
 		self._mail_counter = torch.zeros(1, dtype=torch.int32, device=dev)
 		self._expected = 0
 		self._posts = False
+		self._warmup = warmup
+		self._capture()
 
+	def _hyper_signature(self):
+		sig = getattr(self.optimizer, "hyper_signature", None)
+		return sig() if (callable(sig) and self.step_in_graph) else None
+
+	def _capture(self):
+		"""Warm-up + capture.  Runs at construction and again whenever the optimizer's by-value hyper-parameters (lr,
+		betas, eps, weight decay -- kernel scalar arguments frozen into the graph) or its state tensors have changed."""
+		net, optimizer, warmup = self.net, self.optimizer, self._warmup
+		dev = net.device
+		self._sig = self._hyper_signature()
 		# Snapshot what the warm-up iterations would change: capture must not advance the training state.
 		params = [p for p in net.parameters()]
 		saved_params = [p.detach().clone() for p in params]
@@ -135,6 +147,9 @@ class GraphedTrainStep:
 				self.x.copy_(self._xs[k], non_blocking=True)
 				self.y.copy_(self._ys[k], non_blocking=True)
 				self._consumed[k].record(main)
+		if self.step_in_graph and self._sig is not None and self._hyper_signature() != self._sig:
+			torch.cuda.current_stream(self.x.device).synchronize()
+			self._capture()       # e.g. an LR scheduler stepped: the captured launch still carries the old scalars
 		self.graph.replay()
 		self._expected = (self._expected + 1) & 0xFFFFFFFF
 		if not self.step_in_graph:

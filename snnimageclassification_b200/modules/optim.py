@@ -26,6 +26,48 @@ class FusedAdam(torch.optim.Adam):
 		self.reduces_gradients = False
 		self._dp_group = None
 		self._dp_ctx = {}
+		self._state_version = 0      # bumped whenever the state tensors are replaced (captured graphs hold their pointers)
+		self._lr_cache = {}          # python value of a tensor lr, read outside graph capture by hyper_signature()
+
+	def load_state_dict(self, state_dict):
+		"""Accepts the state of a plain ``torch.optim.Adam`` / a reference checkpoint (snn.py:443-448) as well as its
+		own.  torch's loader copies the SAVED group options over this optimizer's (``capturable=False``,
+		``foreach=None``, ...) and leaves ``state['step']`` wherever ``torch.load`` put it (a CPU tensor under
+		``map_location='cpu'``, an int in very old files); ``step()`` hands the counters' device pointers to the
+		kernel, so they are normalised here: capturable groups, float32 0-d counters and moments on the parameter's
+		device."""
+		super().load_state_dict(state_dict)
+		self._state_version += 1
+		for group in self.param_groups:
+			group["capturable"], group["foreach"], group["fused"] = True, False, None
+			group.setdefault("maximize", False)
+			group.setdefault("amsgrad", False)
+			if group.get("maximize") or group.get("amsgrad"):
+				raise RuntimeError("FusedAdam implements torch.optim.Adam without amsgrad / maximize only")
+			for p in group["params"]:
+				st = self.state.get(p)
+				if not st:
+					continue
+				step = st.get("step", 0.0)
+				step = step.detach().to(device=p.device, dtype=torch.float32) if torch.is_tensor(step) else torch.tensor(
+					float(step), dtype=torch.float32, device=p.device)
+				st["step"] = step.reshape(()).clone()
+				for k in ("exp_avg", "exp_avg_sq"):
+					if k in st:
+						st[k] = st[k].detach().to(device=p.device, dtype=torch.float32).contiguous()
+
+	def hyper_signature(self):
+		"""The scalar hyper-parameters ``step()`` passes to the kernel BY VALUE.  A captured CUDA graph freezes them, so
+		``GraphedTrainStep`` compares this signature before every replay and re-captures when a scheduler (or the
+		user) has changed ``param_groups`` in between."""
+		sig = [self._state_version]
+		for gi, g in enumerate(self.param_groups):
+			lr = g["lr"]
+			if torch.is_tensor(lr):      # a host read: legal here (never called while capturing), not inside step()
+				self._lr_cache[gi] = float(lr.item())
+				lr = self._lr_cache[gi]
+			sig.append((float(lr), tuple(float(b) for b in g["betas"]), float(g["eps"]), float(g["weight_decay"])))
+		return tuple(sig)
 
 	def enable_data_parallel(self, group=None) -> bool:
 		"""Fuse the cross-rank gradient mean into ``step()``.  Returns False (and leaves the optimizer as it was:
@@ -113,7 +155,15 @@ class FusedAdam(torch.optim.Adam):
 					p.grad = p.grad.contiguous()
 				g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
 				ps.append(p); gs.append(g); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"]); ss.append(st["step"])
-			lr = float(group["lr"]) if not torch.is_tensor(group["lr"]) else float(group["lr"].item())
+			lr = group["lr"]
+			if torch.is_tensor(lr):
+				if torch.cuda.is_current_stream_capturing():
+					if gi not in self._lr_cache:
+						raise RuntimeError("FusedAdam: a tensor lr must be read before graph capture (call hyper_signature())")
+					lr = self._lr_cache[gi]
+				else:
+					lr = self._lr_cache[gi] = float(lr.item())
+			lr = float(lr)
 			b1, b2 = group["betas"]
 			for k0 in range(0, len(ps), 16):
 				chunk = slice(k0, k0 + 16)

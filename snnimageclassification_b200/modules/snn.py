@@ -330,6 +330,7 @@ class SNN(torch.nn.Module):
 				f"{meta} already exists. Set force_overwrite flag to True to overwrite existing saves.")
 			if have_meta and force_overwrite and self._is_writer():
 				shutil.rmtree(self.checkpoint_folder)
+			self._dp_barrier()      # nobody runs ahead (and writes) while rank 0 is still removing the old folder
 			return 0
 		try:
 			ck = self.load_checkpoint(load_checkpoint_mode)       # also loads the weights
@@ -381,6 +382,10 @@ class SNN(torch.nn.Module):
 			unit="epoch", leave=p_bar_leave)
 		for epoch in p_bar:
 			epoch_loss = self._exec_phase(train_dataloader, val_dataloader, criterion, optimizer)
+			# data parallel: every rank sees the same (mean) epoch losses, so is_best, the checkpoint index and the
+			# early-stopping break are decided identically everywhere (a rank leaving the loop alone would leave the
+			# others waiting in the gradient exchange)
+			epoch_loss, self.last_eval_accuracy = self._dp_mean_epoch_stats(epoch_loss, self.last_eval_accuracy)
 			epoch_val_acc = self.last_eval_accuracy     # counted in the validation pass that produced the loss
 			self.loss_history.concat(epoch_loss)
 			is_best = epoch_loss["val"] < best_loss
@@ -399,6 +404,30 @@ class SNN(torch.nn.Module):
 			p_bar.close()
 		self.plot_loss_history(show=False)
 		return self.loss_history
+
+	@staticmethod
+	def _dp_world() -> int:
+		import torch.distributed as dist
+		return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+	def _dp_barrier(self):
+		if self._dp_world() > 1:
+			import torch.distributed as dist
+			dist.barrier()
+
+	def _dp_mean_epoch_stats(self, epoch_loss: Dict[str, float], acc: float):
+		"""Mean over the ranks of the epoch's train / validation loss and validation accuracy (the loss
+		for logging is the all-reduce mean).  One tiny collective per epoch; identity on a single rank."""
+		world = self._dp_world()
+		if world == 1:
+			return epoch_loss, acc
+		import torch.distributed as dist
+		keys = sorted(epoch_loss)
+		dev = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
+		t = torch.tensor([float(epoch_loss[k]) for k in keys] + [float(acc)], dtype=torch.float64, device=dev)
+		dist.all_reduce(t, op=dist.ReduceOp.SUM)
+		t = (t / world).tolist()
+		return {k: v for k, v in zip(keys, t[:-1])}, t[-1]
 
 	def _exec_phase(self, train_dataloader, val_dataloader, criterion, optimizer):
 		self.train()
@@ -537,10 +566,28 @@ class SNN(torch.nn.Module):
 	def _load_file(self, path: str) -> dict:
 		"""Checkpoints written here hold tensors and plain Python numbers only, so they load under torch's safe
 		``weights_only`` unpickler; files written by the reference (numpy scalars in the loss entry, snn.py:443-448,
-		which torch >= 2.6 refuses by default, :481) fall back to the full unpickler -- they are the user's own files."""
+		which torch >= 2.6 refuses by default, :481) are retried with exactly those numpy types allow-listed; anything that
+		still needs the unrestricted unpickler is refused unless SNNK_TRUST_CHECKPOINTS=1 (it can run arbitrary code)."""
+		import pickle
+		import warnings
 		try:
 			return torch.load(path, map_location=self.device, weights_only=True)
-		except Exception:
+		except pickle.UnpicklingError:
+			pass       # only the safe unpickler's refusal is retried; I/O errors and corrupt files propagate
+		# reference-written files: the loss entry holds numpy scalars (snn.py:443-448) -- allow exactly those types
+		allowed = [np.dtype, np.ndarray, np.float64, np.float32, np.int64, type(np.dtype(np.float64)),
+			type(np.dtype(np.float32)), type(np.dtype(np.int64))]
+		core = getattr(np, "_core", None) or getattr(np, "core")
+		allowed += [core.multiarray.scalar, core.multiarray._reconstruct]
+		try:
+			with torch.serialization.safe_globals(allowed):
+				return torch.load(path, map_location=self.device, weights_only=True)
+		except pickle.UnpicklingError as e:
+			if os.environ.get("SNNK_TRUST_CHECKPOINTS", "0") != "1":
+				raise RuntimeError(
+					f"{path} needs the unrestricted unpickler ({e}); it can execute arbitrary code. Set "
+					"SNNK_TRUST_CHECKPOINTS=1 to load files you trust.") from e
+			warnings.warn(f"loading {path} with the unrestricted unpickler (SNNK_TRUST_CHECKPOINTS=1)")
 			return torch.load(path, map_location=self.device, weights_only=False)
 
 	def plot_loss_history(self, loss_history: LossHistory = None, show=False):

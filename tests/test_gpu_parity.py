@@ -542,3 +542,84 @@ def test_fused_adam_matches_torch_adam():
 	assert float(sd["state"][0]["step"]) == 6.0 and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
 	other = torch.optim.Adam([p.detach().clone().requires_grad_() for p in my_p], lr=1e-3, weight_decay=1e-5)
 	other.load_state_dict(sd)                 # checkpoints interchange with the reference's optimizer
+
+
+def test_fused_adam_loads_plain_adam_state_then_steps():
+	"""The other direction of the interchange: a torch.optim.Adam / reference-checkpoint state -- non-capturable
+	groups, `step` on the CPU under map_location='cpu' -- loaded into FusedAdam, followed by step()."""
+	from snnimageclassification_b200 import FusedAdam
+	g = torch.Generator().manual_seed(1)
+	shapes = [(40, 32), (32, 32), (32, 10), (10,)]
+	ref_p = [torch.randn(s, generator=g).to(DEV).requires_grad_() for s in shapes]
+	ref = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=1e-5)
+	grads = [[torch.randn(s, generator=g).to(DEV) for s in shapes] for _ in range(5)]
+	for it in range(3):
+		for p, gr in zip(ref_p, grads[it]):
+			p.grad = gr.clone()
+		ref.step()
+	import io
+	buf = io.BytesIO()
+	torch.save(ref.state_dict(), buf)
+	buf.seek(0)
+	sd = torch.load(buf, map_location="cpu")            # what a resume under map_location='cpu' hands over
+	assert sd["state"][0]["step"].device.type == "cpu" and not sd["param_groups"][0]["capturable"]
+	my_p = [p.detach().clone().requires_grad_() for p in ref_p]
+	mine = FusedAdam(my_p, lr=1e-3, weight_decay=1e-5)
+	mine.load_state_dict(sd)
+	assert all(gr["capturable"] and gr["foreach"] is False for gr in mine.param_groups)
+	for p in my_p:
+		st = mine.state[p]
+		assert st["step"].device == p.device and st["step"].dtype == torch.float32 and st["step"].ndim == 0
+		assert st["exp_avg"].device == p.device
+	for it in range(3, 5):
+		for a, b, gr in zip(ref_p, my_p, grads[it]):
+			a.grad, b.grad = gr.clone(), gr.clone()
+		ref.step(); mine.step()
+	for a, b in zip(ref_p, my_p):
+		assert rel_err(npy(b), npy(a)) <= 1e-6
+	assert float(mine.state[my_p[0]]["step"]) == 5.0
+
+
+def test_graphed_step_follows_lr_changes():
+	"""lr / betas / eps / weight decay are kernel scalars frozen into a captured graph: the graphed step re-captures
+	when they change, so a scheduler behaves as in eager mode."""
+	from snnimageclassification_b200 import FusedAdam, LayerType, SNN, SpikeFuncType
+	def make():
+		torch.manual_seed(4)
+		net = SNN(64, 10, 32, use_recurrent_connection=True, int_time_steps=12, spike_func=SpikeFuncType.FastSigmoid,
+			hidden_layer_type=LayerType.ALIF, device=DEV, learn_beta=True)
+		net.train()
+		return net, FusedAdam(net.parameters(), lr=1e-2, weight_decay=1e-5)
+	g = torch.Generator().manual_seed(9)
+	xs = [(torch.rand(16, 12, 64, generator=g) < 0.2).float() for _ in range(6)]
+	ys = [torch.randint(0, 10, (16,), generator=g) for _ in range(6)]
+	crit = torch.nn.NLLLoss()
+	(eager, oe), (graphed, og) = make(), make()
+	eager.cuda_graphs = False
+	for it, (x, y) in enumerate(zip(xs, ys)):
+		if it == 3:
+			for o in (oe, og):
+				o.param_groups[0]["lr"] = 1e-4
+		eager._exec_batch(x, y, crit, oe)
+		graphed._exec_batch(x, y, crit, og)
+	for pe, pg in zip(eager.parameters(), graphed.parameters()):
+		assert rel_err(npy(pg), npy(pe)) <= 1e-5
+
+
+def test_head_label_semantics():
+	"""ignore_index rows are excluded from the mean and get no gradient; other out-of-range labels poison the loss."""
+	from snnimageclassification_b200.modules import functional as F_
+	g = torch.Generator().manual_seed(2)
+	logits = torch.randn(37, 10, generator=g).to(DEV)
+	labels = torch.randint(0, 10, (37,), generator=g)
+	labels[3] = labels[20] = -100
+	loss, logp, gl = F_.run_head_nll(logits, labels.to(DEV))
+	ref_lp = torch.log_softmax(logits.cpu(), -1).requires_grad_()
+	lg = logits.cpu().clone().requires_grad_()
+	ref = torch.nn.functional.nll_loss(torch.log_softmax(lg, -1), labels)
+	ref.backward()
+	assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
+	assert rel_err(npy(gl), lg.grad.numpy()) <= 1e-6 and float(gl[3].abs().sum()) == 0.0
+	labels[5] = 12
+	loss, _, gl = F_.run_head_nll(logits, labels.to(DEV))
+	assert torch.isnan(loss).item() and torch.isnan(gl[5]).all().item() and not torch.isnan(gl[4]).any().item()

@@ -172,3 +172,45 @@ def test_run_table_tag_is_validated():
 	mark_binary(x, runs=torch.zeros(need, dtype=torch.int32))
 	assert get_runs(x) is not None
 	assert get_runs(mark_binary(torch.zeros(2, 5, 8), runs=torch.zeros(need, dtype=torch.int64))) is None
+
+
+def test_fused_adam_load_state_dict_normalises_foreign_state():
+	"""Loading a plain torch.optim.Adam state: capturable groups, float32 0-d step tensors on the parameter's
+	device -- checked on CPU parameters (step() itself needs the GPU and is covered by the gpu tests)."""
+	from snnimageclassification_b200 import FusedAdam
+	ps = [torch.randn(4, 3, requires_grad=True), torch.randn(3, requires_grad=True)]
+	ref = torch.optim.Adam(ps, lr=2e-3, weight_decay=1e-5)
+	for p in ps:
+		p.grad = torch.randn_like(p)
+	ref.step(); ref.step()
+	mine = FusedAdam([p.detach().clone().requires_grad_() for p in ps], lr=1e-3)
+	v0 = mine.hyper_signature()
+	mine.load_state_dict(ref.state_dict())
+	assert mine.hyper_signature() != v0             # a captured graph would be re-captured
+	for g in mine.param_groups:
+		assert g["capturable"] is True and g["foreach"] is False and g["lr"] == 2e-3
+	for p in mine.param_groups[0]["params"]:
+		st = mine.state[p]
+		assert st["step"].dtype == torch.float32 and st["step"].ndim == 0 and float(st["step"]) == 2.0
+
+
+def test_reference_style_checkpoint_loads_without_full_unpickling(tmp_path):
+	"""A checkpoint as the reference writes it (numpy scalars in the loss entry, snn.py:443-448) loads through the
+	allow-listed safe unpickler; a file that needs arbitrary globals is refused unless explicitly trusted."""
+	net = SNN(6, 10, 32, hidden_layer_type=LayerType.LIF, device=CPU, int_time_steps=5,
+		checkpoint_folder=str(tmp_path / "ck"), model_name="m")
+	path = str(tmp_path / "ref.pth")
+	torch.save({"epoch": 3, "model_state_dict": net.state_dict(), "optimizer_state_dict": {},
+		"loss": {"train": np.float64(0.25), "val": np.float32(0.5)}}, path)
+	ck = net._load_file(path)
+	assert ck["epoch"] == 3 and float(ck["loss"]["train"]) == 0.25
+
+	class Evil:
+		def __reduce__(self):
+			return (os.getcwd, ())
+	bad = str(tmp_path / "bad.pth")
+	torch.save({"epoch": 0, "payload": Evil()}, bad)
+	with pytest.raises(RuntimeError, match="SNNK_TRUST_CHECKPOINTS"):
+		net._load_file(bad)
+	with pytest.raises(FileNotFoundError):
+		net._load_file(str(tmp_path / "missing.pth"))
