@@ -332,34 +332,52 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_bwd_gen(const BwdParam
 }
 
 // dW_out[i][c] = sum_{b,t} Z[b,t,i] gy[b,t,c];  db[c] = sum_{b,t} gy[b,t,c]   as per-CTA partials for k_finalize_grads.
-// grid = (nparts, H / 128), block = 128: thread = neuron; CTA column q handles rows r = q, q + nparts, ...
+// grid = (nparts, H / 128), block = 128: thread = neuron; CTA column q owns the CONTIGUOUS rows [q per, (q+1) per) of the
+// (B T) axis, stages their adjoint rows (64 B each) and spike words through shared memory with coalesced loads, then
+// accumulates from shared memory (a load-use chain per row from global memory made this kernel latency-bound: 59 us
+// at B T = 25 600; it runs beside the BPTT sweep and must not outlast it).
+constexpr int kWoutStage = 128;      // rows staged per pass
 __global__ void __launch_bounds__(128) k_wout_grad(int BT, int H, int O, const uint32_t* __restrict__ zbits,
                                                   const float* __restrict__ gy_scan, float* __restrict__ part_wout,
                                                   float* __restrict__ part_db)
 {
+    __shared__ __align__(16) float s_gy[kWoutStage * kOMax];
+    __shared__ uint32_t s_zw[kWoutStage * 4];
     const int tid = threadIdx.x, lane = tid & 31, W32 = H / 32;
     const int i = blockIdx.y * 128 + tid;
+    const int per = (BT + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * per, r1 = min(BT, r0 + per);
     float acc[kOMax], dbacc[kOMax];
 #pragma unroll
     for (int c = 0; c < kOMax; ++c) { acc[c] = 0.f; dbacc[c] = 0.f; }
-    for (int r = blockIdx.x; r < BT; r += gridDim.x) {
-        float gy[kOMax];
-        const float4* g4 = reinterpret_cast<const float4*>(gy_scan + (size_t)r * kOMax);
+    for (int base = r0; base < r1; base += kWoutStage) {
+        const int n = min(kWoutStage, r1 - base);
+        __syncthreads();
+        for (int idx = tid; idx < n * (kOMax / 4); idx += 128)
+            reinterpret_cast<float4*>(s_gy)[idx] = __ldg(reinterpret_cast<const float4*>(gy_scan + (size_t)base * kOMax) + idx);
+        for (int idx = tid; idx < n * 4; idx += 128)      // the four words of this CTA's 128 neurons
+            s_zw[idx] = __ldg(zbits + (size_t)(base + (idx >> 2)) * W32 + blockIdx.y * 4 + (idx & 3));
+        __syncthreads();
+        for (int r = 0; r < n; ++r) {
+            const float z = (float)((s_zw[r * 4 + (tid >> 5)] >> lane) & 1u);
+            const float4* g4 = reinterpret_cast<const float4*>(s_gy + r * kOMax);
 #pragma unroll
-        for (int q = 0; q < kOMax / 4; ++q) {
-            const float4 g = __ldg(g4 + q);
-            gy[4 * q] = g.x; gy[4 * q + 1] = g.y; gy[4 * q + 2] = g.z; gy[4 * q + 3] = g.w;
-        }
-        const float z = (float)((__ldg(zbits + (size_t)r * W32 + (i >> 5)) >> lane) & 1u);
-#pragma unroll
-        for (int c = 0; c < kOMax; ++c) {
-            acc[c] = fmaf(z, gy[c], acc[c]);
-            dbacc[c] += gy[c];
+            for (int q = 0; q < kOMax / 4; ++q) {
+                const float4 g = g4[q];
+                acc[4 * q] = fmaf(z, g.x, acc[4 * q]); acc[4 * q + 1] = fmaf(z, g.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(z, g.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(z, g.w, acc[4 * q + 3]);
+                dbacc[4 * q] += g.x; dbacc[4 * q + 1] += g.y; dbacc[4 * q + 2] += g.z; dbacc[4 * q + 3] += g.w;
+            }
         }
     }
-    for (int c = 0; c < O; ++c) part_wout[((size_t)blockIdx.x * H + i) * O + c] = acc[c];
-    if (blockIdx.y == 0 && tid == 0)
-        for (int c = 0; c < O; ++c) part_db[(size_t)blockIdx.x * O + c] = dbacc[c];
+#pragma unroll
+    for (int c = 0; c < kOMax; ++c)
+        if (c < O) part_wout[((size_t)blockIdx.x * H + i) * O + c] = acc[c];
+    if (blockIdx.y == 0 && tid == 0) {
+#pragma unroll
+        for (int c = 0; c < kOMax; ++c)
+            if (c < O) part_db[(size_t)blockIdx.x * O + c] = dbacc[c];
+    }
 }
 
 }  // namespace snnk

@@ -16,7 +16,7 @@
 #include "recur_bwd.cuh"
 #include "recur_fwd.cuh"
 #include "recur_gen.cuh"
-#include "recur_mma.cuh"
+#include "recur_tc.cuh"
 #include "runs.cuh"
 
 using namespace snnk;
@@ -65,7 +65,7 @@ struct ProfScope {
 // gets two parallel branches.  The call still returns with everything ordered behind the caller's stream.
 struct Fork {
     cudaStream_t side = nullptr;
-    cudaEvent_t forked = nullptr, joined = nullptr, mid = nullptr, forked2 = nullptr;
+    cudaEvent_t forked = nullptr, joined = nullptr, mid = nullptr, forked2 = nullptr, forked3 = nullptr, joined3 = nullptr;
     bool ok = false;
 };
 Fork* fork_for_device()
@@ -82,6 +82,8 @@ Fork* fork_for_device()
         if (cudaEventCreateWithFlags(&f.joined, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&f.mid, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&f.forked2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.forked3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.joined3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         f.ok = true;
     }
     return &f;
@@ -119,6 +121,7 @@ struct Plan {
     bool check;       // tensor-core path must verify on the device that x is tf32-exact (caller did not vouch)
     int kpad;         // K of the projection padded to the k-block
     bool wide;        // H > 128: generic recurrence kernels (recur_gen.cuh), N-tiled tensor-core GEMMs
+    bool tcrec;       // tensor-core recurrence kernels (recur_tc.cuh): gy scan + k_wout_grad beside the sweep
     int tileN;        // N extent of one tensor-core tile
     int ntiles_tc;
     int n_pwout, n_pdb;   // number of dW_out / db partial buffers
@@ -156,17 +159,20 @@ IzhConsts izh_consts(const SnnkDesc* d)
     return z;
 }
 
+bool use_tc_recur(const SnnkDesc* d);
+
 Plan make_plan(const SnnkDesc* d)
 {
     Plan p{};
     p.wide = d->H > 128;
+    p.tcrec = use_tc_recur(d) && bwd_tc_smem_bytes(d->T) <= 200 * 1024 && fwd_tc_smem_bytes(d->T) <= 200 * 1024;
     p.R = p.wide ? gen_rows(d->H) : (d->B > 1024 ? 2 : 1);
     p.grid_rows = (d->B + p.R - 1) / p.R;
     const int BT = d->B * d->T;
     p.tileN = p.wide ? 128 : d->H;
     p.ntiles_tc = d->H / p.tileN;
-    p.n_pwout = p.wide ? (BT < 256 ? BT : 256) : p.grid_rows;
-    p.n_pdb = p.wide ? p.n_pwout : p.grid_rows * p.R;
+    p.n_pwout = (p.wide || p.tcrec) ? (BT < 256 ? BT : 256) : p.grid_rows;
+    p.n_pdb = (p.wide || p.tcrec) ? p.n_pwout : p.grid_rows * p.R;
     p.BN = d->H >= 64 ? 64 : 32;
     p.ntiles = d->H / p.BN;
     p.mtiles_x = (d->N + kGemmBM - 1) / kGemmBM;
@@ -195,7 +201,7 @@ Plan make_plan(const SnnkDesc* d)
     p.off_pw = off;     off = align_up(off + sizeof(float) * (size_t)p.S * p.m_total * d->H, 256);
     p.off_flag = off;   off = align_up(off + 256, 256);
     p.off_weffT = off;  off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
-    p.off_gyscan = off; off = align_up(off + (p.wide ? sizeof(float) * (size_t)BT * kOMax : 0), 256);
+    p.off_gyscan = off; off = align_up(off + ((p.wide || p.tcrec) ? sizeof(float) * (size_t)BT * kOMax : 0), 256);
     p.runs = p.tc && !p.wide;
     if (p.runs) {
         const int cap = run_cap(BT);
@@ -369,30 +375,53 @@ int launch_fwd_rec(const FwdParams& fp, bool rec, int grid, cudaStream_t st)
     return rec ? launch_fwd<H, R, true>(fp, grid, st) : launch_fwd<H, R, false>(fp, grid, st);
 }
 
-// Tensor-core recurrence (recur_mma.cuh): H = 128, selected by SNNK_F_TENSOR_CORE; SNNK_MMA_RECUR=0 keeps the SIMT kernel.
-bool use_mma_recur(const SnnkDesc* d)
+// Tensor-core recurrence (recur_tc.cuh): H = 128 recurrent LIF / ALIF layers in tensor-core mode.
+// Measured on B200 (profiles/r02_*): a step of an 8-row tile takes ~1400 (forward) / ~3000 (backward) cycles on one
+// SM whatever the batch -- bound by the dependent-issue latency of its ~200 / ~580 instructions per warp, not by the
+// 36 / 54 MMAs -- so these kernels win once the tiles fill the chip (B = 4096: K3 0.58 ms vs 0.73 ms) and lose to
+// the one-row-per-CTA SIMT kernels, which spread a small batch over all SMs (B = 256: 82 / 168 us vs 55 / 72 us).
+// SNNK_MMA_RECUR = 0 / 1 forces the choice (measuring switch; read per call, tools/sanitize_run.py toggles it).
+bool use_tc_recur(const SnnkDesc* d)
 {
-    // Measured on B200 (profiles/): a 16-row tile keeps one SM busy for ~1.8 us per step whatever the batch, so the
-    // MMA kernel wins once there are enough tiles to fill the chip (B=4096: 0.38 ms vs 1.07 ms) and loses to the
-    // 128-threads-per-row SIMT kernel, which spreads a small batch over all SMs (B=256: 180 us vs 64 us).
-    if (d->layer_type == SNNK_IZHIKEVICH) return false;   // the MMA recurrence implements the LIF / ALIF update only
-    const char* env = getenv("SNNK_MMA_RECUR");   // read per call: tools/sanitize_run.py toggles it inside one process
-    if (env) return env[0] != '0' && d->H == kMmaH;
-    return (d->flags & SNNK_F_TENSOR_CORE) != 0 && d->H == kMmaH && d->B >= 768;
+    if (d->layer_type == SNNK_IZHIKEVICH || !d->recurrent || d->H != kTcH) return false;
+    if ((d->flags & SNNK_F_TENSOR_CORE) == 0) return false;
+    const char* env = getenv("SNNK_MMA_RECUR");
+    if (env) return env[0] != '0';
+    return d->B >= 1024;
 }
 
-int launch_fwd_mma(const FwdParams& fp, bool rec, cudaStream_t st)
+int launch_fwd_tc(const FwdParams& fp, cudaStream_t st)
 {
-    const size_t smem = fwd_mma_smem_bytes();
-    const int grid = (fp.B + kMmaRows - 1) / kMmaRows;
+    const size_t smem = fwd_tc_smem_bytes(fp.T);
+    if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
+    const int grid = (fp.B + kTcRows - 1) / kTcRows;
     ProfScope ps(SNNK_K_RECUR_FWD, st);
-    if (rec) {
-        SNNK_CUDA(cudaFuncSetAttribute(k_recur_fwd_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_recur_fwd_mma<true><<<grid, kMmaThreads, smem, st>>>(fp);
+    if (fp.alif) {
+        SNNK_CUDA(cudaFuncSetAttribute(k_recur_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_recur_fwd_tc<true><<<grid, kTcThreads, smem, st>>>(fp);
     } else {
-        SNNK_CUDA(cudaFuncSetAttribute(k_recur_fwd_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_recur_fwd_mma<false><<<grid, kMmaThreads, smem, st>>>(fp);
+        SNNK_CUDA(cudaFuncSetAttribute(k_recur_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_recur_fwd_tc<false><<<grid, kTcThreads, smem, st>>>(fp);
     }
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int launch_bwd_tc(const BwdParams& bp, const float* gy_scan, cudaStream_t st)
+{
+    const size_t smem = bwd_tc_smem_bytes(bp.T);
+    if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
+    const int grid = (bp.B + kTcRows - 1) / kTcRows;
+    void (*kern)(const BwdParams, const float*) = nullptr;
+    switch ((bp.alif ? 2 : 0) + (bp.surrogate ? 1 : 0)) {
+    case 0: kern = k_recur_bwd_tc<false, 0>; break;
+    case 1: kern = k_recur_bwd_tc<false, 1>; break;
+    case 2: kern = k_recur_bwd_tc<true, 0>; break;
+    default: kern = k_recur_bwd_tc<true, 1>; break;
+    }
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(SNNK_K_RECUR_BWD, st);
+    kern<<<grid, kTcThreads, smem, st>>>(bp, gy_scan);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -822,7 +851,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
                 if (fk) SNNK_CUDA(cudaStreamWaitEvent(st, fk->mid, 0));
                 rc = launch_proj_tc<32>(d, pl, Xu, W_in, Iu, planes, nullptr, st, runs, 1);
                 if (rc != SNNK_OK) return rc;
-                if (pl.wide || use_mma_recur(d)) {   // k_recur_fwd fetches the compact rows itself
+                if (pl.wide) {   // k_recur_fwd / k_recur_fwd_tc fetch the compact rows themselves
                     const long long nthr = (long long)M * (d->H / 4);
                     k_expand_rows<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(Iu, runs, M, d->H, I_in);
                     SNNK_CUDA(cudaGetLastError());
@@ -863,7 +892,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     fp.run_table = compact_table; fp.I_u = compact_rows;
     const bool rec = d->recurrent != 0;
     if (pl.wide) return launch_fwd_wide(d, fp, rec, pl, st);
-    if (use_mma_recur(d)) return launch_fwd_mma(fp, rec, st);
+    if (pl.tcrec) return launch_fwd_tc(fp, st);
     switch (d->H) {
     case 32: return launch_fwd_r<32>(fp, rec, pl.R, pl.grid_rows, st);
     case 64: return launch_fwd_r<64>(fp, rec, pl.R, pl.grid_rows, st);
@@ -1035,8 +1064,32 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         bp.Gu_hi = reinterpret_cast<float*>(ws + pl.off_gu);
         bp.Gu_lo = reinterpret_cast<float*>(ws + pl.off_gu + pl.gu_plane);
     }
+    Fork* fkw = nullptr;
     if (pl.wide) {
         rc = launch_bwd_wide(d, bp, rec, pl, reinterpret_cast<float*>(ws + pl.off_gyscan), zbits, st);
+    } else if (pl.tcrec) {
+        // readout-adjoint scan first; dW_out / db (a contraction of it with the spike raster) beside the sweep
+        float* gy_scan = reinterpret_cast<float*>(ws + pl.off_gyscan);
+        {
+            ProfScope ps(SNNK_K_REDUCE_OUT, st);
+            k_gy_scan<<<(d->B * kOMax + 255) / 256, 256, 0, st>>>(d->B, d->T, d->O, d->kappa, bp.g_y, bp.g_logits, bp.tstar,
+                                                               bp.g_scale, gy_scan);
+            SNNK_CUDA(cudaGetLastError());
+        }
+        fkw = fork_for_device();
+        cudaStream_t st_w = st;
+        if (fkw) {
+            SNNK_CUDA(cudaEventRecord(fkw->forked3, st));
+            SNNK_CUDA(cudaStreamWaitEvent(fkw->side, fkw->forked3, 0));
+            st_w = fkw->side;
+        }
+        {
+            ProfScope ps(SNNK_K_REDUCE_OUT, st_w);
+            k_wout_grad<<<dim3(pl.n_pwout, d->H / 128), 128, 0, st_w>>>(d->B * d->T, d->H, d->O, zbits, gy_scan, pwout, pdb);
+            SNNK_CUDA(cudaGetLastError());
+        }
+        if (fkw) SNNK_CUDA(cudaEventRecord(fkw->joined3, fkw->side));
+        rc = launch_bwd_tc(bp, gy_scan, st);
     } else {
         switch (d->H) {
         case 32: rc = launch_bwd_r<32>(bp, rec, pl.R, pl.grid_rows, st); break;
@@ -1114,6 +1167,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
             else k_wgrad_simt<32><<<grid, kGemmThreads, 0, st>>>(wp);
             SNNK_CUDA(cudaGetLastError());
         }
+        if (fkw) SNNK_CUDA(cudaStreamWaitEvent(st, fkw->joined3, 0));      // dW_out / db partials of the side branch
         // every partial buffer (dW_in, dW_rec, dW_out, db) reduced by one launch
         FinalizeParams fz{};
         fz.pw = pw; fz.S = pl.S; fz.w_stride = (size_t)pl.m_total * d->H; fz.n_in = d->N * d->H;

@@ -21,6 +21,13 @@ from snnimageclassification_b200.modules import functional as F_  # noqa: E402
 DEV = torch.device("cuda:0")
 
 
+@pytest.fixture(autouse=True)
+def _force_tc_recurrence(monkeypatch):
+	"""The library selects recur_tc.cuh from B >= 1024; these tests exercise it at every batch size (SNNK_MMA_RECUR is
+	read per call)."""
+	monkeypatch.setenv("SNNK_MMA_RECUR", "1")
+
+
 def npy(t):
 	return None if t is None else t.detach().cpu().numpy()
 
@@ -64,9 +71,13 @@ def test_tensor_core_matches_simt(B, T, N, H, rec, layer):
 	loss, logp, gl = F_.run_head_nll(f0["logits"], d["labels"])
 	kw = dict(g_logits=gl, tstar=f0["tstar"])
 	g0, g1 = _bwd(d, consts(False), f0, **kw), _bwd(d, consts(True), f0, **kw)
-	assert torch.equal(g0["gI"](), g1["gI"]())          # the two tf32 planes of gI sum back to gI exactly
+	tc_sweep = rec and H == 128         # recur_tc.cuh: the sweep itself runs on the tensor cores (22-bit operands)
+	if tc_sweep:
+		assert rel_err(npy(g1["gI"]()), npy(g0["gI"]())) <= 1e-5
+	else:
+		assert torch.equal(g0["gI"](), g1["gI"]())          # the two tf32 planes of gI sum back to gI exactly
 	for k in ("dW_in", "dW_out", "db") + (("dW_rec",) if rec else ()):
-		assert rel_err(npy(g1[k]), npy(g0[k])) <= 1e-5, k
+		assert rel_err(npy(g1[k]), npy(g0[k])) <= (5e-5 if tc_sweep else 1e-5), (k, rel_err(npy(g1[k]), npy(g0[k])))
 	if rec:
 		assert np.all(np.diag(npy(g1["dW_rec"])) == 0.0)
 
@@ -114,12 +125,15 @@ def test_inexact_input_falls_back_on_device():
 	d, consts = _setup(16, 20, 64, 128, 10, True, 1, 0.3)
 	d["x"] = d["x"] * torch.rand_like(d["x"])          # arbitrary fp32 currents: not representable in tf32
 	f0, f1 = _fwd(d, consts(False)), _fwd(d, consts(True))
-	for k in ("I_in", "V", "a", "Z", "y"):     # B = 16: the SIMT recurrence runs in both modes, so everything is bit-identical
-		assert torch.equal(f0[k], f1[k]), k
+	assert torch.equal(f0["I_in"], f1["I_in"])     # the projection fell back to the fp32 kernel: bit-identical
+	same = ~(f0["Z"] != f1["Z"]).flatten(1).any(dim=1)      # the recurrence runs on the tensor cores in mode 1 (H = 128)
+	assert same.float().mean().item() >= 0.9
+	for k in ("V", "a", "y"):
+		assert rel_err(npy(f1[k][same]), npy(f0[k][same])) <= 1e-5, k
 	g_y = torch.randn(16, 20, 10, device=DEV)
 	g0, g1 = _bwd(d, consts(False), f0, g_y=g_y), _bwd(d, consts(True), f0, g_y=g_y)
 	for k in ("dW_in", "dW_rec", "dW_out", "db"):
-		assert rel_err(npy(g1[k]), npy(g0[k])) <= 1e-6, k
+		assert rel_err(npy(g1[k]), npy(g0[k])) <= 1e-5, k
 	# a single inexact element anywhere in the batch is enough
 	d2, _ = _setup(16, 20, 64, 128, 10, True, 1, 0.3)
 	d2["x"][7, 13, 5] = 0.3
@@ -198,7 +212,7 @@ def test_binary_input_flag_skips_the_check_but_not_the_result():
 
 @pytest.mark.parametrize("B,T,rec,layer", [(1024, 100, True, 1), (800, 23, True, 0), (770, 5, False, 1), (1000, 9, True, 1)])
 def test_mma_recurrence_self_consistency_and_vs_simt(B, T, rec, layer):
-	"""recur_mma.cuh (H = 128, tensor-core mode): internal consistency of everything it writes, and agreement with the
+	"""recur_tc.cuh (H = 128, tensor-core mode): internal consistency of everything it writes, and agreement with the
 	fp32 SIMT kernel on the samples that did not fork."""
 	d, consts = _setup(B, T, 784, 128, 10, rec, layer, 0.1 if layer else 0.03, seed=B)
 	f0, f1 = _fwd(d, consts(False)), _fwd(d, consts(True))

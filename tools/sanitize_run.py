@@ -7,7 +7,7 @@
 One tool per gpurun call (profiling guide).  Shapes are tiny (racecheck slows kernels ~100x) but reach every code
 path with barriers / mbarrier rings / aliased staging / peer-protocol words: K5 encoder (+ run table, lazy rows, bit
 raster), K1/K4 tcgen05 GEMMs (dense, compact, Z-only), SIMT GEMMs, K2/K3 SIMT recurrences (H = 32/64/128, R = 1),
-the MMA recurrences (forced with SNNK_MMA_RECUR=1), the wide path, K6 head, Adam and the data-parallel Adam with
+the tensor-core recurrences (recur_tc.cuh; SNNK_MMA_RECUR=0 for the SIMT ones in that mode), the wide path, K6 head, Adam and the data-parallel Adam with
 world = 1.  Prints one line per stage; exits non-zero if a result is not finite.
 """
 import ctypes
@@ -80,15 +80,15 @@ def main():
 		with torch.no_grad():
 			lg = net.get_prediction_logits(x20, re_outputs_trace=False, re_hidden_states=False)
 		print(f"wide H={H} inference finite={bool(torch.isfinite(lg).all())}", flush=True)
-	# MMA recurrences at a small batch (the library picks them from B >= 768 on its own)
-	os.environ["SNNK_MMA_RECUR"] = "1"
+	# the tensor-core recurrences (recur_tc.cuh) forced at a small, ragged batch (21 rows: a partial 8-row tile)
+	img2 = (torch.randint(1, 256, (21, N), generator=g).float() / 255.0) * (torch.rand(21, N, generator=g) < 0.3)
+	lab2 = torch.randint(0, O, (21,), generator=g).to(DEV)
 	torch.manual_seed(4)
 	net = SNN(N, O, 128, use_recurrent_connection=True, int_time_steps=T, spike_func=SpikeFuncType.FastSigmoid,
 		hidden_layer_type=LayerType.ALIF, device=DEV, learn_beta=True)
-	img2 = (torch.randint(1, 256, (21, N), generator=g).float() / 255.0) * (torch.rand(21, N, generator=g) < 0.3)
-	lab2 = torch.randint(0, O, (21,), generator=g).to(DEV)
-	train_step(net, ToSpikes(T, use_periods=True).encode_batch(img2.to(DEV)), lab2, "MMA recurrence B=21 (forced)")
-	train_step(net, ToSpikes(T, use_periods=False, tau=20.0).encode_batch(img2.to(DEV)), lab2, "MMA recurrence dense input")
+	os.environ["SNNK_MMA_RECUR"] = "1"      # the library picks them from B >= 1024 on its own
+	train_step(net, ToSpikes(T, use_periods=True).encode_batch(img2.to(DEV)), lab2, "tensor-core recurrence B=21, dedup input")
+	train_step(net, ToSpikes(T, use_periods=False, tau=20.0).encode_batch(img2.to(DEV)), lab2, "tensor-core recurrence B=21, dense input")
 	os.environ.pop("SNNK_MMA_RECUR")
 
 	# optimizer: plain and data-parallel form with world = 1 (its own buffer is the only peer)
