@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 #include "common.cuh"
 #include "encode_head.cuh"
@@ -17,6 +18,7 @@
 #include "recur_fwd.cuh"
 #include "recur_gen.cuh"
 #include "recur_tc.cuh"
+#include "recur_wide.cuh"
 #include "runs.cuh"
 
 using namespace snnk;
@@ -122,6 +124,9 @@ struct Plan {
     int kpad;         // K of the projection padded to the k-block
     bool wide;        // H > 128: generic recurrence kernels (recur_gen.cuh), N-tiled tensor-core GEMMs
     bool tcrec;       // tensor-core recurrence kernels (recur_tc.cuh): gy scan + k_wout_grad beside the sweep
+    bool widetc;      // wide layer on the weight-stationary tensor-core kernels (recur_wide.cuh)
+    int w_nmt, w_nnt; // their grid: m-tiles of the batch x n-slices of the hidden axis
+    size_t off_zx, off_wflags;
     int tileN;        // N extent of one tensor-core tile
     int ntiles_tc;
     int n_pwout, n_pdb;   // number of dW_out / db partial buffers
@@ -160,11 +165,19 @@ IzhConsts izh_consts(const SnnkDesc* d)
 }
 
 bool use_tc_recur(const SnnkDesc* d);
+bool use_wide_tc(const SnnkDesc* d);
 
 Plan make_plan(const SnnkDesc* d)
 {
     Plan p{};
     p.wide = d->H > 128;
+    p.widetc = use_wide_tc(d);
+    if (p.widetc) {
+        const int nsm = wide_nsm(d->H), mt = wide_mt(nsm);
+        p.w_nnt = d->H / (16 * nsm);
+        p.w_nmt = std::min(sm_count() / p.w_nnt, (d->B + mt - 1) / mt);
+        if (p.w_nmt < 1) p.widetc = false;
+    }
     p.tcrec = use_tc_recur(d) && bwd_tc_smem_bytes(d->T) <= 200 * 1024 && fwd_tc_smem_bytes(d->T) <= 200 * 1024;
     p.R = p.wide ? gen_rows(d->H) : (d->B > 1024 ? 2 : 1);
     p.grid_rows = (d->B + p.R - 1) / p.R;
@@ -219,6 +232,11 @@ Plan make_plan(const SnnkDesc* d)
     p.off_wplanes = off; off = align_up(off + (p.tc ? sizeof(float) * 3 * (size_t)d->H * p.kpad : 0), 256);
     p.off_fflag = off;   off = align_up(off + 256, 256);
     p.off_weff = off;    off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
+    if (p.widetc) {
+        const int mt = wide_mt(wide_nsm(d->H));
+        p.off_zx = off;     off = align_up(off + sizeof(uint32_t) * 2 * (size_t)p.w_nmt * (d->H / 32) * mt, 256);
+        p.off_wflags = off; off = align_up(off + sizeof(unsigned int) * (size_t)p.w_nmt * kWideFlagStride, 256);
+    }
     if (p.runs) {
         p.off_xu_f = off; off = align_up(off + sizeof(float) * (size_t)p.run_rows * p.kpad, 1024);   // tiled, k padded
         p.off_iu = off;   off = align_up(off + sizeof(float) * (size_t)p.run_rows * d->H, 256);
@@ -390,6 +408,54 @@ bool use_tc_recur(const SnnkDesc* d)
     return d->B >= 1024;
 }
 
+// Wide layers (H > 128) in tensor-core mode: weight-stationary, grid-synchronous kernels (recur_wide.cuh).
+// SNNK_WIDE_TC=0 keeps the fp32 kernels of recur_gen.cuh (measuring switch).
+bool use_wide_tc(const SnnkDesc* d)
+{
+    if (d->H <= 128 || d->H % 128 != 0 || d->H > 2048) return false;
+    if (d->layer_type == SNNK_IZHIKEVICH || !d->recurrent || (d->flags & SNNK_F_TENSOR_CORE) == 0) return false;
+    const char* env = getenv("SNNK_WIDE_TC");
+    if (env && env[0] == '0') return false;
+    return wide_fwd_smem_bytes(d->H) <= 220 * 1024;
+}
+
+WideParams wide_params(const FwdParams& fp, const Plan& pl, char* ws)
+{
+    WideParams wp{};
+    wp.B = fp.B; wp.T = fp.T; wp.H = fp.H; wp.O = fp.O; wp.alif = fp.alif; wp.traces = fp.traces;
+    wp.alpha = fp.alpha; wp.rho = fp.rho; wp.theta = fp.theta;
+    wp.I_in = fp.I_in; wp.W = fp.W_eff; wp.beta = fp.beta; wp.V0 = fp.V0; wp.a0 = fp.a0; wp.Z0 = fp.Z0;
+    wp.V = fp.V; wp.a = fp.a; wp.Z = fp.Z; wp.zbits = fp.zbits;
+    wp.zx = reinterpret_cast<uint32_t*>(ws + pl.off_zx);
+    wp.flags = reinterpret_cast<unsigned int*>(ws + pl.off_wflags);
+    wp.n_mt = pl.w_nmt; wp.n_nt = pl.w_nnt;
+    return wp;
+}
+
+template <int NSM>
+int launch_wide_fwd_t(const WideParams& wp, cudaStream_t st)
+{
+    const size_t smem = wide_fwd_smem_bytes(wp.H);
+    void* kern = wp.alif ? (void*)k_wide_fwd<NSM, true> : (void*)k_wide_fwd<NSM, false>;
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SNNK_CUDA(cudaMemsetAsync(wp.flags, 0, sizeof(unsigned int) * (size_t)wp.n_mt * kWideFlagStride, st));
+    WideParams arg = wp;
+    void* args[] = {&arg};
+    ProfScope ps(SNNK_K_RECUR_FWD, st);
+    // cooperative: every CTA waits for its m-tile's peers each step, so all of them must be resident
+    SNNK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(wp.n_mt * wp.n_nt), dim3(kWideThreads), args, smem, st));
+    return SNNK_OK;
+}
+
+int launch_wide_fwd(const WideParams& wp, cudaStream_t st)
+{
+    switch (wide_nsm(wp.H)) {
+    case 4: return launch_wide_fwd_t<4>(wp, st);
+    case 2: return launch_wide_fwd_t<2>(wp, st);
+    default: return launch_wide_fwd_t<1>(wp, st);
+    }
+}
+
 int launch_fwd_tc(const FwdParams& fp, cudaStream_t st)
 {
     const size_t smem = fwd_tc_smem_bytes(fp.T);
@@ -466,6 +532,18 @@ int launch_bwd_r(const BwdParams& bp, bool rec, int R, int grid, cudaStream_t st
 }
 
 // ---- wide hidden layers (H > 128): generic recurrence + separate readout / dW_out kernels -------------------------
+int launch_readout_scan(const SnnkDesc* d, const FwdParams& fp, cudaStream_t st)
+{
+    const size_t smem2 = sizeof(uint32_t) * (size_t)d->T * (d->H / 32) + sizeof(float) * ((size_t)d->H * d->O + (size_t)d->T * d->O);
+    if (smem2 > 200 * 1024) return SNNK_ERR_SHAPE;
+    SNNK_CUDA(cudaFuncSetAttribute(k_readout_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    ProfScope ps2(SNNK_K_HEAD, st);
+    k_readout_scan<<<d->B, 128, smem2, st>>>(d->T, d->H, d->O, d->kappa, fp.zbits, fp.W_out, fp.b_out, fp.y, fp.logits,
+                                             fp.tstar);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
 template <int NPT, int R>
 int launch_fwd_wide_t(const SnnkDesc* d, const FwdParams& fp, bool rec, const Plan& pl, cudaStream_t st)
 {
@@ -484,14 +562,7 @@ int launch_fwd_wide_t(const SnnkDesc* d, const FwdParams& fp, bool rec, const Pl
         }
     }
     SNNK_CUDA(cudaGetLastError());
-    const size_t smem2 = sizeof(uint32_t) * (size_t)d->T * (d->H / 32) + sizeof(float) * ((size_t)d->H * d->O + (size_t)d->T * d->O);
-    if (smem2 > 200 * 1024) return SNNK_ERR_SHAPE;
-    SNNK_CUDA(cudaFuncSetAttribute(k_readout_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    ProfScope ps2(SNNK_K_HEAD, st);
-    k_readout_scan<<<d->B, 128, smem2, st>>>(d->T, d->H, d->O, d->kappa, fp.zbits, fp.W_out, fp.b_out, fp.y, fp.logits,
-                                             fp.tstar);
-    SNNK_CUDA(cudaGetLastError());
-    return SNNK_OK;
+    return launch_readout_scan(d, fp, st);
 }
 
 int launch_fwd_wide(const SnnkDesc* d, const FwdParams& fp, bool rec, const Plan& pl, cudaStream_t st)
@@ -891,6 +962,11 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     fp.logits = logits; fp.tstar = tstar;
     fp.run_table = compact_table; fp.I_u = compact_rows;
     const bool rec = d->recurrent != 0;
+    if (pl.wide && pl.widetc) {
+        rc = launch_wide_fwd(wide_params(fp, pl, static_cast<char*>(workspace)), st);
+        if (rc != SNNK_OK) return rc;
+        return launch_readout_scan(d, fp, st);
+    }
     if (pl.wide) return launch_fwd_wide(d, fp, rec, pl, st);
     if (pl.tcrec) return launch_fwd_tc(fp, st);
     switch (d->H) {
