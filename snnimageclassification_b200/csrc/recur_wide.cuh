@@ -316,4 +316,327 @@ __global__ void __launch_bounds__(kWideThreads, 1) k_wide_fwd(const WideParams p
     }
 }
 
+
+// ---- backward -------------------------------------------------------------------------------------------------------
+// Reverse-time sweep of a wide layer (same recurrences as recur_bwd.cuh / recur_tc.cuh):
+//     gZ_t = gy_t W_out^T + gI_{t+1} (W_rec . M)^T ;  gV_t = gZ_t sigma'_t + alpha gV_{t+1} (1 - Z_t) ;  gI_t = gV_t (1 - Z_{t-1})
+// with the matvec as  gZ^T (NS x MT) = W_eff[slice rows] (NS x H) . gI_{t+1}^T (H x MT)  on the tensor cores.  The slice of
+// W_eff is resident as in the forward kernel; what the CTAs of an m-tile exchange per step is the REAL-valued tile
+// gI_t: every CTA writes its NS columns in fp32 into a chunked, padded tile in global memory (L2) together with the
+// exponent classes it contains (atomicOr into a per-step mask word), releases the m-tile's counter, and the readers
+// stream the tile through a two-buffer shared-memory ring with one bulk copy per 36 KB chunk and split every value
+// into fp16 hi + lo / 2048 in registers, with the power-of-two scale the mask dictates (recur_tc.cuh explains the
+// scale).  Products hi.hi, hi.lo, lo.hi: 24 MMAs per 16 x 16 x 16 block pair, i.e. 1.5x the forward kernel.
+struct WideBwdParams {
+    int B, T, H, O;
+    int alif, surrogate;
+    float alpha, theta, gamma;
+    const float* W;             // W_effT [k][i] = W_eff[i][k]
+    const float* beta; const float* W_out;      // (H,O)
+    const float* V; const float* a; const uint32_t* zbits; const float* Z0;
+    const float* gy_scan;       // (B,T,kOMax) from k_gy_scan
+    const float* g_V; const float* g_Z;         // optional (B,T,H) seeds
+    float* gI; float* gI_lo;    // (B,T,H): gI, or its two tf32 planes
+    float* gx;                  // [2][n_mt][H / KC][MT][KC + 8] fp32 exchange tiles
+    unsigned int* gmask;        // [n_mt][n_pass * T] exponent-class masks, zero at launch
+    unsigned int* flags;        // [n_mt] arrival counters, zero at launch
+    int n_mt, n_nt;
+};
+
+__host__ __device__ constexpr int wide_bwd_ntw(int nsm) { return nsm == 4 ? 1 : 2; }       // n-tiles (8 rows) per warp
+__host__ __device__ constexpr int wide_bwd_mt(int nsm) { return 64 * wide_bwd_ntw(nsm); }   // rows per m-tile: 8 warps x 8 NTW
+__host__ __device__ constexpr int wide_bwd_kc(int nsm) { return nsm == 4 ? 128 : 64; }      // k per exchange chunk
+__host__ __device__ constexpr size_t wide_bwd_chunk_floats(int nsm) { return (size_t)wide_bwd_mt(nsm) * (wide_bwd_kc(nsm) + 8); }
+
+__host__ __device__ constexpr size_t wide_bwd_smem_bytes(int H)
+{
+    return sizeof(__half) * 2 * (size_t)(16 * wide_nsm(H)) * wide_wstride(H)        // weight slice, two planes
+           + sizeof(float) * 2 * wide_bwd_chunk_floats(wide_nsm(H))                   // two chunk buffers
+           + sizeof(float) * (size_t)wide_bwd_mt(wide_nsm(H)) * kOMax                 // readout adjoint of the step
+           + sizeof(float) * (size_t)(16 * wide_nsm(H)) * kOMax                       // W_out rows of the slice
+           + 128;
+}
+
+template <int NSM, bool ALIF, int SURR>
+__global__ void __launch_bounds__(kWideThreads, 1) k_wide_bwd(const WideBwdParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NS = 16 * NSM, NTW = wide_bwd_ntw(NSM), MT = wide_bwd_mt(NSM), KC = wide_bwd_kc(NSM), CS = KC + 8;
+    constexpr uint32_t kChunkBytes = (uint32_t)(MT * CS * sizeof(float));
+    const int T = p.T, H = p.H, B = p.B, O = p.O, KW = H / 32, ws = wide_wstride(H);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int m = blockIdx.x / p.n_nt, n = blockIdx.x - m * p.n_nt;
+    const int i0 = n * NS;
+    const int wrow = warp * 8 * NTW;       // this warp: all NSM m-tiles of the slice x rows [wrow, wrow + 8 NTW)
+    const int n_chunks = H / KC;
+
+    __half* s_w = reinterpret_cast<__half*>(smem_raw);                              // [2][NS][H + 8]
+    float* s_ch = reinterpret_cast<float*>(s_w + 2 * (size_t)NS * ws);              // [2][MT][CS]
+    float* s_gy = s_ch + 2 * (size_t)MT * CS;                                       // [MT][kOMax]
+    float* s_wo = s_gy + MT * kOMax;                                                // [NS][kOMax]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_wo + NS * kOMax);               // [2]
+    float* s_red = reinterpret_cast<float*>(s_bar + 2);                             // [8]
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_red + 8);                      // [0] mask read, [1] classes written
+
+    const float inv_sw = wide_load_slice<NSM>(p.W, H, i0, s_w, s_red);
+    for (int idx = tid; idx < NS * kOMax; idx += kWideThreads) {
+        const int r = idx / kOMax, c = idx - r * kOMax;
+        s_wo[idx] = c < O ? __ldg(p.W_out + (size_t)(i0 + r) * O + c) : 0.f;
+    }
+    if (tid == 0) {
+        tc::mbar_init(s_bar, 1);
+        tc::mbar_init(s_bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_misc[0] = 0u; s_misc[1] = 0u;
+    }
+    const float beta = (ALIF && p.beta) ? __ldg(p.beta) : 0.f;
+    unsigned int* flag = p.flags + (size_t)m * kWideFlagStride;
+    uint32_t ph0 = 0u, ph1 = 0u;    // mbarrier phase of the two chunk buffers (every thread waits on every chunk)
+
+    // ldmatrix source of this lane for the A tile of m-tile 0 (+ mt * 16 rows); see k_wide_fwd
+    const uint32_t a_base = tc::smem_u32(s_w) + (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * ws + 8 * (lane >> 4)) * 2;
+    const uint32_t a_plane = (uint32_t)(NS * ws) * 2, a_mt = (uint32_t)(16 * ws) * 2;
+    const int rows_per_pass = p.n_mt * MT;
+    const int n_pass = (B + rows_per_pass - 1) / rows_per_pass;
+    const uint16_t* zb16 = reinterpret_cast<const uint16_t*>(p.zbits);
+    __syncthreads();
+
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int row0 = pass * rows_per_pass + m * MT;
+        // element (mt, nt, e): neuron i0 + 16 mt + g + 8 (e >> 1), row row0 + wrow + 8 nt + 2 tig + (e & 1)
+        float gv[NSM][NTW][4];
+        uint32_t zt[NSM][NTW][2];           // 16 spike bits of (row, m-tile) at the step being processed (carried to the next)
+        bool ok[NTW][2];
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh) ok[nt][rh] = row0 + wrow + 8 * nt + 2 * tig + rh < B;
+        auto load_bits = [&](int tl, uint32_t (&dst)[NSM][NTW][2]) {      // Z_tl of this thread's rows (tl = -1: initial state)
+#pragma unroll
+            for (int mt = 0; mt < NSM; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh) {
+                        const int row = row0 + wrow + 8 * nt + 2 * tig + rh, hc = n * NSM + mt;
+                        uint32_t w = 0u;
+                        if (ok[nt][rh]) {
+                            if (tl >= 0) w = zb16[(((size_t)row * T + tl) * KW + (hc >> 1)) * 2 + (hc & 1)];
+                            else if (p.Z0) {
+                                for (int l = 0; l < 16; ++l)
+                                    if (__ldg(p.Z0 + (size_t)row * H + i0 + 16 * mt + l) != 0.f) w |= 1u << l;
+                            }
+                        }
+                        dst[mt][nt][rh] = w;
+                    }
+        };
+#pragma unroll
+        for (int mt = 0; mt < NSM; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) gv[mt][nt][e] = 0.f;
+        load_bits(T - 1, zt);
+        if (pass > 0) {      // everybody is done with the previous pass before its exchange tiles are overwritten
+            if (tid == 0) wide_wait_flag(flag, (unsigned int)p.n_nt * (unsigned int)(pass * T));
+            __syncthreads();
+        }
+
+        for (int s = 0; s < T; ++s) {
+            const int t = T - 1 - s;
+            const unsigned int gstep = (unsigned int)(pass * T + s);
+            const float* tile = p.gx + ((size_t)((gstep + 1) & 1) * p.n_mt + m) * n_chunks * (size_t)(MT * CS);     // written at step s - 1
+            if (s > 0 && tid == 0) {
+                wide_wait_flag(flag, (unsigned int)p.n_nt * gstep);
+                s_misc[0] = __ldcg(p.gmask + (size_t)m * n_pass * T + gstep - 1);
+                asm volatile("fence.proxy.async;" ::: "memory");      // the bulk copies below read what the peers just wrote
+                for (int c = 0; c < 2 && c < n_chunks; ++c) {
+                    tc::mbar_expect_tx(s_bar + c, kChunkBytes);
+                    tc::bulk_g2s(s_ch + (size_t)c * MT * CS, tile + (size_t)c * MT * CS, kChunkBytes, s_bar + c);
+                }
+            }
+            // readout adjoint rows of this step, saved traces and previous spikes: issued before the MMA phase
+            for (int idx = tid; idx < MT * (kOMax / 4); idx += kWideThreads) {
+                const int r = idx / (kOMax / 4);
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + r < B) q = __ldg(reinterpret_cast<const float4*>(p.gy_scan + ((size_t)(row0 + r) * T + t) * kOMax) + (idx - r * (kOMax / 4)));
+                reinterpret_cast<float4*>(s_gy)[idx] = q;
+            }
+            float vt[NSM][NTW][4], at[NSM][NTW][4];
+            uint32_t zp[NSM][NTW][2];
+            {
+                const size_t ob = ((size_t)(row0 + wrow + 2 * tig) * T + t) * H + i0 + g;
+                const uint32_t TH = (uint32_t)T * (uint32_t)H;
+#pragma unroll
+                for (int mt = 0; mt < NSM; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t o = (uint32_t)(8 * nt + (e & 1)) * TH + 16u * mt + 8u * (e >> 1);
+                            vt[mt][nt][e] = ok[nt][e & 1] ? __ldg(p.V + ob + o) : 0.f;
+                            at[mt][nt][e] = (ALIF && ok[nt][e & 1]) ? __ldg(p.a + ob + o) : 0.f;
+                        }
+            }
+            load_bits(t - 1, zp);
+            __syncthreads();      // s_misc[0], s_gy visible
+            float chh[NSM][NTW][4], cx[NSM][NTW][4];
+#pragma unroll
+            for (int mt = 0; mt < NSM; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { chh[mt][nt][e] = 0.f; cx[mt][nt][e] = 0.f; }
+            float inv_sg = 1.0f;
+            if (s > 0) {
+                const uint32_t mask = s_misc[0];
+                float sg = 1.0f;
+                if (mask) {
+                    int kexp = 133 - 8 * (31 - __clz(mask));      // classes of 8 binades: scaled maximum < 2^14
+                    kexp = kexp > 126 ? 126 : kexp;
+                    sg = __uint_as_float((uint32_t)(kexp + 127) << 23);
+                }
+                inv_sg = __fdiv_rn(1.0f, sg);
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int b = c & 1;
+                    tc::mbar_wait(s_bar + b, b ? ph1 : ph0);
+                    if (b) ph1 ^= 1u; else ph0 ^= 1u;
+                    const float* ch = s_ch + (size_t)b * MT * CS;
+#pragma unroll 2
+                    for (int kt = 0; kt < KC / 16; ++kt) {
+                        const uint32_t koff = (uint32_t)(c * KC + kt * 16) * 2;
+                        uint32_t bh[NTW][2], bl[NTW][2];
+#pragma unroll
+                        for (int nt = 0; nt < NTW; ++nt) {
+                            const float* src = ch + (wrow + 8 * nt + g) * CS + kt * 16 + 2 * tig;
+                            const float2 x0 = *reinterpret_cast<const float2*>(src), x1 = *reinterpret_cast<const float2*>(src + 8);
+                            const float2 y0 = make_float2(__fmul_rn(x0.x, sg), __fmul_rn(x0.y, sg));
+                            const float2 y1 = make_float2(__fmul_rn(x1.x, sg), __fmul_rn(x1.y, sg));
+                            const __half2 h0 = __float22half2_rn(y0), h1 = __float22half2_rn(y1);
+                            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                            const __half2 l0 = __floats2half2_rn(__fmul_rn(__fsub_rn(y0.x, f0.x), 2048.0f), __fmul_rn(__fsub_rn(y0.y, f0.y), 2048.0f));
+                            const __half2 l1 = __floats2half2_rn(__fmul_rn(__fsub_rn(y1.x, f1.x), 2048.0f), __fmul_rn(__fsub_rn(y1.y, f1.y), 2048.0f));
+                            bh[nt][0] = *reinterpret_cast<const uint32_t*>(&h0); bh[nt][1] = *reinterpret_cast<const uint32_t*>(&h1);
+                            bl[nt][0] = *reinterpret_cast<const uint32_t*>(&l0); bl[nt][1] = *reinterpret_cast<const uint32_t*>(&l1);
+                        }
+#pragma unroll
+                        for (int mt = 0; mt < NSM; ++mt) {
+                            uint32_t ah[4], al[4];
+                            ldsm_x4(ah, a_base + mt * a_mt + koff);
+                            ldsm_x4(al, a_base + a_plane + mt * a_mt + koff);
+#pragma unroll
+                            for (int nt = 0; nt < NTW; ++nt) {
+                                mma_f16(chh[mt][nt], ah, bh[nt]);
+                                mma_f16(cx[mt][nt], ah, bl[nt]);
+                                mma_f16(cx[mt][nt], al, bh[nt]);
+                            }
+                        }
+                    }
+                    __syncthreads();      // everybody is done with buffer b: refill it with chunk c + 2
+                    if (tid == 0 && c + 2 < n_chunks) {
+                        tc::mbar_expect_tx(s_bar + b, kChunkBytes);
+                        tc::bulk_g2s(s_ch + (size_t)b * MT * CS, tile + (size_t)(c + 2) * MT * CS, kChunkBytes, s_bar + b);
+                    }
+                }
+            }
+            // ---- elementwise part of the step ----
+            const float sc = __fmul_rn(inv_sw, inv_sg);
+            float gi[NSM][NTW][4];
+            uint32_t cls = 0u;
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    const int rl = wrow + 8 * nt + 2 * tig + rh;      // row within the m-tile
+                    float gy[kOMax];
+#pragma unroll
+                    for (int q = 0; q < kOMax / 4; ++q) {
+                        const float4 v4 = reinterpret_cast<const float4*>(s_gy + rl * kOMax)[q];
+                        gy[4 * q] = v4.x; gy[4 * q + 1] = v4.y; gy[4 * q + 2] = v4.z; gy[4 * q + 3] = v4.w;
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < NSM; ++mt)
+#pragma unroll
+                        for (int nh = 0; nh < 2; ++nh) {
+                            const int e = 2 * nh + rh, il = 16 * mt + g + 8 * nh;      // neuron within the slice
+                            float rdo = 0.f;
+#pragma unroll
+                            for (int q = 0; q < kOMax / 4; ++q) {
+                                const float4 w4 = reinterpret_cast<const float4*>(s_wo + il * kOMax)[q];
+                                rdo = fmaf(gy[4 * q], w4.x, rdo); rdo = fmaf(gy[4 * q + 1], w4.y, rdo);
+                                rdo = fmaf(gy[4 * q + 2], w4.z, rdo); rdo = fmaf(gy[4 * q + 3], w4.w, rdo);
+                            }
+                            const float rec = __fmul_rn(fmaf(cx[mt][nt][e], 1.0f / 2048.0f, chh[mt][nt][e]), sc);
+                            float sum = __fadd_rn(rdo, rec);
+                            const bool o_ = ok[nt][rh];
+                            const size_t o = ((size_t)(row0 + rl) * T + t) * H + i0 + il;
+                            if (p.g_Z && o_) sum = __fadd_rn(sum, __ldg(p.g_Z + o));
+                            float thr = p.theta;
+                            if constexpr (ALIF) thr = __fadd_rn(p.theta, __fmul_rn(beta, at[mt][nt][e]));
+                            const float zcur = (float)((zt[mt][nt][rh] >> (g + 8 * nh)) & 1u);
+                            const float zprev = (float)((zp[mt][nt][rh] >> (g + 8 * nh)) & 1u);
+                            const float sgr = surrogate_grad(SURR, p.gamma, vt[mt][nt][e], thr);
+                            const float carry = __fmul_rn(__fmul_rn(p.alpha, gv[mt][nt][e]), __fsub_rn(1.0f, zcur));
+                            float gq = __fadd_rn(__fmul_rn(sum, sgr), carry);
+                            if (p.g_V && o_) gq = __fadd_rn(gq, __ldg(p.g_V + o));
+                            gv[mt][nt][e] = gq;
+                            const float gix = o_ ? __fmul_rn(gq, __fsub_rn(1.0f, zprev)) : 0.f;
+                            gi[mt][nt][e] = gix;
+                            cls |= gix != 0.f ? 1u << (((__float_as_uint(gix) >> 23) & 0xFFu) >> 3) : 0u;
+                        }
+                }
+            // ---- publish gI_t: this CTA's NS columns of the exchange tile of step s, its exponent classes, the counter ----
+            {
+                float* out = p.gx + ((size_t)(gstep & 1) * p.n_mt + m) * n_chunks * (size_t)(MT * CS) + (size_t)(i0 / KC) * (MT * CS) + (i0 % KC);
+#pragma unroll
+                for (int mt = 0; mt < NSM; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            out[(wrow + 8 * nt + 2 * tig + (e & 1)) * CS + 16 * mt + g + 8 * (e >> 1)] = gi[mt][nt][e];
+                const uint32_t wor = __reduce_or_sync(0xffffffffu, cls);
+                if (lane == 0 && wor) atomicOr(s_misc + 1, wor);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t mine = s_misc[1];
+                s_misc[1] = 0u;
+                if (mine) atomicOr(p.gmask + (size_t)m * n_pass * T + gstep, mine);
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+            }
+            // ---- gI of this step for the weight-gradient GEMM (after the publish: see k_wide_fwd) ----
+            {
+                const size_t ob = ((size_t)(row0 + wrow + 2 * tig) * T + t) * H + i0 + g;
+                const uint32_t TH = (uint32_t)T * (uint32_t)H;
+#pragma unroll
+                for (int mt = 0; mt < NSM; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (!ok[nt][e & 1]) continue;
+                            const uint32_t o = (uint32_t)(8 * nt + (e & 1)) * TH + 16u * mt + 8u * (e >> 1);
+                            const float x = gi[mt][nt][e];
+                            if (p.gI_lo) {      // exact two-plane tf32 split
+                                const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                                p.gI[ob + o] = hi;
+                                p.gI_lo[ob + o] = __fsub_rn(x, hi);
+                            } else {
+                                p.gI[ob + o] = x;
+                            }
+                        }
+            }
+#pragma unroll
+            for (int mt = 0; mt < NSM; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh) zt[mt][nt][rh] = zp[mt][nt][rh];
+        }
+    }
+}
+
 }  // namespace snnk

@@ -126,7 +126,8 @@ struct Plan {
     bool tcrec;       // tensor-core recurrence kernels (recur_tc.cuh): gy scan + k_wout_grad beside the sweep
     bool widetc;      // wide layer on the weight-stationary tensor-core kernels (recur_wide.cuh)
     int w_nmt, w_nnt; // their grid: m-tiles of the batch x n-slices of the hidden axis
-    size_t off_zx, off_wflags;
+    int w_nmt_b, w_npass_b;   // backward: m-tiles (its row tile differs) and passes over the batch
+    size_t off_zx, off_wflags, off_gx, off_gmask, off_wflags_b;
     int tileN;        // N extent of one tensor-core tile
     int ntiles_tc;
     int n_pwout, n_pdb;   // number of dW_out / db partial buffers
@@ -177,6 +178,10 @@ Plan make_plan(const SnnkDesc* d)
         p.w_nnt = d->H / (16 * nsm);
         p.w_nmt = std::min(sm_count() / p.w_nnt, (d->B + mt - 1) / mt);
         if (p.w_nmt < 1) p.widetc = false;
+        const int mtb = wide_bwd_mt(nsm);
+        p.w_nmt_b = std::min(sm_count() / p.w_nnt, (d->B + mtb - 1) / mtb);
+        if (p.w_nmt_b < 1) p.widetc = false;
+        else p.w_npass_b = (d->B + p.w_nmt_b * mtb - 1) / (p.w_nmt_b * mtb);
     }
     p.tcrec = use_tc_recur(d) && bwd_tc_smem_bytes(d->T) <= 200 * 1024 && fwd_tc_smem_bytes(d->T) <= 200 * 1024;
     p.R = p.wide ? gen_rows(d->H) : (d->B > 1024 ? 2 : 1);
@@ -215,6 +220,12 @@ Plan make_plan(const SnnkDesc* d)
     p.off_flag = off;   off = align_up(off + 256, 256);
     p.off_weffT = off;  off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
     p.off_gyscan = off; off = align_up(off + ((p.wide || p.tcrec) ? sizeof(float) * (size_t)BT * kOMax : 0), 256);
+    if (p.widetc) {
+        const int nsm = wide_nsm(d->H);
+        p.off_gx = off;       off = align_up(off + sizeof(float) * 2 * (size_t)p.w_nmt_b * (d->H / wide_bwd_kc(nsm)) * wide_bwd_chunk_floats(nsm), 256);
+        p.off_gmask = off;    off = align_up(off + sizeof(unsigned int) * (size_t)p.w_nmt_b * p.w_npass_b * d->T, 256);
+        p.off_wflags_b = off; off = align_up(off + sizeof(unsigned int) * (size_t)p.w_nmt_b * kWideFlagStride, 256);
+    }
     p.runs = p.tc && !p.wide;
     if (p.runs) {
         const int cap = run_cap(BT);
@@ -416,7 +427,7 @@ bool use_wide_tc(const SnnkDesc* d)
     if (d->layer_type == SNNK_IZHIKEVICH || !d->recurrent || (d->flags & SNNK_F_TENSOR_CORE) == 0) return false;
     const char* env = getenv("SNNK_WIDE_TC");
     if (env && env[0] == '0') return false;
-    return wide_fwd_smem_bytes(d->H) <= 220 * 1024;
+    return wide_fwd_smem_bytes(d->H) <= 225 * 1024 && wide_bwd_smem_bytes(d->H) <= 225 * 1024;
 }
 
 WideParams wide_params(const FwdParams& fp, const Plan& pl, char* ws)
@@ -453,6 +464,36 @@ int launch_wide_fwd(const WideParams& wp, cudaStream_t st)
     case 4: return launch_wide_fwd_t<4>(wp, st);
     case 2: return launch_wide_fwd_t<2>(wp, st);
     default: return launch_wide_fwd_t<1>(wp, st);
+    }
+}
+
+template <int NSM>
+int launch_wide_bwd_t(const WideBwdParams& wp, int n_pass, cudaStream_t st)
+{
+    const size_t smem = wide_bwd_smem_bytes(wp.H);
+    void* kern = nullptr;
+    switch ((wp.alif ? 2 : 0) + (wp.surrogate ? 1 : 0)) {
+    case 0: kern = (void*)k_wide_bwd<NSM, false, 0>; break;
+    case 1: kern = (void*)k_wide_bwd<NSM, false, 1>; break;
+    case 2: kern = (void*)k_wide_bwd<NSM, true, 0>; break;
+    default: kern = (void*)k_wide_bwd<NSM, true, 1>; break;
+    }
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SNNK_CUDA(cudaMemsetAsync(wp.flags, 0, sizeof(unsigned int) * (size_t)wp.n_mt * kWideFlagStride, st));
+    SNNK_CUDA(cudaMemsetAsync(wp.gmask, 0, sizeof(unsigned int) * (size_t)wp.n_mt * n_pass * wp.T, st));
+    WideBwdParams arg = wp;
+    void* args[] = {&arg};
+    ProfScope ps(SNNK_K_RECUR_BWD, st);
+    SNNK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(wp.n_mt * wp.n_nt), dim3(kWideThreads), args, smem, st));
+    return SNNK_OK;
+}
+
+int launch_wide_bwd(const WideBwdParams& wp, int n_pass, cudaStream_t st)
+{
+    switch (wide_nsm(wp.H)) {
+    case 4: return launch_wide_bwd_t<4>(wp, n_pass, st);
+    case 2: return launch_wide_bwd_t<2>(wp, n_pass, st);
+    default: return launch_wide_bwd_t<1>(wp, n_pass, st);
     }
 }
 
@@ -1141,7 +1182,30 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         bp.Gu_lo = reinterpret_cast<float*>(ws + pl.off_gu + pl.gu_plane);
     }
     Fork* fkw = nullptr;
-    if (pl.wide) {
+    if (pl.wide && pl.widetc) {
+        // weight-stationary tensor-core sweep (recur_wide.cuh): adjoint scan, sweep, then dW_out / db from the scan
+        float* gy_scan = reinterpret_cast<float*>(ws + pl.off_gyscan);
+        {
+            ProfScope ps(SNNK_K_REDUCE_OUT, st);
+            k_gy_scan<<<(d->B * kOMax + 255) / 256, 256, 0, st>>>(d->B, d->T, d->O, d->kappa, bp.g_y, bp.g_logits, bp.tstar,
+                                                               bp.g_scale, gy_scan);
+            SNNK_CUDA(cudaGetLastError());
+        }
+        WideBwdParams wp{};
+        wp.B = d->B; wp.T = d->T; wp.H = d->H; wp.O = d->O; wp.alif = bp.alif; wp.surrogate = bp.surrogate;
+        wp.alpha = bp.alpha; wp.theta = bp.theta; wp.gamma = bp.gamma;
+        wp.W = bp.W_effT; wp.beta = bp.beta; wp.W_out = bp.W_out; wp.V = bp.V; wp.a = bp.a; wp.zbits = bp.zbits; wp.Z0 = bp.Z0;
+        wp.gy_scan = gy_scan; wp.g_V = bp.g_V; wp.g_Z = bp.g_Z; wp.gI = bp.gI; wp.gI_lo = bp.gI_lo;
+        wp.gx = reinterpret_cast<float*>(ws + pl.off_gx);
+        wp.gmask = reinterpret_cast<unsigned int*>(ws + pl.off_gmask);
+        wp.flags = reinterpret_cast<unsigned int*>(ws + pl.off_wflags_b);
+        wp.n_mt = pl.w_nmt_b; wp.n_nt = pl.w_nnt;
+        rc = launch_wide_bwd(wp, pl.w_npass_b, st);
+        if (rc != SNNK_OK) return rc;
+        ProfScope ps2(SNNK_K_REDUCE_OUT, st);
+        k_wout_grad<<<dim3(pl.n_pwout, d->H / 128), 128, 0, st>>>(d->B * d->T, d->H, d->O, zbits, gy_scan, pwout, pdb);
+        SNNK_CUDA(cudaGetLastError());
+    } else if (pl.wide) {
         rc = launch_bwd_wide(d, bp, rec, pl, reinterpret_cast<float*>(ws + pl.off_gyscan), zbits, st);
     } else if (pl.tcrec) {
         // readout-adjoint scan first; dW_out / db (a contraction of it with the spike raster) beside the sweep

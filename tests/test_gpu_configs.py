@@ -68,7 +68,7 @@ def weights(net):
 		mask=npy(L.rec_mask) if rec else None, W_out=npy(R.forward_weights), b=npy(R.bias_weights))
 
 
-def check_training_step(net, x_dev, labels, rows=None, min_same=0.9999, max_forked=0.05):
+def check_training_step(net, x_dev, labels, rows=None, min_same=0.9999, max_forked=0.05, elem_floor=1e-3, elem_tol=1e-3):
 	"""One training step of ``net`` on the device raster ``x_dev`` through the public API, against the oracle.
 	``rows``: batch rows the oracle evaluates for the forward comparison (None = all)."""
 	B = x_dev.shape[0]
@@ -113,7 +113,7 @@ def check_training_step(net, x_dev, labels, rows=None, min_same=0.9999, max_fork
 		assert np.all(np.diag(npy(got["dW_rec"])) == 0.0)
 	for k, gt in got.items():
 		assert rel_err(npy(gt), gr[k]) <= 1e-4, (k, rel_err(npy(gt), gr[k]))
-		assert elementwise_err(npy(gt), gr[k]) <= 1e-3, (k, elementwise_err(npy(gt), gr[k]))
+		assert elementwise_err(npy(gt), gr[k], elem_floor) <= elem_tol, (k, elementwise_err(npy(gt), gr[k], elem_floor))
 	return dict(same=same, forked=forked, loss=loss.item())
 
 
@@ -216,7 +216,10 @@ def test_c4_wide_recurrent_shard():
 	Bs = 24
 	xs, ls = x[:Bs].contiguous(), lab[:Bs]
 	F_.mark_binary(xs)
-	check_training_step(net, xs, ls, max_forked=0.1)
+	# elementwise bar: the tensor-core sweep carries 22-bit operands through T = 100 steps of a recurrence whose
+	# gradients grow by ~1e8 at this width (|dW_in| ~ 1e5): 100 x 2^-22 = 2.4e-5 of the LARGEST entries (measured 2e-5;
+	# the max-norm bar of 1e-4 above holds), i.e. up to 2.4e-3 relative for an entry at 1 % of the largest
+	check_training_step(net, xs, ls, max_forked=0.1, elem_floor=1e-2, elem_tol=1e-2)
 	# and the 512-row gradients are the mean of the per-chunk gradients (linearity over independent rows)
 	net.zero_grad()
 	net.batch_loss(x, lab.to(DEV)).backward()
