@@ -504,7 +504,8 @@ def run_inference_sweep(dev, quick=False):
 
 
 # ---- ncu evidence parsed from the committed summaries (never hand-copied numbers) --------------------------------------
-_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "": 1.0}
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "": 1.0, "ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0,
+	"ms": 1e3, "msecond": 1e3}      # durations end up in microseconds
 
 
 def ncu_summary_rows(path):
@@ -535,7 +536,8 @@ def ncu_summary_rows(path):
 
 
 NCU_SUMMARIES = ["profiles/r02_ncu_full_summary.csv", "profiles/r01_ncu_full_summary_final.csv"]
-KERNEL_REGEX = {"K1": "k_proj_tc", "K2": "k_recur_fwd", "K3": "k_recur_bwd", "K4": "k_wgrad_tc", "K5": "k_encode", "K6": "k_head_nll"}
+# the kernels the HEADLINE configuration launches (B = 256: the one-row-per-CTA SIMT recurrences)
+KERNEL_REGEX = {"K1": "k_proj_tc", "K2": "k_recur_fwd<", "K3": "k_recur_bwd<", "K4": "k_wgrad_tc", "K5": "k_encode", "K6": "k_head_nll"}
 
 
 def ncu_evidence(kernel_key):
@@ -550,7 +552,7 @@ def ncu_evidence(kernel_key):
 			r = max(rows, key=lambda q: q.get("gpu__time_duration.sum", 0.0))
 			return {"traffic": r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0),
 				"smem_wavefronts": r.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), "kernel": r["kernel"],
-				"ncu_duration_us": r.get("gpu__time_duration.sum", 0.0) * (1.0 if r.get("gpu__time_duration.sum", 0) > 1e3 else 1.0),
+				"ncu_duration_us": r.get("gpu__time_duration.sum", 0.0),
 				"source": rel}
 	return None
 

@@ -153,8 +153,30 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
         }
     }
     __syncthreads();   // barrier inits (and the compact-row table) visible before anyone issues or waits
-    if (i == 0)
-        for (int c = 0; c < kRing && c < nchunks; ++c) issue_chunk(c);
+    // Frame-dedup variant: the compact rows of one sample are CONSECUTIVE rows of I_u (three for the production encoder),
+    // so they are fetched ONCE, with one bulk copy per sample, into the memory of the ring and indexed per step.  A copy
+    // per (row, step) -- what the ring does for this variant -- costs the SM's TMA unit ~270 cycles per 512-byte
+    // cp.async.bulk (measured, profiles/r02_*): two CTAs per SM made that 540 of the ~1000 cycles of a step.
+    constexpr int kCacheRows = kRing * kChunk;      // compact rows per sample that fit the ring's memory
+    int first[R];
+    bool cached = compact;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        first[r] = (compact && r < nvalid) ? s_r2c[r * T] : 0;
+        if (compact && r < nvalid && s_r2c[r * T + T - 1] - first[r] + 1 > kCacheRows) cached = false;
+    }
+    if (i == 0) {
+        if (cached) {
+            uint32_t total = 0;
+            for (int r = 0; r < nvalid; ++r) total += (uint32_t)(s_r2c[r * T + T - 1] - first[r] + 1) * H * sizeof(float);
+            tc::mbar_expect_tx(s_bar, total);
+            for (int r = 0; r < nvalid; ++r)
+                tc::bulk_g2s(s_in + r * kCacheRows * H, p.I_u + (size_t)first[r] * H,
+                             (uint32_t)(s_r2c[r * T + T - 1] - first[r] + 1) * H * sizeof(float), s_bar);
+        } else {
+            for (int c = 0; c < kRing && c < nchunks; ++c) issue_chunk(c);
+        }
+    }
 
     // column i of W_rec (.) rec_mask -> registers for the whole sequence
     float w[REC ? H : 16];
@@ -181,16 +203,22 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
 
     for (int t = 0; t < T; ++t) {
         const int c = t / kChunk, tt = t - c * kChunk, slot = c % kRing;
-        if (tt == 0) {
-            // every thread is past its last read of chunk c-1 (REC: the step barrier; otherwise sync here), so
-            // its slot can be refilled with chunk c-1+kRing; then wait for chunk c to have landed
-            if (!REC) __syncthreads();
-            if (i == 0 && c >= 1 && c - 1 + kRing < nchunks) issue_chunk(c - 1 + kRing);
-            tc::mbar_wait(s_bar + slot, (c / kRing) & 1);
-        }
         float cur[R];
+        if (cached) {
+            if (t == 0) tc::mbar_wait(s_bar, 0);
 #pragma unroll
-        for (int r = 0; r < R; ++r) cur[r] = valid[r] ? s_in[((slot * R + r) * kChunk + tt) * H + i] : 0.f;
+            for (int r = 0; r < R; ++r) cur[r] = valid[r] ? s_in[(r * kCacheRows + s_r2c[r * T + t] - first[r]) * H + i] : 0.f;
+        } else {
+            if (tt == 0) {
+                // every thread is past its last read of chunk c-1 (REC: the step barrier; otherwise sync here), so
+                // its slot can be refilled with chunk c-1+kRing; then wait for chunk c to have landed
+                if (!REC) __syncthreads();
+                if (i == 0 && c >= 1 && c - 1 + kRing < nchunks) issue_chunk(c - 1 + kRing);
+                tc::mbar_wait(s_bar + slot, (c / kRing) & 1);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) cur[r] = valid[r] ? s_in[((slot * R + r) * kChunk + tt) * H + i] : 0.f;
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float rec = 0.0f;

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_bwd_gen(const BwdParam
 }
 
 // dW_out[i][c] = sum_{b,t} Z[b,t,i] gy[b,t,c];  db[c] = sum_{b,t} gy[b,t,c]   as per-CTA partials for k_finalize_grads.
-// grid = (nparts, H / 128), block = 128: thread = neuron; CTA column q owns the CONTIGUOUS rows [q per, (q+1) per) of the
+// grid = (nparts, ceil(H / 128)), block = 128: thread = neuron; CTA column q owns the CONTIGUOUS rows [q per, (q+1) per) of the
 // (B T) axis, stages their adjoint rows (64 B each) and spike words through shared memory with coalesced loads, then
 // accumulates from shared memory (a load-use chain per row from global memory made this kernel latency-bound: 59 us
 // at B T = 25 600; it runs beside the BPTT sweep and must not outlast it).
@@ -355,11 +355,14 @@ __global__ void __launch_bounds__(128) k_wout_grad(int BT, int H, int O, const u
         __syncthreads();
         for (int idx = tid; idx < n * (kOMax / 4); idx += 128)
             reinterpret_cast<float4*>(s_gy)[idx] = __ldg(reinterpret_cast<const float4*>(gy_scan + (size_t)base * kOMax) + idx);
-        for (int idx = tid; idx < n * 4; idx += 128)      // the four words of this CTA's 128 neurons
-            s_zw[idx] = __ldg(zbits + (size_t)(base + (idx >> 2)) * W32 + blockIdx.y * 4 + (idx & 3));
+        const int wpc = W32 < 4 ? W32 : 4;                // spike words of this CTA's (up to) 128 neurons
+        for (int idx = tid; idx < n * wpc; idx += 128) {
+            const int r = idx / wpc, w = idx - r * wpc;
+            s_zw[r * 4 + w] = __ldg(zbits + (size_t)(base + r) * W32 + blockIdx.y * 4 + w);
+        }
         __syncthreads();
         for (int r = 0; r < n; ++r) {
-            const float z = (float)((s_zw[r * 4 + (tid >> 5)] >> lane) & 1u);
+            const float z = i < H ? (float)((s_zw[r * 4 + (tid >> 5)] >> lane) & 1u) : 0.f;
             const float4* g4 = reinterpret_cast<const float4*>(s_gy + r * kOMax);
 #pragma unroll
             for (int q = 0; q < kOMax / 4; ++q) {
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(128) k_wout_grad(int BT, int H, int O, const u
     }
 #pragma unroll
     for (int c = 0; c < kOMax; ++c)
-        if (c < O) part_wout[((size_t)blockIdx.x * H + i) * O + c] = acc[c];
+        if (c < O && i < H) part_wout[((size_t)blockIdx.x * H + i) * O + c] = acc[c];
     if (blockIdx.y == 0 && tid == 0) {
 #pragma unroll
         for (int c = 0; c < kOMax; ++c)

@@ -17,6 +17,7 @@
 #include "recur_bwd.cuh"
 #include "recur_fwd.cuh"
 #include "recur_gen.cuh"
+#include "recur_nr.cuh"
 #include "recur_tc.cuh"
 #include "recur_wide.cuh"
 #include "runs.cuh"
@@ -124,6 +125,7 @@ struct Plan {
     int kpad;         // K of the projection padded to the k-block
     bool wide;        // H > 128: generic recurrence kernels (recur_gen.cuh), N-tiled tensor-core GEMMs
     bool tcrec;       // tensor-core recurrence kernels (recur_tc.cuh): gy scan + k_wout_grad beside the sweep
+    bool nr;          // non-recurrent layer on the lean scan kernels (recur_nr.cuh)
     bool widetc;      // wide layer on the weight-stationary tensor-core kernels (recur_wide.cuh)
     int w_nmt, w_nnt; // their grid: m-tiles of the batch x n-slices of the hidden axis
     int w_nmt_b, w_npass_b;   // backward: m-tiles (its row tile differs) and passes over the batch
@@ -167,6 +169,7 @@ IzhConsts izh_consts(const SnnkDesc* d)
 
 bool use_tc_recur(const SnnkDesc* d);
 bool use_wide_tc(const SnnkDesc* d);
+bool use_nonrec(const SnnkDesc* d);
 
 Plan make_plan(const SnnkDesc* d)
 {
@@ -183,14 +186,15 @@ Plan make_plan(const SnnkDesc* d)
         if (p.w_nmt_b < 1) p.widetc = false;
         else p.w_npass_b = (d->B + p.w_nmt_b * mtb - 1) / (p.w_nmt_b * mtb);
     }
+    p.nr = use_nonrec(d);
     p.tcrec = use_tc_recur(d) && bwd_tc_smem_bytes(d->T) <= 200 * 1024 && fwd_tc_smem_bytes(d->T) <= 200 * 1024;
     p.R = p.wide ? gen_rows(d->H) : (d->B > 1024 ? 2 : 1);
     p.grid_rows = (d->B + p.R - 1) / p.R;
     const int BT = d->B * d->T;
     p.tileN = p.wide ? 128 : d->H;
     p.ntiles_tc = d->H / p.tileN;
-    p.n_pwout = (p.wide || p.tcrec) ? (BT < 256 ? BT : 256) : p.grid_rows;
-    p.n_pdb = (p.wide || p.tcrec) ? p.n_pwout : p.grid_rows * p.R;
+    p.n_pwout = (p.wide || p.tcrec || p.nr) ? (BT < 256 ? BT : 256) : p.grid_rows;
+    p.n_pdb = (p.wide || p.tcrec || p.nr) ? p.n_pwout : p.grid_rows * p.R;
     p.BN = d->H >= 64 ? 64 : 32;
     p.ntiles = d->H / p.BN;
     p.mtiles_x = (d->N + kGemmBM - 1) / kGemmBM;
@@ -219,7 +223,7 @@ Plan make_plan(const SnnkDesc* d)
     p.off_pw = off;     off = align_up(off + sizeof(float) * (size_t)p.S * p.m_total * d->H, 256);
     p.off_flag = off;   off = align_up(off + 256, 256);
     p.off_weffT = off;  off = align_up(off + sizeof(float) * (size_t)d->H * d->H, 256);
-    p.off_gyscan = off; off = align_up(off + ((p.wide || p.tcrec) ? sizeof(float) * (size_t)BT * kOMax : 0), 256);
+    p.off_gyscan = off; off = align_up(off + ((p.wide || p.tcrec || p.nr) ? sizeof(float) * (size_t)BT * kOMax : 0), 256);
     if (p.widetc) {
         const int nsm = wide_nsm(d->H);
         p.off_gx = off;       off = align_up(off + sizeof(float) * 2 * (size_t)p.w_nmt_b * (d->H / wide_bwd_kc(nsm)) * wide_bwd_chunk_floats(nsm), 256);
@@ -494,6 +498,66 @@ int launch_wide_bwd(const WideBwdParams& wp, int n_pass, cudaStream_t st)
     case 4: return launch_wide_bwd_t<4>(wp, n_pass, st);
     case 2: return launch_wide_bwd_t<2>(wp, n_pass, st);
     default: return launch_wide_bwd_t<1>(wp, n_pass, st);
+    }
+}
+
+// Non-recurrent LIF / ALIF layers of width 32 / 64 / 128 in tensor-core mode: lean scan kernels (recur_nr.cuh).
+// SNNK_NONREC=0 keeps the generic kernels (measuring switch).
+bool use_nonrec(const SnnkDesc* d)
+{
+    if (d->recurrent || d->layer_type == SNNK_IZHIKEVICH || (d->flags & SNNK_F_TENSOR_CORE) == 0) return false;
+    if (d->H != 32 && d->H != 64 && d->H != 128) return false;
+    const char* env = getenv("SNNK_NONREC");
+    return !(env && env[0] == '0');
+}
+
+template <int H>
+int launch_nonrec_fwd_t(const FwdParams& fp, cudaStream_t st)
+{
+    const size_t smem = nonrec_fwd_smem_bytes<H>(fp.T, fp.O);
+    if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
+    auto kern = fp.alif ? k_nonrec_fwd<H, true> : k_nonrec_fwd<H, false>;
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(SNNK_K_RECUR_FWD, st);
+    kern<<<fp.B, H, smem, st>>>(fp);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int launch_nonrec_fwd(const FwdParams& fp, cudaStream_t st)
+{
+    switch (fp.H) {
+    case 32: return launch_nonrec_fwd_t<32>(fp, st);
+    case 64: return launch_nonrec_fwd_t<64>(fp, st);
+    default: return launch_nonrec_fwd_t<128>(fp, st);
+    }
+}
+
+template <int H>
+int launch_nonrec_bwd_t(const BwdParams& bp, const float* gy_scan, cudaStream_t st)
+{
+    const size_t smem = nonrec_bwd_smem_bytes<H>(bp.T);
+    if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
+    void (*kern)(const BwdParams, const float*) = nullptr;
+    switch ((bp.alif ? 2 : 0) + (bp.surrogate ? 1 : 0)) {
+    case 0: kern = k_nonrec_bwd<H, false, 0>; break;
+    case 1: kern = k_nonrec_bwd<H, false, 1>; break;
+    case 2: kern = k_nonrec_bwd<H, true, 0>; break;
+    default: kern = k_nonrec_bwd<H, true, 1>; break;
+    }
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(SNNK_K_RECUR_BWD, st);
+    kern<<<bp.B, H, smem, st>>>(bp, gy_scan);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int launch_nonrec_bwd(const BwdParams& bp, const float* gy_scan, cudaStream_t st)
+{
+    switch (bp.H) {
+    case 32: return launch_nonrec_bwd_t<32>(bp, gy_scan, st);
+    case 64: return launch_nonrec_bwd_t<64>(bp, gy_scan, st);
+    default: return launch_nonrec_bwd_t<128>(bp, gy_scan, st);
     }
 }
 
@@ -1010,6 +1074,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     }
     if (pl.wide) return launch_fwd_wide(d, fp, rec, pl, st);
     if (pl.tcrec) return launch_fwd_tc(fp, st);
+    if (pl.nr) return launch_nonrec_fwd(fp, st);
     switch (d->H) {
     case 32: return launch_fwd_r<32>(fp, rec, pl.R, pl.grid_rows, st);
     case 64: return launch_fwd_r<64>(fp, rec, pl.R, pl.grid_rows, st);
@@ -1207,7 +1272,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         SNNK_CUDA(cudaGetLastError());
     } else if (pl.wide) {
         rc = launch_bwd_wide(d, bp, rec, pl, reinterpret_cast<float*>(ws + pl.off_gyscan), zbits, st);
-    } else if (pl.tcrec) {
+    } else if (pl.tcrec || pl.nr) {
         // readout-adjoint scan first; dW_out / db (a contraction of it with the spike raster) beside the sweep
         float* gy_scan = reinterpret_cast<float*>(ws + pl.off_gyscan);
         {
@@ -1225,11 +1290,11 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         }
         {
             ProfScope ps(SNNK_K_REDUCE_OUT, st_w);
-            k_wout_grad<<<dim3(pl.n_pwout, d->H / 128), 128, 0, st_w>>>(d->B * d->T, d->H, d->O, zbits, gy_scan, pwout, pdb);
+            k_wout_grad<<<dim3(pl.n_pwout, (d->H + 127) / 128), 128, 0, st_w>>>(d->B * d->T, d->H, d->O, zbits, gy_scan, pwout, pdb);
             SNNK_CUDA(cudaGetLastError());
         }
         if (fkw) SNNK_CUDA(cudaEventRecord(fkw->joined3, fkw->side));
-        rc = launch_bwd_tc(bp, gy_scan, st);
+        rc = pl.tcrec ? launch_bwd_tc(bp, gy_scan, st) : launch_nonrec_bwd(bp, gy_scan, st);
     } else {
         switch (d->H) {
         case 32: rc = launch_bwd_r<32>(bp, rec, pl.R, pl.grid_rows, st); break;
