@@ -72,7 +72,7 @@ def test_tensor_core_matches_simt(B, T, N, H, rec, layer):
 	kw = dict(g_logits=gl, tstar=f0["tstar"])
 	g0, g1 = _bwd(d, consts(False), f0, **kw), _bwd(d, consts(True), f0, **kw)
 	tc_sweep = rec and H == 128         # recur_tc.cuh: the sweep itself runs on the tensor cores (22-bit operands)
-	if tc_sweep:
+	if tc_sweep or not rec:             # recur_nr.cuh sums the readout adjoint as four chains: summation order only
 		assert rel_err(npy(g1["gI"]()), npy(g0["gI"]())) <= 1e-5
 	else:
 		assert torch.equal(g0["gI"](), g1["gI"]())          # the two tf32 planes of gI sum back to gI exactly
