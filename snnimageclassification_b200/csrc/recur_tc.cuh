@@ -88,7 +88,8 @@ __device__ __forceinline__ float pow2_scale_for(float mx)
     return __uint_as_float((uint32_t)(k + 127) << 23);
 }
 
-// Block-wide maximum of a non-negative value (all kTcThreads threads call it; s_red: 9 floats of shared memory).
+// Block-wide maximum of a non-negative value (all NT threads of the block call it; s_red: NT / 32 floats of shared memory).
+template <int NT = kTcThreads>
 __device__ __forceinline__ float block_max_tc(float v, float* s_red)
 {
 #pragma unroll
@@ -97,7 +98,7 @@ __device__ __forceinline__ float block_max_tc(float v, float* s_red)
     __syncthreads();
     float m = s_red[0];
 #pragma unroll
-    for (int q = 1; q < kTcThreads / 32; ++q) m = fmaxf(m, s_red[q]);
+    for (int q = 1; q < NT / 32; ++q) m = fmaxf(m, s_red[q]);
     __syncthreads();
     return m;
 }
@@ -146,20 +147,80 @@ __device__ __forceinline__ float absmax_raw(const float (&raw)[KT][8])
     return m;
 }
 
+// ---- forward --------------------------------------------------------------------------------------------------------
+// What bounds this kernel is the SM's load/store pipe, not the tensor pipe and not issue slots (ncu, profiles/r02_*: a
+// step of the first versions moved ~730 shared/global "wavefronts" of 128 B through the LSU and took ~1300 cycles
+// for 290 cycles of MMA; every shared-memory load of the dependency chain queued behind trace stores that touch four
+// cache lines per instruction).  So the design minimises LSU wavefronts per step and keeps everything that merely
+// FOLLOWS the dependency chain off the warps that carry it:
+//
+//   8 NEURON warps (warp w: neurons 16 w ..+15; element e = 2 nh + rh: neuron 16 w + g + 8 nh, row 2 tig + rh), step t:
+//       4 ldmatrix (Z_{t-1}) -> 16 MMAs -> update of the 4 elements (input current: 4 LDS from the ring) -> V_t, a_t,
+//       Z_t as 12 conflict-free STS into a 128B-swizzled staging box -> Z_t by stmatrix into the fp16 spike tile -> the
+//       step's ONE barrier.  No global memory instruction at all.
+//   the traces leave by TMA: every kTcK steps ONE cp.async.bulk.tensor store per array writes the box
+//       {32 neurons, 8 rows, 4 neuron groups, kTcK steps} of the (B, T, H) tensor (a 4-D view: H = 4 x 32) straight
+//       from the staging buffer -- no LSU traffic, full-line writes; rows past the batch are clipped by the map.
+//   4 HELPER warps (helper h: neurons 32 h ..+31), one step behind: cp.async of the input current of step t + kTcDist
+//       into the ring (same swizzled layout); 4 MMAs: readout partial of Z_{t-1} over its 32 neurons, whose spare row
+//       15 (A[15][k] = 2^k) returns the 16 spike bits of each k-tile per row, exact in fp32 -> bit-packed raster.
+//   1 SCAN warp: sums the four readout partials, leaky scan, max over time (two steps behind); its lane 0 issues the
+//       TMA stores.
+constexpr int kTcFwdThreads = 13 * 32;
+constexpr int kTcSlots = 8;        // ring slots (steps of input current resident in shared memory)
+constexpr int kTcDist = 6;         // steps between a copy and its use
+constexpr int kTcK = 4;            // steps per trace box (one TMA store per array)
+constexpr int kTcSlab = 4096;      // bytes of one step of one array in the swizzled layout: [4 hq][8 rows][32 hr] floats
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Byte offset of element (row b, neuron n) inside a 4 KB slab: line = (n / 32) * 8 + b, the 16-byte chunk index
+// (n % 32) / 4 XOR-ed with line % 8 = b  (TMA SWIZZLE_128B over 128-byte lines; the slab is 1024-byte aligned).
+__host__ __device__ constexpr uint32_t tc_slab_off(int b, int n)
+{
+    return (uint32_t)((((n >> 5) * 8 + b) << 7) | (((((n & 31) >> 2) ^ b) & 7) << 4) | ((n & 3) << 2));
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t saddr, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(saddr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 constexpr size_t fwd_tc_smem_bytes(int T)
 {
-    return sizeof(__half) * 2 * kTcRows * kTcTileStride                                   // spike tiles
-           + sizeof(float) * 2 * 8 * 32 * 4                                               // readout partials [2][warp][lane][4]
+    return 1024                                                                           // alignment slack (swizzle atoms)
+           + (size_t)2 * 3 * kTcK * kTcSlab                                               // staging [2][V, a, Z][kTcK] slabs
+           + (size_t)kTcSlots * kTcSlab                                                   // input-current ring
+           + sizeof(__half) * 2 * kTcRows * kTcTileStride                                 // spike tiles [2][8][136]
+           + sizeof(float) * 2 * 4 * 32 * 4                                               // readout partials [2][helper][lane][4]
            + sizeof(int) * (size_t)((kTcRows * T + 3) & ~3)                               // compact row of every (row, step)
            + sizeof(float) * 16;
 }
 
-// ---- forward --------------------------------------------------------------------------------------------------------
-// grid = ceil(B / 8), block = 288.  Recurrent layers only (without the matvec the SIMT kernel has nothing to lose).
+// grid = ceil(B / 8), block = 416.  Recurrent layers only (without the matvec the scan kernels have nothing to lose).
+// mV / mA / mZ: 4-D maps {32, B, 4, T} (strides T H, 32, H floats) of the trace tensors, box {32, 8, 4, kTcK}, SWIZZLE_128B.
 template <bool ALIF>
-__global__ void __launch_bounds__(kTcThreads, 1) k_recur_fwd_tc(const FwdParams p)
+__global__ void __launch_bounds__(kTcFwdThreads, 1) k_recur_fwd_tc(const FwdParams p, const __grid_constant__ CUtensorMap mV,
+                                                                  const __grid_constant__ CUtensorMap mA,
+                                                                  const __grid_constant__ CUtensorMap mZ)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
     constexpr int H = kTcH;
     const int T = p.T, O = p.O, B = p.B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -167,171 +228,225 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_fwd_tc(const FwdParams 
     const int b0 = blockIdx.x * kTcRows;
     const int nvalid = min(kTcRows, B - b0);
 
-    __half* s_z = reinterpret_cast<__half*>(smem_raw);                                          // [2][8][136]
-    float* s_yp = reinterpret_cast<float*>(s_z + 2 * kTcRows * kTcTileStride);                   // [2][8][32][4]
-    int* s_r2c = reinterpret_cast<int*>(s_yp + 2 * 8 * 32 * 4);                                  // [8][T]
+    unsigned char* smem_raw = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* s_stage = smem_raw;                                                           // [2][3][kTcK][4096]
+    unsigned char* s_ring = s_stage + 2 * 3 * kTcK * kTcSlab;                                    // [kTcSlots][4096]
+    __half* s_z = reinterpret_cast<__half*>(s_ring + kTcSlots * kTcSlab);                        // [2][8][136]
+    float* s_yp = reinterpret_cast<float*>(s_z + 2 * kTcRows * kTcTileStride);                   // [2][4][32][4]
+    int* s_r2c = reinterpret_cast<int*>(s_yp + 2 * 4 * 32 * 4);                                  // [8][T]
     float* s_red = reinterpret_cast<float*>(s_r2c + ((kTcRows * T + 3) & ~3));                   // [16]
 
-    // The input current is read straight from global memory / L2 into registers, two steps ahead of its use (four
-    // coalesced 32-byte segments per warp load).  A shared-memory ring fed by per-(row, step) bulk copies was measured
-    // first: the SM's TMA unit takes ~270 cycles per 512-byte cp.async.bulk, 8 of them per step -> 2000 cycles per step.
     // frame-dedup variant: row table[b*T + t] of the compact projection I_u instead of row b*T + t of I_in.
     const bool compact = p.run_table != nullptr && p.run_table[1] == 1;
     if (compact)
-        for (int idx = tid; idx < nvalid * T; idx += kTcThreads)
+        for (int idx = tid; idx < nvalid * T; idx += kTcFwdThreads)
             s_r2c[idx] = __ldg(p.run_table + kRunHdrInts + (size_t)b0 * T + idx);      // rows b0.. are consecutive
     // spike tiles: buffer 1 holds Z_{-1} (the initial state), read by step 0
-    for (int idx = tid; idx < 2 * kTcRows * kTcTileStride; idx += kTcThreads) s_z[idx] = __float2half_rn(0.f);
+    for (int idx = tid; idx < 2 * kTcRows * kTcTileStride; idx += kTcFwdThreads) s_z[idx] = __float2half_rn(0.f);
     __syncthreads();
     if (p.Z0)
-        for (int idx = tid; idx < kTcRows * H; idx += kTcThreads) {
+        for (int idx = tid; idx < kTcRows * H; idx += kTcFwdThreads) {
             const int r = idx / H, c = idx - r * H;
             if (b0 + r < B) s_z[(kTcRows + r) * kTcTileStride + c] = __float2half_rn(p.Z0[(size_t)(b0 + r) * H + c]);
         }
-
-    // ldmatrix source of this lane inside a tile: matrix j = lane >> 3 covers k = 8 j .. 8 j + 7 of a 32-wide k group
-    const uint32_t tile_base = tc::smem_u32(s_z) + (uint32_t)((lane & 7) * kTcTileStride + 8 * (lane >> 3)) * 2;
     constexpr uint32_t kTileBytes = kTcRows * kTcTileStride * 2;
+    const uint32_t z_u32 = tc::smem_u32(s_z);
+    const bool traces = p.traces != 0;
+    // barrier count of every role: 1 (above) + 4 (two block maxima) + 1 (ready) + T + 1
 
     if (warp < 8) {
         // ---------------- neuron warps: neurons 16 warp .. 16 warp + 15 ----------------
         const int i0 = 16 * warp;
         uint32_t ah[8][4], al[8][4];          // W_eff^T fragments, two fp16 planes: 64 registers for the whole sequence
-        uint32_t oh[4], ol[4];                // W_out^T fragment of this warp's 16 neurons (readout partial)
-        float inv_s, inv_so;
+        float inv_s;
         {
             float raw[8][8];
             load_a_raw<8>(p.W_eff, H, i0, H, g, tig, raw);
-            const float mx = block_max_tc(absmax_raw<8>(raw), s_red);
+            const float mx = block_max_tc<kTcFwdThreads>(absmax_raw<8>(raw), s_red);
             const float s = pow2_scale_for(mx);
             inv_s = __fdiv_rn(1.0f, s);
             split_a<8>(raw, s, ah, al);
-            // readout: A[m = class][k = neuron i0 + k] = W_out[i0 + k][m]
-            float ro[1][8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k = 2 * tig + (q & 1) + 8 * (q >> 2), m = g + 8 * ((q >> 1) & 1);
-                ro[0][q] = m < O ? __ldg(p.W_out + (size_t)(i0 + k) * O + m) : 0.f;
-            }
-            const float mo = block_max_tc(absmax_raw<1>(ro), s_red);
-            const float so = pow2_scale_for(mo);
-            inv_so = __fdiv_rn(1.0f, so);
-            uint32_t th[1][4], tl[1][4];
-            split_a<1>(ro, so, th, tl);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { oh[r] = th[0][r]; ol[r] = tl[0][r]; }
+            block_max_tc<kTcFwdThreads>(0.f, s_red);      // the helpers' reduction (readout scale)
         }
         const float beta = (ALIF && p.beta) ? __ldg(p.beta) : 0.f;
-        // element e = 2 nh + rh: neuron i0 + g + 8 nh, row 2 tig + rh   (the accumulator fragment layout)
-        float v[4], a[4], zp[4];
-        bool ok[4];
+        const float alpha = p.alpha, rho = p.rho, theta = p.theta;
+        // Rows past the batch compute on a copy of the last valid row (their columns of the MMA are independent); the
+        // trace boxes are clipped at the batch by the tensor maps.
+        float v[4], a[4], zp[4], nz[4];       // zp = Z_{t-1}, nz = 1 - Z_{t-1}
+        uint32_t eo[4];                       // slab offsets of the 4 elements
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int row = 2 * tig + (e & 1), col = i0 + g + 8 * (e >> 1);
-            ok[e] = b0 + row < B;
-            const size_t s = (size_t)(ok[e] ? b0 + row : 0) * H + col;
-            v[e] = (ok[e] && p.V0) ? p.V0[s] : 0.f;
-            a[e] = (ok[e] && p.a0) ? p.a0[s] : 0.f;
-            zp[e] = (ok[e] && p.Z0) ? p.Z0[s] : 0.f;
+            const int rowc = min(2 * tig + (e & 1), nvalid - 1);
+            const size_t s = (size_t)(b0 + rowc) * H + i0 + g + 8 * (e >> 1);
+            v[e] = p.V0 ? p.V0[s] : 0.f;
+            a[e] = p.a0 ? p.a0[s] : 0.f;
+            zp[e] = p.Z0 ? p.Z0[s] : 0.f;
+            nz[e] = __fsub_rn(1.0f, zp[e]);
+            eo[e] = tc_slab_off(2 * tig + (e & 1), i0 + g + 8 * (e >> 1));
         }
-        const size_t o_base = ((size_t)(b0 + 2 * tig) * T) * H + i0 + g;      // (row 2 tig, t = 0, neuron i0 + g)
-        const size_t o_row = (size_t)T * H;
-        __syncthreads();      // tiles and the compact-row table initialised
-        auto load_cur = [&](int tl, float (&dst)[4]) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                dst[e] = 0.f;
-                if (tl < T && ok[e]) {
-                    const int rh = e & 1;
-                    const float* src = compact ? p.I_u + (size_t)s_r2c[(2 * tig + rh) * T + tl] * H + i0 + g
-                                               : p.I_in + o_base + (size_t)tl * H + rh * o_row;
-                    dst[e] = __ldg(src + 8 * (e >> 1));
-                }
-            }
-        };
-        float cur[4], nx1[4], nx2[4];
-        load_cur(0, cur);
-        load_cur(1, nx1);
+        // ldmatrix source of this lane inside a tile: matrix j = lane >> 3 covers k = 8 j .. 8 j + 7 of a 32-wide k group
+        const uint32_t tile_base = z_u32 + (uint32_t)((lane & 7) * kTcTileStride + 8 * (lane >> 3)) * 2;
+        const uint32_t st_off = (uint32_t)((lane & 7) * kTcTileStride + i0 + 8 * ((lane >> 3) & 1)) * 2;
+        const uint32_t ring_u32 = tc::smem_u32(s_ring), stage_u32 = tc::smem_u32(s_stage);
+        __syncthreads();      // ready: tiles, table and the first ring slot
 
-        for (int t = 0; t <= T; ++t) {
-            load_cur(t + 2, nx2);
+        for (int t = 0; t < T; ++t) {
+            const uint32_t rd = ((t + 1) & 1) * kTileBytes;
             // B fragments of Z_{t-1}: bfr[kt] = (k = 16 kt + 2 tig + {0,1}, n = g), (k + 8 ..)
             uint32_t bfr[8][2];
-            const uint32_t tb = tile_base + ((t + 1) & 1) * kTileBytes;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t r[4];
-                ldsm_x4(r, tb + q * 64);
+                ldsm_x4(r, tile_base + rd + q * 64);
                 bfr[2 * q][0] = r[0]; bfr[2 * q][1] = r[1]; bfr[2 * q + 1][0] = r[2]; bfr[2 * q + 1][1] = r[3];
             }
-            if (t >= 1) {
-                // readout partial of step t-1 over this warp's 16 neurons: (classes x rows) += W_out^T[:, i0..] Z_{t-1}^T
-                // (its B fragment = k-tile `warp` of the tile, fetched by address: indexing bfr[] with the warp number
-                // would put the array into local memory)
-                float yh[4] = {0.f, 0.f, 0.f, 0.f}, yl[4] = {0.f, 0.f, 0.f, 0.f};
-                const uint32_t* own = reinterpret_cast<const uint32_t*>(s_z + (((t + 1) & 1) * kTcRows + g) * kTcTileStride + i0 + 2 * tig);
-                const uint32_t bo[2] = {own[0], own[4]};
-                mma_f16(yh, oh, bo);
-                mma_f16(yl, ol, bo);
-                float4 part;
-                part.x = __fmul_rn(fmaf(yl[0], 1.0f / 2048.0f, yh[0]), inv_so);
-                part.y = __fmul_rn(fmaf(yl[1], 1.0f / 2048.0f, yh[1]), inv_so);
-                part.z = __fmul_rn(fmaf(yl[2], 1.0f / 2048.0f, yh[2]), inv_so);
-                part.w = __fmul_rn(fmaf(yl[3], 1.0f / 2048.0f, yh[3]), inv_so);
-                reinterpret_cast<float4*>(s_yp)[((t & 1) * 8 + warp) * 32 + lane] = part;
+            float cur[4];
+            {
+                const uint32_t cs = ring_u32 + (uint32_t)(t & (kTcSlots - 1)) * kTcSlab;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur[e]) : "r"(cs + eo[e]));
             }
-            if (t < T) {
-                float ch[4] = {0.f, 0.f, 0.f, 0.f}, cl[4] = {0.f, 0.f, 0.f, 0.f};
+            float ch[4] = {0.f, 0.f, 0.f, 0.f}, cl[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int kt = 0; kt < 8; ++kt) {
-                    mma_f16(ch, ah[kt], bfr[kt]);
-                    mma_f16(cl, al[kt], bfr[kt]);
-                }
-                uint32_t zpk[2];
-#pragma unroll
-                for (int nh = 0; nh < 2; ++nh) {
-                    __half zh[2];
-#pragma unroll
-                    for (int rh = 0; rh < 2; ++rh) {
-                        const int e = 2 * nh + rh;
-                        const float rec = __fmul_rn(fmaf(cl[e], 1.0f / 2048.0f, ch[e]), inv_s);
-                        // V' = (alpha V + I_in + I_rec)(1 - Z.detach())          spiking_layers.py:169/239
-                        const float t1 = __fmul_rn(p.alpha, v[e]);
-                        const float t2 = __fadd_rn(t1, cur[e]);
-                        const float t3 = __fadd_rn(t2, rec);
-                        const float vn = __fmul_rn(t3, __fsub_rn(1.0f, zp[e]));
-                        float thr = p.theta;
-                        if constexpr (ALIF) {
-                            a[e] = __fadd_rn(__fmul_rn(p.rho, a[e]), zp[e]);          // :240
-                            thr = __fadd_rn(p.theta, __fmul_rn(beta, a[e]));          // :241
-                        }
-                        const float zn = vn >= thr ? 1.0f : 0.0f;                     // spike_funcs.py:27-28
-                        if (p.traces && ok[e]) {
-                            const size_t o = o_base + (size_t)t * H + rh * o_row + 8 * nh;
-                            p.V[o] = vn;
-                            p.Z[o] = zn;
-                            if constexpr (ALIF) p.a[o] = a[e];
-                        }
-                        v[e] = vn;
-                        zp[e] = zn;
-                        zh[rh] = __float2half_rn(zn);
-                    }
-                    zpk[nh] = pack_h2(zh[0], zh[1]);
-                }
-                // publish Z_t: tile[t & 1][row n][i0 + 8 j + m]  (matrix j: lanes 8 j .. 8 j + 7 give the row addresses)
-                const uint32_t sa = tc::smem_u32(s_z) + (uint32_t)(((t & 1) * kTcRows + (lane & 7)) * kTcTileStride + i0 +
-                                                                   8 * ((lane >> 3) & 1)) * 2;
-                stsm_x2_trans(sa, zpk[0], zpk[1]);
+            for (int kt = 0; kt < 8; ++kt) {
+                mma_f16(ch, ah[kt], bfr[kt]);
+                mma_f16(cl, al[kt], bfr[kt]);
             }
+            bool spk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { cur[e] = nx1[e]; nx1[e] = nx2[e]; }
+            for (int e = 0; e < 4; ++e) {
+                const float rec = __fmul_rn(fmaf(cl[e], 1.0f / 2048.0f, ch[e]), inv_s);
+                // V' = (alpha V + I_in + I_rec)(1 - Z.detach())          spiking_layers.py:169/239
+                const float t1 = __fmul_rn(alpha, v[e]);
+                const float t2 = __fadd_rn(t1, cur[e]);
+                const float t3 = __fadd_rn(t2, rec);
+                const float vn = __fmul_rn(t3, nz[e]);
+                float thr = theta;
+                if constexpr (ALIF) {
+                    a[e] = __fadd_rn(__fmul_rn(rho, a[e]), zp[e]);                   // :240
+                    thr = __fadd_rn(theta, __fmul_rn(beta, a[e]));                   // :241
+                }
+                spk[e] = vn >= thr;                                                  // spike_funcs.py:27-28
+                zp[e] = spk[e] ? 1.0f : 0.0f;
+                nz[e] = spk[e] ? 0.0f : 1.0f;
+                v[e] = vn;
+            }
+            if (traces) {      // V_t, a_t, Z_t into the staging box of steps kTcK * (t / kTcK) ..
+                const uint32_t sb = stage_u32 + (uint32_t)(((t / kTcK) & 1) * 3 * kTcK + (t % kTcK)) * kTcSlab;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + eo[e]), "f"(v[e]) : "memory");
+                    if constexpr (ALIF) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + eo[e] + kTcK * kTcSlab), "f"(a[e]) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + eo[e] + 2 * kTcK * kTcSlab), "f"(zp[e]) : "memory");
+                }
+                if ((t % kTcK) == kTcK - 1 || t == T - 1) fence_proxy_async();      // box complete: visible to the TMA store
+            }
+            // publish Z_t: tile[t & 1][row n][i0 + 8 j + m]  (matrix j: lanes 8 j .. 8 j + 7 give the row addresses);
+            // fp16 1.0 = 0x3C00
+            const uint32_t zp0 = (spk[0] ? 0x3C00u : 0u) | (spk[1] ? 0x3C000000u : 0u);
+            const uint32_t zp1 = (spk[2] ? 0x3C00u : 0u) | (spk[3] ? 0x3C000000u : 0u);
+            stsm_x2_trans(z_u32 + (t & 1) * kTileBytes + st_off, zp0, zp1);
             __syncthreads();
         }
+        __syncthreads();      // the helpers' / scan warp's flush step
+    } else if (warp < 12) {
+        // ---------------- helper warps: neurons 32 h .. 32 h + 31 ----------------
+        const int h = warp - 8;
+        block_max_tc<kTcFwdThreads>(0.f, s_red);      // the neuron warps' reduction (recurrent scale)
+        // readout: A[m = class][k = neuron 32 h + 16 j + k] = W_out[.][m] for the two k-tiles j = 0, 1 of this helper
+        uint32_t oh[2][4], ol[2][4];
+        float inv_so;
+        {
+            float ro[2][8];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = 2 * tig + (q & 1) + 8 * (q >> 2), m = g + 8 * ((q >> 1) & 1);
+                    ro[j][q] = m < O ? __ldg(p.W_out + (size_t)(32 * h + 16 * j + k) * O + m) : 0.f;
+                }
+            const float mo = block_max_tc<kTcFwdThreads>(absmax_raw<2>(ro), s_red);
+            const float so = pow2_scale_for(mo);
+            inv_so = __fdiv_rn(1.0f, so);
+            split_a<2>(ro, so, oh, ol);
+            if (g == 7) {
+                // row m = 15 (no class lives there: O <= 15 on this path) of the hi planes: A[15][k] = 2^k, so that
+                // D[15][n] = sum_k 2^k Z[n][k-tile neuron k] = the 16 spike bits of row n, exact in fp32.  This thread
+                // holds a1 = (m 15, k 2 tig, 2 tig + 1) and a3 = (m 15, k 2 tig + 8, 2 tig + 9).
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    oh[j][1] = pack_h2(__float2half_rn((float)(1u << (2 * tig))), __float2half_rn((float)(2u << (2 * tig))));
+                    oh[j][3] = pack_h2(__float2half_rn((float)(256u << (2 * tig))), __float2half_rn((float)(512u << (2 * tig))));
+                    ol[j][1] = 0u;
+                    ol[j][3] = 0u;
+                }
+            }
+        }
+        // input current of step ts: this helper fills the 8 lines (rows) of neuron group h of the slot, 64 chunks of
+        // 16 bytes, two per lane: chunk (row = lane >> 3 (+ 4), c = lane & 7) -> swizzled position c ^ row
+        const int c = lane & 7;
+        const int rwA = lane >> 3, rwB = rwA + 4;
+        const int rcA = min(rwA, nvalid - 1), rcB = min(rwB, nvalid - 1);
+        const float* srcA = p.I_in + ((size_t)(b0 + rcA) * T) * H + 32 * h + 4 * c;
+        const float* srcB = p.I_in + ((size_t)(b0 + rcB) * T) * H + 32 * h + 4 * c;
+        const float* src_u = p.I_u + 32 * h + 4 * c;
+        const int* r2cA = s_r2c + rcA * T;
+        const int* r2cB = s_r2c + rcB * T;
+        const uint32_t dA = tc::smem_u32(s_ring) + (uint32_t)(((h * 8 + rwA) << 7) | ((c ^ rwA) << 4));
+        const uint32_t dB = tc::smem_u32(s_ring) + (uint32_t)(((h * 8 + rwB) << 7) | ((c ^ rwB) << 4));
+        auto prefetch = [&](int ts) {
+            if (ts < T) {
+                const uint32_t so = (uint32_t)(ts & (kTcSlots - 1)) * kTcSlab;
+                cp_async16(dA + so, compact ? src_u + (size_t)r2cA[ts] * H : srcA + (size_t)ts * H);
+                cp_async16(dB + so, compact ? src_u + (size_t)r2cB[ts] * H : srcB + (size_t)ts * H);
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int d = 0; d < kTcDist; ++d) prefetch(d);
+        cp_async_wait<kTcDist - 1>();      // step 0 has landed
+        const uint32_t own_off = (uint32_t)(g * kTcTileStride + 32 * h + 2 * tig) * 2;      // B fragment (n = g) of k-tile 2 h
+        const int rA = 2 * tig, rB = 2 * tig + 1;                                            // rows of this lane's D fragment
+        const bool zstA = g == 7 && rA < nvalid, zstB = g == 7 && rB < nvalid;
+        size_t zoffA = ((size_t)(b0 + min(rA, nvalid - 1)) * T) * (H / 32) + h;
+        size_t zoffB = ((size_t)(b0 + min(rB, nvalid - 1)) * T) * (H / 32) + h;
+        __syncthreads();      // ready
+
+        for (int t = 0; t <= T; ++t) {
+            prefetch(t + kTcDist);
+            if (t >= 1) {
+                const int pb = (t + 1) & 1;      // tile written during step t - 1
+                // ---- readout partial of step t-1 over this helper's 32 neurons + the spike bits ----
+                float yh0[4] = {0.f, 0.f, 0.f, 0.f}, yh1[4] = {0.f, 0.f, 0.f, 0.f}, yl[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t bA[2], bB[2];
+                const uint32_t ta = z_u32 + pb * kTileBytes + own_off;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bA[0]) : "r"(ta));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bA[1]) : "r"(ta + 16));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bB[0]) : "r"(ta + 32));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bB[1]) : "r"(ta + 48));
+                mma_f16(yh0, oh[0], bA);
+                mma_f16(yh1, oh[1], bB);
+                mma_f16(yl, ol[0], bA);
+                mma_f16(yl, ol[1], bB);
+                if (zstA) p.zbits[zoffA] = __float2uint_rn(yh0[2]) | (__float2uint_rn(yh1[2]) << 16);
+                if (zstB) p.zbits[zoffB] = __float2uint_rn(yh0[3]) | (__float2uint_rn(yh1[3]) << 16);
+                zoffA += H / 32;
+                zoffB += H / 32;
+                float4 part;
+                part.x = __fmul_rn(fmaf(yl[0], 1.0f / 2048.0f, __fadd_rn(yh0[0], yh1[0])), inv_so);
+                part.y = __fmul_rn(fmaf(yl[1], 1.0f / 2048.0f, __fadd_rn(yh0[1], yh1[1])), inv_so);
+                part.z = __fmul_rn(fmaf(yl[2], 1.0f / 2048.0f, __fadd_rn(yh0[2], yh1[2])), inv_so);
+                part.w = __fmul_rn(fmaf(yl[3], 1.0f / 2048.0f, __fadd_rn(yh0[3], yh1[3])), inv_so);
+                reinterpret_cast<float4*>(s_yp)[((t & 1) * 4 + h) * 32 + lane] = part;
+            }
+            cp_async_wait<kTcDist - 1>();      // the input current of step t + 1 has landed
+            __syncthreads();
+        }
+        cp_async_wait<0>();
     } else {
-        // ---------------- service warp: bit-packed raster, readout scan + max over time ----------------
-        // (two block_max_tc calls above contain __syncthreads: take part in them)
-        block_max_tc(0.f, s_red);
-        block_max_tc(0.f, s_red);
+        // ---------------- scan warp: TMA trace stores; readout scan + max over time, two steps behind ----------------
+        block_max_tc<kTcFwdThreads>(0.f, s_red);
+        block_max_tc<kTcFwdThreads>(0.f, s_red);
         float yv[4], mx[4], bias[4];
         int mt[4];
 #pragma unroll
@@ -340,42 +455,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_fwd_tc(const FwdParams 
             yv[e] = 0.f; mx[e] = 0.f; mt[e] = 0;
             bias[e] = cls < O ? __ldg(p.b_out + cls) : 0.f;
         }
-        auto finish_y = [&](int ty, int buf) {      // y_ty = kappa y_{ty-1} + sum of the 8 warps' partials + b
-            float4 acc = reinterpret_cast<const float4*>(s_yp)[(buf * 8 + 0) * 32 + lane];
+        const float kappa = p.kappa;
+        auto finish_y = [&](int ty, int buf) {      // y_ty = kappa y_{ty-1} + sum of the 4 helpers' partials + b
+            float4 q[4];
 #pragma unroll
-            for (int w = 1; w < 8; ++w) {
-                const float4 q = reinterpret_cast<const float4*>(s_yp)[(buf * 8 + w) * 32 + lane];
-                acc.x = __fadd_rn(acc.x, q.x); acc.y = __fadd_rn(acc.y, q.y);
-                acc.z = __fadd_rn(acc.z, q.z); acc.w = __fadd_rn(acc.w, q.w);
+            for (int w = 0; w < 4; ++w) q[w] = reinterpret_cast<const float4*>(s_yp)[(buf * 4 + w) * 32 + lane];
+            float s4[4] = {q[0].x, q[0].y, q[0].z, q[0].w};
+            // ascending neuron blocks (the order of the fp32 kernels' neuron sum, coarsened to 32-neuron blocks)
+#pragma unroll
+            for (int w = 1; w < 4; ++w) {
+                s4[0] = __fadd_rn(s4[0], q[w].x); s4[1] = __fadd_rn(s4[1], q[w].y);
+                s4[2] = __fadd_rn(s4[2], q[w].z); s4[3] = __fadd_rn(s4[3], q[w].w);
             }
-            const float s4[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int cls = g + 8 * (e >> 1), row = 2 * tig + (e & 1);
-                const float y = __fadd_rn(__fadd_rn(__fmul_rn(p.kappa, yv[e]), s4[e]), bias[e]);     // spiking_layers.py:407
+                const float y = __fadd_rn(__fadd_rn(__fmul_rn(kappa, yv[e]), s4[e]), bias[e]);     // spiking_layers.py:407
                 yv[e] = y;
                 if (ty == 0 || y > mx[e]) { mx[e] = y; mt[e] = ty; }                                 // first max wins (snn.py:228)
                 if (cls < O && b0 + row < B) p.y[((size_t)(b0 + row) * T + ty) * O + cls] = y;
             }
         };
-        __syncthreads();
+        const uint32_t stage_u32 = tc::smem_u32(s_stage);
+        if (lane == 0 && traces) {
+            tc::prefetch_tmap(&mV);
+            tc::prefetch_tmap(&mZ);
+            if (ALIF) tc::prefetch_tmap(&mA);
+        }
+        __syncthreads();      // ready
         for (int t = 0; t <= T; ++t) {
-            if (t >= 1) {
-                // bit-packed raster of step t - 1 from its fp16 tile (1.0 = 0x3C00: bit 13 of each half)
-                const int row = lane >> 2, qd = lane & 3;
-                const uint4* src = reinterpret_cast<const uint4*>(s_z + (((t + 1) & 1) * kTcRows + row) * kTcTileStride + 32 * qd);
-                uint32_t word = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint4 h = src[q];
-                    const uint32_t xs[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        word |= (((xs[j] >> 13) & 1u) | ((xs[j] >> 28) & 2u)) << (8 * q + 2 * j);
-                }
-                if (b0 + row < B) p.zbits[((size_t)(b0 + row) * T + (t - 1)) * (H / 32) + qd] = word;
+            // the box of steps kTcK q .. was completed by step t - 1 (t a multiple of kTcK, or the last, partial box)
+            if (traces && lane == 0 && t >= 1 && ((t % kTcK) == 0 || t == T)) {
+                const int q = (t - 1) / kTcK;
+                const uint32_t sb = stage_u32 + (uint32_t)((q & 1) * 3 * kTcK) * kTcSlab;
+                tma_store_4d(&mV, sb, 0, b0, 0, q * kTcK);
+                if (ALIF) tma_store_4d(&mA, sb + kTcK * kTcSlab, 0, b0, 0, q * kTcK);
+                tma_store_4d(&mZ, sb + 2 * kTcK * kTcSlab, 0, b0, 0, q * kTcK);
+                tma_store_commit();
             }
             if (t >= 2) finish_y(t - 2, (t - 1) & 1);
+            // the other staging buffer is written again from step t + 1 on: its store must have read it by then
+            if (traces && lane == 0 && (t % kTcK) == kTcK - 1) tma_store_wait_read();
             __syncthreads();
         }
         finish_y(T - 1, T & 1);
@@ -387,6 +507,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_fwd_tc(const FwdParams 
                 p.tstar[(size_t)(b0 + row) * O + cls] = mt[e];
             }
         }
+        if (lane == 0) tma_store_wait_all();
     }
 }
 
@@ -425,14 +546,66 @@ __global__ void __launch_bounds__(256) k_gy_scan(int B, int T, int O, float kapp
 }
 
 // ---- backward -------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int tc_zstride(int T) { return ((T + 1) * (kTcH / 32) + 3) & ~3; }      // words per row of the spike-word table
+
 constexpr size_t bwd_tc_smem_bytes(int T)
 {
     return sizeof(__half) * 2 * 2 * kTcRows * kTcTileStride                                 // gI tiles [buf][plane][8][136]
            + sizeof(__half) * 2 * (size_t)T * kTcRows * 16                                  // gy planes [plane][T][8][16]
-           + sizeof(uint32_t) * (size_t)kTcRows * (((T + 1) * (kTcH / 32) + 3) & ~3)         // spike words [8][T+1][4] (slot 0: Z_{-1})
+           + sizeof(float) * 8 * 256 * kTcSlots                                             // V / a ring: 32 B per thread and cell
+           + sizeof(uint32_t) * (size_t)kTcRows * tc_zstride(T)                             // spike words [8][T+1][4] (slot 0: Z_{-1})
            + sizeof(uint32_t) * (size_t)kTcRows * ((T + 31) / 32 + 1)                        // run-start bits
            + sizeof(float) * 16;
 }
+
+// Surrogate derivatives with the hardware reciprocal (1 ulp): the tensor-core sweep does not promise the fp32 kernels'
+// bit pattern anyway (22-bit operands), and __frcp_rn / __fdiv_rn are 8-15 instructions each on this issue-bound path.
+__device__ __forceinline__ float rcp_fast(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+template <int SURR>
+__device__ __forceinline__ float surrogate_grad_fast(float gamma, float v, float thr)
+{
+    if constexpr (SURR == 0) {      // spike_funcs.py:59-62
+        const float d = fmaf(gamma, fabsf(__fsub_rn(v, thr)), 1.0f);
+        return rcp_fast(__fmul_rn(d, d));
+    } else {                        // spike_funcs.py:75-79
+        const float inv = rcp_fast(__fadd_rn(thr, 1e-5f));
+        const float r = fmaxf(__fsub_rn(1.0f, fabsf(__fmul_rn(__fsub_rn(v, thr), inv))), 0.f);
+        return __fmul_rn(__fmul_rn(gamma, inv), r);
+    }
+}
+
+// The gradient tile of a step is published as two fp16 planes under a power-of-two scale 2^kexp that is STICKY: it
+// changes only when the largest exponent class of a tile (classes of 8 binades, OR-ed into a shared word before the
+// step's barrier) leaves the window in which fp16 still carries 22 bits relative to the tile's maximum
+// (scaled maximum in [2^-14, 2^10): one class up, two classes down).  A tile found outside the window when it is
+// about to be read is re-published under the new scale (one extra barrier; happens a handful of times per sequence),
+// so the common step has ONE barrier.  All threads derive the decision from the same shared word: it is uniform.
+struct TcScale {
+    int top;          // exponent class the current scale was chosen for
+    float s, inv;     // 2^kexp and its reciprocal
+    __device__ __forceinline__ void set(int t)
+    {
+        top = t;
+        int kexp = 129 - 8 * t;                          // scaled maximum in [2^2, 2^10)
+        kexp = kexp > 126 ? 126 : (kexp < -126 ? -126 : kexp);
+        s = __uint_as_float((uint32_t)(kexp + 127) << 23);
+        inv = __uint_as_float((uint32_t)(127 - kexp) << 23);
+    }
+    // mask: exponent classes present in the tile about to be read; true -> the tile must be re-published
+    __device__ __forceinline__ bool update(uint32_t mask)
+    {
+        if (!mask) return false;
+        const int t = 31 - __clz(mask);
+        if (t <= top && t >= top - 2) return false;
+        set(t);
+        return true;
+    }
+};
 
 // grid = ceil(B / 8), block = 288.  gy_scan: output of k_gy_scan.  Writes gI (one or two tf32 planes) and, with a
 // frame-run table, the run sums; dW_out / db are NOT produced here (k_wout_grad).
@@ -446,18 +619,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
     const int g = lane >> 2, tig = lane & 3;
     const int b0 = blockIdx.x * kTcRows;
     const int nvalid = min(kTcRows, B - b0);
-    const int zstride = ((T + 1) * W32 + 3) & ~3;      // words per row of the spike-word table
+    const int zstride = tc_zstride(T);
     const int TW = (T + 31) / 32 + 1;
 
     __half* s_g = reinterpret_cast<__half*>(smem_raw);                                       // [2][2][8][136]
     __half* s_gy = s_g + 2 * 2 * kTcRows * kTcTileStride;                                    // [2][T][8][16]
-    uint32_t* s_zw = reinterpret_cast<uint32_t*>(s_gy + 2 * (size_t)T * kTcRows * 16);       // [8][zstride]
+    float* s_ring = reinterpret_cast<float*>(s_gy + 2 * (size_t)T * kTcRows * 16);           // [kTcSlots][256][8]
+    uint32_t* s_zw = reinterpret_cast<uint32_t*>(s_ring + 8 * 256 * kTcSlots);               // [8][zstride]
     uint32_t* s_start = s_zw + (size_t)kTcRows * zstride;                                    // [8][TW]
-    float* s_red = reinterpret_cast<float*>(s_start + kTcRows * TW);                         // [12] + exponent-class words [2]
+    float* s_red = reinterpret_cast<float*>(s_start + kTcRows * TW);                         // [12] + exponent-class words [3]
     uint32_t* s_cls = reinterpret_cast<uint32_t*>(s_red + 12);
 
     const bool run_sums = p.run_table != nullptr && p.run_table[1] == 1;
-    if (tid == 256) s_cls[0] = s_cls[1] = 0u;
+    if (tid == 256) s_cls[0] = s_cls[1] = s_cls[2] = 0u;
     // gradient tiles start at zero (gI_T = 0)
     for (int idx = tid; idx < 2 * 2 * kTcRows * kTcTileStride; idx += kTcThreads) s_g[idx] = __float2half_rn(0.f);
     // spike words: slot 0 of a row is Z_{-1} (initial state), slot t + 1 is Z_t
@@ -508,9 +682,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
     }
 
     constexpr uint32_t kTileBytes = kTcRows * kTcTileStride * 2;       // one plane of one buffer
-    const uint32_t tile_base = tc::smem_u32(s_g) + (uint32_t)((lane & 7) * kTcTileStride + 8 * (lane >> 3)) * 2;
+    const uint32_t g_u32 = tc::smem_u32(s_g);
+    const uint32_t tile_base = g_u32 + (uint32_t)((lane & 7) * kTcTileStride + 8 * (lane >> 3)) * 2;
     // ldmatrix.x4 source inside the gy planes: matrices (hi k 0-7, hi k 8-15, lo k 0-7, lo k 8-15)
     const uint32_t gy_base = tc::smem_u32(s_gy) + (uint32_t)(((lane >> 4) * T * kTcRows + (lane & 7)) * 16 + 8 * ((lane >> 3) & 1)) * 2;
+
+    TcScale sc;
+    sc.set(16);
+    int c_rd = 0, c_wr = 1, c_zr = 2;      // exponent-class words: of the tile being read, being written, to clear
 
     if (warp < 8) {
         const int i0 = 16 * warp;
@@ -537,42 +716,94 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
             for (int r = 0; r < 4; ++r) { oh[r] = th[0][r]; ol[r] = tl[0][r]; }
         }
         const float beta = (ALIF && p.beta) ? __ldg(p.beta) : 0.f;
-        float gv[4], racc[4];
-        int crow[2];
-        uint32_t sbits[2];
-        bool ok[4];
+        const float alpha = p.alpha, theta = p.theta, gamma = p.gamma;
+        // element e = 2 nh + rh: neuron i0 + g + 8 nh, row 2 tig + rh.  Rows past the batch sweep a copy of the last
+        // valid row (their columns of the MMA are independent) and store nothing.
+        float gv[4], racc[4], gi[4];
+        int crow[2], rowc[2];
+        uint32_t sbits[2], wt[2];
+        bool okr[2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { gv[e] = 0.f; racc[e] = 0.f; ok[e] = b0 + 2 * tig + (e & 1) < B; }
+        for (int e = 0; e < 4; ++e) { gv[e] = 0.f; racc[e] = 0.f; gi[e] = 0.f; }
 #pragma unroll
         for (int rh = 0; rh < 2; ++rh) {
-            crow[rh] = (run_sums && ok[rh]) ? __ldg(p.run_table + kRunHdrInts + (size_t)(b0 + 2 * tig + rh) * T + T - 1) : 0;
+            okr[rh] = b0 + 2 * tig + rh < B;
+            rowc[rh] = min(2 * tig + rh, nvalid - 1);
+            crow[rh] = run_sums ? __ldg(p.run_table + kRunHdrInts + (size_t)(b0 + rowc[rh]) * T + T - 1) : 0;
             sbits[rh] = 0u;
         }
-        const size_t o_base = ((size_t)(b0 + 2 * tig) * T) * H + i0 + g;
-        const size_t o_row = (size_t)T * H;
+        const bool sums0 = run_sums && okr[0], sums1 = run_sums && okr[1];
+        // element offset of (row 2 tig + rh, step T - 1, neuron i0 + g) in the (B, T, H) tensors
+        size_t off0 = ((size_t)(b0 + rowc[0]) * T + (T - 1)) * H + i0 + g, off1 = ((size_t)(b0 + rowc[1]) * T + (T - 1)) * H + i0 + g;
+        const float* v0 = p.V + ((size_t)(b0 + rowc[0]) * T) * H + i0 + g;
+        const float* v1 = p.V + ((size_t)(b0 + rowc[1]) * T) * H + i0 + g;
+        const float* a0p = ALIF ? p.a + ((size_t)(b0 + rowc[0]) * T) * H + i0 + g : nullptr;
+        const float* a1p = ALIF ? p.a + ((size_t)(b0 + rowc[1]) * T) * H + i0 + g : nullptr;
         const int zword = warp >> 1, zsh = 16 * (warp & 1) + g;      // this thread's neurons in a spike word: bits zsh, zsh + 8
-        float inv_sg = 1.0f;      // 1 / scale of the gradient tile being READ (gI_{t+1}); the first tile is all zero
-        __syncthreads();          // planes and tables visible
-        // saved traces V_t (and a_t): straight from global memory into registers, two steps ahead (see k_recur_fwd_tc)
-        auto load_va = [&](int tl, float (&dv)[4], float (&da)[4]) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                dv[e] = 0.f; da[e] = 0.f;
-                if (tl >= 0 && ok[e]) {
-                    const size_t o = o_base + (size_t)tl * H + (e & 1) * o_row + 8 * (e >> 1);
-                    dv[e] = __ldg(p.V + o);
-                    if constexpr (ALIF) da[e] = __ldg(p.a + o);
+        const uint32_t* zw0 = s_zw + rowc[0] * zstride + zword;
+        const uint32_t* zw1 = s_zw + rowc[1] * zstride + zword;
+        const uint32_t* st0p = s_start + rowc[0] * TW;
+        const uint32_t* st1p = s_start + rowc[1] * TW;
+        const uint32_t cell = tc::smem_u32(s_ring) + (uint32_t)tid * 32;
+        auto prefetch = [&](int ts) {      // V_ts (and a_ts) of this thread's four elements -> cell ts % kTcSlots
+            if (ts >= 0) {
+                const uint32_t dst = cell + (uint32_t)(ts & (kTcSlots - 1)) * (256 * 32);
+                const float* q0 = v0 + (size_t)ts * H;
+                const float* q1 = v1 + (size_t)ts * H;
+                cp_async4(dst, q0);
+                cp_async4(dst + 4, q1);
+                cp_async4(dst + 8, q0 + 8);
+                cp_async4(dst + 12, q1 + 8);
+                if constexpr (ALIF) {
+                    const float* r0 = a0p + (size_t)ts * H;
+                    const float* r1 = a1p + (size_t)ts * H;
+                    cp_async4(dst + 16, r0);
+                    cp_async4(dst + 20, r1);
+                    cp_async4(dst + 24, r0 + 8);
+                    cp_async4(dst + 28, r1 + 8);
                 }
             }
+            cp_async_commit();
         };
-        float vcur[4], acur[4], vn1[4], an1[4], vn2[4], an2[4];
-        load_va(T - 1, vcur, acur);
-        load_va(T - 2, vn1, an1);
+        auto publish = [&](int buf) {      // gi (registers) -> tile `buf` as two fp16 planes under the current scale
+            uint32_t pk[4];
+#pragma unroll
+            for (int nh = 0; nh < 2; ++nh) {
+                __half h0, l0, h1, l1;
+                split_h2(__fmul_rn(gi[2 * nh], sc.s), h0, l0);
+                split_h2(__fmul_rn(gi[2 * nh + 1], sc.s), h1, l1);
+                pk[nh] = pack_h2(h0, h1);
+                pk[2 + nh] = pack_h2(l0, l1);
+            }
+            // matrices: (hi, neurons i0..+7), (hi, i0+8..), (lo, i0..), (lo, i0+8..); lane 8 j + n gives row n of matrix j
+            const uint32_t sa = g_u32 + (uint32_t)(((buf * 2 + (lane >> 4)) * kTcRows + (lane & 7)) * kTcTileStride + i0 +
+                                                   8 * ((lane >> 3) & 1)) * 2;
+            stsm_x4_trans(sa, pk[0], pk[1], pk[2], pk[3]);
+        };
+        __syncthreads();          // planes and tables visible
+#pragma unroll
+        for (int d = 0; d < kTcDist; ++d) prefetch(T - 1 - d);
+        wt[0] = zw0[T * W32];     // Z_{T-1}
+        wt[1] = zw1[T * W32];
+        const bool has_gZ = p.g_Z != nullptr, has_gV = p.g_V != nullptr;
 
         for (int t = T - 1; t >= 0; --t) {
-            load_va(t - 2, vn2, an2);
+            prefetch(t - kTcDist);
+            if (sc.update(s_cls[c_rd])) {      // rare: the tile about to be read needs another scale
+                publish((t + 1) & 1);
+                __syncthreads();
+            }
             // ---- gZ^T = W_eff gI_{t+1}^T  +  W_out gy_t^T ----
             float chh[4] = {0.f, 0.f, 0.f, 0.f}, chl[4] = {0.f, 0.f, 0.f, 0.f}, clh[4] = {0.f, 0.f, 0.f, 0.f};
+            float ohh[4] = {0.f, 0.f, 0.f, 0.f}, ox[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                uint32_t r4[4];
+                ldsm_x4(r4, gy_base + (uint32_t)(t * kTcRows * 16) * 2);
+                const uint32_t byh[2] = {r4[0], r4[1]}, byl[2] = {r4[2], r4[3]};
+                mma_f16(ohh, oh, byh);
+                mma_f16(ox, oh, byl);
+                mma_f16(ox, ol, byh);
+            }
             const uint32_t tb = tile_base + ((t + 1) & 1) * 2 * kTileBytes;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -588,101 +819,97 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
                 mma_f16(chl, ah[2 * q + 1], bl1);
                 mma_f16(clh, al[2 * q + 1], bh1);
             }
-            float ohh[4] = {0.f, 0.f, 0.f, 0.f}, ox[4] = {0.f, 0.f, 0.f, 0.f};
-            {
-                uint32_t r4[4];
-                ldsm_x4(r4, gy_base + (uint32_t)(t * kTcRows * 16) * 2);
-                const uint32_t byh[2] = {r4[0], r4[1]}, byl[2] = {r4[2], r4[3]};
-                mma_f16(ohh, oh, byh);
-                mma_f16(ox, oh, byl);
-                mma_f16(ox, ol, byh);
-            }
-            const float sc_rec = __fmul_rn(inv_sw, inv_sg);
-            float gi[4];
-            uint32_t cls = 0u;
+            cp_async_wait<kTcDist>();
+            const float4* rc4 = reinterpret_cast<const float4*>(s_ring + (size_t)(t & (kTcSlots - 1)) * (256 * 8) + tid * 8);
+            const float4 v4 = rc4[0];
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (ALIF) a4 = rc4[1];
+            const float vt[4] = {v4.x, v4.y, v4.z, v4.w}, at[4] = {a4.x, a4.y, a4.z, a4.w};
+            const uint32_t wp[2] = {zw0[t * W32], zw1[t * W32]};      // Z_{t-1}
+            const float sc_rec = __fmul_rn(inv_sw, sc.inv);
+            float amax = 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int nh = e >> 1, rh = e & 1, row = 2 * tig + rh;
+                const int nh = e >> 1, rh = e & 1;
                 const float rec = __fmul_rn(fmaf(__fadd_rn(chl[e], clh[e]), 1.0f / 2048.0f, chh[e]), sc_rec);
                 const float rdo = __fmul_rn(fmaf(ox[e], 1.0f / 2048.0f, ohh[e]), inv_so);
                 float s = __fadd_rn(rdo, rec);
-                const size_t o = o_base + (size_t)t * H + rh * o_row + 8 * nh;
-                if (p.g_Z && ok[e]) s = __fadd_rn(s, __ldg(p.g_Z + o));
-                const float vt = vcur[e];
-                float thr = p.theta;
-                if constexpr (ALIF) thr = __fadd_rn(p.theta, __fmul_rn(beta, acur[e]));
-                const uint32_t wt = s_zw[row * zstride + (t + 1) * W32 + zword], wp = s_zw[row * zstride + t * W32 + zword];
-                const float zt = (float)((wt >> (zsh + 8 * nh)) & 1u), zprev = (float)((wp >> (zsh + 8 * nh)) & 1u);
-                const float sg = surrogate_grad(SURR, p.gamma, vt, thr);
-                const float carry = __fmul_rn(__fmul_rn(p.alpha, gv[e]), __fsub_rn(1.0f, zt));
+                const size_t o = (rh ? off1 : off0) + 8 * nh;
+                if (has_gZ) s = __fadd_rn(s, __ldg(p.g_Z + o));
+                float thr = theta;
+                if constexpr (ALIF) thr = __fadd_rn(theta, __fmul_rn(beta, at[e]));
+                const bool zt = (wt[rh] >> (zsh + 8 * nh)) & 1u, zprev = (wp[rh] >> (zsh + 8 * nh)) & 1u;
+                const float sg = surrogate_grad_fast<SURR>(gamma, vt[e], thr);
+                const float carry = zt ? 0.f : __fmul_rn(alpha, gv[e]);             // alpha gV_{t+1} (1 - Z_t)
                 float gq = __fadd_rn(__fmul_rn(s, sg), carry);
-                if (p.g_V && ok[e]) gq = __fadd_rn(gq, __ldg(p.g_V + o));
+                if (has_gV) gq = __fadd_rn(gq, __ldg(p.g_V + o));
                 gv[e] = gq;
-                gi[e] = ok[e] ? __fmul_rn(gq, __fsub_rn(1.0f, zprev)) : 0.f;
-                if (ok[e]) {
-                    if (p.gI_lo) {      // exact two-plane tf32 split for the weight-gradient GEMM
-                        const float hi = __uint_as_float(__float_as_uint(gi[e]) & 0xFFFFE000u);
-                        p.gI[o] = hi;
-                        p.gI_lo[o] = __fsub_rn(gi[e], hi);
-                    } else {
-                        p.gI[o] = gi[e];
-                    }
+                gi[e] = zprev ? 0.f : gq;                                           // gI_t = gV_t (1 - Z_{t-1})
+                amax = fmaxf(amax, fabsf(gi[e]));
+            }
+            // gI for the weight-gradient GEMM
+            if (p.gI_lo) {      // exact two-plane tf32 split
+                float hi[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hi[e] = __uint_as_float(__float_as_uint(gi[e]) & 0xFFFFE000u);
+                if (okr[0]) {
+                    p.gI[off0] = hi[0]; p.gI[off0 + 8] = hi[2];
+                    p.gI_lo[off0] = __fsub_rn(gi[0], hi[0]); p.gI_lo[off0 + 8] = __fsub_rn(gi[2], hi[2]);
                 }
-                cls |= gi[e] != 0.f ? 1u << (((__float_as_uint(gi[e]) >> 23) & 0xFFu) >> 3) : 0u;
-                if (run_sums) {      // sum of gI over the run of equal input frames this step belongs to
-                    racc[e] = __fadd_rn(racc[e], gi[e]);
-                    if (nh == 0 && (t == T - 1 || (t & 31) == 31)) sbits[rh] = s_start[row * TW + (t >> 5)];
+                if (okr[1]) {
+                    p.gI[off1] = hi[1]; p.gI[off1 + 8] = hi[3];
+                    p.gI_lo[off1] = __fsub_rn(gi[1], hi[1]); p.gI_lo[off1 + 8] = __fsub_rn(gi[3], hi[3]);
+                }
+            } else {
+                if (okr[0]) { p.gI[off0] = gi[0]; p.gI[off0 + 8] = gi[2]; }
+                if (okr[1]) { p.gI[off1] = gi[1]; p.gI[off1 + 8] = gi[3]; }
+            }
+            off0 -= H;
+            off1 -= H;
+            if (run_sums) {      // sum of gI over the run of equal input frames this step belongs to
+#pragma unroll
+                for (int e = 0; e < 4; ++e) racc[e] = __fadd_rn(racc[e], gi[e]);
+                if (t == T - 1 || (t & 31) == 31) { sbits[0] = st0p[t >> 5]; sbits[1] = st1p[t >> 5]; }
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
                     if ((sbits[rh] >> (t & 31)) & 1u) {
-                        if (ok[e]) {
-                            const float hi = __uint_as_float(__float_as_uint(racc[e]) & 0xFFFFE000u);
-                            const size_t ro = (size_t)crow[rh] * H + i0 + g + 8 * nh;
-                            p.Gu_hi[ro] = hi;
-                            p.Gu_lo[ro] = __fsub_rn(racc[e], hi);
+                        if (rh ? sums1 : sums0) {
+#pragma unroll
+                            for (int nh = 0; nh < 2; ++nh) {
+                                const float r = racc[2 * nh + rh];
+                                const float hi = __uint_as_float(__float_as_uint(r) & 0xFFFFE000u);
+                                const size_t ro = (size_t)crow[rh] * H + i0 + g + 8 * nh;
+                                p.Gu_hi[ro] = hi;
+                                p.Gu_lo[ro] = __fsub_rn(r, hi);
+                            }
                         }
-                        racc[e] = 0.f;
-                        if (nh == 1) --crow[rh];
+                        racc[rh] = 0.f;
+                        racc[2 + rh] = 0.f;
+                        --crow[rh];
                     }
                 }
             }
-            // tile-wide scale for gI_t from the largest exponent class present (classes of 8 binades): warp OR
-            // (redux.sync), one shared-memory atomicOr per warp, the barrier, one read
-            const uint32_t wor = __reduce_or_sync(0xffffffffu, cls);
-            if (lane == 0 && wor) atomicOr(s_cls + (t & 1), wor);
-            __syncthreads();
-            const uint32_t mask = s_cls[t & 1];
-            if (tid == 0) s_cls[(t + 1) & 1] = 0u;      // the word of step t - 1 (last read before the barrier that ended step t + 1)
-            float sg_new = 1.0f;
-            if (mask) {
-                const int top = 31 - __clz(mask);                  // exponents 8 top .. 8 top + 7: |gI| < 2^(8 top + 8 - 127)
-                int kexp = 133 - 8 * top;                          // scaled maximum < 2^14
-                kexp = kexp > 126 ? 126 : kexp;
-                sg_new = __uint_as_float((uint32_t)(kexp + 127) << 23);
-            }
-            uint32_t pk[4];
-#pragma unroll
-            for (int nh = 0; nh < 2; ++nh) {
-                __half h0, l0, h1, l1;
-                split_h2(__fmul_rn(gi[2 * nh], sg_new), h0, l0);
-                split_h2(__fmul_rn(gi[2 * nh + 1], sg_new), h1, l1);
-                pk[nh] = pack_h2(h0, h1);
-                pk[2 + nh] = pack_h2(l0, l1);
-            }
-            // matrices: (hi, neurons i0..+7), (hi, i0+8..), (lo, i0..), (lo, i0+8..); lane 8 j + n gives row n of matrix j
-            const uint32_t sa = tc::smem_u32(s_g) + (uint32_t)((((t & 1) * 2 + (lane >> 4)) * kTcRows + (lane & 7)) * kTcTileStride +
-                                                              i0 + 8 * ((lane >> 3) & 1)) * 2;
-            stsm_x4_trans(sa, pk[0], pk[1], pk[2], pk[3]);
-            inv_sg = __fdiv_rn(1.0f, sg_new);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { vcur[e] = vn1[e]; acur[e] = an1[e]; vn1[e] = vn2[e]; an1[e] = an2[e]; }
+            // exponent class of the tile's largest element: warp maximum (positive floats order like their bit
+            // patterns), one shared-memory atomicOr per warp
+            const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+            if (lane == 0 && (wmax >> 23) != 0u) atomicOr(s_cls + c_wr, 1u << (wmax >> 26));
+            if (tid == 0) s_cls[c_zr] = 0u;
+            publish(t & 1);
+            wt[0] = wp[0];
+            wt[1] = wp[1];
+            { const int r = c_rd; c_rd = c_wr; c_wr = c_zr; c_zr = r; }
             __syncthreads();
         }
+        cp_async_wait<0>();
     } else {
-        // ninth warp: only takes part in the barriers (the block-wide reductions of the prologue count 288 threads)
+        // ninth warp: takes part in the barriers (the block-wide reductions of the prologue count 288 threads) and
+        // follows the scale decisions, which may add a barrier
         block_max_tc(0.f, s_red);
         block_max_tc(0.f, s_red);
         __syncthreads();
         for (int t = T - 1; t >= 0; --t) {
-            __syncthreads();
+            if (sc.update(s_cls[c_rd])) __syncthreads();
+            { const int r = c_rd; c_rd = c_wr; c_wr = c_zr; c_zr = r; }
             __syncthreads();
         }
     }

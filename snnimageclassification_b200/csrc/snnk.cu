@@ -416,7 +416,7 @@ int launch_fwd_rec(const FwdParams& fp, bool rec, int grid, cudaStream_t st)
 // SNNK_MMA_RECUR = 0 / 1 forces the choice (measuring switch; read per call, tools/sanitize_run.py toggles it).
 bool use_tc_recur(const SnnkDesc* d)
 {
-    if (d->layer_type == SNNK_IZHIKEVICH || !d->recurrent || d->H != kTcH) return false;
+    if (d->layer_type == SNNK_IZHIKEVICH || !d->recurrent || d->H != kTcH || d->O > 15) return false;   // row 15 of the readout MMA packs the spike bits
     if ((d->flags & SNNK_F_TENSOR_CORE) == 0) return false;
     const char* env = getenv("SNNK_MMA_RECUR");
     if (env) return env[0] != '0';
@@ -561,18 +561,35 @@ int launch_nonrec_bwd(const BwdParams& bp, const float* gy_scan, cudaStream_t st
     }
 }
 
+// 4-D view {32, B, 4, T} of a (B, T, 128) fp32 trace (H = 4 groups of 32 neurons) with the box {32, rows, 4, steps} the
+// tensor-core recurrence kernels move per TMA operation (recur_tc.cuh); 128-byte swizzle
+int make_trace_map(CUtensorMap* m, const float* base, int B, int T, int rows, int steps)
+{
+    const cuuint64_t dims[4] = {32, (cuuint64_t)B, 4, (cuuint64_t)T};
+    const cuuint64_t str[3] = {(cuuint64_t)T * kTcH * 4, 128, (cuuint64_t)kTcH * 4};
+    const cuuint32_t box[4] = {32, (cuuint32_t)rows, 4, (cuuint32_t)steps};
+    return make_map(m, base, 4, dims, str, box);
+}
+
 int launch_fwd_tc(const FwdParams& fp, cudaStream_t st)
 {
     const size_t smem = fwd_tc_smem_bytes(fp.T);
     if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
     const int grid = (fp.B + kTcRows - 1) / kTcRows;
+    CUtensorMap mV{}, mA{}, mZ{};
+    if (fp.traces) {
+        int rc = make_trace_map(&mV, fp.V, fp.B, fp.T, kTcRows, kTcK);
+        if (rc == SNNK_OK) rc = make_trace_map(&mZ, fp.Z, fp.B, fp.T, kTcRows, kTcK);
+        if (rc == SNNK_OK && fp.alif) rc = make_trace_map(&mA, fp.a, fp.B, fp.T, kTcRows, kTcK);
+        if (rc != SNNK_OK) return rc;
+    }
     ProfScope ps(SNNK_K_RECUR_FWD, st);
     if (fp.alif) {
         SNNK_CUDA(cudaFuncSetAttribute(k_recur_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_recur_fwd_tc<true><<<grid, kTcThreads, smem, st>>>(fp);
+        k_recur_fwd_tc<true><<<grid, kTcFwdThreads, smem, st>>>(fp, mV, mA, mZ);
     } else {
         SNNK_CUDA(cudaFuncSetAttribute(k_recur_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_recur_fwd_tc<false><<<grid, kTcThreads, smem, st>>>(fp);
+        k_recur_fwd_tc<false><<<grid, kTcFwdThreads, smem, st>>>(fp, mV, mV, mZ);
     }
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;

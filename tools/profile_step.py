@@ -26,6 +26,7 @@ def main():
 	ap.add_argument("--T", type=int, default=100)
 	ap.add_argument("--dense", action="store_true", help="drop the run table: dense kernels")
 	ap.add_argument("--infer", action="store_true", help="no-trace inference instead of training steps")
+	ap.add_argument("--time", action="store_true", help="print the library's per-kernel CUDA-event times (eager launches)")
 	a = ap.parse_args()
 	H, layer, rec, ink, B = CFG[a.config]
 	B = a.batch or B
@@ -47,13 +48,24 @@ def main():
 		print("logits", float(out.abs().mean()))
 		return
 	net.train()
-	for _ in range(a.steps):
-		loss = net.batch_loss(x, lab)
-		opt.zero_grad()
-		loss.backward()
-		opt.step()
+
+	def steps(n):
+		for _ in range(n):
+			loss = net.batch_loss(x, lab)
+			opt.zero_grad()
+			loss.backward()
+			opt.step()
+		return loss
+	loss = steps(a.steps)
 	torch.cuda.synchronize()
 	print("loss", loss.item())
+	if a.time:
+		from snnimageclassification_b200 import _cabi
+		with _cabi.kernel_profile() as prof:
+			steps(20)
+			torch.cuda.synchronize()
+		for name, (ms, n) in prof.result.items():
+			print(f"  {name:55s} {1e3 * ms / 20:9.1f} us/step  ({n // 20} launches)")
 
 
 if __name__ == "__main__":
