@@ -58,6 +58,11 @@ class GraphedTrainStep:
 			self._staged = [torch.cuda.Event() for _ in range(2)]
 			self._consumed = [torch.cuda.Event() for _ in range(2)]
 			self._flip = 0
+		# Image batches that the network's own GPU encoder turns into spike trains (``input_encoder``): the encoder of the
+		# NEXT batch is replayed on the copy stream, behind that batch's H2D copy, while the compute stream still runs
+		# the current step (whose recurrence kernels leave SMs idle) -- two sets of encoder outputs, two captured steps.
+		self._pre = (not static_inputs and getattr(net, "input_encoder", None) is not None and x_example.ndim == 2
+			and not x_example.is_cuda)
 		self.step_in_graph = _optimizer_is_capturable(optimizer)
 		self.loss: Optional[torch.Tensor] = None
 		# Loss mailbox: the fused head posts {launch number, loss} into this pinned host word, so the host reads the
@@ -90,19 +95,45 @@ class GraphedTrainStep:
 		side.wait_stream(torch.cuda.current_stream(dev))
 		F_.LOSS_MAILBOX = (self._mail, self._mail_counter)
 		try:
+			if self._pre:
+				for k in range(2):
+					self._xs[k].copy_(self.x)
+					self._ys[k].copy_(self.y)
+				side.wait_stream(torch.cuda.current_stream(dev))
 			with torch.cuda.stream(side):
 				for _ in range(warmup):
-					self._body()
+					if self._pre:
+						self._body(net._encode_if_needed(self._xs[0]), self._ys[0])
+					else:
+						self._body()
 			torch.cuda.current_stream(dev).wait_stream(side)
 			torch.cuda.synchronize(dev)
 			self._expected = int(self._mail_counter.item())       # launches so far (warm-up); 0 if the head never posted
 			self._posts = self._expected > 0
 
-			optimizer.zero_grad(set_to_none=True)
-			gc.collect()
-			self.graph = torch.cuda.CUDAGraph()
-			with torch.cuda.graph(self.graph):
-				self.loss = self._body()
+			if self._pre:
+				self._enc_graphs, self._step_graphs, self._losses, self._grads = [], [], [], []
+				for k in range(2):
+					optimizer.zero_grad(set_to_none=True)
+					gc.collect()
+					ge = torch.cuda.CUDAGraph()
+					with torch.cuda.graph(ge):
+						xr = net._encode_if_needed(self._xs[k])
+					gs = torch.cuda.CUDAGraph()
+					with torch.cuda.graph(gs):
+						loss = self._body(xr, self._ys[k])
+					self._enc_graphs.append(ge)
+					self._step_graphs.append(gs)
+					self._losses.append(loss)
+					self._grads.append([p.grad for p in params])
+				self._rasters = xr      # keep-alive is the graph's pool; the attribute only documents the hand-over
+				self.graph, self.loss = self._step_graphs[0], self._losses[0]
+			else:
+				optimizer.zero_grad(set_to_none=True)
+				gc.collect()
+				self.graph = torch.cuda.CUDAGraph()
+				with torch.cuda.graph(self.graph):
+					self.loss = self._body()
 		finally:
 			F_.LOSS_MAILBOX = None
 		with torch.no_grad():
@@ -118,9 +149,9 @@ class GraphedTrainStep:
 			raise RuntimeError("the network of this graphed training step no longer exists")
 		return net
 
-	def _body(self) -> torch.Tensor:
+	def _body(self, x=None, y=None) -> torch.Tensor:
 		net = self.net
-		loss = net.batch_loss(self.x, self.y, self.criterion)
+		loss = net.batch_loss(self.x if x is None else x, self.y if y is None else y, self.criterion)
 		self.optimizer.zero_grad(set_to_none=True)
 		loss.backward(gradient=_const_scalar(1.0, loss.device))     # cached root gradient: no ones_like fill per step
 		net._allreduce_gradients(self.optimizer)
@@ -128,7 +159,38 @@ class GraphedTrainStep:
 			self.optimizer.step()
 		return loss
 
+	def _call_pre(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+		"""Encoder of this batch on the copy stream (overlapping the previous step), then the step on the compute stream."""
+		if self.step_in_graph and self._sig is not None and self._hyper_signature() != self._sig:
+			torch.cuda.synchronize(self.x.device)
+			self._capture()
+		k = self._flip
+		self._flip ^= 1
+		main = torch.cuda.current_stream(self.x.device)
+		cs = self._copy_stream if not (x.is_cuda or y.is_cuda) else main
+		if cs is not main:
+			cs.wait_event(self._consumed[k])          # the step that read this set of encoder outputs (two calls ago) is done
+		with torch.cuda.stream(cs):
+			self._xs[k].copy_(x, non_blocking=True)
+			self._ys[k].copy_(y, non_blocking=True)
+			self._enc_graphs[k].replay()
+			if cs is not main:
+				self._staged[k].record(cs)
+		if cs is not main:
+			main.wait_event(self._staged[k])
+		self._step_graphs[k].replay()
+		self._consumed[k].record(main)
+		self._expected = (self._expected + 1) & 0xFFFFFFFF
+		self.loss = self._losses[k]
+		for p, g in zip(self.net.parameters(), self._grads[k]):
+			p.grad = g
+		if not self.step_in_graph:
+			self.optimizer.step()
+		return self.loss
+
 	def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+		if self._pre:
+			return self._call_pre(x, y)
 		if not self.static_inputs:
 			if x.is_cuda or y.is_cuda:     # device inputs are ordered on the compute stream: copy there
 				self.x.copy_(x, non_blocking=True)
