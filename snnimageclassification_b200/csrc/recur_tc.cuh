@@ -548,14 +548,18 @@ __global__ void __launch_bounds__(256) k_gy_scan(int B, int T, int O, float kapp
 // ---- backward -------------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int tc_zstride(int T) { return ((T + 1) * (kTcH / 32) + 3) & ~3; }      // words per row of the spike-word table
 
+constexpr int kTcKb = 2;           // steps per gI box (one TMA store per plane); the saved traces arrive in boxes of kTcK steps
+
 constexpr size_t bwd_tc_smem_bytes(int T)
 {
-    return sizeof(__half) * 2 * 2 * kTcRows * kTcTileStride                                 // gI tiles [buf][plane][8][136]
+    return 1024                                                                             // alignment slack (swizzle atoms)
+           + (size_t)2 * 2 * kTcK * kTcSlab                                                 // trace boxes [2][V, a][kTcK] slabs
+           + (size_t)3 * 2 * kTcKb * kTcSlab                                                // gI staging [3][hi, lo][kTcKb] slabs
+           + sizeof(__half) * 2 * 2 * kTcRows * kTcTileStride                               // gI tiles [buf][plane][8][136]
            + sizeof(__half) * 2 * (size_t)T * kTcRows * 16                                  // gy planes [plane][T][8][16]
-           + sizeof(float) * 8 * 256 * kTcSlots                                             // V / a ring: 32 B per thread and cell
            + sizeof(uint32_t) * (size_t)kTcRows * tc_zstride(T)                             // spike words [8][T+1][4] (slot 0: Z_{-1})
            + sizeof(uint32_t) * (size_t)kTcRows * ((T + 31) / 32 + 1)                        // run-start bits
-           + sizeof(float) * 16;
+           + sizeof(float) * 16 + sizeof(uint64_t) * 2 + 8;
 }
 
 // Surrogate derivatives with the hardware reciprocal (1 ulp): the tensor-core sweep does not promise the fp32 kernels'
@@ -609,10 +613,18 @@ struct TcScale {
 
 // grid = ceil(B / 8), block = 288.  gy_scan: output of k_gy_scan.  Writes gI (one or two tf32 planes) and, with a
 // frame-run table, the run sums; dW_out / db are NOT produced here (k_wout_grad).
+// Memory paths (same reasoning as the forward kernel: the LSU is the bound, so nothing avoidable goes through it): the
+// saved traces V_t (a_t) arrive as TMA tensor loads of {32, 8, 4, kTcK} boxes into 128B-swizzled slabs (two boxes, one
+// in use, one in flight; mbarrier completion), gI leaves through swizzled staging slabs by TMA tensor stores every
+// kTcKb steps; both are issued by lane 0 of the ninth warp.  mV / mA: box kTcK steps; mG / mGlo: box kTcKb steps.
 template <bool ALIF, int SURR>
-__global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams p, const float* __restrict__ gy_scan)
+__global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams p, const float* __restrict__ gy_scan,
+                                                               const __grid_constant__ CUtensorMap mV,
+                                                               const __grid_constant__ CUtensorMap mA,
+                                                               const __grid_constant__ CUtensorMap mG,
+                                                               const __grid_constant__ CUtensorMap mGlo)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
     constexpr int H = kTcH, W32 = kTcH / 32;
     const int T = p.T, B = p.B, O = p.O;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -622,13 +634,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
     const int zstride = tc_zstride(T);
     const int TW = (T + 31) / 32 + 1;
 
-    __half* s_g = reinterpret_cast<__half*>(smem_raw);                                       // [2][2][8][136]
+    unsigned char* smem_raw = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* s_in = smem_raw;                                                          // [2][2][kTcK][4096]
+    unsigned char* s_out = s_in + 2 * 2 * kTcK * kTcSlab;                                    // [3][2][kTcKb][4096]
+    __half* s_g = reinterpret_cast<__half*>(s_out + 3 * 2 * kTcKb * kTcSlab);                // [2][2][8][136]
     __half* s_gy = s_g + 2 * 2 * kTcRows * kTcTileStride;                                    // [2][T][8][16]
-    float* s_ring = reinterpret_cast<float*>(s_gy + 2 * (size_t)T * kTcRows * 16);           // [kTcSlots][256][8]
-    uint32_t* s_zw = reinterpret_cast<uint32_t*>(s_ring + 8 * 256 * kTcSlots);               // [8][zstride]
+    uint32_t* s_zw = reinterpret_cast<uint32_t*>(s_gy + 2 * (size_t)T * kTcRows * 16);       // [8][zstride]
     uint32_t* s_start = s_zw + (size_t)kTcRows * zstride;                                    // [8][TW]
     float* s_red = reinterpret_cast<float*>(s_start + kTcRows * TW);                         // [12] + exponent-class words [3]
     uint32_t* s_cls = reinterpret_cast<uint32_t*>(s_red + 12);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_cls + 4) + 7) & ~uintptr_t(7));   // [2]
+
+    // trace boxes in processing order j = 0, 1, ...: steps kTcK (nbox - 1 - j) .., buffer j & 1, parity (j >> 1) & 1
+    const int nbox = (T + kTcK - 1) / kTcK;
+    constexpr uint32_t kInBox = 2 * kTcK * kTcSlab;                                          // one buffer: V slabs then a slabs
+    auto issue_box = [&](int j) {      // lane 0 of the ninth warp
+        const int q = nbox - 1 - j;
+        uint64_t* bar = s_full + (j & 1);
+        unsigned char* dst = s_in + (size_t)(j & 1) * kInBox;
+        tc::mbar_expect_tx(bar, (uint32_t)(kTcK * kTcSlab) * (ALIF ? 2u : 1u));
+        tc::tma_load_4d(dst, &mV, bar, 0, b0, 0, q * kTcK);
+        if (ALIF) tc::tma_load_4d(dst + kTcK * kTcSlab, &mA, bar, 0, b0, 0, q * kTcK);
+    };
+    if (tid == 256) {
+        tc::mbar_init(s_full, 1);
+        tc::mbar_init(s_full + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tc::prefetch_tmap(&mV);
+        tc::prefetch_tmap(&mG);
+        issue_box(0);
+        if (nbox > 1) issue_box(1);
+    }
 
     const bool run_sums = p.run_table != nullptr && p.run_table[1] == 1;
     if (tid == 256) s_cls[0] = s_cls[1] = s_cls[2] = 0u;
@@ -733,38 +769,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
             sbits[rh] = 0u;
         }
         const bool sums0 = run_sums && okr[0], sums1 = run_sums && okr[1];
-        // element offset of (row 2 tig + rh, step T - 1, neuron i0 + g) in the (B, T, H) tensors
+        uint32_t eo[4];      // slab offsets of the 4 elements (trace boxes and gI staging share the layout)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) eo[e] = tc_slab_off(2 * tig + (e & 1), i0 + g + 8 * (e >> 1));
+        // element offset of (row 2 tig + rh, step T - 1, neuron i0 + g) in the (B, T, H) tensors (optional seeds)
         size_t off0 = ((size_t)(b0 + rowc[0]) * T + (T - 1)) * H + i0 + g, off1 = ((size_t)(b0 + rowc[1]) * T + (T - 1)) * H + i0 + g;
-        const float* v0 = p.V + ((size_t)(b0 + rowc[0]) * T) * H + i0 + g;
-        const float* v1 = p.V + ((size_t)(b0 + rowc[1]) * T) * H + i0 + g;
-        const float* a0p = ALIF ? p.a + ((size_t)(b0 + rowc[0]) * T) * H + i0 + g : nullptr;
-        const float* a1p = ALIF ? p.a + ((size_t)(b0 + rowc[1]) * T) * H + i0 + g : nullptr;
         const int zword = warp >> 1, zsh = 16 * (warp & 1) + g;      // this thread's neurons in a spike word: bits zsh, zsh + 8
         const uint32_t* zw0 = s_zw + rowc[0] * zstride + zword;
         const uint32_t* zw1 = s_zw + rowc[1] * zstride + zword;
         const uint32_t* st0p = s_start + rowc[0] * TW;
         const uint32_t* st1p = s_start + rowc[1] * TW;
-        const uint32_t cell = tc::smem_u32(s_ring) + (uint32_t)tid * 32;
-        auto prefetch = [&](int ts) {      // V_ts (and a_ts) of this thread's four elements -> cell ts % kTcSlots
-            if (ts >= 0) {
-                const uint32_t dst = cell + (uint32_t)(ts & (kTcSlots - 1)) * (256 * 32);
-                const float* q0 = v0 + (size_t)ts * H;
-                const float* q1 = v1 + (size_t)ts * H;
-                cp_async4(dst, q0);
-                cp_async4(dst + 4, q1);
-                cp_async4(dst + 8, q0 + 8);
-                cp_async4(dst + 12, q1 + 8);
-                if constexpr (ALIF) {
-                    const float* r0 = a0p + (size_t)ts * H;
-                    const float* r1 = a1p + (size_t)ts * H;
-                    cp_async4(dst + 16, r0);
-                    cp_async4(dst + 20, r1);
-                    cp_async4(dst + 24, r0 + 8);
-                    cp_async4(dst + 28, r1 + 8);
-                }
-            }
-            cp_async_commit();
-        };
+        const uint32_t in_u32 = tc::smem_u32(s_in), out_u32 = tc::smem_u32(s_out);
+        const bool two_planes = p.gI_lo != nullptr;
         auto publish = [&](int buf) {      // gi (registers) -> tile `buf` as two fp16 planes under the current scale
             uint32_t pk[4];
 #pragma unroll
@@ -781,14 +797,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
             stsm_x4_trans(sa, pk[0], pk[1], pk[2], pk[3]);
         };
         __syncthreads();          // planes and tables visible
-#pragma unroll
-        for (int d = 0; d < kTcDist; ++d) prefetch(T - 1 - d);
         wt[0] = zw0[T * W32];     // Z_{T-1}
         wt[1] = zw1[T * W32];
         const bool has_gZ = p.g_Z != nullptr, has_gV = p.g_V != nullptr;
 
+        int ob = 0;      // gI staging buffer of the current box (rotates over 3)
         for (int t = T - 1; t >= 0; --t) {
-            prefetch(t - kTcDist);
             if (sc.update(s_cls[c_rd])) {      // rare: the tile about to be read needs another scale
                 publish((t + 1) & 1);
                 __syncthreads();
@@ -819,12 +833,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
                 mma_f16(chl, ah[2 * q + 1], bl1);
                 mma_f16(clh, al[2 * q + 1], bh1);
             }
-            cp_async_wait<kTcDist>();
-            const float4* rc4 = reinterpret_cast<const float4*>(s_ring + (size_t)(t & (kTcSlots - 1)) * (256 * 8) + tid * 8);
-            const float4 v4 = rc4[0];
-            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (ALIF) a4 = rc4[1];
-            const float vt[4] = {v4.x, v4.y, v4.z, v4.w}, at[4] = {a4.x, a4.y, a4.z, a4.w};
+            // saved traces of step t: box j (processing order), buffer j & 1; the first step of a box waits for its load
+            float vt[4], at[4];
+            {
+                const int j = nbox - 1 - t / kTcK;
+                if (t == T - 1 || (t % kTcK) == kTcK - 1) tc::mbar_wait(s_full + (j & 1), (uint32_t)((j >> 1) & 1));
+                const uint32_t vb = in_u32 + (uint32_t)(j & 1) * kInBox + (uint32_t)(t % kTcK) * kTcSlab;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(vt[e]) : "r"(vb + eo[e]));
+                    if constexpr (ALIF) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(at[e]) : "r"(vb + eo[e] + kTcK * kTcSlab));
+                    else at[e] = 0.f;
+                }
+            }
             const uint32_t wp[2] = {zw0[t * W32], zw1[t * W32]};      // Z_{t-1}
             const float sc_rec = __fmul_rn(inv_sw, sc.inv);
             float amax = 0.f;
@@ -847,22 +868,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
                 gi[e] = zprev ? 0.f : gq;                                           // gI_t = gV_t (1 - Z_{t-1})
                 amax = fmaxf(amax, fabsf(gi[e]));
             }
-            // gI for the weight-gradient GEMM
-            if (p.gI_lo) {      // exact two-plane tf32 split
-                float hi[4];
+            // gI for the weight-gradient GEMM: staging slab of step t (box t / kTcKb), exact two-plane tf32 split
+            {
+                const uint32_t sb = out_u32 + (uint32_t)(ob * 2 * kTcKb + (t % kTcKb)) * kTcSlab;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) hi[e] = __uint_as_float(__float_as_uint(gi[e]) & 0xFFFFE000u);
-                if (okr[0]) {
-                    p.gI[off0] = hi[0]; p.gI[off0 + 8] = hi[2];
-                    p.gI_lo[off0] = __fsub_rn(gi[0], hi[0]); p.gI_lo[off0 + 8] = __fsub_rn(gi[2], hi[2]);
+                for (int e = 0; e < 4; ++e) {
+                    if (two_planes) {
+                        const float hi = __uint_as_float(__float_as_uint(gi[e]) & 0xFFFFE000u);
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + eo[e]), "f"(hi) : "memory");
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + eo[e] + kTcKb * kTcSlab), "f"(__fsub_rn(gi[e], hi)) : "memory");
+                    } else {
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + eo[e]), "f"(gi[e]) : "memory");
+                    }
                 }
-                if (okr[1]) {
-                    p.gI[off1] = hi[1]; p.gI[off1 + 8] = hi[3];
-                    p.gI_lo[off1] = __fsub_rn(gi[1], hi[1]); p.gI_lo[off1 + 8] = __fsub_rn(gi[3], hi[3]);
+                if ((t % kTcKb) == 0) {      // box complete: visible to the TMA store; next box, next buffer
+                    fence_proxy_async();
+                    ob = ob == 2 ? 0 : ob + 1;
                 }
-            } else {
-                if (okr[0]) { p.gI[off0] = gi[0]; p.gI[off0 + 8] = gi[2]; }
-                if (okr[1]) { p.gI[off1] = gi[1]; p.gI[off1 + 8] = gi[3]; }
             }
             off0 -= H;
             off1 -= H;
@@ -900,18 +922,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_recur_bwd_tc(const BwdParams 
             { const int r = c_rd; c_rd = c_wr; c_wr = c_zr; c_zr = r; }
             __syncthreads();
         }
-        cp_async_wait<0>();
     } else {
-        // ninth warp: takes part in the barriers (the block-wide reductions of the prologue count 288 threads) and
-        // follows the scale decisions, which may add a barrier
+        // ninth warp: takes part in the barriers (the block-wide reductions of the prologue count 288 threads), follows
+        // the scale decisions, which may add a barrier, and its lane 0 issues the TMA loads and stores
         block_max_tc(0.f, s_red);
         block_max_tc(0.f, s_red);
         __syncthreads();
+        const uint32_t out_u32 = tc::smem_u32(s_out);
+        const bool two_planes = p.gI_lo != nullptr;
+        int ob = 0;      // staging buffer of the next box to store
+        auto after_step = [&](int td) {      // td: the step whose barrier has just completed
+            if (lane != 0) return;
+            if ((td % kTcK) == 0) {          // last step of trace box j: its buffer is free for box j + 2
+                const int j = nbox - 1 - td / kTcK;
+                if (j + 2 < nbox) issue_box(j + 2);
+            }
+            if ((td % kTcKb) == 0) {         // gI box td / kTcKb is complete
+                const uint32_t sb = out_u32 + (uint32_t)(ob * 2 * kTcKb) * kTcSlab;
+                tma_store_4d(&mG, sb, 0, b0, 0, td);
+                if (two_planes) tma_store_4d(&mGlo, sb + kTcKb * kTcSlab, 0, b0, 0, td);
+                tma_store_commit();
+                ob = ob == 2 ? 0 : ob + 1;
+            }
+        };
         for (int t = T - 1; t >= 0; --t) {
+            if (t < T - 1) after_step(t + 1);
             if (sc.update(s_cls[c_rd])) __syncthreads();
             { const int r = c_rd; c_rd = c_wr; c_wr = c_zr; c_zr = r; }
+            // staging buffers rotate over three: the store issued two boxes ago must have read its buffer before the
+            // box after this one is written (at most the latest store may still be reading)
+            if (lane == 0 && (t % kTcKb) == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             __syncthreads();
         }
+        after_step(0);
+        if (lane == 0) tma_store_wait_all();
     }
 }
 

@@ -600,7 +600,15 @@ int launch_bwd_tc(const BwdParams& bp, const float* gy_scan, cudaStream_t st)
     const size_t smem = bwd_tc_smem_bytes(bp.T);
     if (smem > 200 * 1024) return SNNK_ERR_SHAPE;
     const int grid = (bp.B + kTcRows - 1) / kTcRows;
-    void (*kern)(const BwdParams, const float*) = nullptr;
+    CUtensorMap mV{}, mA{}, mG{}, mGlo{};
+    {
+        int rc = make_trace_map(&mV, bp.V, bp.B, bp.T, kTcRows, kTcK);
+        if (rc == SNNK_OK && bp.alif) rc = make_trace_map(&mA, bp.a, bp.B, bp.T, kTcRows, kTcK);
+        if (rc == SNNK_OK) rc = make_trace_map(&mG, bp.gI, bp.B, bp.T, kTcRows, kTcKb);
+        if (rc == SNNK_OK && bp.gI_lo) rc = make_trace_map(&mGlo, bp.gI_lo, bp.B, bp.T, kTcRows, kTcKb);
+        if (rc != SNNK_OK) return rc;
+    }
+    void (*kern)(const BwdParams, const float*, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap) = nullptr;
     switch ((bp.alif ? 2 : 0) + (bp.surrogate ? 1 : 0)) {
     case 0: kern = k_recur_bwd_tc<false, 0>; break;
     case 1: kern = k_recur_bwd_tc<false, 1>; break;
@@ -609,7 +617,7 @@ int launch_bwd_tc(const BwdParams& bp, const float* gy_scan, cudaStream_t st)
     }
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(SNNK_K_RECUR_BWD, st);
-    kern<<<grid, kTcThreads, smem, st>>>(bp, gy_scan);
+    kern<<<grid, kTcThreads, smem, st>>>(bp, gy_scan, mV, bp.alif ? mA : mV, mG, bp.gI_lo ? mGlo : mG);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
