@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SNNK_ABI_VERSION 5   /* 5: loss mailbox of snnk_head_nll; 4: W_effT_out / W_effT_in; 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
+#define SNNK_ABI_VERSION 6   /* 6: SNNK_F_INPUT_BITS; 5: loss mailbox of snnk_head_nll; 4: W_effT_out / W_effT_in; 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
 
 typedef void* snnk_stream_t; /* cudaStream_t */
 
@@ -71,6 +71,14 @@ enum {
 #define SNNK_F_INPUT_BINARY 0x4u /* the caller guarantees x is exactly {0,1} (its own encoder's output, or the
                                   spike trace of the layer below): the tensor-core kernels skip their on-device
                                   exactness check and the gated fp32 fallback launches */
+
+#define SNNK_F_INPUT_BITS 0x8u  /* x is the BIT-PACKED raster (B*T, ceil(N/32)) uint32 -- the SNNK_BITS output of
+                                  snnk_encode, bit l of word w = feature 32w+l, padding bits zero -- instead of fp32
+                                  (cast the pointer).  Needs SNNK_F_TENSOR_CORE and N % 4 == 0, else
+                                  SNNK_ERR_UNSUPPORTED (unpack with snnk_unpack_raster then).  The projection and
+                                  the weight-gradient contraction expand the words inside shared memory
+                                  (k_proj_bits / k_wgrad_bits): the fp32 raster of datasets.py:93-97 never exists.
+                                  A run table is ignored with this flag (dense kernels). */
 
 /* Geometry and constants of one hidden spiking layer + leaky readout. */
 typedef struct SnnkDesc {

@@ -15,12 +15,14 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libsnnk.so")
+# measuring switch: a differently built copy of the SAME library (kernel experiments); never a fallback
+LIB_PATH = os.environ.get("SNNK_LIB_PATH", LIB_PATH)
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "snnk.h")
 
 SNNK_LIF, SNNK_ALIF, SNNK_IZHIKEVICH = 0, 1, 2
 SNNK_FAST_SIGMOID, SNNK_PHI = 0, 1
 SNNK_F32, SNNK_F64, SNNK_U8, SNNK_I64, SNNK_BITS = 0, 1, 2, 3, 4
-SNNK_F_TRACES, SNNK_F_TENSOR_CORE, SNNK_F_INPUT_BINARY = 0x1, 0x2, 0x4
+SNNK_F_TRACES, SNNK_F_TENSOR_CORE, SNNK_F_INPUT_BINARY, SNNK_F_INPUT_BITS = 0x1, 0x2, 0x4, 0x8
 
 NVCC_FLAGS = [
 	"-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -111,7 +113,7 @@ def lib() -> ctypes.CDLL:
 			fn = getattr(l, name)
 			fn.restype = res
 			fn.argtypes = args
-		if l.snnk_abi_version() != 5:
+		if l.snnk_abi_version() != 6:
 			raise RuntimeError("libsnnk.so ABI version mismatch; rebuild the extension")
 		_lib = l
 	return _lib

@@ -14,6 +14,7 @@
 #include "encode_head.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_bits.cuh"
 #include "recur_bwd.cuh"
 #include "recur_fwd.cuh"
 #include "recur_gen.cuh"
@@ -111,6 +112,8 @@ int sm_count()
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+constexpr int kBitsMT = 2;   // row / feature tiles per CTA of the bit-fed GEMMs (both accumulators fit TMEM)
+
 // How the batch is cut into CTAs and how the weight-gradient GEMM is split; shared by the workspace
 // query and the launches so they can never disagree.
 struct Plan {
@@ -122,6 +125,7 @@ struct Plan {
     int samples_per_split;
     bool tc;          // tcgen05 GEMMs eligible for this geometry (the flag asks for them and TMA can address x)
     bool check;       // tensor-core path must verify on the device that x is tf32-exact (caller did not vouch)
+    bool bits;        // x is the bit-packed raster (SNNK_F_INPUT_BITS): k_proj_bits / k_wgrad_bits
     int kpad;         // K of the projection padded to the k-block
     bool wide;        // H > 128: generic recurrence kernels (recur_gen.cuh), N-tiled tensor-core GEMMs
     bool tcrec;       // tensor-core recurrence kernels (recur_tc.cuh): gy scan + k_wout_grad beside the sweep
@@ -202,10 +206,13 @@ Plan make_plan(const SnnkDesc* d)
     p.m_total = d->N + (d->recurrent ? d->H : 0);
     // TMA needs 16-byte global strides: N % 4 == 0 (H is a multiple of 32 already)
     p.tc = (d->flags & SNNK_F_TENSOR_CORE) != 0 && d->N % 4 == 0;
-    p.check = p.tc && (d->flags & SNNK_F_INPUT_BINARY) == 0;
+    p.bits = p.tc && (d->flags & SNNK_F_INPUT_BITS) != 0;
+    p.check = p.tc && !p.bits && (d->flags & SNNK_F_INPUT_BINARY) == 0;
     p.kpad = (d->N + tc::kBlockK - 1) / tc::kBlockK * tc::kBlockK;
     int S;
-    if (p.tc) {
+    if (p.bits) {
+        S = 148 / (((p.mtiles_x + p.mtiles_z + kBitsMT - 1) / kBitsMT) * p.ntiles_tc);   // kBitsMT feature tiles per CTA
+    } else if (p.tc) {
         S = 148 / ((p.mtiles_x + p.mtiles_z) * p.ntiles_tc);   // one CTA per SM: the tcgen05 kernel owns the whole smem
     } else {
         const int tiles = (p.mtiles_x + p.mtiles_z) * p.ntiles;
@@ -230,7 +237,7 @@ Plan make_plan(const SnnkDesc* d)
         p.off_gmask = off;    off = align_up(off + sizeof(unsigned int) * (size_t)p.w_nmt_b * p.w_npass_b * d->T, 256);
         p.off_wflags_b = off; off = align_up(off + sizeof(unsigned int) * (size_t)p.w_nmt_b * kWideFlagStride, 256);
     }
-    p.runs = p.tc && !p.wide;
+    p.runs = p.tc && !p.wide && !p.bits;
     if (p.runs) {
         const int cap = run_cap(BT);
         p.run_rows = (cap + 127) / 128 * 128;
@@ -376,6 +383,55 @@ int launch_wgrad_tc(const SnnkDesc* d, const WgradGeom& g, cudaStream_t st)
     dim3 grid(g.mtiles_x + g.mtiles_z, g.S, d->H / H);
     ProfScope ps(SNNK_K_WGRAD, st);
     kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mx, mz, mg, wp);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+// ---- bit-packed input (SNNK_F_INPUT_BITS, gemm_bits.cuh) --------------------------------------------------------------
+template <int H>
+int launch_proj_bits(const SnnkDesc* d, const uint32_t* xbits, const float* W_in, float* I_in, void* plane_ws, cudaStream_t st)
+{
+    using Cfg = tc::ProjBitsCfg<H, kBitsMT>;
+    const int M = d->B * d->T, Hf = d->H;
+    const int kblocks = (d->N + tc::kBitsBlockK - 1) / tc::kBitsBlockK, wd = (d->N + 31) / 32;
+    __half* planes = static_cast<__half*>(plane_ws);
+    // the per-column scales sit behind the two planes (the region was sized for three tf32 planes: always larger)
+    float* inv_scale = reinterpret_cast<float*>(planes + 2 * (size_t)kblocks * Hf * tc::kBitsBlockK);
+    tc::k_split_w_h<<<Hf, 256, 0, st>>>(W_in, d->N, Hf, kblocks, planes, inv_scale);
+    SNNK_CUDA(cudaGetLastError());
+    auto kern = tc::k_proj_bits<H, kBitsMT>;
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    ProfScope ps(SNNK_K_PROJ, st);
+    dim3 grid((M + kBitsMT * tc::kBlockM - 1) / (kBitsMT * tc::kBlockM), Hf / H);
+    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(xbits, wd, planes, inv_scale, I_in, M, kblocks, Hf);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+template <int H>
+int launch_wgrad_bits(const SnnkDesc* d, const Plan& pl, const uint32_t* xbits, const uint32_t* zbits, const float* g_planes,
+                      size_t g_plane_stride, float* part, cudaStream_t st)
+{
+    constexpr int P = 2;
+    using Cfg = tc::WgradBitsCfg<H, kBitsMT>;
+    const cuuint64_t T = d->T, B = d->B, Hf = d->H;
+    CUtensorMap mg;
+    {
+        const cuuint64_t dims[4] = {Hf, T, B, (cuuint64_t)P};
+        const cuuint64_t str[3] = {Hf * 4, T * Hf * 4, (cuuint64_t)g_plane_stride};
+        const cuuint32_t box[4] = {32, tc::kBlockK, 1, 1};
+        int rc = make_map(&mg, g_planes, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc != SNNK_OK) return rc;
+    }
+    tc::WgradBitsParams wp{};
+    wp.N = d->N; wp.T = d->T; wp.B = d->B; wp.mtiles_x = pl.mtiles_x; wp.mtiles_z = pl.mtiles_z; wp.m_total = pl.m_total;
+    wp.H_full = d->H; wp.samples_per_split = pl.samples_per_split;
+    wp.xbits = xbits; wp.wd_x = (d->N + 31) / 32; wp.zbits = zbits; wp.wd_z = d->H / 32; wp.part = part;
+    auto kern = tc::k_wgrad_bits<H, kBitsMT>;
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    dim3 grid((pl.mtiles_x + pl.mtiles_z + kBitsMT - 1) / kBitsMT, pl.S, d->H / H);
+    ProfScope ps(SNNK_K_WGRAD, st);
+    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mg, wp);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -1011,7 +1067,18 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     {
         const int M = d->B * d->T;
         unsigned int* flag = nullptr;
-        if (pl.tc) {
+        if ((d->flags & SNNK_F_INPUT_BITS) && !pl.bits) return SNNK_ERR_UNSUPPORTED;
+        if (pl.bits) {
+            // bit-packed raster: the words are expanded inside the GEMM's shared-memory tiles (gemm_bits.cuh)
+            void* planes_h = static_cast<char*>(workspace) + pl.off_wplanes;
+            const uint32_t* xb = reinterpret_cast<const uint32_t*>(x);
+            switch (pl.tileN) {
+            case 32: rc = launch_proj_bits<32>(d, xb, W_in, I_in, planes_h, st); break;
+            case 64: rc = launch_proj_bits<64>(d, xb, W_in, I_in, planes_h, st); break;
+            default: rc = launch_proj_bits<128>(d, xb, W_in, I_in, planes_h, st); break;
+            }
+            if (rc != SNNK_OK) return rc;
+        } else if (pl.tc) {
             char* ws = static_cast<char*>(workspace);
             float* planes = reinterpret_cast<float*>(ws + pl.off_wplanes);
             if (pl.check) {
@@ -1062,7 +1129,7 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
                 }
             }
         }
-        if (!pl.tc || pl.check) {
+        if (!pl.bits && (!pl.tc || pl.check)) {
             dim3 grid((M + kGemmBM - 1) / kGemmBM, pl.ntiles);
             ProfScope ps(pl.tc ? SNNK_K_PROJ_FALLBACK : SNNK_K_PROJ, st);
             if (pl.BN == 64) k_proj_simt<64><<<grid, kGemmThreads, 0, st>>>(x, W_in, I_in, M, d->N, d->H, flag);
@@ -1332,7 +1399,17 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
     // K4: weight-gradient GEMM (split-K partials over whole samples, then a fixed-order reduction)
     {
         unsigned int* flag = nullptr;
-        if (pl.tc) {
+        if ((d->flags & SNNK_F_INPUT_BITS) && !pl.bits) return SNNK_ERR_UNSUPPORTED;
+        if (pl.bits) {
+            const uint32_t* xb = reinterpret_cast<const uint32_t*>(x);
+            const size_t gstride = pl.off_gIlo - pl.off_gI;
+            switch (pl.tileN) {
+            case 32: rc = launch_wgrad_bits<32>(d, pl, xb, zbits, gI, gstride, pw, st); break;
+            case 64: rc = launch_wgrad_bits<64>(d, pl, xb, zbits, gI, gstride, pw, st); break;
+            default: rc = launch_wgrad_bits<128>(d, pl, xb, zbits, gI, gstride, pw, st); break;
+            }
+            if (rc != SNNK_OK) return rc;
+        } else if (pl.tc) {
             if (pl.check) {
                 flag = reinterpret_cast<unsigned int*>(ws + pl.off_flag);
                 SNNK_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
@@ -1390,7 +1467,7 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         wp.mtiles_x = pl.mtiles_x; wp.rows_per_split = pl.samples_per_split * d->T;
         wp.x = x; wp.zbits = zbits; wp.Z0 = Z0; wp.gI = gI; wp.gI_lo = gI_lo; wp.run_if_flag = flag;
         wp.part = pw; wp.m_total = pl.m_total;
-        if (!pl.tc || pl.check) {
+        if (!pl.bits && (!pl.tc || pl.check)) {
             dim3 grid(pl.mtiles_x + pl.mtiles_z, pl.ntiles, pl.S);
             ProfScope ps(pl.tc ? SNNK_K_WGRAD_FALLBACK : SNNK_K_WGRAD, st);
             if (pl.BN == 64) k_wgrad_simt<64><<<grid, kGemmThreads, 0, st>>>(wp);

@@ -43,6 +43,31 @@ BINARY_TAG = "_snnk_binary"   # python attribute on tensors known to hold exactl
 RUNS_TAG = "_snnk_runs"       # python attribute: the int32 run table of an encoded batch (include/snnk.h, snnk_encode_runs)
 
 
+BITS_TAG = "_snnk_bits"       # python attribute on a BIT-PACKED raster (B, T, ceil(N/32)) int32: its feature count N
+
+
+def mark_bits(t: torch.Tensor, n_pix: int) -> torch.Tensor:
+	"""Tags an int32 tensor as the packed raster of ``n_pix`` features (SNNK_F_INPUT_BITS, include/snnk.h): the
+	projection and weight-gradient kernels then expand the words in shared memory instead of reading fp32 rows."""
+	if t.dtype != torch.int32 or t.ndim != 3 or t.shape[-1] != (n_pix + 31) // 32:
+		raise ValueError("a packed raster is an int32 tensor (B, T, ceil(n_pix / 32))")
+	setattr(t, BITS_TAG, int(n_pix))
+	return t
+
+
+def bits_width(t) -> Optional[int]:
+	"""Feature count of a packed raster, None for anything else."""
+	n = getattr(t, BITS_TAG, None)
+	if n is None or t.dtype != torch.int32 or t.ndim != 3 or t.shape[-1] != (n + 31) // 32:
+		return None
+	return n
+
+
+def bits_eligible(n_pix: int, tensor_core: bool) -> bool:
+	"""Whether snnk_forward / snnk_backward take a packed raster of this width directly (else: unpack first)."""
+	return bool(tensor_core) and n_pix % 4 == 0
+
+
 def mark_binary(t: torch.Tensor, runs: Optional[torch.Tensor] = None) -> torch.Tensor:
 	setattr(t, BINARY_TAG, True)
 	if runs is not None:
@@ -65,9 +90,10 @@ def get_runs(t) -> Optional[torch.Tensor]:
 	return runs
 
 
-def make_desc(c: LayerConsts, B: int, T: int, N: int, H: int, O: int, traces: bool, binary: bool = False) -> _cabi.SnnkDesc:
+def make_desc(c: LayerConsts, B: int, T: int, N: int, H: int, O: int, traces: bool, binary: bool = False,
+		bits: bool = False) -> _cabi.SnnkDesc:
 	flags = (_cabi.SNNK_F_TRACES if traces else 0) | (_cabi.SNNK_F_TENSOR_CORE if c.tensor_core else 0) | (
-		_cabi.SNNK_F_INPUT_BINARY if binary else 0)
+		_cabi.SNNK_F_INPUT_BINARY if (binary or bits) else 0) | (_cabi.SNNK_F_INPUT_BITS if bits else 0)
 	izh = tuple(c.izh) if c.izh is not None else (0.0,) * 10
 	return _cabi.SnnkDesc(
 		B, T, N, H, O, c.layer_type, c.surrogate, int(c.recurrent), c.alpha, c.rho, c.theta, c.gamma, c.kappa, flags,
@@ -118,6 +144,8 @@ def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 	if t is None:
 		return None
 	r = t.detach()
+	if bits_width(t) is not None:      # packed raster: stays int32 words
+		return mark_bits(r if r.is_contiguous() else r.contiguous(), bits_width(t))
 	if r.dtype != torch.float32:
 		r = r.float()
 	r = r if r.is_contiguous() else r.contiguous()
@@ -134,11 +162,14 @@ def run_forward(
 	lib = _cabi.lib()
 	_cabi.require_b200(x.device)
 	B, T, N = x.shape
+	nbits = bits_width(x)
+	if nbits is not None:
+		N = nbits
 	H, O = W_out.shape
 	if W_in.shape != (N, H):
 		raise RuntimeError(f"forward_weights has shape {tuple(W_in.shape)}, expected {(N, H)}")
-	desc = make_desc(c, B, T, N, H, O, traces, binary=is_binary(x))
-	runs = get_runs(x)
+	desc = make_desc(c, B, T, N, H, O, traces, binary=is_binary(x), bits=nbits is not None)
+	runs = get_runs(x) if nbits is None else None
 	dev = x.device
 	f32 = dict(dtype=torch.float32, device=dev)
 	alif = c.layer_type != _cabi.SNNK_LIF     # three-state layers: ALIF (V, a, Z) and Izhikevich (V, u, Z)
@@ -177,8 +208,11 @@ def run_backward(
 	(the tensor-core mode stores it as two planes; summing them is only worth it when somebody asks)."""
 	lib = _cabi.lib()
 	B, T, N = x.shape
+	nbits = bits_width(x)
+	if nbits is not None:
+		N, runs = nbits, None
 	H, O = W_out.shape
-	desc = make_desc(c, B, T, N, H, O, True, binary=binary_input or is_binary(x))
+	desc = make_desc(c, B, T, N, H, O, True, binary=binary_input or is_binary(x), bits=nbits is not None)
 	dev = x.device
 	f32 = dict(dtype=torch.float32, device=dev)
 	dW_in = torch.empty((N, H), **f32)
@@ -192,7 +226,7 @@ def run_backward(
 			_cabi.ptr(W_out), _cabi.ptr(Z0), _cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(g_y),
 			_cabi.ptr(g_logits), _cabi.ptr(tstar), _cabi.ptr(g_scale), _cabi.ptr(g_V), _cabi.ptr(g_Z), _cabi.ptr(dW_in),
 			_cabi.ptr(dW_rec), _cabi.ptr(dW_out), _cabi.ptr(db), _cabi.ptr(ws), ws.numel(),
-			_cabi.ptr(runs if runs is not None else get_runs(x)), _cabi.ptr(W_effT), _cabi.stream_ptr())
+			_cabi.ptr(runs if (runs is not None or nbits is not None) else get_runs(x)), _cabi.ptr(W_effT), _cabi.stream_ptr())
 	_cabi.check(rc, "snnk_backward")
 	n = B * T * H * 4
 	planes = c.tensor_core and N % 4 == 0   # stored as two tf32 planes (high, exact remainder); see include/snnk.h

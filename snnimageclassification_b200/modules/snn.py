@@ -171,6 +171,8 @@ class SNN(torch.nn.Module):
 	# ---- input formatting (reference snn.py:159-184) ------------------------------------------------------------
 	def _format_inputs(self, inputs: torch.Tensor) -> torch.Tensor:
 		"""(B, F) -> repeated over int_time_steps; (B, T' <= T, F) -> zero-padded to T; cast to float32."""
+		if F_.bits_width(inputs) is not None:      # packed raster kept packed by _encode_if_needed: T already matches
+			return inputs
 		with torch.no_grad():
 			if inputs.ndim == 2:
 				inputs = torch.unsqueeze(inputs, 1).repeat(1, self.int_time_steps, 1)
@@ -188,8 +190,15 @@ class SNN(torch.nn.Module):
 		rasters (int32, last dimension ceil(F/32): ``ToSpikes.encode_batch_bits``) are unpacked on the device."""
 		if inputs.dtype == torch.int32 and inputs.ndim == 3 and inputs.shape[-1] == (self.input_size + 31) // 32 \
 				and inputs.shape[-1] != self.input_size:
+			inputs = inputs.to(self.device, non_blocking=True)
+			# the tensor-core GEMMs expand the words inside their shared-memory tiles (SNNK_F_INPUT_BITS): the fp32
+			# raster is never materialised.  Otherwise (fp32 mode, ragged width, fewer steps than int_time_steps,
+			# SNNK_PACKED_GEMM=0) the words are unpacked on the device first.
+			if (F_.bits_eligible(self.input_size, self.tensor_core) and inputs.shape[1] == self.int_time_steps
+					and os.environ.get("SNNK_PACKED_GEMM", "1") != "0"):
+				return F_.mark_bits(inputs.contiguous(), self.input_size)
 			from ..datasets.datasets import unpack_raster
-			return unpack_raster(inputs.to(self.device, non_blocking=True), self.input_size)
+			return unpack_raster(inputs, self.input_size)
 		if self.input_encoder is not None and inputs.ndim == 2:
 			# the raster is an intermediate nobody but the first layer's kernels reads: with the frame-dedup variant
 			# active those read only the first row of every run, so the rest need not be written (lazy raster)

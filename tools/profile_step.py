@@ -26,6 +26,7 @@ def main():
 	ap.add_argument("--T", type=int, default=100)
 	ap.add_argument("--dense", action="store_true", help="drop the run table: dense kernels")
 	ap.add_argument("--infer", action="store_true", help="no-trace inference instead of training steps")
+	ap.add_argument("--bits", action="store_true", help="feed the bit-packed raster (SNNK_F_INPUT_BITS kernels)")
 	ap.add_argument("--time", action="store_true", help="print the library's per-kernel CUDA-event times (eager launches)")
 	a = ap.parse_args()
 	H, layer, rec, ink, B = CFG[a.config]
@@ -38,7 +39,8 @@ def main():
 	g = torch.Generator().manual_seed(1)
 	img = (torch.randint(1, 256, (B, 784), generator=g).float() / 255.0) * (torch.rand(B, 784, generator=g) < ink)
 	lab = torch.randint(0, 10, (B,), generator=g).to(dev)
-	x = ToSpikes(a.T, use_periods=True).encode_batch(img.to(dev), frame_runs=not a.dense)
+	enc = ToSpikes(a.T, use_periods=True)
+	x = enc.encode_batch_bits(img.to(dev)) if a.bits else enc.encode_batch(img.to(dev), frame_runs=not a.dense)
 	if a.infer:
 		net.eval()
 		with torch.no_grad():
@@ -46,6 +48,14 @@ def main():
 				out = net.get_prediction_logits(x, re_outputs_trace=False, re_hidden_states=False)
 		torch.cuda.synchronize()
 		print("logits", float(out.abs().mean()))
+		if a.time:
+			from snnimageclassification_b200 import _cabi
+			with torch.no_grad(), _cabi.kernel_profile() as prof:
+				for _ in range(10):
+					net.get_prediction_logits(x, re_outputs_trace=False, re_hidden_states=False)
+				torch.cuda.synchronize()
+			for name, (ms, n) in prof.result.items():
+				print(f"  {name:55s} {1e3 * ms / 10:9.1f} us/call  ({n // 10} launches)")
 		return
 	net.train()
 
