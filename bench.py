@@ -236,6 +236,19 @@ def main():
 	dedup["value_dense_kernels"] = world * B_PER_GPU * args.steps / (ms_dense * 1e-3)
 	dedup["ms_per_step_dense_kernels"] = ms_dense / args.steps
 	del dense_graphs, dense_rasters
+	# ... and the same batches as BIT-PACKED rasters resident in HBM (2.5 MB instead of 80 MB per batch): the projection
+	# and weight-gradient GEMMs expand the words in shared memory (SNNK_F_INPUT_BITS; no run table: dense kernels)
+	from snnimageclassification_b200.modules.functional import mark_bits
+	packed_rasters = [mark_bits(enc.encode_batch_bits(img.to(dev)), N) for img in pool_img]
+	packed_graphs = [net.graphed_train_step(packed_rasters[i], labels_dev[i], crit, opt, static_inputs=True) for i in range(N_POOL)]
+	def step_packed(i):
+		return packed_graphs[i % N_POOL]()
+	for i in range(args.warmup):
+		step_packed(i)
+	ms_packed = timed(step_packed, args.steps)
+	packed = {"value": world * B_PER_GPU * args.steps / (ms_packed * 1e-3), "ms_per_step": ms_packed / args.steps,
+		"input": "bit-packed rasters (B,T,25) int32 resident in HBM, dense kernels k_proj_bits / k_wgrad_bits"}
+	del packed_graphs
 
 	# end to end through the public API: pinned host images -> H2D -> GPU encoder -> train step -> loss read-back
 	def step_e2e(i):
@@ -325,7 +338,7 @@ def main():
 		"vs_baseline": None, "dtype": "f32", "data": "synthetic",
 		"config": base_config(world),
 		"details": {"optimizer_kernel": "snnk_adam_step (one launch for all tensors)", "launch": "one CUDA graph per step",
-			"frame_dedup": dedup,
+			"frame_dedup": dedup, "packed_input": packed,
 			"grad_exchange": ("none (1 rank)" if world == 1 else
 				"fused into snnk_adam_step_dp over NVLink peer memory" if dp_fused else "NCCL all-reduce (mean)"),
 			"exchange_timeline_us": ({"columns": ["stores_issued", "peers_seen", "done"], "per_rank": timeline}
@@ -482,9 +495,13 @@ def run_inference_sweep(dev, quick=False):
 		x = ToSpikes(Tt, use_periods=True).encode_batch(img, frame_runs=False)      # (B,T,N) fp32 resident, > L2 from T = 10 on
 		ms = measure(net, x, 3 if Hh >= 512 and Tt >= 32 else 10)
 		v = B / (ms * 1e-3)
+		del x
+		xb = ToSpikes(Tt, use_periods=True).encode_batch_bits(img)                  # the same raster as (B,T,25) int32 words
+		ms_b = measure(net, xb, 3 if Hh >= 512 and Tt >= 32 else 10)
 		rows.append({"H": Hh, "layer": layer, "T": Tt, "input": "periodic to_spikes, ink 0.19", "ms": round(ms, 4), "value": v,
-			"roofline": step_roofline(v, Hh, True, alif, False, traces=False, Tt=Tt)})
-		del net, x
+			"roofline": step_roofline(v, Hh, True, alif, False, traces=False, Tt=Tt),
+			"packed_input": {"ms": round(ms_b, 4), "value": B / (ms_b * 1e-3)}})
+		del net, xb
 		torch.cuda.empty_cache()
 	for p in (0.004, 0.01, 0.1, 0.4):
 		torch.manual_seed(0)
@@ -500,7 +517,9 @@ def run_inference_sweep(dev, quick=False):
 	best = max(rows, key=lambda r: r["value"])
 	return {"workload": "inference only (no traces), recurrent LIF/ALIF, batch 8192, 1 GPU; eager launches, rasters resident in HBM",
 		"unit": "samples/s", "value": next(r["value"] for r in rows if (r["H"], r["layer"], r["T"], r["input"][:3]) == (128, "ALIF", 100, "per")),
-		"value_of": "ALIF H=128, T=100", "sweep": rows, "best": {k: best[k] for k in ("H", "layer", "T", "input", "value")}}
+		"value_of": "ALIF H=128, T=100 from the fp32 raster (SURVEY 8d); packed_input = the same rasters bit-packed",
+		"value_packed_input": next(r["packed_input"]["value"] for r in rows if (r["H"], r["layer"], r["T"], r["input"][:3]) == (128, "ALIF", 100, "per")),
+		"sweep": rows, "best": {k: best[k] for k in ("H", "layer", "T", "input", "value")}}
 
 
 # ---- ncu evidence parsed from the committed summaries (never hand-copied numbers) --------------------------------------
@@ -592,6 +611,31 @@ def large_batch_rooflines(net, enc, dev, B=4096, iters=5):
 			gbs = algo[key] / (ms / iters * 1e-3) / 1e9
 			out[name] = {"ms": round(ms / iters, 4), "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 3)}
 	del x
+	# the bit-fed GEMMs on the same batch (tensor-pipe bound: achieved 2-plane FLOP/s against the sustained bf16 peak;
+	# kind::f16 runs at the bf16 rate, kind::tf32 at half of it)
+	xb = enc.encode_batch_bits(img.to(dev))
+	def step_b():
+		loss = net.batch_loss(xb, lab, crit)
+		net.zero_grad()
+		loss.backward()
+	for _ in range(2):
+		step_b()
+	torch.cuda.synchronize()
+	with _cabi.kernel_profile() as prof:
+		for _ in range(iters):
+			step_b()
+	_, tf, _src = load_peaks()
+	flops = {"K1": 2.0 * BT * 832 * 2 * H, "K4": 2.0 * BT * 1024 * 2 * H}      # k / feature extents padded to the tiles
+	rate = {"K1": 1.0, "K4": 0.5}
+	bits = {}
+	for name, (ms, n) in prof.result.items():
+		key = name.split()[0]
+		if key in flops:
+			ach = flops[key] / (ms / iters * 1e-3) / 1e12
+			bits[name] = {"ms": round(ms / iters, 4), "TFLOPs": round(ach, 1), "frac_of_tensor_peak": round(ach / (tf * rate[key]), 3),
+				"kind": "f16, two fp16 planes" if key == "K1" else "tf32, two tf32 planes"}
+	out["bit_packed_input"] = bits
+	del xb
 	return out
 
 

@@ -46,11 +46,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Two raster bits (b0 = bit 0, b1 = bit 1 of t) -> two fp16 values {0, 1.0} packed in one word: the selector nibbles
-// 1 and 3 of a byte permute pick byte 1 (0x3C) or byte 0 (0x00) of 0x00003C00.
-__device__ __forceinline__ uint32_t bits2_to_half2(uint32_t t)
+// Threads of the bit-fed kernels: warp 0 producer, warp 1 MMA issue, then four expander / epilogue warps PER row tile
+// (one warp per scheduler could not expand a tile in the time the tensor pipe needs for it; ncu, profiles/r02_*).
+template <int MT> constexpr int bits_threads() { return 64 + MT * 128; }
+
+// A spike enters the fp16 tile as 2.0 (0x4000: ONE set bit, so two raster bits become two halves with a multiply and a
+// mask); the factor 2 is divided out, exactly, together with the column scale in the epilogue.
+constexpr float kSpikeHalfValue = 2.0f;
+__device__ __forceinline__ uint32_t bits2_to_half2(uint32_t t)      // t = b0 + 2 b1  ->  b0 << 14 | b1 << 30
 {
-    return __byte_perm(0x00003C00u, 0u, (t * 0x810u) & 0x1010u);
+    return (t * 0x20004000u) & 0x40004000u;
 }
 
 // ---- weight planes ---------------------------------------------------------------------------------------------------
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(256) k_split_w_h(const float* __restrict__ W, 
         s = 15 - e;                 // m 2^s in [2^14, 2^15)
         s = s > 120 ? 120 : (s < -120 ? -120 : s);
     }
-    if (threadIdx.x == 0) inv_scale[h] = ldexpf(1.0f, -s);
+    if (threadIdx.x == 0) inv_scale[h] = ldexpf(1.0f, -s) / kSpikeHalfValue;   // exact: both are powers of two
     const size_t plane = (size_t)kblocks * H * kBitsBlockK;
     for (int k = threadIdx.x; k < kblocks * kBitsBlockK; k += blockDim.x) {
         const float w = k < K ? ldexpf(W[(size_t)k * H + h], s) : 0.f;      // exact scaling
@@ -110,7 +115,7 @@ struct ProjBitsCfg {
 // bits : (M, wd) uint32 raster words.  Warp 0: bulk copies of the weight planes; warp 1: TMEM + MMA issue; warps 2-5:
 // expansion of the raster words into the A tiles (thread = row), then the epilogue.
 template <int H, int MT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(bits_threads<MT>(), 1)
 k_proj_bits(const uint32_t* __restrict__ bits, int wd, const __half* __restrict__ planes, const float* __restrict__ inv_scale,
             float* __restrict__ C, int M, int kblocks, int ldc)
 {
@@ -130,7 +135,7 @@ k_proj_bits(const uint32_t* __restrict__ bits, int wd, const __half* __restrict_
     const int n0 = blockIdx.y * H;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_b + s, 1); mbar_init(full_a + s, 4); mbar_init(empty + s, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_b + s, 1); mbar_init(full_a + s, 4 * MT); mbar_init(empty + s, 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -178,50 +183,33 @@ k_proj_bits(const uint32_t* __restrict__ bits, int wd, const __half* __restrict_
             umma_commit(tmem_full);
         }
     } else {
-        const int q = warp & 3;                    // TMEM lane quarter of this warp = its rows of every tile
+        const int q = warp & 3;                    // TMEM lane quarter of this warp = its rows of its tile
+        const int mt = (warp - 2) >> 2;            // warps 2-5: row tile 0, warps 6-9: row tile 1
         const int trow = 32 * q + lane;
-        const uint32_t* rowp[MT];
-        bool rvalid[MT];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int row = m0 + mt * kBlockM + trow;
-            rvalid[mt] = row < M;
-            rowp[mt] = bits + (size_t)(rvalid[mt] ? row : 0) * wd;
-        }
-        uint32_t w0[MT], w1[MT];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            w0[mt] = (rvalid[mt] && 0 < wd) ? __ldg(rowp[mt]) : 0u;
-            w1[mt] = (rvalid[mt] && 1 < wd) ? __ldg(rowp[mt] + 1) : 0u;
-        }
+        const int row = m0 + mt * kBlockM + trow;
+        const bool rvalid = row < M;
+        const uint32_t* rowp = bits + (size_t)(rvalid ? row : 0) * wd;
+        uint32_t w0 = (rvalid && 0 < wd) ? __ldg(rowp) : 0u;
+        uint32_t w1 = (rvalid && 1 < wd) ? __ldg(rowp + 1) : 0u;
+        const uint32_t dst0 = smem_u32(smem) + mt * Cfg::kABytes + trow * 128;
+        const uint32_t sw = (uint32_t)(trow & 7);
         for (int kb = 0; kb < kblocks; ++kb) {
             const int s = kb % kStages;
             const uint32_t ph = (kb / kStages) & 1;
-            uint32_t c0[MT], c1[MT];
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) { c0[mt] = w0[mt]; c1[mt] = w1[mt]; }
+            const uint32_t c0 = w0, c1 = w1;
             if (kb + 1 < kblocks) {   // the next k-block's words, in flight while this one is expanded
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    w0[mt] = (rvalid[mt] && 2 * kb + 2 < wd) ? __ldg(rowp[mt] + 2 * kb + 2) : 0u;
-                    w1[mt] = (rvalid[mt] && 2 * kb + 3 < wd) ? __ldg(rowp[mt] + 2 * kb + 3) : 0u;
-                }
+                w0 = (rvalid && 2 * kb + 2 < wd) ? __ldg(rowp + 2 * kb + 2) : 0u;
+                w1 = (rvalid && 2 * kb + 3 < wd) ? __ldg(rowp + 2 * kb + 3) : 0u;
             }
             mbar_wait(empty + s, ph ^ 1);
-            unsigned char* st = smem + (size_t)s * Cfg::kStageBytes;
+            const uint32_t rowdst = dst0 + (uint32_t)s * Cfg::kStageBytes;
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                unsigned char* rowdst = st + mt * Cfg::kABytes + trow * 128;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {      // chunk c = elements 8c .. 8c+7 = byte (c & 3) of word (c >> 2)
-                    const uint32_t v8 = ((c < 4 ? c0[mt] : c1[mt]) >> (8 * (c & 3))) & 0xFFu;
-                    uint4 o;
-                    o.x = bits2_to_half2(v8 & 3u);
-                    o.y = bits2_to_half2((v8 >> 2) & 3u);
-                    o.z = bits2_to_half2((v8 >> 4) & 3u);
-                    o.w = bits2_to_half2(v8 >> 6);
-                    *reinterpret_cast<uint4*>(rowdst + ((c ^ (trow & 7)) << 4)) = o;
-                }
+            for (int c = 0; c < 8; ++c) {      // chunk c = elements 8c .. 8c+7 = byte (c & 3) of word (c >> 2)
+                const uint32_t v8 = (c < 4 ? c0 : c1) >> (8 * (c & 3));
+                const uint32_t o0 = bits2_to_half2(v8 & 3u), o1 = bits2_to_half2((v8 >> 2) & 3u);
+                const uint32_t o2 = bits2_to_half2((v8 >> 4) & 3u), o3 = bits2_to_half2((v8 >> 6) & 3u);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowdst + (((uint32_t)c ^ sw) << 4)), "r"(o0), "r"(o1),
+                             "r"(o2), "r"(o3) : "memory");
             }
             fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor pipe's async-proxy reads
             __syncwarp();
@@ -231,21 +219,24 @@ k_proj_bits(const uint32_t* __restrict__ bits, int wd, const __half* __restrict_
         mbar_wait(tmem_full, 0);
         tc_fence_after();
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int row = m0 + mt * kBlockM + trow;
+        for (int cc = 0; cc < H; cc += 32) {
+            float v[32], u[32];
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + mt * Cfg::kColsPerTile + cc;
+            tmem_ld32(ta, v);
+            tmem_ld32(ta + H, u);
+            const float4* sc4 = reinterpret_cast<const float4*>(inv_scale + n0 + cc);
 #pragma unroll
-            for (int cc = 0; cc < H; cc += 32) {
-                float v[32], u[32];
-                const uint32_t ta = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + mt * Cfg::kColsPerTile + cc;
-                tmem_ld32(ta, v);
-                tmem_ld32(ta + H, u);
+            for (int j = 0; j < 8; ++j) {
+                const float4 sc = __ldg(sc4 + j);
+                v[4 * j + 0] = __fmul_rn(__fadd_rn(v[4 * j + 0], u[4 * j + 0]), sc.x);
+                v[4 * j + 1] = __fmul_rn(__fadd_rn(v[4 * j + 1], u[4 * j + 1]), sc.y);
+                v[4 * j + 2] = __fmul_rn(__fadd_rn(v[4 * j + 2], u[4 * j + 2]), sc.z);
+                v[4 * j + 3] = __fmul_rn(__fadd_rn(v[4 * j + 3], u[4 * j + 3]), sc.w);
+            }
+            if (rvalid) {
+                float4* dst = reinterpret_cast<float4*>(C + (size_t)row * ldc + n0 + cc);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__fadd_rn(v[j], u[j]), __ldg(inv_scale + n0 + cc + j));
-                if (row < M) {
-                    float4* dst = reinterpret_cast<float4*>(C + (size_t)row * ldc + n0 + cc);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
         }
     }
@@ -287,7 +278,7 @@ struct WgradBitsParams {
 };
 
 template <int H, int MT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(bits_threads<MT>(), 1)
 k_wgrad_bits(const __grid_constant__ CUtensorMap map_g, const WgradBitsParams p)
 {
     using Cfg = WgradBitsCfg<H, MT>;
@@ -312,7 +303,7 @@ k_wgrad_bits(const __grid_constant__ CUtensorMap map_g, const WgradBitsParams p)
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_g);
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_b + s, 1); mbar_init(full_a + s, 4); mbar_init(empty + s, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_b + s, 1); mbar_init(full_a + s, 4 * MT); mbar_init(empty + s, 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -362,71 +353,62 @@ k_wgrad_bits(const __grid_constant__ CUtensorMap map_g, const WgradBitsParams p)
             umma_commit(tmem_full);
         }
     } else {
-        // expansion: this warp fills box j = q of every tile, lane = time step of the k-block
+        // expansion: this warp fills box j = q of ITS tile (warps 2-5: tile 0, warps 6-9: tile 1), lane = time step
         const int q = warp & 3;
-        const uint32_t* src[MT]; int wd[MT], wcol[MT], shift[MT];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int tile = tile0 + mt;
-            const bool fx = tile < p.mtiles_x;
-            src[mt] = fx ? p.xbits : p.zbits;
-            wd[mt] = fx ? p.wd_x : p.wd_z;
-            wcol[mt] = (fx ? tile : tile - p.mtiles_x) * (kBlockM / 32) + q;
-            shift[mt] = fx ? 0 : 1;                       // the recurrent operand is the PREVIOUS step's raster
-            if (tile >= ntile || wcol[mt] >= wd[mt]) src[mt] = nullptr;
-        }
-        auto fetch = [&](int kb, uint32_t (&wv)[MT]) {
-            const int b = b_lo + kb / tblocks, t = (kb % tblocks) * kBlockK + lane;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int tt = t - shift[mt];
-                wv[mt] = (src[mt] && tt >= 0 && tt < p.T) ? __ldg(src[mt] + ((size_t)b * p.T + tt) * wd[mt] + wcol[mt]) : 0u;
-            }
+        const int mt = (warp - 2) >> 2;
+        const int tile = tile0 + mt;
+        const bool fx = tile < p.mtiles_x;
+        const bool live = tile < ntile;             // a CTA of the last tile pair may own one tile only
+        const int wd = fx ? p.wd_x : p.wd_z;
+        const int wcol = (fx ? tile : tile - p.mtiles_x) * (kBlockM / 32) + q;
+        const int shift = fx ? 0 : 1;               // the recurrent operand is the PREVIOUS step's raster
+        const uint32_t* src = (live && wcol < wd) ? (fx ? p.xbits : p.zbits) : nullptr;
+        auto fetch = [&](int kb) -> uint32_t {
+            const int b = b_lo + kb / tblocks, tt = (kb % tblocks) * kBlockK + lane - shift;
+            return (src && tt >= 0 && tt < p.T) ? __ldg(src + ((size_t)b * p.T + tt) * wd + wcol) : 0u;
         };
-        uint32_t nxt[MT];
-        if (kblocks > 0) fetch(0, nxt);
-        const int hsel = (lane >> 2) & 1;     // lanes t and t+4 share (t & 3): they start on different 16-byte halves
-        for (int kb = 0; kb < kblocks; ++kb) {
-            const int s = kb % kStages;
-            const uint32_t ph = (kb / kStages) & 1;
-            uint32_t cur[MT];
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) cur[mt] = nxt[mt];
-            if (kb + 1 < kblocks) fetch(kb + 1, nxt);
-            mbar_wait(empty + s, ph ^ 1);
-            unsigned char* st = smem + (size_t)s * Cfg::kStageBytes;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                if (tile0 + mt >= ntile) break;
-                unsigned char* rowdst = st + mt * kATileBytes + q * Cfg::kBoxBytes + lane * 128;
+        uint32_t nxt = kblocks > 0 ? fetch(0) : 0u;
+        const uint32_t hsel = (lane >> 2) & 1;      // lanes t and t+4 share (t & 3): they start on different 16-byte halves
+        const uint32_t dst0 = smem_u32(smem) + mt * kATileBytes + q * Cfg::kBoxBytes + lane * 128;
+        if (live) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                const uint32_t cur = nxt;
+                if (kb + 1 < kblocks) nxt = fetch(kb + 1);
+                mbar_wait(empty + s, ph ^ 1);
+                const uint32_t rowdst = dst0 + (uint32_t)s * Cfg::kStageBytes;
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const int h = hh ^ hsel;
-                        const uint32_t v4 = (cur[mt] >> (8 * a + 4 * h)) & 0xFu;      // elements 8a+4h .. 8a+4h+3
-                        uint4 o;
-                        o.x = (0u - (v4 & 1u)) & 0x3F800000u;
-                        o.y = (0u - ((v4 >> 1) & 1u)) & 0x3F800000u;
-                        o.z = (0u - ((v4 >> 2) & 1u)) & 0x3F800000u;
-                        o.w = (0u - (v4 >> 3)) & 0x3F800000u;
-                        *reinterpret_cast<uint4*>(rowdst + ((a ^ (lane & 3)) << 5) + (h << 4)) = o;
+                        const uint32_t h = (uint32_t)hh ^ hsel;
+                        const uint32_t v4 = cur >> (8 * a + 4 * h);      // elements 8a+4h .. 8a+4h+3 in its low four bits
+                        const uint32_t o0 = (0u - (v4 & 1u)) & 0x3F800000u, o1 = (0u - ((v4 >> 1) & 1u)) & 0x3F800000u;
+                        const uint32_t o2 = (0u - ((v4 >> 2) & 1u)) & 0x3F800000u, o3 = (0u - ((v4 >> 3) & 1u)) & 0x3F800000u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowdst + ((((uint32_t)a ^ (lane & 3)) << 5) | (h << 4))),
+                                     "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
                     }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_a + s);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_a + s);
+        } else {
+            // no tile: the MMA warp still waits for 4*MT arrivals per stage
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_a + s);
+            }
         }
 
         if (kblocks > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
         }
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int tile = tile0 + mt;
-            if (tile >= ntile) break;
-            const bool fx = tile < p.mtiles_x;
+        if (live) {
             const int m = (fx ? tile : tile - p.mtiles_x) * kBlockM + 32 * q + lane;
             const int mlim = fx ? p.N : p.H_full;
             const int mbase = fx ? 0 : p.N;

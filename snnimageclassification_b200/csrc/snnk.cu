@@ -403,7 +403,7 @@ int launch_proj_bits(const SnnkDesc* d, const uint32_t* xbits, const float* W_in
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     ProfScope ps(SNNK_K_PROJ, st);
     dim3 grid((M + kBitsMT * tc::kBlockM - 1) / (kBitsMT * tc::kBlockM), Hf / H);
-    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(xbits, wd, planes, inv_scale, I_in, M, kblocks, Hf);
+    kern<<<grid, tc::bits_threads<kBitsMT>(), Cfg::kSmemBytes, st>>>(xbits, wd, planes, inv_scale, I_in, M, kblocks, Hf);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -431,7 +431,7 @@ int launch_wgrad_bits(const SnnkDesc* d, const Plan& pl, const uint32_t* xbits, 
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     dim3 grid((pl.mtiles_x + pl.mtiles_z + kBitsMT - 1) / kBitsMT, pl.S, d->H / H);
     ProfScope ps(SNNK_K_WGRAD, st);
-    kern<<<grid, tc::kThreads, Cfg::kSmemBytes, st>>>(mg, wp);
+    kern<<<grid, tc::bits_threads<kBitsMT>(), Cfg::kSmemBytes, st>>>(mg, wp);
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
