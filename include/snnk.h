@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SNNK_ABI_VERSION 6   /* 6: SNNK_F_INPUT_BITS; 5: loss mailbox of snnk_head_nll; 4: W_effT_out / W_effT_in; 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
+#define SNNK_ABI_VERSION 7   /* 7: snnk_forward_nll; 6: SNNK_F_INPUT_BITS; 5: loss mailbox of snnk_head_nll; 4: W_effT_out / W_effT_in; 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
 
 typedef void* snnk_stream_t; /* cudaStream_t */
 
@@ -229,6 +229,25 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
 int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labels, float* logp,
                   float* loss, float* g_logits, uint64_t* loss_mailbox, uint32_t* mailbox_counter,
                   snnk_stream_t stream);
+
+/*
+ * snnk_forward followed by snnk_head_nll as ONE call (what SNN._exec_batch does for its default criterion,
+ * snn.py:384-412: forward, max over time :228, log_softmax :258, NLLLoss :297).  Same arguments and results as the two
+ * calls.  For layers on the register-resident recurrence kernel (H <= 128, batch below the tensor-core recurrence's
+ * threshold) the head is evaluated in that kernel's tail -- the CTA that owns a row computes its log-probabilities, NLL
+ * term and dL/dlogits, the last CTA to finish reduces the loss in the stand-alone kernel's order (bit-identical,
+ * deterministic) -- so no launch sits between the forward pass and the BPTT sweep; other geometries launch
+ * k_head_nll behind the forward kernels.
+ *   head_ws  (B + 1) * 4 bytes of device memory, ZERO before the first call that uses it (the library leaves its last
+ *            word, a ticket counter, zero again after every launch); must not be shared by launches that may overlap
+ */
+int snnk_forward_nll(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec,
+                     const float* rec_mask, const float* beta, const float* W_out, const float* b_out,
+                     const float* V0, const float* a0, const float* Z0, float* V, float* a, float* Z,
+                     uint32_t* zbits, float* y, float* logits, int32_t* tstar, void* workspace,
+                     size_t workspace_bytes, const int32_t* run_table, float* W_effT_out, const int64_t* labels,
+                     float* logp, float* loss, float* g_logits, void* head_ws, uint64_t* loss_mailbox,
+                     uint32_t* mailbox_counter, snnk_stream_t stream);
 
 /*
  * Reverse-time BPTT.  Replaces autograd's sweep for batch_loss.backward() (snn.py:413) over the graph

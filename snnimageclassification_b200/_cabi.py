@@ -87,6 +87,7 @@ _SIGNATURES = {
 		_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_double,
 		ctypes.c_double, ctypes.c_double, ctypes.c_int32, _p, ctypes.c_int32, _p, _p, _p, ctypes.c_int32, _p]),
 	"snnk_forward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 18 + [ctypes.c_size_t, _p, _p, _p]),
+	"snnk_forward_nll": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 18 + [ctypes.c_size_t, _p, _p] + [_p] * 7 + [_p]),
 	"snnk_head_nll": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _p, _p, _p, _p, _p, _p, _p, _p]),
 	"snnk_input_grad": (ctypes.c_int, [ctypes.POINTER(SnnkDesc), _p, _p, _p, _p]),
 	"snnk_backward": (ctypes.c_int, [ctypes.POINTER(SnnkDesc)] + [_p] * 21 + [ctypes.c_size_t, _p, _p, _p]),
@@ -113,7 +114,7 @@ def lib() -> ctypes.CDLL:
 			fn = getattr(l, name)
 			fn.restype = res
 			fn.argtypes = args
-		if l.snnk_abi_version() != 6:
+		if l.snnk_abi_version() != 7:
 			raise RuntimeError("libsnnk.so ABI version mismatch; rebuild the extension")
 		_lib = l
 	return _lib

@@ -34,6 +34,12 @@ struct FwdParams {
     // table[4 + b*T + t] of the compact projection I_u instead of row b*T+t of I_in
     const int* run_table; const float* I_u;
     IzhConsts iz;           // Izhikevich layer: the `a` trace / a0 state hold the recovery variable u
+    // Fused head (k_recur_fwd, snnk_forward_nll): the CTA that owns a row also evaluates its log_softmax, NLL term and
+    // dL/dlogits in the kernel's tail; the last CTA to finish reduces the loss.  labels == nullptr: no head.
+    const long long* labels; float* logp; float* g_logits; float* loss;
+    float* part_nll;        // (B) per-row NLL terms
+    unsigned int* ticket;   // zero before the launch; the last CTA leaves it zero again
+    unsigned long long* mailbox; unsigned int* mail_counter;
 };
 
 struct BwdParams {

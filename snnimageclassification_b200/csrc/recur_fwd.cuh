@@ -38,7 +38,7 @@ constexpr size_t fwd_smem_bytes(int T, int O)
 // time (snn.py:228) from the T spike words kept in shared memory.  tid/nthr: thread index and block size.
 template <int H, int R>
 __device__ __forceinline__ void fwd_tail(const FwdParams& p, const uint32_t* s_mask, const float* s_wout, float* s_s, int b0,
-                                         int tid, int nthr)
+                                         int tid, int nthr, float* s_logit = nullptr)
 {
     constexpr int W32 = H / 32;
     const int T = p.T, O = p.O, B = p.B;
@@ -90,12 +90,99 @@ __device__ __forceinline__ void fwd_tail(const FwdParams& p, const uint32_t* s_m
             p.logits[(size_t)(b0 + r) * O + c] = mx;
             p.tstar[(size_t)(b0 + r) * O + c] = mt;
         }
+        if (s_logit) s_logit[r * kOMax + c] = mx;      // for the fused head
     }
     __syncthreads();
     // (C) coalesced write of the output trace
     for (int idx = tid; idx < R * T * O; idx += nthr) {
         const int r = idx / (T * O), rem = idx - r * (T * O);
         if (b0 + r < B) p.y[(size_t)(b0 + r) * T * O + rem] = s_s[idx];
+    }
+}
+
+// ---- fused head (snn.py:228 -> :258 -> :297) ---------------------------------------------------------------------------
+// The arithmetic and the summation order of k_head_nll (encode_head.cuh), moved into the tail of the forward kernel:
+// a separate one-CTA launch between the forward pass and the BPTT sweep cost ~10 us of an 180 us step.
+// head_count: batch-wide label statistics (every CTA counts them itself, in its prologue).
+// head_tail : thread r < R evaluates row b0 + r exactly like k_head_nll's per-row body; the last CTA to take a ticket
+//             sums the per-row NLL terms as k_head_nll's 256 threads would (virtual thread v: rows v, v+256, ...; xor
+//             shuffle tree per virtual warp; the eight warp sums in order) -- the loss is bit-identical to the
+//             stand-alone kernel's and run-to-run deterministic.
+__device__ __forceinline__ void head_count(const FwdParams& p, int* s_hd, int tid, int nthr)
+{
+    constexpr long long kIgnore = -100;
+    int nv = 0, nbad = 0;
+    for (int b = tid; b < p.B; b += nthr) {
+        const long long l = p.labels[b];
+        nv += (l >= 0 && l < p.O);
+        nbad += (l != kIgnore && (l < 0 || l >= p.O));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        nbad += __shfl_xor_sync(0xffffffffu, nbad, o);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&s_hd[0], nv); atomicAdd(&s_hd[1], nbad); }
+}
+
+template <int R>
+__device__ __forceinline__ void head_tail(const FwdParams& p, const float* s_logit, int* s_hd, double* s_hp, int b0, int tid, int nthr)
+{
+    constexpr long long kIgnore = -100;
+    const int O = p.O, B = p.B;
+    const int n_valid = s_hd[0];
+    const bool bad = s_hd[1] != 0;
+    if (tid < R && b0 + tid < B) {
+        const int b = b0 + tid;
+        float lg[kOMax];
+        float mx = -INFINITY;
+        for (int c = 0; c < O; ++c) { lg[c] = s_logit[tid * kOMax + c]; mx = fmaxf(mx, lg[c]); }
+        float se = 0.f;
+        for (int c = 0; c < O; ++c) se += expf(lg[c] - mx);
+        const float lse = logf(se);
+        const long long lab = p.labels[b];
+        const bool row_ok = lab >= 0 && lab < O, row_bad = !row_ok && lab != kIgnore;
+        float nll = 0.f;
+        for (int c = 0; c < O; ++c) {
+            const float lp = (lg[c] - mx) - lse;
+            if (p.logp) p.logp[(size_t)b * O + c] = lp;
+            if (c == lab) nll = -lp;
+            if (p.g_logits) {
+                float g = row_ok ? __fdiv_rn(expf(lp) - (c == lab ? 1.0f : 0.0f), (float)n_valid) : 0.0f;
+                if (row_bad) g = __int_as_float(0x7fc00000);
+                p.g_logits[(size_t)b * O + c] = g;
+            }
+        }
+        p.part_nll[b] = nll;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) s_hd[2] = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_hd[2]) return;
+    __threadfence();
+    const int lane = tid & 31;
+    for (int vw = tid >> 5; vw < 8; vw += nthr >> 5) {
+        double acc = 0.0;
+        for (int b = vw * 32 + lane; b < B; b += 256) acc += (double)__ldcg(p.part_nll + b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_hp[vw] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+        for (int q = 0; q < 8; ++q) sum += s_hp[q];
+        const float lossf = bad ? __int_as_float(0x7fc00000) : (float)(sum / (double)n_valid);
+        *p.loss = lossf;
+        *p.ticket = 0u;
+        if (p.mailbox) {      // {launch number, loss} as one 8-byte store into pinned host memory (see k_head_nll)
+            const unsigned int seq = *p.mail_counter + 1u;
+            *p.mail_counter = seq;
+            *reinterpret_cast<volatile unsigned long long*>(p.mailbox) =
+                (static_cast<unsigned long long>(seq) << 32) | __float_as_uint(lossf);
+            __threadfence_system();
+        }
     }
 }
 
@@ -144,7 +231,11 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
     if (compact)
         for (int idx = i; idx < nvalid * T; idx += H)
             s_r2c[idx] = __ldg(p.run_table + kRunHdrInts + (size_t)b0 * T + idx);   // rows b0.. are consecutive
+    __shared__ int s_hd[4];                 // fused head: valid labels, bad labels, "this is the last CTA"
+    __shared__ double s_hp[8];
+    __shared__ float s_logit[R * kOMax];
     if (i == 0) {
+        s_hd[0] = s_hd[1] = s_hd[2] = 0;
         for (int s = 0; s <= kRing; ++s) tc::mbar_init(s_bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (REC) {   // the whole masked recurrent matrix in one bulk copy (64 KB at H = 128)
@@ -153,6 +244,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
         }
     }
     __syncthreads();   // barrier inits (and the compact-row table) visible before anyone issues or waits
+    if (p.labels) head_count(p, s_hd, i, H);      // its global loads overlap the weight staging below
     // Frame-dedup variant: the compact rows of one sample are CONSECUTIVE rows of I_u (three for the production encoder),
     // so they are fetched ONCE, with one bulk copy per sample, into the memory of the ring and indexed per step.  A copy
     // per (row, step) -- what the ring does for this variant -- costs the SM's TMA unit ~270 cycles per 512-byte
@@ -265,7 +357,8 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd(const FwdParams p)
     }
     __syncthreads();
 
-    fwd_tail<H, R>(p, s_mask, s_wout, s_s, b0, i, H);
+    fwd_tail<H, R>(p, s_mask, s_wout, s_s, b0, i, H, s_logit);
+    if (p.labels) head_tail<R>(p, s_logit, s_hd, s_hp, b0, i, H);
 }
 
 // A k-split variant (two, then eight lanes per neuron; 8 warps per row) was built and measured twice: 76 us and 74 us

@@ -1040,11 +1040,16 @@ size_t snnk_backward_workspace_bytes(const SnnkDesc* d)
     return make_plan(d).bwd_bytes;
 }
 
-int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec, const float* rec_mask,
+// Head arguments of snnk_forward_nll (null for snnk_forward)
+struct HeadArgs {
+    const int64_t* labels; float* logp; float* loss; float* g_logits; void* head_ws; uint64_t* mailbox; uint32_t* counter;
+};
+
+static int forward_impl(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec, const float* rec_mask,
                  const float* beta, const float* W_out, const float* b_out, const float* V0, const float* a0,
                  const float* Z0, float* V, float* a, float* Z, uint32_t* zbits, float* y, float* logits,
                  int32_t* tstar, void* workspace, size_t workspace_bytes, const int32_t* run_table, float* W_effT_out,
-                 snnk_stream_t stream)
+                 snnk_stream_t stream, const HeadArgs* head)
 {
     int rc = check_desc(d);
     if (rc != SNNK_OK) return rc;
@@ -1159,20 +1164,59 @@ int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const flo
     fp.logits = logits; fp.tstar = tstar;
     fp.run_table = compact_table; fp.I_u = compact_rows;
     const bool rec = d->recurrent != 0;
+    // the register-resident recurrence evaluates the head in its own tail; every other kernel family is followed by
+    // the stand-alone head kernel (same arithmetic, same summation order)
+    const bool fused_head = head && !pl.wide && !pl.tcrec && !pl.nr;
+    if (fused_head) {
+        fp.labels = reinterpret_cast<const long long*>(head->labels); fp.logp = head->logp; fp.g_logits = head->g_logits;
+        fp.loss = head->loss; fp.part_nll = static_cast<float*>(head->head_ws);
+        fp.ticket = reinterpret_cast<unsigned int*>(static_cast<float*>(head->head_ws) + d->B);
+        fp.mailbox = reinterpret_cast<unsigned long long*>(head->mailbox); fp.mail_counter = head->counter;
+    }
     if (pl.wide && pl.widetc) {
         rc = launch_wide_fwd(wide_params(fp, pl, static_cast<char*>(workspace)), st);
-        if (rc != SNNK_OK) return rc;
-        return launch_readout_scan(d, fp, st);
+        if (rc == SNNK_OK) rc = launch_readout_scan(d, fp, st);
+    } else if (pl.wide) {
+        rc = launch_fwd_wide(d, fp, rec, pl, st);
+    } else if (pl.tcrec) {
+        rc = launch_fwd_tc(fp, st);
+    } else if (pl.nr) {
+        rc = launch_nonrec_fwd(fp, st);
+    } else {
+        switch (d->H) {
+        case 32: rc = launch_fwd_r<32>(fp, rec, pl.R, pl.grid_rows, st); break;
+        case 64: rc = launch_fwd_r<64>(fp, rec, pl.R, pl.grid_rows, st); break;
+        case 128: rc = launch_fwd_r<128>(fp, rec, pl.R, pl.grid_rows, st); break;
+        default: rc = SNNK_ERR_UNSUPPORTED;
+        }
     }
-    if (pl.wide) return launch_fwd_wide(d, fp, rec, pl, st);
-    if (pl.tcrec) return launch_fwd_tc(fp, st);
-    if (pl.nr) return launch_nonrec_fwd(fp, st);
-    switch (d->H) {
-    case 32: return launch_fwd_r<32>(fp, rec, pl.R, pl.grid_rows, st);
-    case 64: return launch_fwd_r<64>(fp, rec, pl.R, pl.grid_rows, st);
-    case 128: return launch_fwd_r<128>(fp, rec, pl.R, pl.grid_rows, st);
-    default: return SNNK_ERR_UNSUPPORTED;
-    }
+    if (rc != SNNK_OK || !head || fused_head) return rc;
+    return snnk_head_nll(d->B, d->O, logits, head->labels, head->logp, head->loss, head->g_logits, head->mailbox,
+                         head->counter, stream);
+}
+
+int snnk_forward(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec, const float* rec_mask,
+                 const float* beta, const float* W_out, const float* b_out, const float* V0, const float* a0,
+                 const float* Z0, float* V, float* a, float* Z, uint32_t* zbits, float* y, float* logits,
+                 int32_t* tstar, void* workspace, size_t workspace_bytes, const int32_t* run_table, float* W_effT_out,
+                 snnk_stream_t stream)
+{
+    return forward_impl(d, x, W_in, W_rec, rec_mask, beta, W_out, b_out, V0, a0, Z0, V, a, Z, zbits, y, logits, tstar,
+                        workspace, workspace_bytes, run_table, W_effT_out, stream, nullptr);
+}
+
+int snnk_forward_nll(const SnnkDesc* d, const float* x, const float* W_in, const float* W_rec, const float* rec_mask,
+                     const float* beta, const float* W_out, const float* b_out, const float* V0, const float* a0,
+                     const float* Z0, float* V, float* a, float* Z, uint32_t* zbits, float* y, float* logits,
+                     int32_t* tstar, void* workspace, size_t workspace_bytes, const int32_t* run_table, float* W_effT_out,
+                     const int64_t* labels, float* logp, float* loss, float* g_logits, void* head_ws,
+                     uint64_t* loss_mailbox, uint32_t* mailbox_counter, snnk_stream_t stream)
+{
+    if (!labels || !loss || !head_ws) return SNNK_ERR_ARG;
+    if ((loss_mailbox != nullptr) != (mailbox_counter != nullptr)) return SNNK_ERR_ARG;
+    const HeadArgs h{labels, logp, loss, g_logits, head_ws, loss_mailbox, mailbox_counter};
+    return forward_impl(d, x, W_in, W_rec, rec_mask, beta, W_out, b_out, V0, a0, Z0, V, a, Z, zbits, y, logits, tstar,
+                        workspace, workspace_bytes, run_table, W_effT_out, stream, &h);
 }
 
 int snnk_head_nll(int32_t B, int32_t O, const float* logits, const int64_t* labels, float* logp, float* loss,

@@ -154,11 +154,26 @@ def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 	return r
 
 
+_HEAD_WS = {}     # (device, B) -> zeroed scratch of snnk_forward_nll (per-row NLL terms + ticket word)
+
+
+def _head_scratch(dev, B: int) -> torch.Tensor:
+	"""One scratch per device and batch size, allocated (zeroed) on first use and kept: launches that use it are
+	expected to be ordered, as the steps of one training loop are (include/snnk.h, snnk_forward_nll)."""
+	key = (dev.index, B)
+	ws = _HEAD_WS.get(key)
+	if ws is None:
+		ws = _HEAD_WS[key] = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+	return ws
+
+
 def run_forward(
 		c: LayerConsts, x, W_in, W_rec, rec_mask, beta, W_out, b_out, traces: bool = True,
-		state: Optional[Tuple[Optional[torch.Tensor], ...]] = None,
+		state: Optional[Tuple[Optional[torch.Tensor], ...]] = None, labels: Optional[torch.Tensor] = None,
+		want_head_grad: bool = True,
 ):
-	"""Calls ``snnk_forward``.  Returns dict(y, V, a, Z, zbits, logits, tstar, I_in, desc)."""
+	"""Calls ``snnk_forward`` -- or, with ``labels``, ``snnk_forward_nll`` (forward + fused log_softmax / NLL head).
+	Returns dict(y, V, a, Z, zbits, logits, tstar, I_in, desc[, loss, logp, g_logits])."""
 	lib = _cabi.lib()
 	_cabi.require_b200(x.device)
 	B, T, N = x.shape
@@ -189,15 +204,30 @@ def run_forward(
 			V0, a0, Z0 = (_c(s) for s in state)
 		else:
 			V0, Z0 = (_c(s) for s in state)
+	common = (
+		ctypes.byref(desc), _cabi.ptr(x), _cabi.ptr(W_in), _cabi.ptr(W_rec), _cabi.ptr(rec_mask),
+		_cabi.ptr(beta), _cabi.ptr(W_out), _cabi.ptr(b_out), _cabi.ptr(V0), _cabi.ptr(a0), _cabi.ptr(Z0),
+		_cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(y), _cabi.ptr(logits),
+		_cabi.ptr(tstar), _cabi.ptr(ws), ws.numel(), _cabi.ptr(runs), _cabi.ptr(W_effT))
+	head = {}
 	with torch.cuda.device(dev):
-		rc = lib.snnk_forward(
-			ctypes.byref(desc), _cabi.ptr(x), _cabi.ptr(W_in), _cabi.ptr(W_rec), _cabi.ptr(rec_mask),
-			_cabi.ptr(beta), _cabi.ptr(W_out), _cabi.ptr(b_out), _cabi.ptr(V0), _cabi.ptr(a0), _cabi.ptr(Z0),
-			_cabi.ptr(V), _cabi.ptr(a), _cabi.ptr(Z), _cabi.ptr(zbits), _cabi.ptr(y), _cabi.ptr(logits),
-			_cabi.ptr(tstar), _cabi.ptr(ws), ws.numel(), _cabi.ptr(runs), _cabi.ptr(W_effT), _cabi.stream_ptr())
-	_cabi.check(rc, "snnk_forward")
+		if labels is None:
+			rc = lib.snnk_forward(*common, _cabi.stream_ptr())
+		else:
+			labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+			logp = torch.empty((B, O), **f32)
+			loss = torch.empty((), **f32)
+			g = torch.empty((B, O), **f32) if want_head_grad else None
+			box = LOSS_MAILBOX if (LOSS_MAILBOX is not None and LOSS_MAILBOX[1].device == dev) else None
+			rc = lib.snnk_forward_nll(
+				*common, _cabi.ptr(labels), _cabi.ptr(logp), _cabi.ptr(loss), _cabi.ptr(g), _cabi.ptr(_head_scratch(dev, B)),
+				ctypes.c_void_p(box[0].data_ptr()) if box else None, _cabi.ptr(box[1]) if box else None,
+				_cabi.stream_ptr())
+			head = dict(loss=loss, logp=logp, g_logits=g)
+	_cabi.check(rc, "snnk_forward" if labels is None else "snnk_forward_nll")
 	I_in = ws[: B * T * H * 4].view(torch.float32).view(B, T, H)
-	return dict(y=y, V=V, a=a, Z=Z, zbits=zbits, logits=logits, tstar=tstar, I_in=I_in, desc=desc, Z0=Z0, W_effT=W_effT)
+	return dict(y=y, V=V, a=a, Z=Z, zbits=zbits, logits=logits, tstar=tstar, I_in=I_in, desc=desc, Z0=Z0, W_effT=W_effT,
+		**head)
 
 
 def run_backward(
@@ -327,8 +357,9 @@ class SpikingSequenceNLL(torch.autograd.Function):
 		Hp = padded_width(H)
 		Wi, Wr, M, Wo = _pad_hidden(H, Hp, Wi, Wr, M, Wo)
 		need_grad = any(ctx.needs_input_grad)
-		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=traces or need_grad)
-		loss, logp, g_logits = run_head_nll(out["logits"], labels, want_grad=need_grad)
+		out = run_forward(consts, xc, Wi, Wr, M, be, Wo, bo, traces=traces or need_grad, labels=labels,
+			want_head_grad=need_grad)
+		loss, logp, g_logits = out["loss"], out["logp"], out["g_logits"]
 		ctx.consts, ctx.H = consts, H
 		ctx.set_materialize_grads(False)
 		ctx.binary, ctx.runs, ctx.W_effT = is_binary(xc), get_runs(xc), out["W_effT"]

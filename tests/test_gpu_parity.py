@@ -32,7 +32,7 @@ def npy(t):
 
 
 def test_native_library_loaded_and_device_supported():
-	assert _cabi.lib().snnk_abi_version() == 6
+	assert _cabi.lib().snnk_abi_version() == 7
 	_cabi.require_b200(DEV)
 
 
@@ -623,3 +623,43 @@ def test_head_label_semantics():
 	labels[5] = 12
 	loss, _, gl = F_.run_head_nll(logits, labels.to(DEV))
 	assert torch.isnan(loss).item() and torch.isnan(gl[5]).all().item() and not torch.isnan(gl[4]).any().item()
+
+
+# ---- fused head: snnk_forward_nll == snnk_forward + snnk_head_nll ------------------------------------------------------
+@pytest.mark.parametrize("B,T,H,layer,rec,tc", [
+	(256, 20, 128, 1, True, True),      # headline kernel family: register-resident recurrence, head in its tail
+	(300, 7, 128, 1, True, False),      # more rows than the stand-alone kernel's 256 threads
+	(1, 5, 32, 0, True, False), (37, 9, 64, 1, True, True),
+	(1100, 3, 128, 0, True, False),     # two rows per CTA
+	(64, 11, 128, 1, False, True),      # non-recurrent scan kernels: stand-alone head behind the forward kernels
+	(40, 6, 256, 1, True, True),        # wide layer: stand-alone head
+])
+def test_fused_head_is_bit_identical_to_the_standalone_head(B, T, H, layer, rec, tc):
+	N, O = 64, 10
+	g = torch.Generator().manual_seed(B + H)
+	theta = 0.03 if layer else 1.0
+	x = F_.mark_binary((torch.rand(B, T, N, generator=g) < 0.3).float().to(DEV))
+	W_in = (torch.randn(N, H, generator=g) * theta).to(DEV)
+	W_rec = (torch.randn(H, H, generator=g) * theta).to(DEV) if rec else None
+	mask = (1 - torch.eye(H)).to(DEV) if rec else None
+	W_out, b_out = torch.randn(H, O, generator=g).to(DEV), (torch.randn(O, generator=g) * 0.1).to(DEV)
+	beta = torch.tensor([1.6], device=DEV) if layer else None
+	c = F_.LayerConsts(layer, 0, rec, 0.95, 0.995, theta, 0.3 if layer else 1.0, 0.9, tensor_core=tc)
+	labels = torch.randint(0, O, (B,), generator=g).to(DEV)
+	for variant in ("plain", "ignored", "bad"):
+		lab = labels.clone()
+		if variant == "ignored":
+			lab[::3] = -100
+		if variant == "bad" and B > 1:
+			lab[B // 2] = O + 3
+		for _ in range(2):      # twice: the ticket word must be back at zero after a launch
+			f = F_.run_forward(c, x, W_in, W_rec, mask, beta, W_out, b_out, labels=lab)
+		f0 = F_.run_forward(c, x, W_in, W_rec, mask, beta, W_out, b_out)
+		loss, logp, gl = F_.run_head_nll(f0["logits"], lab)
+		assert torch.equal(f["logits"], f0["logits"])
+		assert torch.equal(f["logp"], logp)
+		assert torch.equal(f["loss"].isnan(), loss.isnan()) and (bool(loss.isnan()) or torch.equal(f["loss"], loss)), variant
+		assert torch.equal(f["g_logits"].isnan(), gl.isnan())
+		assert torch.equal(torch.nan_to_num(f["g_logits"]), torch.nan_to_num(gl)), variant
+		if variant == "bad" and B > 1:
+			assert bool(f["loss"].isnan())

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 	for name in declared:
 		assert hasattr(lib, name), f"{name} declared in snnk.h but not exported by libsnnk.so"
 	assert sorted(_cabi.EXPORTS) == declared, "python binding and header disagree on the entry points"
-	assert _cabi.lib().snnk_abi_version() == 6
+	assert _cabi.lib().snnk_abi_version() == 7
 	assert b"sm_100" in _cabi.lib().snnk_strerror(-3)
 
 
