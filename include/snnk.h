@@ -44,7 +44,7 @@ extern "C" {
 
 typedef void* snnk_stream_t; /* cudaStream_t */
 
-/* LayerType, src/modules/spiking_layers.py:11-14.  SNNK_IZHIKEVICH (spiking_layers.py:246-353): H <= 128 only; the
+/* LayerType, src/modules/spiking_layers.py:11-14.  SNNK_IZHIKEVICH (spiking_layers.py:246-353; wider than 128: the fp32 kernels of recur_gen.cuh): the
  * `a` trace and the a0 state hold the recovery variable u; V0 == NULL starts the membrane at v_rest (:309). */
 enum { SNNK_LIF = 0, SNNK_ALIF = 1, SNNK_IZHIKEVICH = 2 };
 /* SpikeFuncType, src/modules/spike_funcs.py:7-9 */

@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_bwd(const BwdParams p)
         __syncthreads();
         tc::mbar_wait(wbar, 0);
         load_w_cb<REC ? H : 16>(w, s_t, i);
+        // the ring's bulk copies (async proxy) will land in this area: order the generic-proxy reads above before them
+        // (a barrier alone does not order the two proxies; recur_lean.cuh has the observed failure)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (i == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(wbar)) : "memory");
     }

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_fwd_gen(const FwdParam
         for (int r = 0; r < R; ++r) {
             const int i = tid + j * BD;
             const size_t s = (size_t)(valid[r] ? b0 + r : 0) * H + i;
-            v[j][r] = (valid[r] && p.V0) ? p.V0[s] : 0.f;
+            v[j][r] = (valid[r] && p.V0) ? p.V0[s] : (p.iz.on ? p.iz.vr : 0.f);   // Izhikevich starts at v_rest (:309)
             a[j][r] = (valid[r] && p.a0) ? p.a0[s] : 0.f;
             zp[j][r] = (valid[r] && p.Z0) ? p.Z0[s] : 0.f;
             if (REC) s_z[(1 * H + i) * R + r] = zp[j][r];
@@ -145,15 +145,26 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_fwd_gen(const FwdParam
             const int i = tid + j * BD;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                // identical arithmetic to k_recur_fwd (spiking_layers.py:169/239-242)
-                const float t1 = __fmul_rn(p.alpha, v[j][r]);
-                const float t2 = __fadd_rn(t1, cur[j][r]);
-                const float t3 = __fadd_rn(t2, rec[j][r]);
-                const float vn = __fmul_rn(t3, __fsub_rn(1.0f, zp[j][r]));
-                float thr = p.theta;
-                if (p.alif) {
-                    a[j][r] = __fadd_rn(__fmul_rn(p.rho, a[j][r]), zp[j][r]);
-                    thr = __fadd_rn(p.theta, __fmul_rn(beta, a[j][r]));
+                // identical arithmetic to k_recur_fwd (spiking_layers.py:169/239-242; Izhikevich :344-349)
+                float vn, thr = p.theta;
+                if (p.iz.on) {
+                    const float I = __fadd_rn(cur[j][r], rec[j][r]);
+                    const float d1 = __fsub_rn(v[j][r], p.iz.vr), d2 = __fsub_rn(v[j][r], p.iz.vth);
+                    const float q = __fsub_rn(__fmul_rn(__fmul_rn(p.iz.k, d1), d2), a[j][r]);
+                    const float inc = __fdiv_rn(__fmul_rn(p.iz.dt, __fadd_rn(q, I)), p.iz.C);
+                    vn = __fadd_rn(__fmul_rn(__fadd_rn(v[j][r], inc), __fsub_rn(1.0f, zp[j][r])), __fmul_rn(p.iz.c, zp[j][r]));
+                    const float du = __fmul_rn(p.iz.a, __fsub_rn(__fmul_rn(p.iz.b, d1), a[j][r]));
+                    a[j][r] = __fadd_rn(__fadd_rn(a[j][r], __fmul_rn(p.iz.dt, du)), __fmul_rn(p.iz.d, zp[j][r]));
+                    thr = p.iz.vpeak;
+                } else {
+                    const float t1 = __fmul_rn(p.alpha, v[j][r]);
+                    const float t2 = __fadd_rn(t1, cur[j][r]);
+                    const float t3 = __fadd_rn(t2, rec[j][r]);
+                    vn = __fmul_rn(t3, __fsub_rn(1.0f, zp[j][r]));
+                    if (p.alif) {
+                        a[j][r] = __fadd_rn(__fmul_rn(p.rho, a[j][r]), zp[j][r]);
+                        thr = __fadd_rn(p.theta, __fmul_rn(beta, a[j][r]));
+                    }
                 }
                 const float zn = vn >= thr ? 1.0f : 0.0f;
                 const unsigned m = __ballot_sync(0xffffffffu, zn != 0.f);
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_fwd_gen(const FwdParam
                     if (p.traces) {
                         p.V[o] = vn;
                         p.Z[o] = zn;
-                        if (p.alif) p.a[o] = a[j][r];
+                        if (p.alif || p.iz.on) p.a[o] = a[j][r];
                     }
                     if (lane == 0) p.zbits[((size_t)(b0 + r) * T + t) * (H / 32) + (i >> 5)] = m;
                 }
@@ -270,14 +281,14 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_bwd_gen(const BwdParam
         if (b0 + r < B) gy_scan[(size_t)(b0 + r) * T * kOMax + rem] = s_gy[idx];
     }
 
-    float gv[NPT][R];
+    float gv[NPT][R], gu[NPT][R];      // gu: adjoint of the Izhikevich recovery variable
     bool valid[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) valid[r] = b0 + r < B;
 #pragma unroll
     for (int j = 0; j < NPT; ++j)
 #pragma unroll
-        for (int r = 0; r < R; ++r) gv[j][r] = 0.f;
+        for (int r = 0; r < R; ++r) gv[j][r] = gu[j][r] = 0.f;
 
     for (int t = T - 1; t >= 0; --t) {
         float rec[NPT][R];
@@ -307,14 +318,29 @@ __global__ void __launch_bounds__(kGenMaxThreads) k_recur_bwd_gen(const BwdParam
                 if (REC) s = __fadd_rn(s, rec[j][r]);
                 if (p.g_Z && valid[r]) s = __fadd_rn(s, __ldg(p.g_Z + o));
                 const float vt = valid[r] ? __ldg(p.V + o) : 0.f;
-                float thr = p.theta;
-                if (p.alif) thr = __fadd_rn(p.theta, __fmul_rn(beta, valid[r] ? __ldg(p.a + o) : 0.f));
-                const float sg = surrogate_grad(p.surrogate, p.gamma, vt, thr);
-                const float carry = __fmul_rn(__fmul_rn(p.alpha, gv[j][r]), __fsub_rn(1.0f, zt));
-                float g = __fadd_rn(__fmul_rn(s, sg), carry);
-                if (p.g_V && valid[r]) g = __fadd_rn(g, __ldg(p.g_V + o));
+                float g, gi;
+                if (p.iz.on) {
+                    // the coupled (gV, gu) adjoint of spiking_layers.py:345-348, operation order of k_recur_bwd
+                    const float sg = surrogate_grad(p.surrogate, p.gamma, vt, p.iz.vpeak);
+                    const float dq = __fmul_rn(p.iz.k, __fadd_rn(__fsub_rn(vt, p.iz.vr), __fsub_rn(vt, p.iz.vth)));
+                    const float A = __fmul_rn(__fadd_rn(1.0f, __fdiv_rn(__fmul_rn(p.iz.dt, dq), p.iz.C)), __fsub_rn(1.0f, zt));
+                    const float dtC = __fdiv_rn(p.iz.dt, p.iz.C);
+                    g = __fadd_rn(__fadd_rn(__fmul_rn(s, sg), __fmul_rn(gv[j][r], A)),
+                                  __fmul_rn(gu[j][r], __fmul_rn(__fmul_rn(p.iz.dt, p.iz.a), p.iz.b)));
+                    if (p.g_V && valid[r]) g = __fadd_rn(g, __ldg(p.g_V + o));
+                    gu[j][r] = __fadd_rn(__fmul_rn(__fmul_rn(gv[j][r], -dtC), __fsub_rn(1.0f, zt)),
+                                         __fmul_rn(gu[j][r], __fsub_rn(1.0f, __fmul_rn(p.iz.dt, p.iz.a))));
+                    gi = __fmul_rn(__fmul_rn(g, dtC), __fsub_rn(1.0f, zprev));
+                } else {
+                    float thr = p.theta;
+                    if (p.alif) thr = __fadd_rn(p.theta, __fmul_rn(beta, valid[r] ? __ldg(p.a + o) : 0.f));
+                    const float sg = surrogate_grad(p.surrogate, p.gamma, vt, thr);
+                    const float carry = __fmul_rn(__fmul_rn(p.alpha, gv[j][r]), __fsub_rn(1.0f, zt));
+                    g = __fadd_rn(__fmul_rn(s, sg), carry);
+                    if (p.g_V && valid[r]) g = __fadd_rn(g, __ldg(p.g_V + o));
+                    gi = __fmul_rn(g, __fsub_rn(1.0f, zprev));
+                }
                 gv[j][r] = g;
-                const float gi = __fmul_rn(g, __fsub_rn(1.0f, zprev));
                 if (valid[r]) {
                     if (p.gI_lo) {
                         const float hi = __uint_as_float(__float_as_uint(gi) & 0xFFFFE000u);

@@ -18,6 +18,7 @@
 #include "recur_bwd.cuh"
 #include "recur_fwd.cuh"
 #include "recur_gen.cuh"
+#include "recur_lean.cuh"
 #include "recur_nr.cuh"
 #include "recur_tc.cuh"
 #include "recur_wide.cuh"
@@ -153,7 +154,6 @@ int check_desc(const SnnkDesc* d)
     if (!d) return SNNK_ERR_ARG;
     if (d->B <= 0 || d->T <= 0 || d->N <= 0 || d->H <= 0 || d->O <= 0) return SNNK_ERR_SHAPE;
     if (d->layer_type != SNNK_LIF && d->layer_type != SNNK_ALIF && d->layer_type != SNNK_IZHIKEVICH) return SNNK_ERR_ARG;
-    if (d->layer_type == SNNK_IZHIKEVICH && d->H > 128) return SNNK_ERR_UNSUPPORTED;   // register-resident kernels only
     if (d->layer_type == SNNK_IZHIKEVICH && !(d->iz_C != 0.0f)) return SNNK_ERR_ARG;
     if (d->surrogate != SNNK_FAST_SIGMOID && d->surrogate != SNNK_PHI) return SNNK_ERR_ARG;
     if (d->O > kOMax) return SNNK_ERR_SHAPE;
@@ -458,6 +458,27 @@ int launch_fwd(const FwdParams& fp, int grid, cudaStream_t st)
     return SNNK_OK;
 }
 
+// Lean forward recurrence (recur_lean.cuh): recurrent LIF / ALIF, H = 128, one row per CTA, the row's input current
+// resident in shared memory.  SNNK_LEAN=0 keeps the general kernel (measuring switch, read per call).
+bool use_lean_fwd(const FwdParams& fp, bool rec, int R)
+{
+    if (!rec || fp.iz.on || fp.H != 128 || R != 1) return false;
+    if (lean_fwd_smem_bytes<128>(fp.T, fp.O) > 110 * 1024) return false;
+    const char* env = getenv("SNNK_LEAN");
+    return !(env && env[0] == '0');
+}
+
+int launch_fwd_lean(const FwdParams& fp, cudaStream_t st)
+{
+    const size_t smem = lean_fwd_smem_bytes<128>(fp.T, fp.O);
+    void (*kern)(const FwdParams) = fp.alif ? (fp.traces ? k_recur_fwd_lean<128, true, true> : k_recur_fwd_lean<128, true, false>)
+                                            : (fp.traces ? k_recur_fwd_lean<128, false, true> : k_recur_fwd_lean<128, false, false>);
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { ProfScope ps(SNNK_K_RECUR_FWD, st); kern<<<fp.B, 128, smem, st>>>(fp); }
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
 template <int H, int R>
 int launch_fwd_rec(const FwdParams& fp, bool rec, int grid, cudaStream_t st)
 {
@@ -703,6 +724,36 @@ int launch_bwd(const BwdParams& bp, int grid, cudaStream_t st)
     { ProfScope ps(SNNK_K_RECUR_BWD, st); kern<<<grid, H, smem, st>>>(bp); }
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
+}
+
+// Lean BPTT sweep (recur_lean.cuh): the training step of the headline geometry -- recurrent LIF / ALIF, H = 128, one row
+// per CTA, sparse seeds from the fused head, no seeds on V / Z.  SNNK_LEAN=0 keeps the general kernel.
+bool use_lean_bwd(const BwdParams& bp, bool rec, int R)
+{
+    if (!rec || bp.iz.on || bp.H != 128 || R != 1 || bp.g_y || bp.g_V || bp.g_Z || !bp.g_logits || !bp.tstar) return false;
+    if (bwd_smem_bytes<128, 1>(bp.T, true) > 110 * 1024) return false;
+    const char* env = getenv("SNNK_LEAN");
+    return !(env && env[0] == '0');
+}
+
+template <bool ALIF, int SURR>
+int launch_bwd_lean_t(const BwdParams& bp, cudaStream_t st)
+{
+    const size_t smem = bwd_smem_bytes<128, 1>(bp.T, true);
+    const bool planes = bp.gI_lo != nullptr, runs = bp.run_table != nullptr;
+    void (*kern)(const BwdParams) =
+        planes ? (runs ? k_recur_bwd_lean<ALIF, SURR, true, true> : k_recur_bwd_lean<ALIF, SURR, true, false>)
+               : (runs ? k_recur_bwd_lean<ALIF, SURR, false, true> : k_recur_bwd_lean<ALIF, SURR, false, false>);
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { ProfScope ps(SNNK_K_RECUR_BWD, st); kern<<<bp.B, 128, smem, st>>>(bp); }
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
+int launch_bwd_lean(const BwdParams& bp, cudaStream_t st)
+{
+    if (bp.alif) return bp.surrogate ? launch_bwd_lean_t<true, 1>(bp, st) : launch_bwd_lean_t<true, 0>(bp, st);
+    return bp.surrogate ? launch_bwd_lean_t<false, 1>(bp, st) : launch_bwd_lean_t<false, 0>(bp, st);
 }
 
 template <int H, int R>
@@ -1183,7 +1234,8 @@ static int forward_impl(const SnnkDesc* d, const float* x, const float* W_in, co
     } else if (pl.nr) {
         rc = launch_nonrec_fwd(fp, st);
     } else {
-        switch (d->H) {
+        if (use_lean_fwd(fp, rec, pl.R)) rc = launch_fwd_lean(fp, st);
+        else switch (d->H) {
         case 32: rc = launch_fwd_r<32>(fp, rec, pl.R, pl.grid_rows, st); break;
         case 64: rc = launch_fwd_r<64>(fp, rec, pl.R, pl.grid_rows, st); break;
         case 128: rc = launch_fwd_r<128>(fp, rec, pl.R, pl.grid_rows, st); break;
@@ -1431,6 +1483,8 @@ int snnk_backward(const SnnkDesc* d, const float* x, const float* W_rec, const f
         }
         if (fkw) SNNK_CUDA(cudaEventRecord(fkw->joined3, fkw->side));
         rc = pl.tcrec ? launch_bwd_tc(bp, gy_scan, st) : launch_nonrec_bwd(bp, gy_scan, st);
+    } else if (use_lean_bwd(bp, rec, pl.R)) {
+        rc = launch_bwd_lean(bp, st);
     } else {
         switch (d->H) {
         case 32: rc = launch_bwd_r<32>(bp, rec, pl.R, pl.grid_rows, st); break;

@@ -227,7 +227,8 @@ class IzhikevichLayer(RNNLayer):
 	"""Third LayerType member of the reference (spiking_layers.py:246-353), SURVEY.md 8f.3.
 
 	V' = (V + dt (k (V - v_rest)(V - v_th) - u + I) / C)(1 - Z) + c Z;  u' = u + dt a (b (V - v_rest) - u) + d Z;
-	Z' = H(V' - v_peak).  Same kernels as LIF/ALIF with a different elementwise body (hidden widths up to 128).
+	Z' = H(V' - v_peak).  Same kernels as LIF/ALIF with a different elementwise body (widths up to 128 on the register-resident kernels,
+	wider layers on the fp32 kernels of recur_gen.cuh).
 	"""
 	SNNK_LAYER_TYPE = _cabi.SNNK_IZHIKEVICH
 
@@ -260,8 +261,6 @@ class IzhikevichLayer(RNNLayer):
 			raise RuntimeError(
 				f"spike function {self.spike_func!r} has no fused surrogate on the B200 path (supported: "
 				"HeavisideSigmoidApprox, HeavisidePhiApprox)")
-		if F_.padded_width(self.output_size) > 128:
-			raise NotImplementedError("IzhikevichLayer is fused for hidden widths up to 128 on the B200 path")
 		izh = tuple(float(v) for v in (self.dt, self.C, self.v_rest, self.v_th, self.k, self.a, self.b, self.c, self.d,
 			self.v_peak))
 		return F_.LayerConsts(

@@ -116,3 +116,54 @@ def test_izhikevich_single_step_and_training():
 	net.train()
 	losses = [net._exec_batch(xb, yb, torch.nn.NLLLoss(), opt) for _ in range(12)]
 	assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("H,rec,surr", [(256, True, 0), (200, True, 1), (384, False, 0)])
+def test_izhikevich_wide_layers_vs_oracle(H, rec, surr):
+	"""The reference puts no limit on the width of an IzhikevichLayer (spiking_layers.py:246-353); wider than 128 it runs
+	on the fp32 kernels of recur_gen.cuh (200 is zero-padded to 256): traces bit-identical to the C oracle, gradients of
+	the oracle's sweep within 1e-4."""
+	from snnimageclassification_b200 import LayerType, SNN, SpikeFuncType
+	B, T, N, O = 6, 25, 48, 10
+	torch.manual_seed(3)
+	net = SNN(N, O, H, use_recurrent_connection=rec, int_time_steps=T, dt=1.0, hidden_layer_type=LayerType.Izhikevich,
+		spike_func=SpikeFuncType.Phi if surr else SpikeFuncType.FastSigmoid, device=DEV, tensor_core=False)
+	L, R = net.layers["input"], net.layers["readout"]
+	with torch.no_grad():
+		L.forward_weights.mul_(25.0).add_(20.0)
+		if rec:
+			L.recurrent_weights.mul_(5.0)
+	g = torch.Generator().manual_seed(4)
+	x = (torch.rand(B, T, N, generator=g) < 0.2).float()
+	lab = torch.randint(0, O, (B,), generator=g)
+	# the oracle (like the kernels) runs the padded width: zero columns / rows for the neurons that do not exist
+	Hp = (H + 127) // 128 * 128
+	cfg = OracleCfg(B, T, N, Hp, O, layer_type=2, surrogate=surr, recurrent=int(rec), gamma=float(L.gamma), kappa=float(R.kappa),
+		dt=float(L.dt), iz_C=float(L.C), iz_vr=float(L.v_rest), iz_vth=float(L.v_th), iz_k=float(L.k), iz_a=float(L.a),
+		iz_b=float(L.b), iz_c=float(L.c), iz_d=float(L.d), iz_vpeak=float(L.v_peak))
+
+	def pad(a, rows, cols):
+		out_ = np.zeros((rows, cols), np.float32)
+		out_[:a.shape[0], :a.shape[1]] = a
+		return out_
+	W_in = pad(npy(L.forward_weights), N, Hp)
+	W_rec = pad(npy(L.recurrent_weights), Hp, Hp) if rec else np.zeros((Hp, Hp), np.float32)
+	mask = pad(npy(L.rec_mask), Hp, Hp) if rec else np.zeros((Hp, Hp), np.float32)
+	W_out = pad(npy(R.forward_weights), Hp, O)
+	f = oracle.forward(cfg, x.numpy(), W_in, W_rec if rec else None, mask if rec else None, W_out, npy(R.bias_weights))
+	net.train()
+	out, hs = net(x.to(DEV))
+	V, u, Z = hs["input"]
+	assert npy(Z).sum() > 0 and V.shape == (B, T, H)
+	assert np.array_equal(npy(Z), f["Z"][..., :H]) and np.array_equal(npy(V), f["V"][..., :H])
+	assert np.array_equal(npy(u), f["a"][..., :H]) and np.array_equal(npy(out), f["y"])
+	net.zero_grad()
+	loss = net.batch_loss(x.to(DEV), lab.to(DEV), torch.nn.NLLLoss())
+	loss.backward()
+	h = oracle.head(f["y"], lab.numpy())
+	assert abs(loss.item() - h["loss"]) <= 1e-5 * abs(h["loss"])
+	gr = oracle.backward(cfg, x.numpy(), W_rec, mask, W_out, f["V"], f["a"], f["Z"], h["g_y"])
+	assert rel_err(npy(L.forward_weights.grad), gr["dW_in"][:, :H]) <= 1e-4
+	assert rel_err(npy(R.forward_weights.grad), gr["dW_out"][:H]) <= 1e-4 and rel_err(npy(R.bias_weights.grad), gr["db"]) <= 1e-4
+	if rec:
+		assert rel_err(npy(L.recurrent_weights.grad), gr["dW_rec"][:H, :H]) <= 1e-4
