@@ -193,15 +193,53 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd_lean(const FwdParams p
 // pointers into the adjoint rows / spike words / gI advance by constants, the previous step's spike word is carried in
 // a register, and layer type, surrogate, plane split and run sums are template parameters -- the 269 instructions of a
 // step of the general kernel contain ~70 of uniform-datapath bookkeeping and branches (profiles/r02_*).
-template <bool ALIF, int SURR, bool PLANES, bool RUNS>
+// OP: readout width padded to whole float4 (12 for ten classes): columns >= O of the adjoint rows and of W_out are zero,
+// so leaving them out of the two FMA chains changes nothing but the instruction count.
+template <bool ALIF, int SURR, bool PLANES, bool RUNS, int OP>
 __global__ void __launch_bounds__(128, 2) k_recur_bwd_lean(const BwdParams p)
 {
     constexpr int H = 128, W32 = H / 32;
+    static_assert(OP % 4 == 0 && OP <= kOMax, "readout padding");
     static_assert(kChunk % 2 == 0, "compile-time parity of the gI double buffer");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = p.T, O = p.O;
     const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
     const int b = blockIdx.x;
+
+    // Everything the prologue needs from global memory is requested FIRST, into registers: the weight staging below
+    // (64 KB through shared memory, which the loop buffers alias) then overlaps those round trips instead of
+    // preceding six of them one after the other (ncu: 15 % of the general kernel was prologue).
+    const bool run_sums = RUNS && p.run_table != nullptr && p.run_table[1] == 1;
+    const int TW = (T + 31) >> 5;
+    uint32_t zw[4];                                        // spike words i, i+H, ... of the row (T * W32 <= 4 H)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int idx = i + q * H;
+        zw[q] = idx < T * W32 ? __ldg(p.zbits + (size_t)b * T * W32 + idx) : 0u;
+    }
+    int rc_t = 0, rc_p = -1, crow = 0;                     // run of step t = i and of step i-1; run of the last step
+    if (run_sums) {
+        const int* rc = p.run_table + kRunHdrInts + (size_t)b * T;
+        if (i < T) {
+            rc_t = __ldg(rc + i);
+            if (i > 0) rc_p = __ldg(rc + i - 1);
+        }
+        crow = __ldg(rc + T - 1);
+    }
+    float seed = 0.f;                                      // thread c < O: the seed of class c at its arg-max step
+    int ts = -1;
+    if (i < O) {
+        const float scale = p.g_scale ? __ldg(p.g_scale) : 1.0f;
+        ts = __ldg(p.tstar + (size_t)b * O + i);
+        seed = __fmul_rn(__ldg(p.g_logits + (size_t)b * O + i), scale);
+    }
+    float wo[OP], dwo[OP];
+#pragma unroll
+    for (int c = 0; c < OP; ++c) {
+        wo[c] = c < O ? __ldg(p.W_out + (size_t)i * O + c) : 0.f;
+        dwo[c] = 0.f;
+    }
+    const float beta = (ALIF && p.beta) ? __ldg(p.beta) : 0.f;
 
     float w[H];
     {
@@ -228,8 +266,6 @@ __global__ void __launch_bounds__(128, 2) k_recur_bwd_lean(const BwdParams p)
     float* s_a = s_v + kRing * kChunk * H;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_a + kRing * kChunk * H);
     uint32_t* s_start = reinterpret_cast<uint32_t*>(s_bar + kRing);        // [ceil(T/32)] run-start bits
-    const bool run_sums = RUNS && p.run_table != nullptr && p.run_table[1] == 1;
-    const int TW = (T + 31) >> 5;
 
     const int nchunks = (T + kChunk - 1) / kChunk;
     auto issue_chunk = [&](int k) {
@@ -246,23 +282,15 @@ __global__ void __launch_bounds__(128, 2) k_recur_bwd_lean(const BwdParams p)
         for (int k = 0; k < kRing && k < nchunks; ++k) issue_chunk(k);
     }
 
-    float wo[kOMax], dwo[kOMax];
-#pragma unroll
-    for (int c = 0; c < kOMax; ++c) {
-        wo[c] = c < O ? __ldg(p.W_out + (size_t)i * O + c) : 0.f;
-        dwo[c] = 0.f;
-    }
-    const float beta = (ALIF && p.beta) ? __ldg(p.beta) : 0.f;
-
     for (int idx = i; idx < 2 * H; idx += H) s_g[idx] = 0.f;
-    for (int idx = i; idx < T * kOMax; idx += H) s_gy[idx] = 0.f;
-    for (int idx = i; idx < T * W32; idx += H) s_mask[idx] = __ldg(p.zbits + (size_t)b * T * W32 + idx);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (i + q * H < T * W32) s_mask[i + q * H] = zw[q];
     if (run_sums) {
-        for (int idx = i; idx < TW; idx += H) s_start[idx] = 0u;
+        if (i < TW) s_start[i] = 0u;
         __syncthreads();
-        const int* rc = p.run_table + kRunHdrInts + (size_t)b * T;
-        for (int t = i; t < T; t += H)
-            if (t == 0 || __ldg(rc + t) != __ldg(rc + t - 1)) atomicOr(s_start + (t >> 5), 1u << (t & 31));
+        // bit t of the word: step t is the first of its run of equal input frames
+        if (i < T && (i == 0 || rc_t != rc_p)) atomicOr(s_start + (i >> 5), 1u << (i & 31));
         if (blockIdx.x == 0) {   // the weight-gradient GEMM contracts whole 32-row blocks: zero the tail of the last one
             const int n_rows = p.run_table[0], n_pad = (n_rows + 31) & ~31;
             for (int idx = i; idx < (n_pad - n_rows) * H; idx += H) {
@@ -271,30 +299,21 @@ __global__ void __launch_bounds__(128, 2) k_recur_bwd_lean(const BwdParams p)
             }
         }
     }
-    __syncthreads();
-    {
-        const float scale = p.g_scale ? __ldg(p.g_scale) : 1.0f;
-        for (int c = i; c < O; c += H) {
-            const int ts = __ldg(p.tstar + (size_t)b * O + c);
-            s_gy[ts * kOMax + c] = __fmul_rn(__ldg(p.g_logits + (size_t)b * O + c), scale);
-        }
-    }
-    __syncthreads();
-    // readout adjoint scan gy_t = seed_t + kappa gy_{t+1}  (spiking_layers.py:407 backwards) and db
-    for (int c = i; c < O; c += H) {
+    // readout adjoint scan gy_t = seed_t + kappa gy_{t+1}  (spiking_layers.py:407 backwards) and db: the seed of a class
+    // sits at one step (its arg-max over time), so the chain runs in registers -- the same two operations per step as
+    // the general kernel's scan over shared memory -- and fills the class's whole column, padding columns with zeros
+    if (i < kOMax) {
         float g = 0.f, sum = 0.f;
         for (int t = T - 1; t >= 0; --t) {
-            float* gp = s_gy + t * kOMax + c;
-            g = __fadd_rn(*gp, __fmul_rn(p.kappa, g));
-            *gp = g;
+            g = __fadd_rn(t == ts ? seed : 0.f, __fmul_rn(p.kappa, g));
+            s_gy[t * kOMax + i] = g;
             sum += g;
         }
-        p.part_db[(size_t)blockIdx.x * O + c] = sum;
+        if (i < O) p.part_db[(size_t)blockIdx.x * O + i] = sum;
     }
     __syncthreads();
 
     float gv = 0.f, racc = 0.f;
-    int crow = run_sums ? __ldg(p.run_table + kRunHdrInts + (size_t)b * T + T - 1) : 0;
     uint32_t sbits = 0u;
     size_t tro = ((size_t)b * T + (T - 1)) * H + i;
     const float4* gyp = reinterpret_cast<const float4*>(s_gy + (T - 1) * kOMax);
@@ -308,9 +327,9 @@ __global__ void __launch_bounds__(128, 2) k_recur_bwd_lean(const BwdParams p)
         constexpr int PAR = decltype(par_tag)::value;
         const float vt = vrow[i];
         const float at = ALIF ? arow[i] : 0.f;
-        float gy[kOMax];
+        float gy[OP];
 #pragma unroll
-        for (int q = 0; q < kOMax / 4; ++q) {
+        for (int q = 0; q < OP / 4; ++q) {
             const float4 g4 = gyp[q];
             gy[4 * q + 0] = g4.x; gy[4 * q + 1] = g4.y; gy[4 * q + 2] = g4.z; gy[4 * q + 3] = g4.w;
         }
@@ -326,7 +345,7 @@ __global__ void __launch_bounds__(128, 2) k_recur_bwd_lean(const BwdParams p)
         }
         float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < kOMax; ++c) {
+        for (int c = 0; c < OP; ++c) {
             s = fmaf(gy[c], wo[c], s);               // gy_t W_out^T
             dwo[c] = fmaf(zt, gy[c], dwo[c]);        // dW_out += Z_t^T gy_t
         }
@@ -382,7 +401,7 @@ __global__ void __launch_bounds__(128, 2) k_recur_bwd_lean(const BwdParams p)
         }
     }
 #pragma unroll
-    for (int c = 0; c < kOMax; ++c)
+    for (int c = 0; c < OP; ++c)
         if (c < O) p.part_wout[((size_t)blockIdx.x * H + i) * O + c] = dwo[c];
 }
 

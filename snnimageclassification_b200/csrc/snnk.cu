@@ -731,23 +731,29 @@ int launch_bwd(const BwdParams& bp, int grid, cudaStream_t st)
 bool use_lean_bwd(const BwdParams& bp, bool rec, int R)
 {
     if (!rec || bp.iz.on || bp.H != 128 || R != 1 || bp.g_y || bp.g_V || bp.g_Z || !bp.g_logits || !bp.tstar) return false;
-    if (bwd_smem_bytes<128, 1>(bp.T, true) > 110 * 1024) return false;
+    if (bwd_smem_bytes<128, 1>(bp.T, true) > 110 * 1024 || bp.T > 128) return false;   // T * 4 spike words <= 4 per thread
     const char* env = getenv("SNNK_LEAN");
     return !(env && env[0] == '0');
+}
+
+template <bool ALIF, int SURR, int OP>
+int launch_bwd_lean_o(const BwdParams& bp, cudaStream_t st)
+{
+    const size_t smem = bwd_smem_bytes<128, 1>(bp.T, true);
+    const bool planes = bp.gI_lo != nullptr, runs = bp.run_table != nullptr;
+    void (*kern)(const BwdParams) =
+        planes ? (runs ? k_recur_bwd_lean<ALIF, SURR, true, true, OP> : k_recur_bwd_lean<ALIF, SURR, true, false, OP>)
+               : (runs ? k_recur_bwd_lean<ALIF, SURR, false, true, OP> : k_recur_bwd_lean<ALIF, SURR, false, false, OP>);
+    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { ProfScope ps(SNNK_K_RECUR_BWD, st); kern<<<bp.B, 128, smem, st>>>(bp); }
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
 }
 
 template <bool ALIF, int SURR>
 int launch_bwd_lean_t(const BwdParams& bp, cudaStream_t st)
 {
-    const size_t smem = bwd_smem_bytes<128, 1>(bp.T, true);
-    const bool planes = bp.gI_lo != nullptr, runs = bp.run_table != nullptr;
-    void (*kern)(const BwdParams) =
-        planes ? (runs ? k_recur_bwd_lean<ALIF, SURR, true, true> : k_recur_bwd_lean<ALIF, SURR, true, false>)
-               : (runs ? k_recur_bwd_lean<ALIF, SURR, false, true> : k_recur_bwd_lean<ALIF, SURR, false, false>);
-    SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { ProfScope ps(SNNK_K_RECUR_BWD, st); kern<<<bp.B, 128, smem, st>>>(bp); }
-    SNNK_CUDA(cudaGetLastError());
-    return SNNK_OK;
+    return bp.O <= 12 ? launch_bwd_lean_o<ALIF, SURR, 12>(bp, st) : launch_bwd_lean_o<ALIF, SURR, 16>(bp, st);
 }
 
 int launch_bwd_lean(const BwdParams& bp, cudaStream_t st)
