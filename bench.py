@@ -566,16 +566,17 @@ def ncu_summary_rows(path):
 
 NCU_SUMMARIES = ["profiles/r02_ncu_full_summary.csv", "profiles/r01_ncu_full_summary_final.csv"]
 # the kernels the HEADLINE configuration launches (B = 256: the one-row-per-CTA SIMT recurrences)
-KERNEL_REGEX = {"K1": "k_proj_tc", "K2": "k_recur_fwd<", "K3": "k_recur_bwd<", "K4": "k_wgrad_tc", "K5": "k_encode", "K6": "k_head_nll"}
+KERNEL_REGEX = {"K1": ("k_proj_tc",), "K2": ("k_recur_fwd_lean", "k_recur_fwd<"), "K3": ("k_recur_bwd_lean", "k_recur_bwd<"),
+	"K4": ("k_wgrad_tc",), "K5": ("k_encode",), "K6": ("k_head_nll",)}      # first pattern with a capture wins
 
 
 def ncu_evidence(kernel_key):
 	"""(dram traffic bytes per launch, shared-memory wavefronts per launch, source file) of the LONGEST launch of the
 	kernel family in the newest committed ncu summary that has it."""
-	pat = KERNEL_REGEX.get(kernel_key)
-	if not pat:
+	pats = KERNEL_REGEX.get(kernel_key)
+	if not pats:
 		return None
-	for rel in NCU_SUMMARIES:
+	for pat, rel in ((p_, r_) for p_ in pats for r_ in NCU_SUMMARIES):
 		rows = [r for r in ncu_summary_rows(os.path.join(ROOT, rel)) if pat in str(r.get("kernel", ""))]
 		if rows:
 			r = max(rows, key=lambda q: q.get("gpu__time_duration.sum", 0.0))
