@@ -663,3 +663,46 @@ def test_fused_head_is_bit_identical_to_the_standalone_head(B, T, H, layer, rec,
 		assert torch.equal(torch.nan_to_num(f["g_logits"]), torch.nan_to_num(gl)), variant
 		if variant == "bad" and B > 1:
 			assert bool(f["loss"].isnan())
+
+
+# ---- lean kernels of the headline geometry == the general kernels, bit for bit -----------------------------------------
+@pytest.mark.parametrize("B,T,layer,phi,tc,dedup", [
+	(256, 100, 1, 0, True, True),       # the bench workload's kernel variants: ALIF, tensor-core GEMMs, run table
+	(256, 100, 1, 0, True, False),
+	(300, 37, 0, 1, False, False),      # LIF, Phi, fp32 GEMMs, T not a multiple of the 8-step chunk
+	(19, 1, 1, 1, True, False),         # T = 1
+	(64, 128, 0, 0, True, True),        # longest sequence the lean BPTT sweep takes
+])
+def test_lean_kernels_match_general_kernels(B, T, layer, phi, tc, dedup, monkeypatch):
+	"""recur_lean.cuh (default for recurrent LIF / ALIF, H = 128, one row per CTA) restates k_recur_fwd / k_recur_bwd with
+	the bookkeeping taken out of the step loop: every output must be IDENTICAL (SNNK_LEAN=0 selects the general kernels)."""
+	N, H, O = 784, 128, 10
+	g = torch.Generator().manual_seed(B + T)
+	theta = 0.03 if layer else 1.0
+	if dedup:
+		img = (torch.randint(1, 256, (B, N), generator=g).float() / 255.0) * (torch.rand(B, N, generator=g) < 0.19)
+		x = ToSpikes(T, use_periods=True).encode_batch(img.to(DEV))
+		assert F_.get_runs(x) is not None
+	else:
+		x = F_.mark_binary((torch.rand(B, T, N, generator=g) < (0.1 if layer else 0.02)).float().to(DEV))
+	W_in = (torch.randn(N, H, generator=g) * theta).to(DEV)
+	W_rec = (torch.randn(H, H, generator=g) * theta).to(DEV)
+	mask = (1 - torch.eye(H)).to(DEV)
+	W_out, b_out = torch.randn(H, O, generator=g).to(DEV), (torch.randn(O, generator=g) * 0.1).to(DEV)
+	beta = torch.tensor([1.6], device=DEV) if layer else None
+	labels = torch.randint(0, O, (B,), generator=g).to(DEV)
+	c = F_.LayerConsts(layer, phi, True, 0.95, 0.995, theta, 0.3 if layer else 1.0, 0.9, tensor_core=tc)
+	res = {}
+	for lean in ("1", "0"):
+		monkeypatch.setenv("SNNK_LEAN", lean)
+		f = F_.run_forward(c, x, W_in, W_rec, mask, beta, W_out, b_out, labels=labels)
+		gr = F_.run_backward(c, x, W_rec, mask, beta, W_out, f["V"], f["a"], f["zbits"], g_logits=f["g_logits"],
+			tstar=f["tstar"], Z=f["Z"], W_effT=f["W_effT"])
+		f2 = F_.run_forward(c, x, W_in, W_rec, mask, beta, W_out, b_out, traces=False)
+		res[lean] = dict(V=f["V"], a=f["a"], Z=f["Z"], y=f["y"], zbits=f["zbits"], logits=f["logits"], tstar=f["tstar"],
+			loss=f["loss"], logp=f["logp"], g_logits=f["g_logits"], gI=gr["gI"]().clone(), dW_in=gr["dW_in"], dW_rec=gr["dW_rec"],
+			dW_out=gr["dW_out"], db=gr["db"], logits_infer=f2["logits"])
+	assert float(res["1"]["Z"].mean()) > 0.001
+	for k, v in res["1"].items():
+		if v is not None:
+			assert torch.equal(v, res["0"][k]), k
