@@ -27,7 +27,7 @@ template <int H>
 constexpr size_t lean_fwd_smem_bytes(int T, int O)
 {
     return sizeof(float) * (size_t)(2 * H) + sizeof(uint32_t) * (size_t)((T * (H / 32) + 3) & ~3) +
-           sizeof(float) * (size_t)((H * O + T * kOMax + 3) & ~3) + sizeof(float) * (size_t)T * H +
+           sizeof(float) * (size_t)((H * 12 + T * kOMax + 3) & ~3) + sizeof(float) * (size_t)T * H +
            sizeof(float) * (size_t)(H / 2) * H + sizeof(uint64_t) * 2;
 }
 
@@ -47,6 +47,139 @@ __device__ __forceinline__ void load_w_cb_half(float (&w)[H], const float* __res
             }
 }
 
+// Tail of the lean forward kernel (one row per CTA): the same sums in the same order as fwd_tail / head_tail, laid out
+// for a CTA that owns ONE row (ncu: the shared tail was 30 % of this kernel).
+//   * readout sums s[t][c] = sum_j Z_t[j] W_out[j][c], ascending j: thread = time step, walking the SET bits of its
+//     four spike words only (adding nothing for a silent neuron is what the predicated add of fwd_tail does too) and
+//     adding the neuron's row of W_out (three LDS.128 from rows padded to 12 floats) to its ten running sums;
+//   * the scan over t per class reads eight sums ahead of its own stores;
+//   * the head: one warp, lane = class -- exponentials and log-probabilities in parallel, the sum of exponentials in
+//     class order as k_head_nll forms it.
+constexpr int kLeanOP = 12;     // row pitch of the readout matrix in shared memory (O <= 12)
+
+template <int H>
+__device__ __forceinline__ void fwd_tail_lean(const FwdParams& p, const uint32_t* s_mask, const float* s_wout, float* s_s,
+                                              float* s_logit, int b, int tid)
+{
+    constexpr int W32 = H / 32;
+    const int T = p.T, O = p.O;
+    for (int idx = tid; idx < T * W32; idx += H) p.zbits[(size_t)b * T * W32 + idx] = s_mask[idx];
+    for (int t = tid; t < T; t += H) {
+        float sum[kLeanOP];
+#pragma unroll
+        for (int c = 0; c < kLeanOP; ++c) sum[c] = 0.f;
+#pragma unroll
+        for (int wd = 0; wd < W32; ++wd) {
+            uint32_t m = s_mask[t * W32 + wd];
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const float4* wr = reinterpret_cast<const float4*>(s_wout + (wd * 32 + l) * kLeanOP);
+#pragma unroll
+                for (int q = 0; q < kLeanOP / 4; ++q) {
+                    const float4 w4 = wr[q];
+                    sum[4 * q + 0] = __fadd_rn(sum[4 * q + 0], w4.x);
+                    sum[4 * q + 1] = __fadd_rn(sum[4 * q + 1], w4.y);
+                    sum[4 * q + 2] = __fadd_rn(sum[4 * q + 2], w4.z);
+                    sum[4 * q + 3] = __fadd_rn(sum[4 * q + 3], w4.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kLeanOP; ++c)
+            if (c < O) s_s[t * O + c] = sum[c];
+    }
+    __syncthreads();
+    // y_t = kappa y_{t-1} + s_t + b (spiking_layers.py:407) and the first maximum over time (snn.py:228)
+    if (tid < O) {
+        const int c = tid;
+        const float bc = __ldg(p.b_out + c);
+        float yv = 0.f, mx = 0.f;
+        int mt = 0;
+        for (int t0 = 0; t0 < T; t0 += 8) {
+            float sv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sv[q] = (t0 + q < T) ? s_s[(t0 + q) * O + c] : 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int t = t0 + q;
+                if (t < T) {
+                    yv = __fadd_rn(__fadd_rn(__fmul_rn(p.kappa, yv), sv[q]), bc);
+                    s_s[t * O + c] = yv;
+                    if (t == 0 || yv > mx) { mx = yv; mt = t; }
+                }
+            }
+        }
+        p.logits[(size_t)b * O + c] = mx;
+        p.tstar[(size_t)b * O + c] = mt;
+        s_logit[c] = mx;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < T * O; idx += H) p.y[(size_t)b * T * O + idx] = s_s[idx];
+}
+
+__device__ __forceinline__ void head_tail_lean(const FwdParams& p, const float* s_logit, int* s_hd, double* s_hp, int b, int tid,
+                                               int nthr)
+{
+    constexpr long long kIgnore = -100;
+    const int O = p.O, B = p.B;
+    const int n_valid = s_hd[0];
+    const bool bad = s_hd[1] != 0;
+    const int lane = tid & 31;
+    if (tid < 32) {
+        const float lg = lane < O ? s_logit[lane] : -INFINITY;
+        float mx = lg;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = lane < O ? expf(lg - mx) : 0.f;
+        float se = 0.f;
+        for (int c = 0; c < O; ++c) se += __shfl_sync(0xffffffffu, e, c);       // class order, as k_head_nll
+        const float lse = logf(se);
+        const float lp = (lg - mx) - lse;
+        const long long lab = p.labels[b];
+        const bool row_ok = lab >= 0 && lab < O, row_bad = !row_ok && lab != kIgnore;
+        if (lane < O) {
+            if (p.logp) p.logp[(size_t)b * O + lane] = lp;
+            if (p.g_logits) {
+                float g = row_ok ? __fdiv_rn(expf(lp) - (lane == lab ? 1.0f : 0.0f), (float)n_valid) : 0.0f;
+                if (row_bad) g = __int_as_float(0x7fc00000);
+                p.g_logits[(size_t)b * O + lane] = g;
+            }
+        }
+        const float nll = -__shfl_sync(0xffffffffu, lp, row_ok ? (int)lab : 0);
+        if (lane == 0) {
+            p.part_nll[b] = row_ok ? nll : 0.f;
+            __threadfence();
+            s_hd[2] = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+        }
+    }
+    __syncthreads();
+    if (!s_hd[2]) return;
+    __threadfence();
+    for (int vw = tid >> 5; vw < 8; vw += nthr >> 5) {
+        double acc = 0.0;
+        for (int bb = vw * 32 + lane; bb < B; bb += 256) acc += (double)__ldcg(p.part_nll + bb);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_hp[vw] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+        for (int q = 0; q < 8; ++q) sum += s_hp[q];
+        const float lossf = bad ? __int_as_float(0x7fc00000) : (float)(sum / (double)n_valid);
+        *p.loss = lossf;
+        *p.ticket = 0u;
+        if (p.mailbox) {
+            const unsigned int seq = *p.mail_counter + 1u;
+            *p.mail_counter = seq;
+            *reinterpret_cast<volatile unsigned long long*>(p.mailbox) =
+                (static_cast<unsigned long long>(seq) << 32) | __float_as_uint(lossf);
+            __threadfence_system();
+        }
+    }
+}
+
 template <int H, bool ALIF, bool TRACES>
 __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd_lean(const FwdParams p)
 {
@@ -58,9 +191,9 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd_lean(const FwdParams p
 
     float* s_z = reinterpret_cast<float*>(smem_raw);                                // [2][H]
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_z + 2 * H);                    // [T][W32]
-    float* s_wout = reinterpret_cast<float*>(s_mask + ((T * W32 + 3) & ~3));        // [H][O]
-    float* s_s = s_wout + H * O;                                                    // [T][O] (tail); compact rows of the steps (prologue)
-    float* s_cur = s_wout + ((H * O + T * kOMax + 3) & ~3);                         // [T][H] input current of the row
+    float* s_wout = reinterpret_cast<float*>(s_mask + ((T * W32 + 3) & ~3));        // [H][12]: rows of W_out padded with zeros
+    float* s_s = s_wout + H * kLeanOP;                                              // [T][O] (tail); compact rows of the steps (prologue)
+    float* s_cur = s_wout + ((H * kLeanOP + T * kOMax + 3) & ~3);                   // [T][H] input current of the row
     float* s_w = s_cur + (size_t)T * H;                                             // [H/2][H] staging, prologue only
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_w + (H / 2) * H);               // [0] weights, [1] input current
     __shared__ int s_hd[4];
@@ -116,7 +249,10 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd_lean(const FwdParams p
     float a = p.a0 ? p.a0[(size_t)b * H + i] : 0.f;
     float zp = p.Z0 ? p.Z0[(size_t)b * H + i] : 0.f;
     s_z[H + i] = zp;                               // step 0 reads buffer 1
-    for (int idx = i; idx < H * O; idx += H) s_wout[idx] = __ldg(p.W_out + idx);
+    for (int idx = i; idx < H * kLeanOP; idx += H) {
+        const int j = idx / kLeanOP, c = idx - j * kLeanOP;
+        s_wout[idx] = c < O ? __ldg(p.W_out + j * O + c) : 0.f;
+    }
     tc::mbar_wait(s_bar, 1);
     load_w_cb_half<H>(w, s_w, i, 1);
     tc::mbar_wait(s_bar + 1, 0);
@@ -180,8 +316,8 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd_lean(const FwdParams p
     if (t < T) step(std::integral_constant<int, 0>{});
     __syncthreads();
 
-    fwd_tail<H, 1>(p, s_mask, s_wout, s_s, b, i, H, s_logit);
-    if (p.labels) head_tail<1>(p, s_logit, s_hd, s_hp, b, i, H);
+    fwd_tail_lean<H>(p, s_mask, s_wout, s_s, s_logit, b, i);
+    if (p.labels) head_tail_lean(p, s_logit, s_hd, s_hp, b, i, H);
 }
 
 // ---- backward -------------------------------------------------------------------------------------------------------

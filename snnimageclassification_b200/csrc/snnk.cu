@@ -462,7 +462,7 @@ int launch_fwd(const FwdParams& fp, int grid, cudaStream_t st)
 // resident in shared memory.  SNNK_LEAN=0 keeps the general kernel (measuring switch, read per call).
 bool use_lean_fwd(const FwdParams& fp, bool rec, int R)
 {
-    if (!rec || fp.iz.on || fp.H != 128 || R != 1) return false;
+    if (!rec || fp.iz.on || fp.H != 128 || R != 1 || fp.O > kLeanOP) return false;
     if (lean_fwd_smem_bytes<128>(fp.T, fp.O) > 110 * 1024) return false;
     const char* env = getenv("SNNK_LEAN");
     return !(env && env[0] == '0');
