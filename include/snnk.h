@@ -295,6 +295,11 @@ int snnk_adam_step(int32_t count, float* const* params, const float* const* grad
  *   state:        16 zero-initialised uint32 in LOCAL device memory: [0] epoch and [2] grid counter (never reset
  *                 them), [3] timeout marker, [4..11] four uint64 %globaltimer stamps of the last launch as seen by
  *                 the first thread (start, stores issued, all peers seen, done) for measuring the exchange.
+ * From 4 ranks on the exchange is two-phase over the same words and buffers: a value goes to the element's OWNER rank
+ * only (contiguous slices of the flat gradient), the owner sums in rank order and stores the tagged mean into the slot
+ * its own value would have had in every peer's buffer -- 1/world of the bytes, one more one-way trip, identical bits
+ * on all ranks.  The environment variable SNNK_DP_RSAG = 0 / 1 (read at every call; it must be the same on all
+ * ranks) forces the one-phase / two-phase form.
  * All ranks must issue the same sequence of calls.  Graph-capturable; a peer that never arrives traps the kernel
  * after 20 s (a sticky CUDA error) instead of hanging.
  */

@@ -1347,6 +1347,11 @@ int snnk_adam_step_dp(int32_t count, float* const* params, float* const* grads, 
     t.start[count] = total;
     AdamDp dp{};
     dp.rank = rank; dp.world = world; dp.state = state;
+    {   // two-phase exchange from 4 ranks on (at 2 the all-to-all IS one hop and one word); SNNK_DP_RSAG=0/1 forces it --
+        // every rank must decide alike, which an environment variable of the launcher guarantees
+        const char* env = getenv("SNNK_DP_RSAG");
+        dp.rsag = env ? (env[0] != '0' && world >= 2) : (world >= 4);
+    }
     for (int r = 0; r < world; ++r) {
         if (!peer_buffers[r]) return SNNK_ERR_ARG;
         if (reinterpret_cast<uintptr_t>(peer_buffers[r]) & 7) return SNNK_ERR_ARG;
