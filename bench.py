@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
 						self.reasons.add(name)
 			except Exception:
 				pass
-			time.sleep(0.001)      # the timed region is a few milliseconds long
+			time.sleep(0.0005)     # the timed region is a few tens of milliseconds long
 
 	def stop(self):
 		self._stop_evt.set()
@@ -133,7 +133,7 @@ def reference_arm(args, rank):
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument("--gpus", type=int, default=1)
-	ap.add_argument("--steps", type=int, default=200)
+	ap.add_argument("--steps", type=int, default=400)
 	ap.add_argument("--warmup", type=int, default=20)
 	ap.add_argument("--impl", default="native", choices=["native", "reference"])
 	ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,6 +210,8 @@ def main():
 		step_resident(i)
 	sampler = ClockSampler(local_rank)
 	sampler.start()
+	for i in range(50):         # the same steps, untimed, while the sampler thread comes up: the GPU is under this load when
+		step_resident(i)        # the first NVML query returns (a 30 ms timed region alone sometimes caught a single sample)
 	ms = timed(step_resident, args.steps)
 	clocks = sampler.stop()
 	timeline = None
