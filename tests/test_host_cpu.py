@@ -214,3 +214,26 @@ def test_reference_style_checkpoint_loads_without_full_unpickling(tmp_path):
 		net._load_file(bad)
 	with pytest.raises(FileNotFoundError):
 		net._load_file(str(tmp_path / "missing.pth"))
+
+
+def test_packed_raster_tagging_and_passthrough():
+	"""Host logic of SNNK_F_INPUT_BITS: which int32 tensors count as packed rasters, when SNN keeps them packed."""
+	from snnimageclassification_b200.modules import functional as F_
+	bits = torch.zeros(2, 5, 25, dtype=torch.int32)
+	assert F_.bits_width(bits) is None
+	assert F_.bits_width(F_.mark_bits(bits, 784)) == 784
+	assert F_.bits_width(F_._c(bits)) == 784 and F_._c(bits).dtype == torch.int32      # stays packed through the glue
+	with pytest.raises(ValueError):
+		F_.mark_bits(torch.zeros(2, 5, 24, dtype=torch.int32), 784)       # 784 features are 25 words
+	with pytest.raises(ValueError):
+		F_.mark_bits(torch.zeros(2, 5, 25), 784)                          # not int32
+	assert F_.bits_eligible(784, True) and not F_.bits_eligible(784, False) and not F_.bits_eligible(786, True)
+	net = SNN(784, 10, 32, device=CPU, int_time_steps=5)
+	kept = net._encode_if_needed(torch.zeros(2, 5, 25, dtype=torch.int32))
+	assert F_.bits_width(kept) == 784 and net._format_inputs(kept) is kept
+	# fewer steps than int_time_steps: must be unpacked (and zero-padded) -- on the GPU; here the unpack refuses the CPU
+	with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+		net._encode_if_needed(torch.zeros(2, 3, 25, dtype=torch.int32))
+	fp32 = SNN(784, 10, 32, device=CPU, int_time_steps=5, tensor_core=False)
+	with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+		fp32._encode_if_needed(torch.zeros(2, 5, 25, dtype=torch.int32))
