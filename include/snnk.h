@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SNNK_ABI_VERSION 7   /* 7: snnk_forward_nll; 6: SNNK_F_INPUT_BITS; 5: loss mailbox of snnk_head_nll; 4: W_effT_out / W_effT_in; 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
+#define SNNK_ABI_VERSION 8   /* 8: SNNK_F_RUNS_TILED, snnk_run_table_tiled_bytes; 7: snnk_forward_nll; 6: SNNK_F_INPUT_BITS; 5: loss mailbox of snnk_head_nll; 4: W_effT_out / W_effT_in; 2: run_table argument of snnk_forward / snnk_backward, snnk_encode_runs, snnk_adam_step_dp; 3: Izhikevich fields of SnnkDesc */
 
 typedef void* snnk_stream_t; /* cudaStream_t */
 
@@ -79,6 +79,10 @@ enum {
                                   the weight-gradient contraction expand the words inside shared memory
                                   (k_proj_bits / k_wgrad_bits): the fp32 raster of datasets.py:93-97 never exists.
                                   A run table is ignored with this flag (dense kernels). */
+
+#define SNNK_F_RUNS_TILED 0x10u /* the run table passed to snnk_forward / snnk_forward_nll is followed by the compact rows
+                                  tiled for the projection (snnk_run_table_tiled_bytes, snnk_encode_runs with lazy & 2):
+                                  the per-step gather of those rows is skipped */
 
 /* Geometry and constants of one hidden spiking layer + leaky readout. */
 typedef struct SnnkDesc {
@@ -165,6 +169,10 @@ int snnk_unpack_raster(const uint32_t* bits, int64_t n_rows, int32_t n_pix, floa
  * the call stays CUDA-graph capturable and a batch with too many runs silently takes the dense kernels.
  */
 size_t snnk_run_table_bytes(int64_t n_items, int32_t n_steps);
+/* Table + (1 KB aligned) the first row of every run as the 128-row x 32-feature swizzled tiles the compact projection
+ * reads (fp32 rasters, n_pix % 4 == 0; else 0).  snnk_encode_runs fills that tail when bit 1 of `lazy` is set (bit 0:
+ * lazy raster), and a forward call given such a table sets SNNK_F_RUNS_TILED. */
+size_t snnk_run_table_tiled_bytes(int64_t n_items, int32_t n_steps, int32_t n_pix);
 int snnk_frame_runs(int64_t n_items, int32_t n_steps, const uint8_t* frame_changed, int32_t* run_table,
                     snnk_stream_t stream);
 int snnk_encode_runs(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps,

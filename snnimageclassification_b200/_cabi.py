@@ -22,7 +22,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "snnk.h")
 SNNK_LIF, SNNK_ALIF, SNNK_IZHIKEVICH = 0, 1, 2
 SNNK_FAST_SIGMOID, SNNK_PHI = 0, 1
 SNNK_F32, SNNK_F64, SNNK_U8, SNNK_I64, SNNK_BITS = 0, 1, 2, 3, 4
-SNNK_F_TRACES, SNNK_F_TENSOR_CORE, SNNK_F_INPUT_BINARY, SNNK_F_INPUT_BITS = 0x1, 0x2, 0x4, 0x8
+SNNK_F_TRACES, SNNK_F_TENSOR_CORE, SNNK_F_INPUT_BINARY, SNNK_F_INPUT_BITS, SNNK_F_RUNS_TILED = 0x1, 0x2, 0x4, 0x8, 0x10
 
 NVCC_FLAGS = [
 	"-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -82,6 +82,7 @@ _SIGNATURES = {
 	"snnk_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(SnnkDesc)]),
 	"snnk_unpack_raster": (ctypes.c_int, [_p, ctypes.c_int64, ctypes.c_int32, _p, _p]),
 	"snnk_run_table_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32]),
+	"snnk_run_table_tiled_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
 	"snnk_frame_runs": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, _p, _p, _p]),
 	"snnk_encode_runs": (ctypes.c_int, [
 		_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_double,
@@ -114,7 +115,7 @@ def lib() -> ctypes.CDLL:
 			fn = getattr(l, name)
 			fn.restype = res
 			fn.argtypes = args
-		if l.snnk_abi_version() != 7:
+		if l.snnk_abi_version() != 8:
 			raise RuntimeError("libsnnk.so ABI version mismatch; rebuild the extension")
 		_lib = l
 	return _lib

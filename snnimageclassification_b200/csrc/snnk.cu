@@ -1015,6 +1015,20 @@ size_t snnk_run_table_bytes(int64_t n_items, int32_t n_steps)
     return sizeof(int32_t) * run_table_ints(n_items, n_steps);
 }
 
+// Run table followed by the compact rows, tiled for the projection kernel (k_gather_rows_tiled's output)
+static size_t run_table_tiled_offset(int64_t n_items, int32_t n_steps)
+{
+    return align_up(sizeof(int32_t) * run_table_ints(n_items, n_steps), 1024);
+}
+
+size_t snnk_run_table_tiled_bytes(int64_t n_items, int32_t n_steps, int32_t n_pix)
+{
+    if (snnk_run_table_bytes(n_items, n_steps) == 0 || n_pix <= 0 || n_pix % 4 != 0) return 0;
+    const size_t rows = ((size_t)run_cap(n_items * n_steps) + 127) / 128 * 128;
+    const size_t kpad = ((size_t)n_pix + tc::kBlockK - 1) / tc::kBlockK * tc::kBlockK;
+    return run_table_tiled_offset(n_items, n_steps) + sizeof(float) * rows * kpad;
+}
+
 int snnk_frame_runs(int64_t n_items, int32_t n_steps, const uint8_t* frame_changed, int32_t* run_table,
                     snnk_stream_t stream)
 {
@@ -1034,6 +1048,22 @@ int snnk_frame_runs(int64_t n_items, int32_t n_steps, const uint8_t* frame_chang
     return SNNK_OK;
 }
 
+// The first row of every run, tiled and swizzled for the compact projection, behind the table (lazy & 2): the gather
+// that snnk_forward would otherwise run at the head of every step is done once, where the raster is made.
+static int tile_compact_rows(const void* out, int32_t out_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps,
+                             int32_t* run_table, cudaStream_t st)
+{
+    if (out_dtype != SNNK_F32 || snnk_run_table_tiled_bytes(n_items, n_steps, (int32_t)n_pix) == 0) return SNNK_ERR_ARG;
+    const int BT = (int)(n_items * n_steps);
+    const int rows = (run_cap(BT) + 127) / 128 * 128;
+    const int kpad = ((int)n_pix + tc::kBlockK - 1) / tc::kBlockK * tc::kBlockK;
+    float* Xu = reinterpret_cast<float*>(reinterpret_cast<char*>(run_table) + run_table_tiled_offset(n_items, n_steps));
+    k_gather_rows_tiled<<<std::min(rows, 8 * sm_count()), 256, 0, st>>>(static_cast<const float*>(out), run_table, BT,
+                                                                      (int)n_pix, kpad, Xu);
+    SNNK_CUDA(cudaGetLastError());
+    return SNNK_OK;
+}
+
 int snnk_encode_runs(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_pix, int32_t n_steps, double t_max,
                      double tau, double thr, double eps, int32_t periodic, void* out, int32_t out_dtype,
                      int64_t* periods, uint8_t* frame_changed, int32_t* run_table, int32_t lazy, snnk_stream_t stream)
@@ -1043,11 +1073,13 @@ int snnk_encode_runs(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_
     if (!x || !out || !frame_changed || !run_table) return SNNK_ERR_ARG;
     if (!device_ok()) return SNNK_ERR_DEVICE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!lazy) {
+    if (!(lazy & 1)) {
         int rc = encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, periods,
                             frame_changed, st);
         if (rc != SNNK_OK) return rc;
-        return snnk_frame_runs(n_items, n_steps, frame_changed, run_table, stream);
+        rc = snnk_frame_runs(n_items, n_steps, frame_changed, run_table, stream);
+        if (rc != SNNK_OK) return rc;
+        return (lazy & 2) ? tile_compact_rows(out, out_dtype, n_items, n_pix, n_steps, run_table, st) : SNNK_OK;
     }
     // lazy raster: flags -> run table -> only the rows the consumers of the table will read (all of them if not ok)
     int rc = encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, periods,
@@ -1055,8 +1087,10 @@ int snnk_encode_runs(const void* x, int32_t x_dtype, int64_t n_items, int64_t n_
     if (rc != SNNK_OK) return rc;
     rc = snnk_frame_runs(n_items, n_steps, frame_changed, run_table, stream);
     if (rc != SNNK_OK) return rc;
-    return encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, nullptr,
-                      frame_changed, st, 2, run_table);
+    rc = encode_any(x, x_dtype, n_items, n_pix, n_steps, t_max, tau, thr, eps, periodic, out, out_dtype, nullptr,
+                    frame_changed, st, 2, run_table);
+    if (rc != SNNK_OK) return rc;
+    return (lazy & 2) ? tile_compact_rows(out, out_dtype, n_items, n_pix, n_steps, run_table, st) : SNNK_OK;
 }
 
 int snnk_spike_forward(const float* v, const float* thr, int64_t n, int64_t thr_n, float* out,
@@ -1171,7 +1205,11 @@ static int forward_impl(const SnnkDesc* d, const float* x, const float* W_in, co
             if (runs) {
                 float* Xu = reinterpret_cast<float*>(ws + pl.off_xu_f);
                 float* Iu = reinterpret_cast<float*>(ws + pl.off_iu);
-                {
+                if (d->flags & SNNK_F_RUNS_TILED) {
+                    // the encoder left the tiled compact rows behind the table (snnk_encode_runs, lazy & 2)
+                    Xu = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<int32_t*>(runs)) +
+                                                  run_table_tiled_offset(d->B, d->T));
+                } else {
                     ProfScope ps(SNNK_K_PROJ, st);
                     k_gather_rows_tiled<<<std::min(pl.run_rows, 8 * sm_count()), 256, 0, st>>>(x, runs, M, d->N, pl.kpad, Xu);
                     SNNK_CUDA(cudaGetLastError());

@@ -164,12 +164,17 @@ class ToSpikes:
 		_cabi.require_b200(x2.device)
 		out = torch.empty((n_items, self.n_steps, n_pix), dtype=out_dtype, device=x2.device)
 		changed = torch.empty((n_items, self.n_steps), dtype=torch.uint8, device=x2.device)
-		table = torch.empty((nbytes // 4,), dtype=torch.int32, device=x2.device)
+		# fp32 rasters: the first row of every run also goes behind the table, tiled for the compact projection, so that
+		# the training step does not gather those rows at its head (include/snnk.h, SNNK_F_RUNS_TILED)
+		tiled = 0
+		if out_dtype == torch.float32 and os.environ.get("SNNK_RUNS_TILED", "1") != "0":
+			tiled = _cabi.lib().snnk_run_table_tiled_bytes(n_items, self.n_steps, n_pix)
+		table = torch.empty(((tiled or nbytes) // 4,), dtype=torch.int32, device=x2.device)
 		with torch.cuda.device(x2.device):
 			rc = _cabi.lib().snnk_encode_runs(
 				_cabi.ptr(x2), _DT[x2.dtype], n_items, n_pix, self.n_steps, float(self.t_max), float(self.tau),
 				float(self.thr), float(self.epsilon), int(self.use_periods), _cabi.ptr(out), _DT[out_dtype], None,
-				_cabi.ptr(changed), _cabi.ptr(table), int(bool(lazy)), _cabi.stream_ptr())
+				_cabi.ptr(changed), _cabi.ptr(table), int(bool(lazy)) | (2 if tiled else 0), _cabi.stream_ptr())
 		_cabi.check(rc, "snnk_encode_runs")
 		out._snnk_binary = True
 		out._snnk_runs = table

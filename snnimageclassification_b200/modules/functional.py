@@ -85,15 +85,27 @@ def get_runs(t) -> Optional[torch.Tensor]:
 	if runs is None or not is_binary(t) or t.ndim != 3:
 		return None
 	need = _cabi.lib().snnk_run_table_bytes(t.shape[0], t.shape[1]) // 4
-	if runs.dtype != torch.int32 or runs.device != t.device or runs.numel() != need or need == 0:
+	if runs.dtype != torch.int32 or runs.device != t.device or need == 0:
+		return None
+	if runs.numel() != need and not runs_tiled(t):
 		return None
 	return runs
 
 
+def runs_tiled(t) -> bool:
+	"""Whether the run table riding on ``t`` is followed by the tiled compact rows (snnk_run_table_tiled_bytes)."""
+	runs = getattr(t, RUNS_TAG, None)
+	if runs is None or t.ndim != 3 or t.dtype != torch.float32:
+		return False
+	need = _cabi.lib().snnk_run_table_tiled_bytes(t.shape[0], t.shape[1], t.shape[2]) // 4
+	return need != 0 and runs.numel() == need
+
+
 def make_desc(c: LayerConsts, B: int, T: int, N: int, H: int, O: int, traces: bool, binary: bool = False,
-		bits: bool = False) -> _cabi.SnnkDesc:
+		bits: bool = False, tiled: bool = False) -> _cabi.SnnkDesc:
 	flags = (_cabi.SNNK_F_TRACES if traces else 0) | (_cabi.SNNK_F_TENSOR_CORE if c.tensor_core else 0) | (
-		_cabi.SNNK_F_INPUT_BINARY if (binary or bits) else 0) | (_cabi.SNNK_F_INPUT_BITS if bits else 0)
+		_cabi.SNNK_F_INPUT_BINARY if (binary or bits) else 0) | (_cabi.SNNK_F_INPUT_BITS if bits else 0) | (
+		_cabi.SNNK_F_RUNS_TILED if tiled else 0)
 	izh = tuple(c.izh) if c.izh is not None else (0.0,) * 10
 	return _cabi.SnnkDesc(
 		B, T, N, H, O, c.layer_type, c.surrogate, int(c.recurrent), c.alpha, c.rho, c.theta, c.gamma, c.kappa, flags,
@@ -183,8 +195,9 @@ def run_forward(
 	H, O = W_out.shape
 	if W_in.shape != (N, H):
 		raise RuntimeError(f"forward_weights has shape {tuple(W_in.shape)}, expected {(N, H)}")
-	desc = make_desc(c, B, T, N, H, O, traces, binary=is_binary(x), bits=nbits is not None)
 	runs = get_runs(x) if nbits is None else None
+	desc = make_desc(c, B, T, N, H, O, traces, binary=is_binary(x), bits=nbits is not None,
+		tiled=runs is not None and runs_tiled(x))
 	dev = x.device
 	f32 = dict(dtype=torch.float32, device=dev)
 	alif = c.layer_type != _cabi.SNNK_LIF     # three-state layers: ALIF (V, a, Z) and Izhikevich (V, u, Z)

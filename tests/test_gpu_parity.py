@@ -32,7 +32,7 @@ def npy(t):
 
 
 def test_native_library_loaded_and_device_supported():
-	assert _cabi.lib().snnk_abi_version() == 7
+	assert _cabi.lib().snnk_abi_version() == 8
 	_cabi.require_b200(DEV)
 
 

@@ -227,3 +227,35 @@ def test_full_size_determinism_and_row_independence():
 	assert torch.equal(outp, out[perm.to(DEV)])
 	for u, v in zip(hidp["input"], hid["input"]):
 		assert torch.equal(u, v[perm.to(DEV)])
+
+
+def test_tiled_compact_rows_behind_the_table(monkeypatch):
+	"""encode_batch leaves the first row of every run behind the run table, tiled for the compact projection
+	(SNNK_F_RUNS_TILED): the step then skips its gather.  Same results, bit for bit, as with the gather."""
+	from snnimageclassification_b200 import ToSpikes
+	from snnimageclassification_b200.modules import functional as F_
+	B, T, N, H, O = 48, 40, 784, 128, 10
+	img = _images(B, N, 3).to(DEV)
+	enc = ToSpikes(T, use_periods=True)
+	x_t = enc.encode_batch(img)
+	monkeypatch.setenv("SNNK_RUNS_TILED", "0")
+	x_g = enc.encode_batch(img)
+	monkeypatch.delenv("SNNK_RUNS_TILED")
+	assert F_.runs_tiled(x_t) and not F_.runs_tiled(x_g) and F_.get_runs(x_g) is not None
+	assert torch.equal(x_t, x_g)
+	ta, tb = F_.get_runs(x_t).cpu().numpy(), F_.get_runs(x_g).cpu().numpy()
+	n_rows, cap = int(tb[0]), int(tb[2])
+	assert np.array_equal(ta[:4 + B * T + n_rows], tb[:4 + B * T + n_rows])                     # header, row -> run, first rows
+	assert np.array_equal(ta[4 + B * T + cap: 4 + B * T + cap + n_rows], tb[4 + B * T + cap: 4 + B * T + cap + n_rows])   # run lengths
+	g = torch.Generator().manual_seed(0)
+	W_in = (torch.randn(N, H, generator=g) * 0.03).to(DEV)
+	W_rec = (torch.randn(H, H, generator=g) * 0.03).to(DEV)
+	mask = (1 - torch.eye(H)).to(DEV)
+	W_out, b_out = torch.randn(H, O, generator=g).to(DEV), torch.zeros(O, device=DEV)
+	beta = torch.tensor([1.6], device=DEV)
+	c = F_.LayerConsts(1, 0, True, 0.95, 0.995, 0.03, 0.3, 0.9, tensor_core=True)
+	f_t = F_.run_forward(c, x_t, W_in, W_rec, mask, beta, W_out, b_out)
+	f_g = F_.run_forward(c, x_g, W_in, W_rec, mask, beta, W_out, b_out)
+	assert float(f_t["Z"].mean()) > 0.0
+	for k in ("V", "a", "Z", "y", "logits"):
+		assert torch.equal(f_t[k], f_g[k]), k

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 	for name in declared:
 		assert hasattr(lib, name), f"{name} declared in snnk.h but not exported by libsnnk.so"
 	assert sorted(_cabi.EXPORTS) == declared, "python binding and header disagree on the entry points"
-	assert _cabi.lib().snnk_abi_version() == 7
+	assert _cabi.lib().snnk_abi_version() == 8
 	assert b"sm_100" in _cabi.lib().snnk_strerror(-3)
 
 
@@ -172,6 +172,14 @@ def test_run_table_tag_is_validated():
 	mark_binary(x, runs=torch.zeros(need, dtype=torch.int32))
 	assert get_runs(x) is not None
 	assert get_runs(mark_binary(torch.zeros(2, 5, 8), runs=torch.zeros(need, dtype=torch.int64))) is None
+	# a table followed by the tiled compact rows (snnk_run_table_tiled_bytes) is accepted too, and recognised as such
+	from snnimageclassification_b200.modules.functional import runs_tiled
+	tiled = _cabi.lib().snnk_run_table_tiled_bytes(2, 5, 8) // 4
+	assert tiled > need and _cabi.lib().snnk_run_table_tiled_bytes(2, 5, 6) == 0          # n_pix % 4 != 0: no tiled form
+	assert not runs_tiled(x)
+	y = mark_binary(torch.zeros(2, 5, 8), runs=torch.zeros(tiled, dtype=torch.int32))
+	assert get_runs(y) is not None and runs_tiled(y)
+	assert get_runs(mark_binary(torch.zeros(2, 5, 8), runs=torch.zeros(tiled - 1, dtype=torch.int32))) is None
 
 
 def test_fused_adam_load_state_dict_normalises_foreign_state():
