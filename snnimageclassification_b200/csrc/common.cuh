@@ -40,6 +40,9 @@ struct FwdParams {
     float* part_nll;        // (B) per-row NLL terms
     unsigned int* ticket;   // zero before the launch; the last CTA leaves it zero again
     unsigned long long* mailbox; unsigned int* mail_counter;
+    // 1: launched as a programmatic dependent of the projection kernel (k_recur_fwd_lean): the kernel may start while the
+    // projection still runs and must execute griddepcontrol.wait before it touches I_in / I_u
+    int pdl;
 };
 
 struct BwdParams {

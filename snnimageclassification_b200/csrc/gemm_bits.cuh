@@ -133,6 +133,7 @@ k_proj_bits(const uint32_t* __restrict__ bits, int wd, const __half* __restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * (MT * kBlockM);
     const int n0 = blockIdx.y * H;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // see k_proj_tc
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_b + s, 1); mbar_init(full_a + s, 4 * MT); mbar_init(empty + s, 1); }

@@ -235,6 +235,10 @@ k_proj_tc(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ p
           int M, int kblocks, int ldc, unsigned int* __restrict__ inexact_flag, const int* __restrict__ run_table,
           int run_variant, const float* __restrict__ a_tiled)
 {
+    // Programmatic dependent launch: the recurrence kernel queued behind this one may start NOW (on SMs this grid does
+    // not occupy) and run its prologue -- weight staging, label statistics -- until its griddepcontrol.wait, which
+    // returns when this grid has completed.  A no-op when the dependent was launched the ordinary way.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // frame-dedup gating (runs.cuh): run_variant 0 = dense kernel, skipped when the table says the compact kernels
     // run; 1 = compact kernel over M = n_rows rows, skipped otherwise.  Decided before any barrier or TMEM allocation.
     if (run_table) {

@@ -209,20 +209,30 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd_lean(const FwdParams p
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tc::mbar_expect_tx(s_bar, kHalfBytes);
         tc::bulk_g2s(s_w, p.W_eff, kHalfBytes, s_bar);
+    }
+    // The row's input current: the contiguous T x H block (dense), or -- frame-dedup variant -- the sample's compact rows,
+    // consecutive rows of I_u (at most T of them), by one bulk copy to the START of the buffer; spread over the steps below.
+    // Launched as a programmatic dependent of the projection (p.pdl) everything above and below runs while the
+    // projection may still be writing I_in / I_u: the copy is issued last, behind griddepcontrol.wait.
+    int cp_first = 0, cp_last = 0;
+    if (i == 0 && compact) {
+        const int* r2c = p.run_table + kRunHdrInts + (size_t)b * T;
+        cp_first = __ldg(r2c);
+        cp_last = __ldg(r2c + T - 1);
+    }
+    auto issue_current = [&]() {      // thread 0 only
+        if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
         if (!compact) {
             const uint32_t bytes = (uint32_t)((size_t)T * H * sizeof(float));
             tc::mbar_expect_tx(s_bar + 1, bytes);
             tc::bulk_g2s(s_cur, p.I_in + (size_t)b * T * H, bytes, s_bar + 1);
         } else {
-            // frame-dedup variant: the compact rows of a sample are consecutive rows of I_u (at most T of them): one bulk
-            // copy brings them to the START of the row's current buffer; they are spread over the steps below
-            const int* r2c = p.run_table + kRunHdrInts + (size_t)b * T;
-            const int first = __ldg(r2c), last = __ldg(r2c + T - 1);
-            const uint32_t bytes = (uint32_t)((size_t)(last - first + 1) * H * sizeof(float));
+            const uint32_t bytes = (uint32_t)((size_t)(cp_last - cp_first + 1) * H * sizeof(float));
             tc::mbar_expect_tx(s_bar + 1, bytes);
-            tc::bulk_g2s(s_cur, p.I_u + (size_t)first * H, bytes, s_bar + 1);
+            tc::bulk_g2s(s_cur, p.I_u + (size_t)cp_first * H, bytes, s_bar + 1);
         }
-    }
+    };
+    if (i == 0 && !p.pdl) issue_current();
     int* s_r2c = reinterpret_cast<int*>(s_s);      // [T] compact row of every step, relative to the sample's first (prologue only)
     if (compact) {
         const int* r2c = p.run_table + kRunHdrInts + (size_t)b * T;
@@ -255,6 +265,7 @@ __global__ void __launch_bounds__(H, 256 / H) k_recur_fwd_lean(const FwdParams p
     }
     tc::mbar_wait(s_bar, 1);
     load_w_cb_half<H>(w, s_w, i, 1);
+    if (i == 0 && p.pdl) issue_current();
     tc::mbar_wait(s_bar + 1, 0);
     if (compact) {
         // step t takes compact row s_r2c[t] <= t (the table never advances by more than one row per step), so walking t

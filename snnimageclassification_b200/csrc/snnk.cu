@@ -113,6 +113,7 @@ int sm_count()
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+constexpr bool kPdlDefault = true;    // programmatic dependent launch of the lean forward recurrence behind the projection
 constexpr int kBitsMT = 2;   // row / feature tiles per CTA of the bit-fed GEMMs (both accumulators fit TMEM)
 
 // How the batch is cut into CTAs and how the weight-gradient GEMM is split; shared by the workspace
@@ -468,13 +469,29 @@ bool use_lean_fwd(const FwdParams& fp, bool rec, int R)
     return !(env && env[0] == '0');
 }
 
-int launch_fwd_lean(const FwdParams& fp, cudaStream_t st)
+// pdl: launch as a programmatic dependent of the kernel queued before it on the stream (the projection GEMM, which
+// executes griddepcontrol.launch_dependents at its start): the recurrence kernel's prologue then overlaps the projection.
+int launch_fwd_lean(FwdParams fp, cudaStream_t st, bool pdl)
 {
     const size_t smem = lean_fwd_smem_bytes<128>(fp.T, fp.O);
     void (*kern)(const FwdParams) = fp.alif ? (fp.traces ? k_recur_fwd_lean<128, true, true> : k_recur_fwd_lean<128, true, false>)
                                             : (fp.traces ? k_recur_fwd_lean<128, false, true> : k_recur_fwd_lean<128, false, false>);
     SNNK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { ProfScope ps(SNNK_K_RECUR_FWD, st); kern<<<fp.B, 128, smem, st>>>(fp); }
+    fp.pdl = pdl ? 1 : 0;
+    {
+        ProfScope ps(SNNK_K_RECUR_FWD, st);
+        if (pdl) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(fp.B); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            SNNK_CUDA(cudaLaunchKernelEx(&cfg, kern, (const FwdParams)fp));
+        } else {
+            kern<<<fp.B, 128, smem, st>>>(fp);
+        }
+    }
     SNNK_CUDA(cudaGetLastError());
     return SNNK_OK;
 }
@@ -1278,7 +1295,13 @@ static int forward_impl(const SnnkDesc* d, const float* x, const float* W_in, co
     } else if (pl.nr) {
         rc = launch_nonrec_fwd(fp, st);
     } else {
-        if (use_lean_fwd(fp, rec, pl.R)) rc = launch_fwd_lean(fp, st);
+        if (use_lean_fwd(fp, rec, pl.R)) {
+            // behind a tensor-core projection on the same stream (not while the per-kernel profiler brackets launches
+            // with events); SNNK_PDL=0/1 is the measuring switch
+            const char* env = getenv("SNNK_PDL");
+            const bool pdl = pl.tc && !g_prof_on && (env ? env[0] != '0' : kPdlDefault);
+            rc = launch_fwd_lean(fp, st, pdl);
+        }
         else switch (d->H) {
         case 32: rc = launch_fwd_r<32>(fp, rec, pl.R, pl.grid_rows, st); break;
         case 64: rc = launch_fwd_r<64>(fp, rec, pl.R, pl.grid_rows, st); break;
