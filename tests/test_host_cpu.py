@@ -245,3 +245,23 @@ def test_packed_raster_tagging_and_passthrough():
 	fp32 = SNN(784, 10, 32, device=CPU, int_time_steps=5, tensor_core=False)
 	with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
 		fp32._encode_if_needed(torch.zeros(2, 5, 25, dtype=torch.int32))
+
+
+def test_bench_parses_the_committed_ncu_summary():
+	"""bench.py takes `roofline.traffic` / `roofline.smem_frac` from profiles/r02_ncu_full_summary.csv (unit row respected):
+	the headline kernels' rows must be found (lean kernels first) and carry sane numbers."""
+	import importlib.util
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+	bench = importlib.util.module_from_spec(spec)
+	spec.loader.exec_module(bench)
+	k3 = bench.ncu_evidence("K3")
+	assert k3 is not None and "k_recur_bwd_lean" in k3["kernel"]
+	assert 20e6 < k3["traffic"] < 60e6                     # bytes per launch: V, a read once (26 MB), gI mostly stays in L2
+	assert 30.0 < k3["ncu_duration_us"] < 100.0            # microseconds, not nanoseconds
+	assert k3["smem_wavefronts"] > 1e6
+	k2 = bench.ncu_evidence("K2")
+	assert k2 is not None and "k_recur_fwd_lean" in k2["kernel"]
+	assert bench.ncu_evidence("K1") is not None and bench.ncu_evidence("nope") is None
+	flops, byts = bench.per_sample_work(128, True, True, True)
+	assert abs(flops - 50.7e6) < 0.5e6 and abs(byts - 942e3) < 5e3      # SURVEY.md 8d: c2 = 50.7 MFLOP, 942 KB per sample
