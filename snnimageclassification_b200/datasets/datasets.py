@@ -169,6 +169,8 @@ class ToSpikes:
 		tiled = 0
 		if out_dtype == torch.float32 and os.environ.get("SNNK_RUNS_TILED", "1") != "0":
 			tiled = _cabi.lib().snnk_run_table_tiled_bytes(n_items, self.n_steps, n_pix)
+			if tiled > (256 << 20):      # sized for the table's capacity (a quarter of the rows): not worth it for huge batches
+				tiled = 0
 		table = torch.empty(((tiled or nbytes) // 4,), dtype=torch.int32, device=x2.device)
 		with torch.cuda.device(x2.device):
 			rc = _cabi.lib().snnk_encode_runs(
